@@ -1,0 +1,192 @@
+/*
+ * xlstm_b200 — C ABI of the B200-native recurrent-inference path for LRAM's xLSTM policy.
+ *
+ * Plain C: pointers, sizes, ints. No torch / C++ types cross this boundary. Every device pointer is owned
+ * by the caller (PyTorch tensors' data_ptr()); the library owns only the opaque handle and a scratch
+ * workspace sized at xl_create(). All work is enqueued on the caller's stream; nothing synchronises unless
+ * the entry point says so (only the *_host call does). A handle is not thread-safe (the reference is
+ * single-threaded per process, one process per GPU: src/algos/builder.py:25-29).
+ *
+ * Each entry point cites the reference interface (file:line under ml-jku/LRAM, or the third-party `xlstm`
+ * v1.0.x symbol the reference calls at that line) it replaces.
+ *
+ * Return value: 0 on success, negative xl_status otherwise; message via xl_last_error() (thread local).
+ */
+#ifndef XLSTM_B200_H
+#define XLSTM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define XL_ABI_VERSION 1
+
+typedef enum {
+  XL_OK = 0,
+  XL_ERR_INVALID_ARG = -1,
+  XL_ERR_UNSUPPORTED = -2,
+  XL_ERR_CUDA = -3,
+  XL_ERR_NOT_READY = -4, /* weights missing */
+  XL_ERR_NO_DEVICE = -5
+} xl_status;
+
+typedef struct xl_handle xl_handle;
+
+/* Shapes of the policy. Mirrors xLSTMConfig.xlstm_config (src/algos/models/decision_xlstm.py:104-133,
+ * configs/agent_params/huggingface/xlstm_*.yaml) and the multi-domain model kwargs
+ * (configs/agent_params/model_kwargs/multi_domain.yaml:1-11). */
+typedef struct {
+  int32_t embedding_dim;      /* d                                              */
+  int32_t num_blocks;         /* L (all mLSTM blocks)                           */
+  int32_t num_heads;          /* NH                                             */
+  int32_t inner_dim;          /* ceil(2d/64)*64                                 */
+  int32_t conv_kernel;        /* KS = 4                                         */
+  int32_t qkv_blocksize;      /* 4 (only 4 is supported)                        */
+  int32_t state_dim;          /* 204 (max_state_dim)                            */
+  int32_t act_dim;            /* 8   (max_act_dim)                              */
+  int32_t action_channels;    /* 256 (tokenizer vocab)                          */
+  int32_t discrete_actions;   /* 18  (tokenizer shift)                          */
+  int32_t tokens_per_step;    /* 3: (s, rtg, r)                                 */
+  int32_t action_token_pos;   /* 1: action is read at the rtg token             */
+  int32_t max_batch;          /* largest B any call will use (workspace sizing) */
+  float ln_eps;               /* 1e-5 xlstm LayerNorm / MultiHeadLayerNorm      */
+  float cell_eps;             /* 1e-6 recurrent_step_stabilized_simple          */
+  float embed_ln_eps;         /* 1e-5 nn.LayerNorm                              */
+  float tok_min_val;          /* -1 MinMaxTokenizer                             */
+  float tok_max_val;          /* +1                                             */
+} xl_config;
+
+/* Weight slots. Names in comments are the reference's state_dict keys. `layer` = block index, or -1 for
+ * policy-level tensors. dtype: 0 = fp32, 1 = bf16. GEMM matrices must be bf16, everything else fp32. */
+typedef enum {
+  /* per block: encoder.layers.blocks.{i}.*                                                  shape */
+  XL_W_XLSTM_NORM = 0,     /* xlstm_norm.weight (gamma = 1 + w)                         fp32 [d]              */
+  XL_W_PROJ_UP = 1,        /* xlstm.proj_up.weight                                      bf16 [2*inner, d]     */
+  XL_W_Q_PROJ = 2,         /* xlstm.q_proj.weight                                       fp32 [inner/4, 4, 4]  */
+  XL_W_K_PROJ = 3,         /* xlstm.k_proj.weight                                       fp32 [inner/4, 4, 4]  */
+  XL_W_V_PROJ = 4,         /* xlstm.v_proj.weight                                       fp32 [inner/4, 4, 4]  */
+  XL_W_CONV_W = 5,         /* xlstm.conv1d.conv.weight                                  fp32 [inner, 1, KS]   */
+  XL_W_CONV_B = 6,         /* xlstm.conv1d.conv.bias                                    fp32 [inner]          */
+  XL_W_IGATE_W = 7,        /* xlstm.mlstm_cell.igate.weight                             fp32 [NH, 3*inner]    */
+  XL_W_IGATE_B = 8,        /* xlstm.mlstm_cell.igate.bias                               fp32 [NH]             */
+  XL_W_FGATE_W = 9,        /* xlstm.mlstm_cell.fgate.weight                             fp32 [NH, 3*inner]    */
+  XL_W_FGATE_B = 10,       /* xlstm.mlstm_cell.fgate.bias                               fp32 [NH]             */
+  XL_W_OUTNORM = 11,       /* xlstm.mlstm_cell.outnorm.weight (gamma = 1 + w)           fp32 [inner]          */
+  XL_W_SKIP = 12,          /* xlstm.learnable_skip                                      fp32 [inner]          */
+  XL_W_PROJ_DOWN = 13,     /* xlstm.proj_down.weight                                    bf16 [d, inner]       */
+  XL_W_PER_BLOCK_COUNT = 14,
+  /* policy level (layer = -1) */
+  XL_W_POST_NORM = 32,     /* encoder.layers.post_blocks_norm.weight (gamma = 1 + w)    fp32 [d]              */
+  XL_W_EMBED_STATE_W = 33, /* embed_state.weight, K zero-padded to xl_state_dim_padded() bf16 [d, Kpad]       */
+  XL_W_EMBED_STATE_B = 34, /* embed_state.bias                                          fp32 [d]              */
+  XL_W_EMBED_RETURN_W = 35,/* embed_return.weight                                       fp32 [d] (=[d,1])     */
+  XL_W_EMBED_RETURN_B = 36,/* embed_return.bias                                         fp32 [d]              */
+  XL_W_EMBED_REWARD_W = 37,/* embed_rewards.weight                                      fp32 [d]              */
+  XL_W_EMBED_REWARD_B = 38,/* embed_rewards.bias                                        fp32 [d]              */
+  XL_W_EMBED_LN_W = 39,    /* embed_ln.weight                                           fp32 [d]              */
+  XL_W_EMBED_LN_B = 40,    /* embed_ln.bias                                             fp32 [d]              */
+  XL_W_HEAD_W = 41,        /* action_net.0.weight                                       bf16 [274*8, d]       */
+  XL_W_HEAD_B = 42         /* action_net.0.bias                                         fp32 [274*8]          */
+} xl_weight_id;
+
+/* Pieces of the recurrent state (`past_key_values`, src/algos/models/decision_xlstm.py:163,168-169:
+ * {"block_i": {"mlstm_state": (C, n, m), "conv_state": (conv,)}}), all fp32, resident in ONE caller-owned
+ * buffer, layer-major so that one block's C is a single contiguous stream:
+ *   for i in 0..L-1:  C[B,NH,DH,DH] | n[B,NH,DH] | m[B,NH] | conv[B,KS,inner]   (each 256-B aligned) */
+typedef enum { XL_STATE_C = 0, XL_STATE_N = 1, XL_STATE_M = 2, XL_STATE_CONV = 3 } xl_state_part;
+
+/* step modes */
+#define XL_MODE_PER_TOKEN 0 /* reference order: for token: for block (decision_xlstm.py:161-165)          */
+#define XL_MODE_FUSED 1     /* for block: all tokens_per_step tokens; C is read/written once per env step  */
+
+/* flags for xl_policy_step */
+#define XL_FLAG_DISCRETE 1u   /* discrete-action branch: argmax over logits[:discrete_actions]             */
+#define XL_FLAG_GRAPH 2u      /* replay the step from a cached CUDA graph (pointers must stay the same)    */
+#define XL_FLAG_SIMPLE_GEMM 4u/* force the CUDA-core GEMM (debug / small M)                               */
+
+int xl_abi_version(void);
+const char* xl_last_error(void);
+
+/* Build a handle for `cfg` on the current CUDA device. Allocates the scratch workspace (activations for
+ * max_batch * tokens_per_step rows). Replaces: xLSTMEncoder.__init__ (decision_xlstm.py:124-136) building
+ * xLSTMBlockStack, plus the policy's embed/head modules (multi_domain_discrete_dt_model.py:12-81). */
+int xl_create(const xl_config* cfg, xl_handle** out);
+void xl_destroy(xl_handle* h);
+
+/* Padded K of the state embedding GEMM (multiple of 64). Host code zero-pads embed_state.weight to it. */
+int xl_state_dim_padded(const xl_handle* h);
+
+/* Bind one device-resident weight tensor (no copy; pointer must outlive the handle).
+ * Replaces load_state_dict of the keys listed at xl_weight_id (loader: decision_transformer_sb3.py:1120-1184). */
+int xl_bind_weight(xl_handle* h, int layer, int which, const void* dev_ptr, int dtype, int64_t numel);
+/* 0 when every slot is bound, XL_ERR_NOT_READY (+message naming the first missing slot) otherwise. */
+int xl_weights_ready(const xl_handle* h);
+
+/* Size / layout of the state buffer for B envs. */
+size_t xl_state_bytes(const xl_handle* h, int B);
+int xl_state_layout(const xl_handle* h, int B, int layer, int part, size_t* offset_bytes, size_t* size_bytes);
+
+/* Zero the state of the envs whose env_mask[b] != 0 (device uint8 [B]); env_mask == NULL resets all.
+ * Equivalent to `model.past_key_values = None` (src/callbacks/evaluation.py:124,251,261) per env:
+ * zero C, n, m (m starts at 0, not -inf) and the conv window. */
+int xl_state_reset(xl_handle* h, void* state, const uint8_t* env_mask, int B, void* stream);
+
+/* xLSTMEncoder.forward(inputs_embeds=x_in, past_key_values=state, use_cache=True)
+ * (src/algos/models/decision_xlstm.py:138-169) == T x xLSTMBlockStack.step + post_blocks_norm.
+ * x_in, x_out: fp32 [B, T, d] (may alias). State updated in place. 1 <= T <= 4. */
+int xl_encoder_step(xl_handle* h, void* state, const float* x_in, float* x_out, int B, int T, int mode,
+                    unsigned flags, void* stream);
+
+/* mLSTMCell.step's recurrent_step_stabilized_simple + MultiHeadLayerNorm alone ([ext-xlstm], reached via
+ * decision_xlstm.py:163), for unit parity. qkv: fp32 [B*T, 3, inner] (q | k | v); igate, fgate: fp32
+ * [B*T, NH] pre-activations (bias already added). C [B,NH,DH,DH], n [B,NH,DH], m [B,NH] updated in place.
+ * h_norm: fp32 [B*T, inner] = GroupNorm_NH(h) * (1 + outnorm_w[inner]); h_raw (nullable): un-normalised h.
+ * rows_split / cols_per_cta: 0 = automatic tiling. */
+int xl_mlstm_cell_step(xl_handle* h, float* C, float* n, float* m, const float* qkv, const float* igate,
+                       const float* fgate, const float* outnorm_w, float* h_norm, float* h_raw, int B, int T,
+                       int rows_split, int cols_per_cta, void* stream);
+
+/* One env step of the whole policy for B envs with device-resident inputs:
+ * MultiDomainDiscreteDecisionXLSTMModel.forward on the inference-cache path (online_decision_transformer_
+ * model.py:326-390 -> compute_hidden_states :392-461 -> encoder -> get_predictions discrete_decision_
+ * transformer_model.py:368-383 -> multi_domain_discrete_dt_model.py:83-108) + MinMaxTokenizer.inv_tokenize
+ * (src/tokenizers_custom/minmax_tokenizer.py:31-47).
+ *   states  fp32 [B, state_dim]  (already zero-padded to 204: src/algos/decision_xlstm.py:16-19)
+ *   rtg     fp32 [B]             returns-to-go of this timestep
+ *   rewards fp32 [B] or NULL     reward token input; NULL = 0 (what the reference feeds, evaluation.py:132)
+ *   tokens  int32 [B, act_dim]   argmax action tokens (continuous) / [B] first column (discrete)
+ *   actions fp32 [B, act_dim]    inv_tokenized actions (continuous) / token as float (discrete)
+ *   logits  fp32 [B, act_dim*num_actions] or NULL;  hidden fp32 [B, T, d] or NULL (last_hidden_state) */
+int xl_policy_step(xl_handle* h, void* state, const float* states, const float* rtg, const float* rewards,
+                   int32_t* tokens, float* actions, float* logits, float* hidden, int B, int mode,
+                   unsigned flags, void* stream);
+
+/* Same, with HOST buffers (pinned recommended): copies inputs H2D, runs the step, copies tokens+actions
+ * D2H and synchronises the stream. This is the call the batched rollout loop makes once per env step
+ * (replacement for src/callbacks/evaluation.py:134-141,152-154: predict + .cpu() + .to(device)). */
+int xl_policy_step_host(xl_handle* h, void* state, const float* h_states, const float* h_rtg,
+                        const float* h_rewards, int32_t* h_tokens, float* h_actions, int B, int mode,
+                        unsigned flags, void* stream);
+
+/* out[M,N] = A[M,K] @ W[N,K]^T (+ bias[N]) (+ residual[M,N]); A fp32, W bf16, fp32 accumulate.
+ * The nn.Linear of proj_up / proj_down / embed_state / action_net. impl: 0 auto, 1 CUDA-core, 2 tcgen05. */
+int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bias, const float* residual,
+              float* out, int M, int N, int K, int impl, void* stream);
+
+/* Counters for bench.py: kernels launched by this handle since the last call (reset on read). */
+int64_t xl_launch_count(xl_handle* h);
+/* Name/duration of nothing: timing is the caller's job (CUDA events on its stream). */
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* XLSTM_B200_H */

@@ -1,0 +1,45 @@
+// Shared device helpers for the xlstm_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define XL_WARP 32
+
+namespace xl {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the whole CTA; result valid in every thread. `red` = >= 32 floats of shared memory.
+// Fixed order (lane tree, then warp 0 tree) -> deterministic for a given block size.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` from a previous use
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float r = (lane < nw) ? red[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+// numerically stable log-sigmoid, the form ATen uses: min(x,0) - log1p(exp(-|x|))
+__device__ __forceinline__ float log_sigmoid(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }
+
+__device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
+
+// streaming (evict-first) 128-bit accesses for the once-touched state stream
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) { __stcs(p, v); }
+
+// L2-coherent load (bypasses the non-coherent L1) for data written by other CTAs of the same launch
+__device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
+
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
+
+}  // namespace xl

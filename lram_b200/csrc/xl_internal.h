@@ -1,0 +1,92 @@
+// Internal launcher declarations shared by the translation units of libxlstm_b200.so.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xl {
+
+// ---- xl_elementwise.cu ---------------------------------------------------------------------------
+// LayerNorm over the last dim for `rows` rows. gamma = (residual_weight ? 1 + w : w), optional bias.
+// in row r at in + r*in_stride, out row r at out + r*out_stride. Optional bf16 hi/lo split outputs
+// (row-major [rows, d], dense) for the tensor-core GEMM A operand.
+void launch_ln_rows(const float* in, int64_t in_stride, float* out, int64_t out_stride, const float* w,
+                    const float* bias, int residual_weight, float eps, int rows, int d, void* a_hi,
+                    void* a_lo, cudaStream_t s);
+
+// Token embedding of one timestep: rows (b, tok) of [B,3,d]:
+//   tok 0 = s_emb[b] (state Linear output incl. bias), tok 1 = rtg[b]*w_ret + b_ret,
+//   tok 2 = rew[b]*w_rew + b_rew (rew == nullptr -> 0), then embed_ln (weight, bias).
+void launch_embed_tokens(const float* s_emb, const float* rtg, const float* rew, const float* w_ret,
+                         const float* b_ret, const float* w_rew, const float* b_rew, const float* ln_w,
+                         const float* ln_b, float eps, float* x, int B, int d, cudaStream_t s);
+
+// zero-pad states [B, K] -> [B, Kpad]
+void launch_pad_rows(const float* in, int K, float* out, int Kpad, int rows, cudaStream_t s);
+// copy rows with strides (token gather / scatter in per-token mode)
+void launch_copy_rows(const float* in, int64_t in_stride, float* out, int64_t out_stride, int rows, int d,
+                      cudaStream_t s);
+
+struct ConvQkvParams {
+  const float* u;       // [M, 2*inner]  (x_m | z) from proj_up
+  float* conv_state;    // [B, KS, inner] in/out
+  const float* conv_w;  // [inner, KS]
+  const float* conv_b;  // [inner]
+  const float* wq;      // [inner/4, 4, 4]
+  const float* wk;
+  const float* wv;
+  const float* wi;      // [NH, 3*inner]
+  const float* wf;      // [NH, 3*inner]
+  float* qkv;           // [M, 3, inner]
+  float* act;           // [M, inner]   a = silu(conv)
+  float* gate_part;     // [M, NCH, 2*NH]  partial gate pre-activations per channel chunk
+  int B, T, inner, NH, KS, NCH;
+};
+void launch_conv_qkv_gates(const ConvQkvParams& p, cudaStream_t s);
+
+// argmax over action logits + inv_tokenize.
+// continuous: logits [B, act_dim*num_actions] -> tokens [B, act_dim], actions = max(tok-shift,0)*bw+min
+// discrete:   tokens[b*act_dim] = argmax(logits[b, :discrete_actions]); actions[b*act_dim] = (float)token
+// logits row b starts at logits + b*row_pitch.
+void launch_argmax_tokens(const float* logits, int64_t row_pitch, int B, int act_dim, int num_actions,
+                          int discrete_actions, int discrete, float bin_width, float min_val,
+                          int32_t* tokens, float* actions, cudaStream_t s);
+
+void launch_state_reset(float* C, float* n, float* m, float* conv, const uint8_t* mask, int B,
+                        int64_t c_per_env, int64_t n_per_env, int64_t m_per_env, int64_t conv_per_env,
+                        cudaStream_t s);
+
+// ---- xl_state_step.cu ----------------------------------------------------------------------------
+struct StateStepParams {
+  float* C;                 // [B, NH, DH, DH]
+  float* n;                 // [B, NH, DH]
+  float* m;                 // [B, NH]
+  const float* qkv;         // [M, 3, inner]
+  const float* gate_part;   // [M, NCH, 2*NH]  (i gates first NH, f gates next NH), summed in order
+  const float* igate_b;     // [NH] or nullptr
+  const float* fgate_b;     // [NH] or nullptr
+  const float* outnorm_w;   // [inner] (gamma = 1 + w)
+  const float* skip;        // [inner] or nullptr  -> out = h_norm when nullptr
+  const float* act;         // [M, inner]   (used when skip != nullptr)
+  const float* u;           // [M, 2*inner] (z = u[:, inner:]) (used when skip != nullptr)
+  float* out;               // [M, inner]  (h_norm + skip*a) * silu(z), or h_norm
+  void* out_hi;             // optional bf16 hi/lo split of `out`
+  void* out_lo;
+  float* h_raw;             // optional [M, inner] un-normalised h
+  float* partial;           // scratch [B*NH, RS, T, DH]
+  unsigned int* counters;   // [B*NH], zero on entry, zero on exit
+  int B, T, NH, DH, inner, NCH;
+  int rows_split;           // RS
+  int cols_per_cta;         // multiple of 4, <= 128, divides DH
+  float ln_eps, cell_eps;
+};
+// Picks a tiling when rows_split / cols_per_cta are 0. Returns cudaError.
+cudaError_t launch_state_step(StateStepParams p, int num_sms, cudaStream_t s);
+void state_step_auto_tiling(int B, int NH, int DH, int num_sms, int* rows_split, int* cols_per_cta);
+
+// ---- xl_gemm.cu ----------------------------------------------------------------------------------
+// out[M,N] = A[M,K] W[N,K]^T (+bias) (+residual), A fp32, W bf16, CUDA cores, fp32 accumulate.
+void launch_gemm_simple(const float* A, const __nv_bfloat16* W, const float* bias, const float* residual,
+                        float* out, int M, int N, int K, cudaStream_t s);
+
+}  // namespace xl
