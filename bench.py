@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the batched xLSTM recurrent inference step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--model 48M] [--envs 64]
+
+Workload (config.workload): BASELINE.json configs[1] — "xLSTM 48M recurrent step, 64 synthetic Meta-World envs
+on 1xB200"; for N > 1 every rank runs the same 64 envs-per-GPU shard (weak scaling; env i -> rank i % N as
+`custom_eval_callback.py:385`), weights replicated, state cache per GPU, ONE all_gather of the int32 action tokens
+per step. A "step" is one env step of all envs: embed + 3 tokens x 12 blocks + head + argmax/inv_tokenize.
+
+  value        env-steps/s, inputs (the whole synthetic stream) resident in HBM before the timed region
+  e2e          same metric through the C-ABI host call xl_policy_step_host: pinned host buffers, H2D of the step's
+               states/rtg and D2H of tokens+actions inside the timed region, one stream sync per step
+  roofline     the mLSTM state-step kernel: algorithmic C/n/m bytes per launch / average launch duration, timed
+               with CUDA events around each of its launches in a profiled replay of the same steps
+  cpu_baseline the oracle (restated xlstm native PyTorch path, fp32) on the box's host cores, bounded sample
+
+--impl reference: times the reference's CPU implementation of the path (the oracle port; the xlstm package is
+absent, see oracle/xlstm_oracle.py header) on the host cores for the same config/metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "env-steps/sec batched xLSTM recurrent inference"
+UNIT = "env-steps/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def time_oracle(cfg, sd, B, n_steps, warmup, threads, budget_s=None):
+    """Oracle env steps on the host cores. Returns (env_steps_per_s, ms list, steps actually timed)."""
+    from lram_b200.synth import make_stream
+    from oracle.xlstm_oracle import OraclePolicy
+    torch.set_num_threads(threads)
+    pol = OraclePolicy(cfg, sd)
+    states, rtg, _ = make_stream(cfg, range(B), n_steps + warmup, domains="metaworld")
+    pkv = None
+    ms = []
+    t_begin = time.perf_counter()
+    for t in range(n_steps + warmup):
+        t0 = time.perf_counter()
+        o = pol.step(torch.from_numpy(states[t]), torch.from_numpy(rtg[t]), past_key_values=pkv)
+        pkv = o["past_key_values"]
+        dt = time.perf_counter() - t0
+        if t >= warmup:
+            ms.append(dt * 1e3)
+            if budget_s is not None and time.perf_counter() - t_begin > budget_s and len(ms) >= 2:
+                break
+    total = sum(ms) / 1e3
+    return B * len(ms) / total, ms, len(ms)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU execution mode for this path (xlstm native PyTorch ops, fp32),
+    i.e. the oracle port, on all host cores. Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from lram_b200.config import preset
+    from lram_b200.synth import make_state_dict
+    cfg = preset(args.model)
+    sd = make_state_dict(cfg, seed=0)
+    cores = os.cpu_count() or 1
+    # bounded sample: B_ref envs of the workload's args.envs, chosen from one calibration step so that
+    # K steps end within ~2 minutes
+    b_ref = min(args.envs, 8)
+    v, ms, _ = time_oracle(cfg, sd, b_ref, 1, 1, cores)
+    per_env_ms = ms[0] / b_ref
+    budget_ms = 120e3
+    b_ref = int(max(1, min(args.envs, budget_ms / max(per_env_ms * (args.steps + args.warmup), 1e-9))))
+    value, ms, timed = time_oracle(cfg, sd, b_ref, args.steps, args.warmup, cores, budget_s=240)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": timed, "warmup": args.warmup, "ms_per_step": statistics.mean(ms), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"xLSTM {args.model} recurrent step, {args.envs} synthetic Meta-World envs",
+                   "model": args.model, "envs_per_gpu": args.envs, "tokens_per_step": 3},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{b_ref} of {args.envs} envs x {timed} env steps, oracle port of the xlstm "
+                                   f"native PyTorch backend (xlstm package absent), fp32, {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="48M")
+    ap.add_argument("--envs", type=int, default=64, help="envs per GPU")
+    ap.add_argument("--mode", default="fused", choices=["fused", "per_token"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=5)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the xlstm_b200 path has no CPU fallback); "
+                         "use --impl reference for the CPU arm")
+    import torch.distributed as dist
+    from lram_b200 import _lib as L
+    from lram_b200.config import preset
+    from lram_b200.engine import XLSTMEngine
+    from lram_b200.rollout import gather_env_results, shard_env_ids
+    from lram_b200.synth import make_state_dict, make_stream
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    cfg = preset(args.model)
+    sd = make_state_dict(cfg, seed=0)
+    B = args.envs
+    n_envs = B * world
+    env_ids = shard_env_ids(n_envs, rank, world)
+    K, W = args.steps, args.warmup
+    mode = L.XL_MODE_FUSED if args.mode == "fused" else L.XL_MODE_PER_TOKEN
+    flags = 0 if args.no_graph else L.XL_FLAG_GRAPH
+
+    eng = XLSTMEngine(cfg, sd, max_batch=B, device=dev)
+    cache = eng.new_state(B)
+    total = K + W
+    n_stream = min(total, 64)                    # the synthetic stream is cycled; values don't affect timing
+    states_np, rtg_np, _ = make_stream(cfg, env_ids, n_stream, domains="metaworld")
+    d_states = torch.from_numpy(states_np).to(dev)      # resident in HBM before the timed region
+    d_rtg = torch.from_numpy(rtg_np).to(dev)
+    s_in = torch.empty(B, cfg.state_dim, device=dev)
+    r_in = torch.empty(B, device=dev)
+    out = {"action_tokens": torch.zeros(B, cfg.act_dim, dtype=torch.int32, device=dev),
+           "action_preds": torch.zeros(B, cfg.act_dim, dtype=torch.float32, device=dev)}
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def dev_step(t):
+        s_in.copy_(d_states[t % n_stream], non_blocking=True)
+        r_in.copy_(d_rtg[t % n_stream], non_blocking=True)
+        eng.policy_step(cache, s_in, r_in, mode=mode, flags=flags, out=out)
+        if world > 1:
+            return gather_env_results(out["action_tokens"], n_envs, rank, world)
+        return out["action_tokens"]
+
+    # ---------------- device-resident throughput ------------------------------------------------------------
+    for t in range(W):
+        dev_step(t)
+    barrier()
+    eng.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for t in range(W, W + K):
+        dev_step(t)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launch_count()
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = tt.item()
+    value = n_envs * K / (ms_total / 1e3)
+
+    # ---------------- end to end through the host-buffer C-ABI call ------------------------------------------
+    cache_e = eng.new_state(B)
+    h_states = torch.from_numpy(states_np).pin_memory()
+    h_rtg = torch.from_numpy(rtg_np).pin_memory()
+    h_tok = torch.zeros(B, cfg.act_dim, dtype=torch.int32).pin_memory()
+    h_act = torch.zeros(B, cfg.act_dim, dtype=torch.float32).pin_memory()
+    g_tok = torch.zeros(B, cfg.act_dim, dtype=torch.int32, device=dev)
+
+    def host_step(t):
+        eng.policy_step_host(cache_e, h_states[t % n_stream], h_rtg[t % n_stream], h_tok, h_act, mode=mode,
+                             flags=flags)
+        if world > 1:
+            g_tok.copy_(h_tok, non_blocking=True)
+            gather_env_results(g_tok, n_envs, rank, world)
+
+    for t in range(W):
+        host_step(t)
+    barrier()
+    lat = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record(stream)
+    for t in range(W, W + K):
+        t0 = time.perf_counter()
+        host_step(t)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), wall_ms)   # host wall clock of the same region (every step ends in a stream sync)
+    if world > 1:
+        tt = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = tt.item()
+    e2e_value = n_envs * K / (e2e_ms / 1e3)
+    h2d = B * cfg.state_dim * 4 + B * 4
+    d2h = B * cfg.act_dim * 4 * 2
+
+    # ---------------- roofline of the state-step kernel (profiled replay, eager launches) --------------------
+    peaks, peak_kind = measured_peaks()
+    nh, dh = cfg.num_heads, cfg.head_dim
+    alg_bytes = B * (8 * nh * dh * dh + 8 * nh * dh + 8 * nh)       # C, n, m read + write, per launch
+    roof = None
+    if rank == 0 and hasattr(eng.lib, "xl_profile_begin"):
+        import ctypes as C
+        eng.lib.xl_profile_begin(eng.handle)
+        for t in range(args.profile_steps):
+            s_in.copy_(d_states[t % n_stream])
+            r_in.copy_(d_rtg[t % n_stream])
+            eng.policy_step(cache, s_in, r_in, mode=mode, flags=0, out=out)
+        torch.cuda.synchronize(dev)
+        ms_sum, cnt, step_ms = C.c_double(), C.c_int64(), C.c_double()
+        eng.lib.xl_profile_end(eng.handle, C.byref(ms_sum), C.byref(cnt), C.byref(step_ms))
+        if cnt.value:
+            avg_ms = ms_sum.value / cnt.value
+            ach = alg_bytes / (avg_ms / 1e3) / 1e9
+            roof = {"bound": "hbm", "kernel": "mlstm_state_step_kernel", "achieved": ach,
+                    "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "avg_launch_us": avg_ms * 1e3,
+                    "launches_timed": cnt.value, "algorithmic_bytes_per_launch": alg_bytes,
+                    "share_of_step": ms_sum.value / max(step_ms.value, 1e-9)}
+    if world > 1:
+        dist.barrier()
+
+    # ---------------- CPU baseline (rank 0, N == 1 only) ------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        b_cpu = min(B, 8)
+        v, ms, timed = time_oracle(cfg, sd, b_cpu, 1000, 2, cores, budget_s=20)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{b_cpu} of {B} envs x {timed} env steps (~20 s), oracle port of the xlstm native "
+                         f"PyTorch backend, fp32, {cores} threads", "p50_ms_per_step": statistics.median(ms)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"xLSTM {args.model} recurrent step, {B} synthetic Meta-World envs per GPU "
+                                   f"(BASELINE.json configs[1])",
+                       "model": args.model, "envs_per_gpu": B, "global_envs": n_envs, "tokens_per_step": 3,
+                       "step_mode": args.mode, "cuda_graph": not args.no_graph, "weights": "bf16 GEMM matrices",
+                       "state": "fp32", "parallelism": f"env-sharded x{world}",
+                       "l2": f"state stream {cache.nbytes() / 2**20:.0f} MiB per step exceeds the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / K, "p50_ms": statistics.median(lat),
+                    "p90_ms": sorted(lat)[int(0.9 * (len(lat) - 1))]},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -181,7 +181,13 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
 
 /* Counters for bench.py: kernels launched by this handle since the last call (reset on read). */
 int64_t xl_launch_count(xl_handle* h);
-/* Name/duration of nothing: timing is the caller's job (CUDA events on its stream). */
+
+/* Measurement aid for bench.py: between begin and end, every EAGER (non-graph) launch of the mLSTM state-step
+ * kernel is bracketed by CUDA events on the launching stream, and every xl_policy_step by another pair.
+ * xl_profile_end synchronises those events and returns the summed state-kernel time, the number of its
+ * launches, and the summed step time (all ms). */
+int xl_profile_begin(xl_handle* h);
+int xl_profile_end(xl_handle* h, double* state_kernel_ms, int64_t* state_kernel_launches, double* step_ms);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -79,7 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(f"nvcc failed on {src}", file=sys.stderr)
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lcuda"]
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     subprocess.run(cmd, check=True)
     with open(STAMP, "w") as fh:
         fh.write(dig)

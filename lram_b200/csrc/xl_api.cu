@@ -70,6 +70,11 @@ struct xl_handle {
   __nv_bfloat16 *a_hi = nullptr, *a_lo = nullptr;
   int64_t launches = 0;
   std::vector<GraphCacheEntry> graphs;
+  size_t a_cap = 0;                    // elements per bf16 hi/lo plane
+  cudaStream_t cap_stream = nullptr;   // graph capture never happens on the caller's (possibly legacy) stream
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_state;  // start/stop pairs around state-step launches
+  std::vector<cudaEvent_t> prof_step;   // start/stop pairs around policy steps
 };
 
 namespace {
@@ -105,7 +110,17 @@ int check_batch(const xl_handle* h, int B) {
 int linear(xl_handle* h, const float* A, const void* W, const float* bias, const float* residual, float* out,
            int M, int N, int K, int impl, cudaStream_t s) {
   if (K % 8 != 0) return fail(XL_ERR_UNSUPPORTED, "linear: K=%d must be a multiple of 8", K);
-  (void)impl;
+  const bool tc_ok = xl::gemm_tc_supported(M, N, K) && (size_t)M * K <= h->a_cap;
+  if (impl == 2 && !tc_ok)
+    return fail(XL_ERR_UNSUPPORTED, "linear: tcgen05 path needs K %% 64 == 0 and M*K <= %zu (got M=%d K=%d)",
+                h->a_cap, M, K);
+  if (impl == 2 || (impl == 0 && tc_ok)) {
+    xl::launch_split_bf16(A, K, h->a_hi, h->a_lo, M, K, s);
+    XL_CUDA(xl::launch_gemm_tc(h->a_hi, h->a_lo, (const __nv_bfloat16*)W, bias, residual, out, M, N, K,
+                               h->num_sms, s));
+    h->launches += 2;
+    return XL_OK;
+  }
   xl::launch_gemm_simple(A, (const __nv_bfloat16*)W, bias, residual, out, M, N, K, s);
   h->launches += 1;
   XL_CUDA(cudaGetLastError());
@@ -165,8 +180,19 @@ int run_blocks(xl_handle* h, void* state, int B, int T, unsigned flags, cudaStre
     sp.counters = h->counters;
     sp.B = B; sp.T = T; sp.NH = NH; sp.DH = h->DH; sp.inner = inner; sp.NCH = h->NCH;
     sp.ln_eps = c.ln_eps; sp.cell_eps = c.cell_eps;
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (h->profiling) {
+      XL_CUDA(cudaEventCreate(&pe0));
+      XL_CUDA(cudaEventCreate(&pe1));
+      XL_CUDA(cudaEventRecord(pe0, s));
+    }
     XL_CUDA(xl::launch_state_step(sp, h->num_sms, s));
     h->launches += 1;
+    if (h->profiling) {
+      XL_CUDA(cudaEventRecord(pe1, s));
+      h->prof_state.push_back(pe0);
+      h->prof_state.push_back(pe1);
+    }
     // x = x + gated @ W_down^T
     rc = linear(h, h->gated, w.w[XL_W_PROJ_DOWN], nullptr, h->x, h->x, M, d, inner, impl, s);
     if (rc) return rc;
@@ -329,7 +355,11 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   const size_t o_ds = carve(4 * B * c.state_dim), o_dr = carve(4 * B), o_dw = carve(4 * B);
   const size_t o_da = carve(4 * B * c.act_dim), o_dt = carve(4 * B * c.act_dim);
   const size_t o_cnt = carve(4 * B * c.num_heads);
-  const size_t o_hi = carve(2 * M * (inner > d ? inner : d)), o_lo = carve(2 * M * (inner > d ? inner : d));
+  size_t a_cap = M * (inner > d ? inner : d);
+  if (a_cap < B * (size_t)h->Kpad) a_cap = B * (size_t)h->Kpad;
+  if (a_cap < (size_t)1 << 20) a_cap = (size_t)1 << 20;   // room for xl_linear unit tests
+  h->a_cap = a_cap;
+  const size_t o_hi = carve(2 * a_cap), o_lo = carve(2 * a_cap);
   h->ws_bytes = off;
   cudaError_t e = cudaMalloc((void**)&h->ws, h->ws_bytes);
   if (e != cudaSuccess) {
@@ -337,6 +367,7 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
     return fail(XL_ERR_CUDA, "cudaMalloc(workspace %zu B) failed: %s", off, cudaGetErrorString(e));
   }
   cudaMemset(h->ws, 0, h->ws_bytes);
+  cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
   h->x = (float*)(h->ws + o_x); h->xn = (float*)(h->ws + o_xn); h->xtok = (float*)(h->ws + o_xtok);
   h->hid = (float*)(h->ws + o_hid);
   h->u = (float*)(h->ws + o_u); h->qkv = (float*)(h->ws + o_qkv); h->act = (float*)(h->ws + o_act);
@@ -356,6 +387,7 @@ void xl_destroy(xl_handle* h) {
   for (auto& g : h->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->ws) cudaFree(h->ws);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
 }
 
@@ -515,7 +547,19 @@ int xl_policy_step(xl_handle* h, void* state, const float* states, const float* 
   if (!(flags & XL_FLAG_GRAPH)) {
     rc = xl_weights_ready(h);
     if (rc) return rc;
-    return run_policy(h, state, states, rtg, rewards, tokens, actions, logits, hidden, B, mode, flags, s);
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (h->profiling) {
+      XL_CUDA(cudaEventCreate(&pe0));
+      XL_CUDA(cudaEventCreate(&pe1));
+      XL_CUDA(cudaEventRecord(pe0, s));
+    }
+    rc = run_policy(h, state, states, rtg, rewards, tokens, actions, logits, hidden, B, mode, flags, s);
+    if (h->profiling) {
+      cudaEventRecord(pe1, s);
+      h->prof_step.push_back(pe0);
+      h->prof_step.push_back(pe1);
+    }
+    return rc;
   }
   // ---- CUDA-graph replay: capture once per distinct argument tuple --------------------------------
   for (auto& g : h->graphs) {
@@ -537,9 +581,9 @@ int xl_policy_step(xl_handle* h, void* state, const float* states, const float* 
   g.logits = logits; g.hidden = hidden; g.B = B; g.mode = mode; g.flags = flags;
   cudaGraph_t graph = nullptr;
   const int64_t before = h->launches;
-  XL_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-  rc = run_policy(h, state, states, rtg, rewards, tokens, actions, logits, hidden, B, mode, flags, s);
-  cudaError_t e = cudaStreamEndCapture(s, &graph);
+  XL_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+  rc = run_policy(h, state, states, rtg, rewards, tokens, actions, logits, hidden, B, mode, flags, h->cap_stream);
+  cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
   g.launches = h->launches - before;
   h->launches = before;
   if (rc) {
@@ -585,6 +629,41 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
   if (!h || !A || !W_bf16 || !out) return fail(XL_ERR_INVALID_ARG, "null argument");
   if (M <= 0 || N <= 0 || K <= 0) return fail(XL_ERR_INVALID_ARG, "bad GEMM shape");
   return linear(h, A, W_bf16, bias, residual, out, M, N, K, impl, (cudaStream_t)stream);
+}
+
+int xl_profile_begin(xl_handle* h) {
+  if (!h) return fail(XL_ERR_INVALID_ARG, "null handle");
+  h->profiling = true;
+  return XL_OK;
+}
+
+int xl_profile_end(xl_handle* h, double* state_kernel_ms, int64_t* state_kernel_launches, double* step_ms) {
+  if (!h || !state_kernel_ms || !state_kernel_launches || !step_ms) return fail(XL_ERR_INVALID_ARG, "null argument");
+  h->profiling = false;
+  double a = 0.0, b = 0.0;
+  auto drain = [](std::vector<cudaEvent_t>& v, double& acc) -> cudaError_t {
+    cudaError_t err = cudaSuccess;
+    for (size_t i = 0; i + 1 < v.size(); i += 2) {
+      float ms = 0.f;
+      cudaError_t e = cudaEventSynchronize(v[i + 1]);
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, v[i], v[i + 1]);
+      if (e != cudaSuccess) err = e;
+      acc += ms;
+      cudaEventDestroy(v[i]);
+      cudaEventDestroy(v[i + 1]);
+    }
+    return err;
+  };
+  const int64_t n = (int64_t)h->prof_state.size() / 2;
+  cudaError_t e1 = drain(h->prof_state, a);
+  cudaError_t e2 = drain(h->prof_step, b);
+  h->prof_state.clear();
+  h->prof_step.clear();
+  *state_kernel_ms = a;
+  *state_kernel_launches = n;
+  *step_ms = b;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(XL_ERR_CUDA, "profile events: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  return XL_OK;
 }
 
 int64_t xl_launch_count(xl_handle* h) {

@@ -89,4 +89,11 @@ void state_step_auto_tiling(int B, int NH, int DH, int num_sms, int* rows_split,
 void launch_gemm_simple(const float* A, const __nv_bfloat16* W, const float* bias, const float* residual,
                         float* out, int M, int N, int K, cudaStream_t s);
 
+// ---- xl_gemm_tc.cu -------------------------------------------------------------------------------
+// tcgen05 path: A given as bf16 hi/lo planes (A = hi + lo), W bf16, fp32 accumulate in TMEM.
+bool gemm_tc_supported(int M, int N, int K);
+void launch_split_bf16(const float* in, int64_t in_stride, void* hi, void* lo, int rows, int K, cudaStream_t s);
+cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat16* W, const float* bias,
+                           const float* residual, float* out, int M, int N, int K, int num_sms, cudaStream_t s);
+
 }  // namespace xl

@@ -1,0 +1,342 @@
+"""GPU parity tests (run on the B200 box: python -m pytest tests -m gpu). Everything goes through the C-ABI
+library; the oracle (oracle/xlstm_oracle.py) and the committed golden vectors are only the checker.
+
+Tolerances (BASELINE.json north_star): action tokens / argmax actions bit-exact; hidden states and
+continuous actions within 1e-3 relative of the fp32 oracle.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from lram_b200 import _lib as L  # noqa: E402
+from lram_b200.config import preset  # noqa: E402
+from lram_b200.synth import make_state_dict, make_stream  # noqa: E402
+
+REL_TOL = 1e-3
+
+
+def _engine(name, B, seed=0, **over):
+    from lram_b200.engine import XLSTMEngine
+    cfg = preset(name, **over)
+    sd = make_state_dict(cfg, seed=seed)
+    return cfg, sd, XLSTMEngine(cfg, sd, max_batch=B)
+
+
+def _rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+def _margin_ok(ref_logits, tok_gpu, tok_ref):
+    """Where tokens differ, report the oracle's top-2 margin (SURVEY §7 hard parts). Returns list of margins."""
+    bad = (tok_gpu != tok_ref).nonzero()
+    out = []
+    for idx in bad:
+        lg = ref_logits[tuple(idx.tolist())]
+        top2 = torch.topk(lg, 2).values
+        out.append(((top2[0] - top2[1]) / top2[0].abs().clamp_min(1e-30)).item())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# unit: the cell kernel alone
+# ------------------------------------------------------------------------------------------------------------
+def test_cell_step_vs_hf_golden(golden_dir):
+    """recurrent step kernel vs vectors from transformers' mlstm_recurrent_step_native (independent impl)."""
+    g = np.load(os.path.join(golden_dir, "hf_mlstm_step.npz"))
+    Tn, B, NH, DH = g["q"].shape
+    cfg, sd, eng = _engine("toy", B)            # toy: NH=4, DH=32, inner=128
+    assert (cfg.num_heads, cfg.head_dim) == (NH, DH)
+    dev = eng.device
+    C = torch.zeros(B, NH, DH, DH, device=dev)
+    n = torch.zeros(B, NH, DH, device=dev)
+    m = torch.zeros(B, NH, device=dev)
+    w0 = torch.zeros(cfg.inner, device=dev)
+    for t in range(Tn):
+        qkv = torch.stack([torch.from_numpy(g[k][t]).reshape(B, NH * DH) for k in ("q", "k", "v")], dim=1).to(dev)
+        ig = torch.from_numpy(g["ig"][t]).reshape(B, NH).to(dev)
+        fg = torch.from_numpy(g["fg"][t]).reshape(B, NH).to(dev)
+        _, h_raw = eng.cell_step(C, n, m, qkv.contiguous(), ig.contiguous(), fg.contiguous(), w0, B, 1)
+        ref = torch.from_numpy(g["h"][t]).reshape(B, NH * DH)
+        assert _rel(h_raw.cpu(), ref) < REL_TOL, f"step {t}"
+    s = math.sqrt(DH)
+    assert _rel(C.cpu() * s, torch.from_numpy(g["c_final"])) < 1e-4
+    assert _rel(n.cpu() * s, torch.from_numpy(g["n_final"])) < 1e-4
+    assert (m.cpu().view(B, NH, 1) - torch.from_numpy(g["m_final"])).abs().max() < 1e-5
+    eng.close()
+
+
+@pytest.mark.parametrize("name,B,T,rs,cols", [("toy", 3, 1, 0, 0), ("toy", 3, 3, 0, 0), ("toy", 2, 4, 2, 16),
+                                              ("toy128", 2, 3, 4, 32), ("16M", 2, 3, 0, 0), ("16M", 1, 1, 8, 64),
+                                              ("48M", 2, 3, 0, 0), ("206M", 1, 3, 0, 0), ("206M", 1, 2, 5, 128)])
+def test_cell_step_vs_oracle(name, B, T, rs, cols):
+    """fused-T kernel == T sequential oracle steps (+ GroupNorm), for every tiling."""
+    from oracle import xlstm_oracle as O
+    cfg, sd, eng = _engine(name, B, num_blocks=1)
+    NH, DH, inner = cfg.num_heads, cfg.head_dim, cfg.inner
+    g = torch.Generator().manual_seed(42)
+    C0 = torch.randn(B, NH, DH, DH, generator=g) * 0.1
+    n0 = torch.randn(B, NH, DH, generator=g) * 0.1
+    m0 = torch.randn(B, NH, generator=g)
+    qkv = torch.randn(B * T, 3, inner, generator=g)
+    ig = torch.randn(B * T, NH, generator=g) * 2
+    fg = torch.randn(B * T, NH, generator=g) * 2 + 2
+    w = torch.randn(inner, generator=g) * 0.1
+    dev = eng.device
+    C, n, m = C0.to(dev), n0.to(dev), m0.to(dev)
+    h_norm, h_raw = eng.cell_step(C, n, m, qkv.to(dev), ig.to(dev), fg.to(dev), w.to(dev), B, T, rs, cols)
+    torch.cuda.synchronize()
+    # oracle: T sequential steps
+    c, nn, mm = C0.clone(), n0.clone().unsqueeze(-1), m0.clone().view(B, NH, 1, 1)
+    qv = qkv.view(B, T, 3, NH, DH)
+    for t in range(T):
+        q, k, v = (qv[:, t, j].unsqueeze(2) for j in range(3))              # [B,NH,1,DH]
+        h, (c, nn, mm) = O.recurrent_step_stabilized_simple(
+            c, nn, mm, q, k, v, ig.view(B, T, NH)[:, t].view(B, NH, 1, 1), fg.view(B, T, NH)[:, t].view(B, NH, 1, 1))
+        hn = O.multihead_layer_norm(h, w).transpose(1, 2).reshape(B, inner)
+        got_raw = h_raw.view(B, T, inner)[:, t].cpu()
+        got = h_norm.view(B, T, inner)[:, t].cpu()
+        assert _rel(got_raw, h.transpose(1, 2).reshape(B, inner)) < REL_TOL, f"h_raw t={t}"
+        assert _rel(got, hn) < REL_TOL, f"h_norm t={t}"
+    assert _rel(C.cpu(), c) < 1e-5
+    assert _rel(n.cpu(), nn.squeeze(-1)) < 1e-5
+    assert (m.cpu() - mm.view(B, NH)).abs().max() < 1e-5
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# unit: Linear
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(1, 64, 64), (3, 2192, 128), (192, 3072, 768), (100, 768, 1536), (64, 512, 256)])
+def test_linear_vs_torch(M, N, K):
+    cfg, sd, eng = _engine("toy", 1)
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    ref = (A.double() @ W.double().t() + bias.double() + res.double()).float()
+    out = eng.linear(A.cuda(), W.cuda(), bias.cuda(), res.cuda())
+    assert _rel(out.cpu(), ref) < 1e-5
+    out2 = eng.linear(A.cuda(), W.cuda())
+    assert _rel(out2.cpu(), (A.double() @ W.double().t()).float()) < 1e-5
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# integration: encoder, both modes
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,B,mode", [("toy", 4, L.XL_MODE_PER_TOKEN), ("toy", 4, L.XL_MODE_FUSED),
+                                         ("toy128", 3, L.XL_MODE_FUSED), ("16M", 2, L.XL_MODE_FUSED),
+                                         ("16M", 1, L.XL_MODE_PER_TOKEN)])
+def test_encoder_step_vs_oracle(name, B, mode):
+    from lram_b200.decision_xlstm import FusedXLSTMEncoder
+    from oracle import xlstm_oracle as O
+    cfg, sd, eng = _engine(name, B)
+    enc = FusedXLSTMEncoder(eng, mode=mode)
+    ora = O.OracleEncoder(cfg, sd)
+    g = torch.Generator().manual_seed(9)
+    pkv_o, pkv = None, None
+    for step in range(3):
+        x = torch.randn(B, 3, cfg.d, generator=g)
+        out = enc(inputs_embeds=x.cuda(), past_key_values=pkv, use_cache=True)
+        pkv = out["past_key_values"]
+        ref, pkv_o = ora.forward_cached(x, pkv_o)
+        assert _rel(out["last_hidden_state"].cpu(), ref) < REL_TOL, f"step {step}"
+    # state export in the reference's past_key_values format
+    exp = pkv.to_past_key_values()
+    for i in range(cfg.num_blocks):
+        c, n, m = pkv_o[f"block_{i}"]["mlstm_state"]
+        ce, ne, me = exp[f"block_{i}"]["mlstm_state"]
+        assert _rel(ce.cpu(), c) < REL_TOL and _rel(ne.cpu(), n) < REL_TOL
+        assert (me.cpu() - m).abs().max() < 1e-4
+        assert _rel(exp[f"block_{i}"]["conv_state"][0].cpu(), pkv_o[f"block_{i}"]["conv_state"][0]) < 1e-5
+    # import: continue from the ORACLE's state and match again
+    x = torch.randn(B, 3, cfg.d, generator=g)
+    out = enc(inputs_embeds=x.cuda(), past_key_values=pkv_o, use_cache=True)
+    ref, _ = ora.forward_cached(x, pkv_o)
+    assert _rel(out["last_hidden_state"].cpu(), ref) < REL_TOL
+    eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# integration: whole policy step vs committed golden vectors + oracle
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["toy", "toy128"])
+@pytest.mark.parametrize("mode", [L.XL_MODE_PER_TOKEN, L.XL_MODE_FUSED])
+def test_policy_step_vs_golden(golden_dir, name, mode):
+    g = np.load(os.path.join(golden_dir, "oracle_toy.npz"))
+    states, rtg = g[f"{name}_states"], g[f"{name}_rtg"]
+    steps, B = rtg.shape
+    cfg, sd, eng = _engine(name, B)
+    cache = eng.new_state(B)
+    for t in range(steps):
+        out = eng.policy_step(cache, torch.from_numpy(states[t]).cuda(), torch.from_numpy(rtg[t]).cuda(), mode=mode,
+                              want_hidden=True, want_logits=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(out["action_tokens"].cpu().numpy().astype(np.int64), g[f"{name}_tokens"][t]), f"t={t}"
+        assert np.array_equal(out["action_preds"].cpu().numpy(), g[f"{name}_actions"][t])
+        assert _rel(out["last_hidden_state"].cpu(), torch.from_numpy(g[f"{name}_hidden"][t])) < REL_TOL
+    last = cfg.num_blocks - 1
+    assert _rel(cache.view(last, L.XL_STATE_C).cpu(), torch.from_numpy(g[f"{name}_C_last"])) < REL_TOL
+    assert _rel(cache.view(last, L.XL_STATE_CONV).cpu(), torch.from_numpy(g[f"{name}_conv_last"])) < 1e-5
+    eng.close()
+
+
+@pytest.mark.parametrize("name,B,steps", [("16M", 4, 4), ("48M", 3, 3)])
+def test_policy_step_real_sizes_vs_oracle(name, B, steps):
+    from oracle import xlstm_oracle as O
+    cfg, sd, eng = _engine(name, B)
+    ora = O.OraclePolicy(cfg, sd)
+    states, rtg, _ = make_stream(cfg, range(B), steps, domains="mixed")
+    cache, pkv = eng.new_state(B), None
+    for t in range(steps):
+        out = eng.policy_step(cache, torch.from_numpy(states[t]).cuda(), torch.from_numpy(rtg[t]).cuda(),
+                              mode=L.XL_MODE_FUSED, want_hidden=True, want_logits=True)
+        ref = ora.step(torch.from_numpy(states[t]), torch.from_numpy(rtg[t]), past_key_values=pkv)
+        pkv = ref["past_key_values"]
+        tok = out["action_tokens"].cpu().long()
+        margins = _margin_ok(ref["action_logits"], tok, ref["action_tokens"])
+        assert not margins, f"token mismatches at t={t}, oracle top-2 relative margins {margins}"
+        assert _rel(out["last_hidden_state"].cpu(), ref["last_hidden_state"]) < REL_TOL
+        assert torch.equal(out["action_preds"].cpu(), ref["action_preds"])
+        assert _rel(out["action_logits"].cpu().view_as(ref["action_logits"]), ref["action_logits"]) < REL_TOL
+    eng.close()
+
+
+def test_discrete_branch_vs_oracle():
+    from oracle import xlstm_oracle as O
+    cfg, sd, eng = _engine("toy128", 5)
+    ora = O.OraclePolicy(cfg, sd)
+    states, rtg, _ = make_stream(cfg, range(5), 3, domains="mixed")
+    cache, pkv = eng.new_state(5), None
+    for t in range(3):
+        out = eng.policy_step(cache, torch.from_numpy(states[t]).cuda(), torch.from_numpy(rtg[t]).cuda(),
+                              flags=L.XL_FLAG_DISCRETE, want_logits=True)
+        ref = ora.step(torch.from_numpy(states[t]), torch.from_numpy(rtg[t]), past_key_values=pkv, discrete=True)
+        pkv = ref["past_key_values"]
+        assert torch.equal(out["action_tokens"].cpu().long()[:, :1], ref["action_tokens"])
+        assert _rel(out["action_logits"].cpu(), ref["action_logits"].view(5, -1)) < REL_TOL
+    eng.close()
+
+
+def test_fused_equals_per_token_and_graph_replay():
+    """Properties that need no oracle: fused == per-token stepping; CUDA-graph replay == eager launches."""
+    cfg, sd, eng = _engine("16M", 8)
+    states, rtg, _ = make_stream(cfg, range(8), 6, domains="mixed")
+    res = {}
+    for tag, mode, flags in (("tok", L.XL_MODE_PER_TOKEN, 0), ("fused", L.XL_MODE_FUSED, 0),
+                             ("graph", L.XL_MODE_FUSED, L.XL_FLAG_GRAPH)):
+        cache = eng.new_state(8)
+        s_dev = torch.empty(8, cfg.state_dim, device="cuda")
+        r_dev = torch.empty(8, device="cuda")
+        out = None
+        toks, hids = [], []
+        for t in range(6):
+            s_dev.copy_(torch.from_numpy(states[t]))
+            r_dev.copy_(torch.from_numpy(rtg[t]))
+            out = eng.policy_step(cache, s_dev, r_dev, mode=mode, flags=flags, want_hidden=True, out=out)
+            torch.cuda.synchronize()
+            toks.append(out["action_tokens"].cpu().clone())
+            hids.append(out["last_hidden_state"].cpu().clone())
+        res[tag] = (torch.stack(toks), torch.stack(hids))
+    assert torch.equal(res["tok"][0], res["fused"][0])
+    assert _rel(res["fused"][1], res["tok"][1]) < 1e-4
+    assert torch.equal(res["graph"][0], res["fused"][0])
+    assert torch.equal(res["graph"][1], res["fused"][1])          # same kernels, same order: bit identical
+    eng.close()
+
+
+def test_per_env_reset_mask():
+    """reset of a subset of envs == those envs starting from past_key_values=None; others untouched."""
+    cfg, sd, eng = _engine("toy128", 4)
+    states, rtg, _ = make_stream(cfg, range(4), 4, domains="mixed")
+    dev = lambda a: torch.from_numpy(a).cuda()
+    cache = eng.new_state(4)
+    for t in range(2):
+        eng.policy_step(cache, dev(states[t]), dev(rtg[t]))
+    eng.reset(cache, torch.tensor([0, 1, 0, 1], dtype=torch.uint8))
+    out = eng.policy_step(cache, dev(states[2]), dev(rtg[2]), want_hidden=True)
+    fresh = eng.new_state(4)
+    out_f = eng.policy_step(fresh, dev(states[2]), dev(rtg[2]), want_hidden=True)
+    cont = eng.new_state(4)
+    for t in range(3):
+        out_c = eng.policy_step(cont, dev(states[t]), dev(rtg[t]), want_hidden=True)
+    torch.cuda.synchronize()
+    h, hf, hc = (o["last_hidden_state"].cpu() for o in (out, out_f, out_c))
+    assert torch.equal(h[[1, 3]], hf[[1, 3]])
+    assert torch.equal(h[[0, 2]], hc[[0, 2]])
+    eng.close()
+
+
+def test_host_step_and_agent_predict_b1():
+    """The reference-facing call chain for one env: agent.predict -> policy.forward -> library; and the host
+    (pinned) step used by the rollout loop."""
+    from lram_b200.decision_xlstm import DiscreteDecisionXLSTM, MultiDomainDiscreteDecisionXLSTMModel
+    from oracle import xlstm_oracle as O
+    cfg = preset("toy128")
+    sd = make_state_dict(cfg, seed=0)
+    policy = MultiDomainDiscreteDecisionXLSTMModel(cfg, sd, max_batch=1)
+    agent = DiscreteDecisionXLSTM(policy)
+    ora = O.OraclePolicy(cfg, sd)
+    states, rtg, envs = make_stream(cfg, [0], 4, domains="metaworld")
+    act_dim = int(envs.act_dims[0])
+    pkv = None
+    actions = torch.zeros((0, act_dim), device="cuda")
+    for t in range(4):
+        actions = torch.cat([actions, torch.zeros((1, act_dim), device="cuda")], dim=0)
+        rewards = torch.zeros(t + 1, device="cuda")
+        obs = torch.from_numpy(states[: t + 1, 0, :39]).cuda()           # raw 39-dim Meta-World obs, unpadded
+        a, _ = agent.predict(policy, obs, actions, rewards, torch.from_numpy(rtg[: t + 1, 0]).cuda().reshape(1, -1),
+                             torch.arange(t + 1, device="cuda").reshape(1, -1), context_len=1, env_act_dim=act_dim)
+        ref = ora.step(torch.from_numpy(states[t]), torch.from_numpy(rtg[t]), past_key_values=pkv)
+        pkv = ref["past_key_values"]
+        assert a.shape == (act_dim,)
+        assert torch.equal(a.cpu(), ref["action_preds"][0, :act_dim])
+        actions[-1] = a
+    # host-buffer entry point
+    eng = policy.engine
+    cache = eng.new_state(1)
+    hs = torch.from_numpy(states[0]).pin_memory()
+    hr = torch.from_numpy(rtg[0]).pin_memory()
+    ht = torch.zeros(1, cfg.act_dim, dtype=torch.int32).pin_memory()
+    ha = torch.zeros(1, cfg.act_dim).pin_memory()
+    eng.policy_step_host(cache, hs, hr, ht, ha)
+    ref0 = ora.step(torch.from_numpy(states[0]), torch.from_numpy(rtg[0]))
+    assert torch.equal(ht.long(), ref0["action_tokens"])
+    eng.close()
+
+
+def test_long_horizon_drift_and_rollout_driver():
+    """200 env steps with resets through the batched rollout driver: tokens must stay bit-exact vs the oracle."""
+    from lram_b200.engine import XLSTMEngine
+    from lram_b200.rollout import BatchedRollout
+    from lram_b200.synth import SyntheticEnvBatch
+    from oracle import xlstm_oracle as O
+    cfg = preset("toy")
+    sd = make_state_dict(cfg, seed=0)
+    B, steps, ep_len = 4, 200, 37
+    eng = XLSTMEngine(cfg, sd, max_batch=B)
+    ro = BatchedRollout(eng, SyntheticEnvBatch(cfg, range(B), domains="mixed", ep_len=ep_len), use_graph=True)
+    res = ro.run(steps, record=True)
+    # oracle replay of the same loop
+    ora = O.OraclePolicy(cfg, sd)
+    envs = SyntheticEnvBatch(cfg, range(B), domains="mixed", ep_len=ep_len)
+    obs, rtg, pkv = envs.reset(), envs.rtg0.copy(), None
+    mism = 0
+    for t in range(steps):
+        o = ora.step(torch.from_numpy(obs), torch.from_numpy(rtg), past_key_values=pkv)
+        pkv = o["past_key_values"]
+        mism += int((o["action_tokens"].numpy() != res["tokens"][t]).sum())
+        obs, rew, done = envs.step(None)
+        rtg = (rtg - rew / envs.reward_scale).astype(np.float32)
+        if done.any():
+            rtg[done] = envs.rtg0[done]
+            pkv = O.reset_state_rows(pkv, torch.from_numpy(done))
+    assert mism == 0, f"{mism} token mismatches over {steps * B * cfg.act_dim}"
+    assert len(res["episode_returns"][0]) == steps // ep_len
+    eng.close()
