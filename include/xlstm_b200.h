@@ -179,6 +179,11 @@ int xl_policy_step_host(xl_handle* h, void* state, const float* h_states, const 
 int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bias, const float* residual,
               float* out, int M, int N, int K, int impl, void* stream);
 
+/* Implementation switches for A/B measurements (defaults in brackets):
+ *   "state_impl": [1] TMA-fed ring for the state stream, 0 register-batched global loads
+ *   "gemm_impl":  [0] auto (tcgen05 when K % 64 == 0), 1 CUDA-core, 2 tcgen05 */
+int xl_set_option(xl_handle* h, const char* name, int value);
+
 /* Counters for bench.py: kernels launched by this handle since the last call (reset on read). */
 int64_t xl_launch_count(xl_handle* h);
 

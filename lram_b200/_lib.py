@@ -103,6 +103,8 @@ def load():
     lib.xl_policy_step_host.restype = i32
     lib.xl_linear.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.xl_linear.restype = i32
+    lib.xl_set_option.argtypes = [vp, C.c_char_p, i32]
+    lib.xl_set_option.restype = i32
     lib.xl_profile_begin.argtypes = [vp]
     lib.xl_profile_begin.restype = i32
     lib.xl_profile_end.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]

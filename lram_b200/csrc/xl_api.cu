@@ -72,6 +72,8 @@ struct xl_handle {
   std::vector<GraphCacheEntry> graphs;
   size_t a_cap = 0;                    // elements per bf16 hi/lo plane
   cudaStream_t cap_stream = nullptr;   // graph capture never happens on the caller's (possibly legacy) stream
+  int state_impl = 1;                  // 1 = TMA ring, 0 = register-batched loads (xl_set_option "state_impl")
+  int gemm_impl = 0;                   // 0 auto, 1 CUDA-core, 2 tcgen05      (xl_set_option "gemm_impl")
   bool profiling = false;
   std::vector<cudaEvent_t> prof_state;  // start/stop pairs around state-step launches
   std::vector<cudaEvent_t> prof_step;   // start/stop pairs around policy steps
@@ -107,18 +109,22 @@ int check_batch(const xl_handle* h, int B) {
 }
 
 // Linear layer dispatch. impl: 0 auto, 1 CUDA-core, 2 tensor-core.
+// presplit: the bf16 hi/lo planes of A already sit in h->a_hi / h->a_lo (written by the producing kernel).
 int linear(xl_handle* h, const float* A, const void* W, const float* bias, const float* residual, float* out,
-           int M, int N, int K, int impl, cudaStream_t s) {
+           int M, int N, int K, int impl, cudaStream_t s, bool presplit = false) {
   if (K % 8 != 0) return fail(XL_ERR_UNSUPPORTED, "linear: K=%d must be a multiple of 8", K);
   const bool tc_ok = xl::gemm_tc_supported(M, N, K) && (size_t)M * K <= h->a_cap;
   if (impl == 2 && !tc_ok)
     return fail(XL_ERR_UNSUPPORTED, "linear: tcgen05 path needs K %% 64 == 0 and M*K <= %zu (got M=%d K=%d)",
                 h->a_cap, M, K);
   if (impl == 2 || (impl == 0 && tc_ok)) {
-    xl::launch_split_bf16(A, K, h->a_hi, h->a_lo, M, K, s);
+    if (!presplit) {
+      xl::launch_split_bf16(A, K, h->a_hi, h->a_lo, M, K, s);
+      h->launches += 1;
+    }
     XL_CUDA(xl::launch_gemm_tc(h->a_hi, h->a_lo, (const __nv_bfloat16*)W, bias, residual, out, M, N, K,
                                h->num_sms, s));
-    h->launches += 2;
+    h->launches += 1;
     return XL_OK;
   }
   xl::launch_gemm_simple(A, (const __nv_bfloat16*)W, bias, residual, out, M, N, K, s);
@@ -133,16 +139,19 @@ int run_blocks(xl_handle* h, void* state, int B, int T, unsigned flags, cudaStre
   const int d = c.embedding_dim, inner = c.inner_dim, NH = c.num_heads;
   const int M = B * T;
   const StateLayout L = state_layout(h, B);
-  const int impl = (flags & XL_FLAG_SIMPLE_GEMM) ? 1 : 0;
+  const int impl = (flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
+  // when the tensor-core Linear will run, the producers write its bf16 hi/lo operand planes directly
+  const bool tc_up = impl != 1 && xl::gemm_tc_supported(M, 2 * inner, d) && (size_t)M * d <= h->a_cap;
+  const bool tc_down = impl != 1 && xl::gemm_tc_supported(M, d, inner) && (size_t)M * inner <= h->a_cap;
   for (int i = 0; i < c.num_blocks; ++i) {
     const BlockWeights& w = h->blocks[i];
     char* base = (char*)state + (size_t)i * L.layer_bytes;
     // x_n = LN(x) (gamma = 1 + w)
-    xl::launch_ln_rows(h->x, d, h->xn, d, (const float*)w.w[XL_W_XLSTM_NORM], nullptr, 1, c.ln_eps, M, d,
-                       nullptr, nullptr, s);
+    xl::launch_ln_rows(h->x, d, tc_up ? nullptr : h->xn, d, (const float*)w.w[XL_W_XLSTM_NORM], nullptr, 1,
+                       c.ln_eps, M, d, tc_up ? h->a_hi : nullptr, tc_up ? h->a_lo : nullptr, s);
     h->launches += 1;
     // u = x_n @ W_up^T   [M, 2*inner]
-    int rc = linear(h, h->xn, w.w[XL_W_PROJ_UP], nullptr, nullptr, h->u, M, 2 * inner, d, impl, s);
+    int rc = linear(h, h->xn, w.w[XL_W_PROJ_UP], nullptr, nullptr, h->u, M, 2 * inner, d, impl, s, tc_up);
     if (rc) return rc;
     // conv + silu + q/k/v + gate partials
     xl::ConvQkvParams cp;
@@ -155,7 +164,8 @@ int run_blocks(xl_handle* h, void* state, int B, int T, unsigned flags, cudaStre
     cp.wv = (const float*)w.w[XL_W_V_PROJ];
     cp.wi = (const float*)w.w[XL_W_IGATE_W];
     cp.wf = (const float*)w.w[XL_W_FGATE_W];
-    cp.qkv = h->qkv;
+    cp.qk = h->qkv;
+    cp.v = h->qkv + (size_t)2 * M * inner;
     cp.act = h->act;
     cp.gate_part = h->gate_part;
     cp.B = B; cp.T = T; cp.inner = inner; cp.NH = NH; cp.KS = c.conv_kernel; cp.NCH = h->NCH;
@@ -167,7 +177,8 @@ int run_blocks(xl_handle* h, void* state, int B, int T, unsigned flags, cudaStre
     sp.C = (float*)(base + L.c_off);
     sp.n = (float*)(base + L.n_off);
     sp.m = (float*)(base + L.m_off);
-    sp.qkv = h->qkv;
+    sp.qk = h->qkv;
+    sp.v = h->qkv + (size_t)2 * M * inner;
     sp.gate_part = h->gate_part;
     sp.igate_b = (const float*)w.w[XL_W_IGATE_B];
     sp.fgate_b = (const float*)w.w[XL_W_FGATE_B];
@@ -175,11 +186,13 @@ int run_blocks(xl_handle* h, void* state, int B, int T, unsigned flags, cudaStre
     sp.skip = (const float*)w.w[XL_W_SKIP];
     sp.act = h->act;
     sp.u = h->u;
-    sp.out = h->gated;
+    sp.out = tc_down ? nullptr : h->gated;
+    sp.out_hi = tc_down ? h->a_hi : nullptr;
+    sp.out_lo = tc_down ? h->a_lo : nullptr;
     sp.partial = h->partial;
-    sp.counters = h->counters;
     sp.B = B; sp.T = T; sp.NH = NH; sp.DH = h->DH; sp.inner = inner; sp.NCH = h->NCH;
     sp.ln_eps = c.ln_eps; sp.cell_eps = c.cell_eps;
+    sp.impl = h->state_impl; sp.num_layers = c.num_blocks;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (h->profiling) {
       XL_CUDA(cudaEventCreate(&pe0));
@@ -187,14 +200,15 @@ int run_blocks(xl_handle* h, void* state, int B, int T, unsigned flags, cudaStre
       XL_CUDA(cudaEventRecord(pe0, s));
     }
     XL_CUDA(xl::launch_state_step(sp, h->num_sms, s));
-    h->launches += 1;
+    h->launches += 2;
     if (h->profiling) {
       XL_CUDA(cudaEventRecord(pe1, s));
       h->prof_state.push_back(pe0);
       h->prof_state.push_back(pe1);
     }
+    XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, s));
     // x = x + gated @ W_down^T
-    rc = linear(h, h->gated, w.w[XL_W_PROJ_DOWN], nullptr, h->x, h->x, M, d, inner, impl, s);
+    rc = linear(h, h->gated, w.w[XL_W_PROJ_DOWN], nullptr, h->x, h->x, M, d, inner, impl, s, tc_down);
     if (rc) return rc;
   }
   XL_CUDA(cudaGetLastError());
@@ -244,7 +258,7 @@ int run_policy(xl_handle* h, void* state, const float* states, const float* rtg,
                cudaStream_t s) {
   const xl_config& c = h->cfg;
   const int d = c.embedding_dim, T = c.tokens_per_step;
-  const int impl = (flags & XL_FLAG_SIMPLE_GEMM) ? 1 : 0;
+  const int impl = (flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
   auto PW = [&](int id) { return h->pw[id - XL_W_POST_NORM]; };
   // embed_state: Linear(204 -> d) on zero-padded K
   xl::launch_pad_rows(states, c.state_dim, h->states_pad, h->Kpad, B, s);
@@ -525,14 +539,18 @@ int xl_mlstm_cell_step(xl_handle* h, float* C, float* n, float* m, const float* 
                             sizeof(float) * NH, M, cudaMemcpyDeviceToDevice, s));
   xl::StateStepParams sp;
   memset(&sp, 0, sizeof(sp));
-  sp.C = C; sp.n = n; sp.m = m; sp.qkv = qkv; sp.gate_part = h->gate_part;
+  xl::launch_repack_qkv(qkv, h->qkv, h->qkv + (size_t)2 * M * c.inner_dim, M, c.inner_dim, s);
+  sp.C = C; sp.n = n; sp.m = m; sp.qk = h->qkv; sp.v = h->qkv + (size_t)2 * M * c.inner_dim;
+  sp.gate_part = h->gate_part;
   sp.outnorm_w = outnorm_w; sp.out = h_norm; sp.h_raw = h_raw;
-  sp.partial = h->partial; sp.counters = h->counters;
+  sp.partial = h->partial;
   sp.B = B; sp.T = T; sp.NH = NH; sp.DH = h->DH; sp.inner = c.inner_dim; sp.NCH = 1;
   sp.rows_split = rows_split; sp.cols_per_cta = cols_per_cta;
   sp.ln_eps = c.ln_eps; sp.cell_eps = c.cell_eps;
+  sp.impl = h->state_impl; sp.num_layers = c.num_blocks;
   XL_CUDA(xl::launch_state_step(sp, h->num_sms, s));
-  h->launches += 1;
+  XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, s));
+  h->launches += 3;
   return XL_OK;
 }
 
@@ -629,6 +647,23 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
   if (!h || !A || !W_bf16 || !out) return fail(XL_ERR_INVALID_ARG, "null argument");
   if (M <= 0 || N <= 0 || K <= 0) return fail(XL_ERR_INVALID_ARG, "bad GEMM shape");
   return linear(h, A, W_bf16, bias, residual, out, M, N, K, impl, (cudaStream_t)stream);
+}
+
+int xl_set_option(xl_handle* h, const char* name, int value) {
+  if (!h || !name) return fail(XL_ERR_INVALID_ARG, "null argument");
+  if (!strcmp(name, "state_impl")) {
+    if (value != 0 && value != 1) return fail(XL_ERR_INVALID_ARG, "state_impl must be 0 or 1");
+    h->state_impl = value;
+  } else if (!strcmp(name, "gemm_impl")) {
+    if (value < 0 || value > 2) return fail(XL_ERR_INVALID_ARG, "gemm_impl must be 0, 1 or 2");
+    h->gemm_impl = value;
+  } else {
+    return fail(XL_ERR_INVALID_ARG, "unknown option %s", name);
+  }
+  for (auto& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+  return XL_OK;
 }
 
 int xl_profile_begin(xl_handle* h) {

@@ -249,10 +249,11 @@ __global__ void __launch_bounds__(256) conv_qkv_gates_kernel(ConvQkvParams p) {
           }
           q[o] = sq; k[o] = sk; v[o] = sv;
         }
-        float* qkv = p.qkv + row * 3 * inner + c;
-        *reinterpret_cast<float4*>(qkv) = make_float4(q[0], q[1], q[2], q[3]);
-        *reinterpret_cast<float4*>(qkv + inner) = make_float4(k[0], k[1], k[2], k[3]);
-        *reinterpret_cast<float4*>(qkv + 2 * inner) = make_float4(v[0], v[1], v[2], v[3]);
+        // channel c of head h sits at (row*NH + h)*DH + (c - h*DH) == row*inner + c: (q,k) pairs interleaved
+        float* qk = p.qk + (row * inner + c) * 2;
+        *reinterpret_cast<float4*>(qk) = make_float4(q[0], k[0], q[1], k[1]);
+        *reinterpret_cast<float4*>(qk + 4) = make_float4(q[2], k[2], q[3], k[3]);
+        *reinterpret_cast<float4*>(p.v + row * inner + c) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(p.act + row * inner + c) = make_float4(a[0], a[1], a[2], a[3]);
 #pragma unroll
         for (int h = 0; h < kMaxNH; ++h) {

@@ -37,7 +37,8 @@ struct ConvQkvParams {
   const float* wv;
   const float* wi;      // [NH, 3*inner]
   const float* wf;      // [NH, 3*inner]
-  float* qkv;           // [M, 3, inner]
+  float* qk;            // [M, NH, DH, 2]  (q, k) interleaved per channel
+  float* v;             // [M, inner]
   float* act;           // [M, inner]   a = silu(conv)
   float* gate_part;     // [M, NCH, 2*NH]  partial gate pre-activations per channel chunk
   int B, T, inner, NH, KS, NCH;
@@ -61,7 +62,8 @@ struct StateStepParams {
   float* C;                 // [B, NH, DH, DH]
   float* n;                 // [B, NH, DH]
   float* m;                 // [B, NH]
-  const float* qkv;         // [M, 3, inner]
+  const float* qk;          // [M, NH, DH, 2]  (q, k) pairs, unscaled
+  const float* v;           // [M, inner]
   const float* gate_part;   // [M, NCH, 2*NH]  (i gates first NH, f gates next NH), summed in order
   const float* igate_b;     // [NH] or nullptr
   const float* fgate_b;     // [NH] or nullptr
@@ -74,15 +76,19 @@ struct StateStepParams {
   void* out_lo;
   float* h_raw;             // optional [M, inner] un-normalised h
   float* partial;           // scratch [B*NH, RS, T, DH]
-  unsigned int* counters;   // [B*NH], zero on entry, zero on exit
   int B, T, NH, DH, inner, NCH;
   int rows_split;           // RS
   int cols_per_cta;         // multiple of 4, <= 128, divides DH
+  int impl;                 // 1 = TMA ring (default), 0 = register-batched global loads
+  int num_layers;           // blocks sharing the L2 with this one (cache-policy choice); 0 = 1
   float ln_eps, cell_eps;
 };
-// Picks a tiling when rows_split / cols_per_cta are 0. Returns cudaError.
+// Kernel 1 (stream C, emit partial numerators) and kernel 2 (n/m update, normalise, gate). Both pick the
+// same tiling when rows_split / cols_per_cta are 0. Return cudaError.
 cudaError_t launch_state_step(StateStepParams p, int num_sms, cudaStream_t s);
+cudaError_t launch_state_finalize(StateStepParams p, int num_sms, cudaStream_t s);
 void state_step_auto_tiling(int B, int NH, int DH, int num_sms, int* rows_split, int* cols_per_cta);
+void launch_repack_qkv(const float* qkv, float* qk, float* v, int M, int inner, cudaStream_t s);
 
 // ---- xl_gemm.cu ----------------------------------------------------------------------------------
 // out[M,N] = A[M,K] W[N,K]^T (+bias) (+residual), A fp32, W bf16, CUDA cores, fp32 accumulate.

@@ -243,6 +243,9 @@ class XLSTMEngine:
                                    _ptr(residual), _ptr(out), M, N, K, impl, self._stream()))
         return out
 
+    def set_option(self, name: str, value: int):
+        L.check(self.lib.xl_set_option(self.handle, name.encode(), int(value)))
+
     def launch_count(self) -> int:
         return int(self.lib.xl_launch_count(self.handle))
 
