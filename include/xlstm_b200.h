@@ -181,7 +181,8 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
 
 /* Implementation switches for A/B measurements (defaults in brackets):
  *   "state_impl": [1] TMA-fed ring for the state stream, 0 register-batched global loads
- *   "gemm_impl":  [0] auto (tcgen05 when K % 64 == 0), 1 CUDA-core, 2 tcgen05 */
+ *   "gemm_impl":  [0] auto (tcgen05 when K % 64 == 0), 1 CUDA-core, 2 tcgen05
+ *   "gemm_splitk": [1] cluster split-K (DSMEM reduction) in the tcgen05 Linear when the cost model asks, 0 never */
 int xl_set_option(xl_handle* h, const char* name, int value);
 
 /* Counters for bench.py: kernels launched by this handle since the last call (reset on read). */

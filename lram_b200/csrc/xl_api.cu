@@ -71,9 +71,11 @@ struct xl_handle {
   int64_t launches = 0;
   std::vector<GraphCacheEntry> graphs;
   size_t a_cap = 0;                    // elements per bf16 hi/lo plane
+  int num_tickets = 0;
   cudaStream_t cap_stream = nullptr;   // graph capture never happens on the caller's (possibly legacy) stream
   int state_impl = 1;                  // 1 = TMA ring, 0 = register-batched loads (xl_set_option "state_impl")
   int gemm_impl = 0;                   // 0 auto, 1 CUDA-core, 2 tcgen05      (xl_set_option "gemm_impl")
+  int gemm_splitk = 0;                 // cluster split-K in the tcgen05 Linear (xl_set_option "gemm_splitk")
   bool profiling = false;
   std::vector<cudaEvent_t> prof_state;  // start/stop pairs around state-step launches
   std::vector<cudaEvent_t> prof_step;   // start/stop pairs around policy steps
@@ -123,7 +125,7 @@ int linear(xl_handle* h, const float* A, const void* W, const float* bias, const
       h->launches += 1;
     }
     XL_CUDA(xl::launch_gemm_tc(h->a_hi, h->a_lo, (const __nv_bfloat16*)W, bias, residual, out, M, N, K,
-                               h->num_sms, s));
+                               h->num_sms, h->gemm_splitk ? 0 : 1, s));
     h->launches += 1;
     return XL_OK;
   }
@@ -169,7 +171,8 @@ int run_blocks(xl_handle* h, void* state, int B, int T, unsigned flags, cudaStre
     cp.act = h->act;
     cp.gate_part = h->gate_part;
     cp.B = B; cp.T = T; cp.inner = inner; cp.NH = NH; cp.KS = c.conv_kernel; cp.NCH = h->NCH;
-    xl::launch_conv_qkv_gates(cp, s);
+    if (!xl::launch_conv_qkv_gates(cp, s))
+      return fail(XL_ERR_UNSUPPORTED, "conv/qkv kernel not instantiated for KS=%d T=%d NH=%d", cp.KS, cp.T, cp.NH);
     h->launches += 1;
     // state step (+ GroupNorm + skip + output gate)
     xl::StateStepParams sp;
@@ -321,7 +324,7 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   if (c.inner_dim <= 0 || c.inner_dim % (4 * c.num_heads) || c.inner_dim % 8)
     return fail(XL_ERR_UNSUPPORTED, "inner_dim must be a multiple of 8 and of 4*num_heads");
   if (c.qkv_blocksize != 4) return fail(XL_ERR_UNSUPPORTED, "qkv_blocksize must be 4");
-  if (c.conv_kernel < 1 || c.conv_kernel > 8) return fail(XL_ERR_UNSUPPORTED, "conv_kernel must be in [1,8]");
+  if (c.conv_kernel < 2 || c.conv_kernel > 4) return fail(XL_ERR_UNSUPPORTED, "conv_kernel must be in [2,4]");
   if (c.tokens_per_step < 1 || c.tokens_per_step > 4) return fail(XL_ERR_UNSUPPORTED, "tokens_per_step in [1,4]");
   if (c.action_token_pos < 0 || c.action_token_pos >= c.tokens_per_step)
     return fail(XL_ERR_INVALID_ARG, "action_token_pos out of range");
@@ -340,7 +343,16 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   if (!h) return fail(XL_ERR_INVALID_ARG, "out of host memory");
   h->cfg = c;
   h->DH = DH;
-  h->NCH = c.num_heads;  // one gate-partial chunk per head's worth of channels
+  {
+    // gate pre-activations are produced as NCH partial sums (64 four-channel blocks per chunk), summed in
+    // fixed order by the state kernels
+    const int nblk = c.inner_dim / 4;
+    int nch = (nblk + 63) / 64;
+    if (nch < 1) nch = 1;
+    if (nch > 16) nch = 16;
+    h->NCH = nch;
+    if ((nblk + nch - 1) / nch > 128) { delete h; return fail(XL_ERR_UNSUPPORTED, "inner_dim too large"); }
+  }
   h->Kpad = (int)align_up((size_t)c.state_dim, 64);
   h->num_actions = c.discrete_actions + c.action_channels;
   h->head_out = h->num_actions * c.act_dim;
@@ -363,12 +375,14 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   const size_t o_x = carve(4 * M * d), o_xn = carve(4 * M * d), o_xtok = carve(4 * M * d);
   const size_t o_hid = carve(4 * M * d);
   const size_t o_u = carve(4 * M * 2 * inner), o_qkv = carve(4 * M * 3 * inner), o_act = carve(4 * M * inner);
-  const size_t o_gp = carve(4 * M * h->NCH * 2 * c.num_heads), o_gated = carve(4 * M * inner);
+  const size_t o_gp = carve(4 * M * 16 * 2 * c.num_heads), o_gated = carve(4 * M * inner);
   const size_t o_part = carve(4 * B * c.num_heads * 32 * 4 * DH);  // RS <= 32, T <= 4
   const size_t o_semb = carve(4 * B * d), o_sp = carve(4 * B * h->Kpad), o_lg = carve(4 * B * h->head_out);
   const size_t o_ds = carve(4 * B * c.state_dim), o_dr = carve(4 * B), o_dw = carve(4 * B);
   const size_t o_da = carve(4 * B * c.act_dim), o_dt = carve(4 * B * c.act_dim);
-  const size_t o_cnt = carve(4 * B * c.num_heads);
+  h->num_tickets = 4096;
+  const size_t o_cnt = carve(4 * (size_t)h->num_tickets);
+
   size_t a_cap = M * (inner > d ? inner : d);
   if (a_cap < B * (size_t)h->Kpad) a_cap = B * (size_t)h->Kpad;
   if (a_cap < (size_t)1 << 20) a_cap = (size_t)1 << 20;   // room for xl_linear unit tests
@@ -391,6 +405,7 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   h->d_states = (float*)(h->ws + o_ds); h->d_rtg = (float*)(h->ws + o_dr); h->d_rew = (float*)(h->ws + o_dw);
   h->d_actions = (float*)(h->ws + o_da); h->d_tokens = (int32_t*)(h->ws + o_dt);
   h->counters = (unsigned int*)(h->ws + o_cnt);
+
   h->a_hi = (__nv_bfloat16*)(h->ws + o_hi); h->a_lo = (__nv_bfloat16*)(h->ws + o_lo);
   *out = h;
   return XL_OK;
@@ -654,6 +669,8 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   if (!strcmp(name, "state_impl")) {
     if (value != 0 && value != 1) return fail(XL_ERR_INVALID_ARG, "state_impl must be 0 or 1");
     h->state_impl = value;
+  } else if (!strcmp(name, "gemm_splitk")) {
+    h->gemm_splitk = value ? 1 : 0;
   } else if (!strcmp(name, "gemm_impl")) {
     if (value < 0 || value > 2) return fail(XL_ERR_INVALID_ARG, "gemm_impl must be 0, 1 or 2");
     h->gemm_impl = value;

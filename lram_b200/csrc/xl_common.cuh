@@ -32,6 +32,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __device__ __forceinline__ float log_sigmoid(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }
 
 __device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
+// SFU version (ex2.approx + rcp.approx, ~2 ulp): used where SiLU sits on a latency-critical tail
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 // streaming (evict-first) 128-bit accesses for the once-touched state stream
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }

@@ -75,10 +75,60 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
   }
 }
 
+// One CTA per row, one float4 per thread held in registers: a single global read, two block reductions.
+__global__ void __launch_bounds__(1024) ln_rows_cta_kernel(const float* __restrict__ in, int64_t in_stride,
+                                                           float* __restrict__ out, int64_t out_stride,
+                                                           const float* __restrict__ w,
+                                                           const float* __restrict__ bias, int residual_weight,
+                                                           float eps, int d, __nv_bfloat16* __restrict__ a_hi,
+                                                           __nv_bfloat16* __restrict__ a_lo) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int i = threadIdx.x;
+  const bool ok = i < (d >> 2);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 g = v, bb = v;
+  if (ok) {
+    v = reinterpret_cast<const float4*>(in + (int64_t)row * in_stride)[i];
+    g = reinterpret_cast<const float4*>(w)[i];
+    if (bias) bb = reinterpret_cast<const float4*>(bias)[i];
+  }
+  const float mean = block_sum((v.x + v.y) + (v.z + v.w), red) / (float)d;
+  const float a = v.x - mean, b = v.y - mean, c = v.z - mean, e = v.w - mean;
+  const float q = ok ? (a * a + b * b) + (c * c + e * e) : 0.f;
+  const float rstd = rsqrtf(block_sum(q, red) / (float)d + eps);
+  if (!ok) return;
+  const float wofs = residual_weight ? 1.f : 0.f;
+  float4 r;
+  r.x = a * rstd * (g.x + wofs) + bb.x;
+  r.y = b * rstd * (g.y + wofs) + bb.y;
+  r.z = c * rstd * (g.z + wofs) + bb.z;
+  r.w = e * rstd * (g.w + wofs) + bb.w;
+  if (out) reinterpret_cast<float4*>(out + (int64_t)row * out_stride)[i] = r;
+  if (a_hi) {
+    const float rr[4] = {r.x, r.y, r.z, r.w};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = __float2bfloat16_rn(rr[j]);
+      lo[j] = __float2bfloat16_rn(rr[j] - __bfloat162float(hi[j]));
+    }
+    const int64_t base = (int64_t)row * d + 4 * i;
+    *reinterpret_cast<uint2*>(a_hi + base) = *reinterpret_cast<uint2*>(hi);
+    *reinterpret_cast<uint2*>(a_lo + base) = *reinterpret_cast<uint2*>(lo);
+  }
+}
+
 void launch_ln_rows(const float* in, int64_t in_stride, float* out, int64_t out_stride, const float* w,
                     const float* bias, int residual_weight, float eps, int rows, int d, void* a_hi,
                     void* a_lo, cudaStream_t s) {
   if (rows <= 0) return;
+  if (d <= 4096) {
+    const int threads = (((d >> 2) + 31) / 32) * 32;
+    ln_rows_cta_kernel<<<rows, threads, 0, s>>>(in, in_stride, out, out_stride, w, bias, residual_weight, eps, d,
+                                                (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo);
+    return;
+  }
   const int warps_per_block = 8;
   dim3 grid((rows + warps_per_block - 1) / warps_per_block);
   ln_rows_kernel<<<grid, warps_per_block * 32, 0, s>>>(in, in_stride, out, out_stride, w, bias,
@@ -162,82 +212,77 @@ void launch_copy_rows(const float* in, int64_t in_stride, float* out, int64_t ou
 // window lives in registers across the tokens of the step. Gate partial sums per chunk are written out
 // and summed in fixed order by the state kernel (deterministic, no float atomics).
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxNH = 8;
-constexpr int kMaxT = 4;
 
-template <int KS>
-__global__ void __launch_bounds__(256) conv_qkv_gates_kernel(ConvQkvParams p) {
-  constexpr int kMaxKS = KS;
-  __shared__ float red[32];
+template <int KS, int T, int NH>
+__global__ void __launch_bounds__(128, 4) conv_qkv_gates_kernel(ConvQkvParams p) {
+  constexpr int kMaxT = T;
+  constexpr int kMaxNH = NH;
+  __shared__ float red[2 * kMaxNH * kMaxT * 4];
   const int b = blockIdx.y;
   const int chunk = blockIdx.x;
-  const int inner = p.inner, NH = p.NH, T = p.T;
+  const int inner = p.inner;
   const int nblk = inner >> 2;                       // 4-channel blocks
   const int blk_per_chunk = (nblk + p.NCH - 1) / p.NCH;
-  const int blk0 = chunk * blk_per_chunk;
-  const int blk1 = min(nblk, blk0 + blk_per_chunk);
+  const int j = chunk * blk_per_chunk + threadIdx.x;
+  const bool active = threadIdx.x < blk_per_chunk && j < nblk;
+  const int c = 4 * (active ? j : 0);
 
-  float gi[kMaxT][kMaxNH], gf[kMaxT][kMaxNH];
+  // ---- phase 1: conv window -> SiLU -> block-diagonal q/k/v for the T tokens -----------------------
+  float q[kMaxT][4], k[kMaxT][4], v[kMaxT][4];
 #pragma unroll
   for (int t = 0; t < kMaxT; ++t)
 #pragma unroll
-    for (int h = 0; h < kMaxNH; ++h) gi[t][h] = gf[t][h] = 0.f;
-
-  for (int j = blk0 + threadIdx.x; j < blk1; j += blockDim.x) {
-    const int c = 4 * j;
-    // conv window: rows 1..KS-1 of the state are the KS-1 most recent inputs (oldest first)
-    float win[kMaxKS][4];
+    for (int o = 0; o < 4; ++o) q[t][o] = k[t][o] = v[t][o] = 0.f;
+  if (active) {
+    // rows 1..KS-1 of the state are the KS-1 most recent inputs (oldest first); row 0 is shifted out
+    float win[KS][4];
     float* cs = p.conv_state + (int64_t)b * KS * inner + c;
 #pragma unroll
-    for (int r = 0; r < kMaxKS; ++r) {
-      if (r < KS) {
-        float4 v = *reinterpret_cast<const float4*>(cs + (int64_t)r * inner);
-        win[r][0] = v.x; win[r][1] = v.y; win[r][2] = v.z; win[r][3] = v.w;
-      }
+    for (int r = 0; r < KS; ++r) {
+      const float4 w4 = *reinterpret_cast<const float4*>(cs + (int64_t)r * inner);
+      win[r][0] = w4.x; win[r][1] = w4.y; win[r][2] = w4.z; win[r][3] = w4.w;
     }
-    float cw[4][kMaxKS];
+    float4 xm4[kMaxT];
+#pragma unroll
+    for (int t = 0; t < kMaxT; ++t)
+      if (t < T) xm4[t] = *reinterpret_cast<const float4*>(p.u + ((int64_t)b * T + t) * 2 * inner + c);
+    float cw[4][KS];
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-      for (int r = 0; r < kMaxKS; ++r)
-        if (r < KS) cw[ch][r] = p.conv_w[(int64_t)(c + ch) * KS + r];
+      for (int r = 0; r < KS; ++r) cw[ch][r] = p.conv_w[(int64_t)(c + ch) * KS + r];
     const float4 cb = *reinterpret_cast<const float4*>(p.conv_b + c);
+    const float cbv[4] = {cb.x, cb.y, cb.z, cb.w};
     float wq[16], wk[16], wv[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      float4 a = reinterpret_cast<const float4*>(p.wq + (int64_t)j * 16)[i];
-      float4 k = reinterpret_cast<const float4*>(p.wk + (int64_t)j * 16)[i];
-      float4 v = reinterpret_cast<const float4*>(p.wv + (int64_t)j * 16)[i];
-      wq[4 * i] = a.x; wq[4 * i + 1] = a.y; wq[4 * i + 2] = a.z; wq[4 * i + 3] = a.w;
-      wk[4 * i] = k.x; wk[4 * i + 1] = k.y; wk[4 * i + 2] = k.z; wk[4 * i + 3] = k.w;
-      wv[4 * i] = v.x; wv[4 * i + 1] = v.y; wv[4 * i + 2] = v.z; wv[4 * i + 3] = v.w;
+      const float4 a4 = reinterpret_cast<const float4*>(p.wq + (int64_t)j * 16)[i];
+      const float4 k4 = reinterpret_cast<const float4*>(p.wk + (int64_t)j * 16)[i];
+      const float4 v4 = reinterpret_cast<const float4*>(p.wv + (int64_t)j * 16)[i];
+      wq[4 * i] = a4.x; wq[4 * i + 1] = a4.y; wq[4 * i + 2] = a4.z; wq[4 * i + 3] = a4.w;
+      wk[4 * i] = k4.x; wk[4 * i + 1] = k4.y; wk[4 * i + 2] = k4.z; wk[4 * i + 3] = k4.w;
+      wv[4 * i] = v4.x; wv[4 * i + 1] = v4.y; wv[4 * i + 2] = v4.z; wv[4 * i + 3] = v4.w;
     }
 #pragma unroll
     for (int t = 0; t < kMaxT; ++t) {
       if (t < T) {
         const int64_t row = (int64_t)b * T + t;
-        const float4 xm4 = *reinterpret_cast<const float4*>(p.u + row * 2 * inner + c);
-        const float xm[4] = {xm4.x, xm4.y, xm4.z, xm4.w};
+        const float xm[4] = {xm4[t].x, xm4[t].y, xm4[t].z, xm4[t].w};
         // roll(-1); state[-1] = x
 #pragma unroll
-        for (int r = 0; r < kMaxKS - 1; ++r)
-          if (r < KS - 1) {
+        for (int r = 0; r < KS - 1; ++r)
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) win[r][ch] = win[r + 1][ch];
-          }
+          for (int ch = 0; ch < 4; ++ch) win[r][ch] = win[r + 1][ch];
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) win[KS - 1][ch] = xm[ch];
         float a[4];
-        const float cbv[4] = {cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           float acc = 0.f;
 #pragma unroll
-          for (int r = 0; r < kMaxKS; ++r)
-            if (r < KS) acc = fmaf(win[r][ch], cw[ch][r], acc);
+          for (int r = 0; r < KS; ++r) acc = fmaf(win[r][ch], cw[ch][r], acc);
           a[ch] = silu(acc + cbv[ch]);
         }
-        float q[4], k[4], v[4];
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
           float sq = 0.f, sk = 0.f, sv = 0.f;
@@ -247,82 +292,98 @@ __global__ void __launch_bounds__(256) conv_qkv_gates_kernel(ConvQkvParams p) {
             sk = fmaf(a[dd], wk[4 * o + dd], sk);
             sv = fmaf(xm[dd], wv[4 * o + dd], sv);
           }
-          q[o] = sq; k[o] = sk; v[o] = sv;
+          q[t][o] = sq; k[t][o] = sk; v[t][o] = sv;
         }
         // channel c of head h sits at (row*NH + h)*DH + (c - h*DH) == row*inner + c: (q,k) pairs interleaved
         float* qk = p.qk + (row * inner + c) * 2;
-        *reinterpret_cast<float4*>(qk) = make_float4(q[0], k[0], q[1], k[1]);
-        *reinterpret_cast<float4*>(qk + 4) = make_float4(q[2], k[2], q[3], k[3]);
-        *reinterpret_cast<float4*>(p.v + row * inner + c) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(qk) = make_float4(q[t][0], k[t][0], q[t][1], k[t][1]);
+        *reinterpret_cast<float4*>(qk + 4) = make_float4(q[t][2], k[t][2], q[t][3], k[t][3]);
+        *reinterpret_cast<float4*>(p.v + row * inner + c) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]);
         *reinterpret_cast<float4*>(p.act + row * inner + c) = make_float4(a[0], a[1], a[2], a[3]);
-#pragma unroll
-        for (int h = 0; h < kMaxNH; ++h) {
-          if (h < NH) {
-            const float* wi = p.wi + (int64_t)h * 3 * inner + c;
-            const float* wf = p.wf + (int64_t)h * 3 * inner + c;
-            const float4 iq = *reinterpret_cast<const float4*>(wi);
-            const float4 ik = *reinterpret_cast<const float4*>(wi + inner);
-            const float4 iv = *reinterpret_cast<const float4*>(wi + 2 * inner);
-            const float4 fq = *reinterpret_cast<const float4*>(wf);
-            const float4 fk = *reinterpret_cast<const float4*>(wf + inner);
-            const float4 fv = *reinterpret_cast<const float4*>(wf + 2 * inner);
-            float si = q[0] * iq.x + q[1] * iq.y + q[2] * iq.z + q[3] * iq.w;
-            si += k[0] * ik.x + k[1] * ik.y + k[2] * ik.z + k[3] * ik.w;
-            si += v[0] * iv.x + v[1] * iv.y + v[2] * iv.z + v[3] * iv.w;
-            float sf = q[0] * fq.x + q[1] * fq.y + q[2] * fq.z + q[3] * fq.w;
-            sf += k[0] * fk.x + k[1] * fk.y + k[2] * fk.z + k[3] * fk.w;
-            sf += v[0] * fv.x + v[1] * fv.y + v[2] * fv.z + v[3] * fv.w;
-            gi[t][h] += si;
-            gf[t][h] += sf;
-          }
-        }
       }
     }
     // write the window back: rows = last KS inputs, oldest first (reference conv_state layout)
 #pragma unroll
-    for (int r = 0; r < kMaxKS; ++r)
-      if (r < KS)
-        *reinterpret_cast<float4*>(cs + (int64_t)r * inner) =
-            make_float4(win[r][0], win[r][1], win[r][2], win[r][3]);
+    for (int r = 0; r < KS; ++r)
+      *reinterpret_cast<float4*>(cs + (int64_t)r * inner) =
+          make_float4(win[r][0], win[r][1], win[r][2], win[r][3]);
   }
-  // block-reduce the gate partials of this chunk
+
+  // ---- phase 2: partial igate / fgate pre-activations of this channel chunk --------------------------
+  // g~ = W[:, c] . q + W[:, inner + c] . k + W[:, 2*inner + c] . v, per head, summed over the chunk's channels
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
 #pragma unroll
-  for (int t = 0; t < kMaxT; ++t) {
-    if (t < T) {
+  for (int h = 0; h < kMaxNH; ++h) {
+    if (h < NH) {
+      float gi[kMaxT], gf[kMaxT];
 #pragma unroll
-      for (int h = 0; h < kMaxNH; ++h) {
-        if (h < NH) {
-          const float si = block_sum(gi[t][h], red);
-          const float sf = block_sum(gf[t][h], red);
-          if (threadIdx.x == 0) {
-            float* gp = p.gate_part + (((int64_t)b * T + t) * p.NCH + chunk) * 2 * NH;
-            gp[h] = si;
-            gp[NH + h] = sf;
+      for (int t = 0; t < kMaxT; ++t) gi[t] = gf[t] = 0.f;
+      if (active) {
+        const float* wi = p.wi + (int64_t)h * 3 * inner + c;
+        const float* wf = p.wf + (int64_t)h * 3 * inner + c;
+        const float4 iq = *reinterpret_cast<const float4*>(wi);
+        const float4 ik = *reinterpret_cast<const float4*>(wi + inner);
+        const float4 iv = *reinterpret_cast<const float4*>(wi + 2 * inner);
+        const float4 fq = *reinterpret_cast<const float4*>(wf);
+        const float4 fk = *reinterpret_cast<const float4*>(wf + inner);
+        const float4 fv = *reinterpret_cast<const float4*>(wf + 2 * inner);
+#pragma unroll
+        for (int t = 0; t < kMaxT; ++t) {
+          if (t < T) {
+            float si = q[t][0] * iq.x + q[t][1] * iq.y + q[t][2] * iq.z + q[t][3] * iq.w;
+            si += k[t][0] * ik.x + k[t][1] * ik.y + k[t][2] * ik.z + k[t][3] * ik.w;
+            si += v[t][0] * iv.x + v[t][1] * iv.y + v[t][2] * iv.z + v[t][3] * iv.w;
+            float sf = q[t][0] * fq.x + q[t][1] * fq.y + q[t][2] * fq.z + q[t][3] * fq.w;
+            sf += k[t][0] * fk.x + k[t][1] * fk.y + k[t][2] * fk.z + k[t][3] * fk.w;
+            sf += v[t][0] * fv.x + v[t][1] * fv.y + v[t][2] * fv.z + v[t][3] * fv.w;
+            gi[t] = si;
+            gf[t] = sf;
+          }
+        }
+      }
+      // warp reduce, then one slot per (gate, token, warp)
+#pragma unroll
+      for (int t = 0; t < kMaxT; ++t) {
+        if (t < T) {
+          const float si = warp_sum(gi[t]);
+          const float sf = warp_sum(gf[t]);
+          if (lane == 0) {
+            red[((h * 2 + 0) * kMaxT + t) * 4 + wid] = si;
+            red[((h * 2 + 1) * kMaxT + t) * 4 + wid] = sf;
           }
         }
       }
     }
   }
+  __syncthreads();
+  // thread x -> (h, gate, t): fixed-order sum over the (<= 4) warps
+  const int nout = NH * 2 * T;
+  if ((int)threadIdx.x < nout) {
+    const int h = threadIdx.x / (2 * T);
+    const int rem = threadIdx.x - h * 2 * T;
+    const int g = rem / T, t = rem - g * T;
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += red[((h * 2 + g) * kMaxT + t) * 4 + w];
+    float* gp = p.gate_part + (((int64_t)b * T + t) * p.NCH + chunk) * 2 * NH;
+    gp[g * NH + h] = s;
+  }
 }
 
-void launch_conv_qkv_gates(const ConvQkvParams& p, cudaStream_t s) {
+bool launch_conv_qkv_gates(const ConvQkvParams& p, cudaStream_t s) {
   const int nblk = p.inner / 4;
   const int per_chunk = (nblk + p.NCH - 1) / p.NCH;
-  int threads = ((per_chunk + 31) / 32) * 32;
-  if (threads > 256) threads = 256;
-  if (threads < 32) threads = 32;
+  const int threads = ((per_chunk + 31) / 32) * 32;   // one thread per 4-channel block; <= 128 (host-checked)
   dim3 grid(p.NCH, p.B);
-  switch (p.KS) {
-    case 1: conv_qkv_gates_kernel<1><<<grid, threads, 0, s>>>(p); break;
-    case 2: conv_qkv_gates_kernel<2><<<grid, threads, 0, s>>>(p); break;
-    case 3: conv_qkv_gates_kernel<3><<<grid, threads, 0, s>>>(p); break;
-    case 4: conv_qkv_gates_kernel<4><<<grid, threads, 0, s>>>(p); break;
-    case 5: conv_qkv_gates_kernel<5><<<grid, threads, 0, s>>>(p); break;
-    case 6: conv_qkv_gates_kernel<6><<<grid, threads, 0, s>>>(p); break;
-    case 7: conv_qkv_gates_kernel<7><<<grid, threads, 0, s>>>(p); break;
-    case 8: conv_qkv_gates_kernel<8><<<grid, threads, 0, s>>>(p); break;
-    default: break;
-  }
+  // instantiated for the shipped presets (KS = 4, NH = 4; 1..4 tokens per step) plus NH = 1, 2, 8
+#define XL_CONV_CASE(KSV, TV, NHV) \
+  if (p.KS == KSV && p.T == TV && p.NH == NHV) { conv_qkv_gates_kernel<KSV, TV, NHV><<<grid, threads, 0, s>>>(p); return true; }
+  XL_CONV_CASE(4, 1, 4) XL_CONV_CASE(4, 2, 4) XL_CONV_CASE(4, 3, 4) XL_CONV_CASE(4, 4, 4)
+  XL_CONV_CASE(4, 1, 8) XL_CONV_CASE(4, 3, 8) XL_CONV_CASE(4, 1, 2) XL_CONV_CASE(4, 3, 2)
+  XL_CONV_CASE(4, 1, 1) XL_CONV_CASE(4, 3, 1) XL_CONV_CASE(2, 1, 4) XL_CONV_CASE(2, 3, 4)
+  XL_CONV_CASE(3, 1, 4) XL_CONV_CASE(3, 3, 4)
+#undef XL_CONV_CASE
+  return false;
 }
 
 // ------------------------------------------------------------------------------------------------

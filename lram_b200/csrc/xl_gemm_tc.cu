@@ -110,7 +110,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * BLOCK_M;
-  const int num_kb = K / BLOCK_K;
+  // split-K: blockIdx.z (== rank in the (1,1,splits) cluster) owns k-blocks [kb0, kb0 + num_kb)
+  const int splits = gridDim.z;
+  const int kb_total = K / BLOCK_K;
+  const int kb_per = (kb_total + splits - 1) / splits;
+  const int kb0 = blockIdx.z * kb_per;
+  const int num_kb = max(0, min(kb_total, kb0 + kb_per) - kb0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
@@ -144,9 +149,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         mbar_wait(empty_bar(s), ph ^ 1);
         const uint32_t st = base + s * S::kStageBytes;
         mbar_expect_tx(full_bar(s), S::kStageBytes);
-        tma_load_2d(st, &map_a_hi, full_bar(s), kb * BLOCK_K, m0);
-        tma_load_2d(st + S::kABytes, &map_a_lo, full_bar(s), kb * BLOCK_K, m0);
-        tma_load_2d(st + 2 * S::kABytes, &map_w, full_bar(s), kb * BLOCK_K, n0);
+        tma_load_2d(st, &map_a_hi, full_bar(s), (kb0 + kb) * BLOCK_K, m0);
+        tma_load_2d(st + S::kABytes, &map_a_lo, full_bar(s), (kb0 + kb) * BLOCK_K, m0);
+        tma_load_2d(st + 2 * S::kABytes, &map_w, full_bar(s), (kb0 + kb) * BLOCK_K, n0);
       }
     }
   } else if (warp == 1) {
@@ -172,58 +177,129 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
       tcgen05_commit(tmem_full_bar);             // accumulator complete
     }
-  } else {
-    // ===== epilogue: warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
-    const int q = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const int row = m0 + q * 32 + lane;
+  }
+
+  // ===== epilogue: warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====================
+  // splits == 1: TMEM -> registers -> bias/residual -> global, 32 columns at a time.
+  // splits  > 1: the CTAs of a cluster hold partial sums of the same tile (split-K). Ranks > 0 push their
+  //   accumulators into the leader's shared memory over DSMEM (the pipeline stages are idle by then), the
+  //   leader adds them in rank order (deterministic) and runs the epilogue. Two cluster barriers, no global
+  //   round trip.
+  const bool is_epi = warp >= 2;
+  const int q = warp & 3;
+  const int row = m0 + q * 32 + lane;
+  constexpr int kPitch = BLOCK_N + 4;                         // floats; +4 breaks the bank alignment of rows
+  uint32_t rank = 0;
+  if (splits > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+
+  auto store_chunk = [&](const float (&v)[32], int c) {       // bias + residual + store of 32 columns
+    if (row >= M) return;
+    const int col0 = n0 + c;
+    float* orow = out + (int64_t)row * N + col0;
+    const float* rrow = residual ? residual + (int64_t)row * N + col0 : nullptr;
+    if (col0 + 32 <= N && (N & 3) == 0) {
 #pragma unroll
-    for (int c = 0; c < BLOCK_N; c += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
-            "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
-            "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < M) {
-        const int col0 = n0 + c;
-        float* orow = out + (int64_t)row * N + col0;
-        const float* rrow = residual ? residual + (int64_t)row * N + col0 : nullptr;
-        if (col0 + 32 <= N && (N & 3) == 0) {
+      for (int j = 0; j < 32; j += 4) {
+        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (bias) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + j);
+          o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+        }
+        if (rrow) {
+          const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
+          o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+        }
+        *reinterpret_cast<float4*>(orow + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (col0 + j < N) {
+          float o = v[j];
+          if (bias) o += bias[col0 + j];
+          if (rrow) o += rrow[j];
+          orow[j] = o;
+        }
+      }
+    }
+  };
+  auto tmem_load_chunk = [&](float (&v)[32], int c) {
+    uint32_t r[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+          "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  };
+
+  if (splits == 1) {
+    if (is_epi) {
+      mbar_wait(tmem_full_bar, 0);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        float v[32];
+        tmem_load_chunk(v, c);
+        store_chunk(v, c);
+      }
+    }
+  } else {
+    if (is_epi) {
+      mbar_wait(tmem_full_bar, 0);          // this CTA's MMAs are complete -> its smem stages are idle
+      tcgen05_fence_after();
+    }
+    __syncwarp();
+    // (1) every CTA of the cluster is done with its main loop
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (is_epi && rank > 0) {
+      // push my partial tile row into the leader's staging area: [rank-1][128 rows][kPitch]
+      const uint32_t local = base + (uint32_t)(((rank - 1) * BLOCK_M + q * 32 + lane) * kPitch * 4);
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+#pragma unroll
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        float v[32];
+        tmem_load_chunk(v, c);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)((c + j) * 4)),
+                       "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
+                       : "memory");
+      }
+    }
+    __syncwarp();
+    // (2) all partials have landed in the leader's shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (is_epi && rank == 0) {
+#pragma unroll
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        float v[32];
+        tmem_load_chunk(v, c);
+        for (int r = 1; r < splits; ++r) {                     // fixed order: rank 1, 2, ...
+          const uint32_t src = base + (uint32_t)((((r - 1) * BLOCK_M + q * 32 + lane) * kPitch + c) * 4);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                   __uint_as_float(r[j + 3]));
-            if (bias) {
-              const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + j);
-              v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-            }
-            if (rrow) {
-              const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
-              v.x += r4.x; v.y += r4.y; v.z += r4.z; v.w += r4.w;
-            }
-            *reinterpret_cast<float4*>(orow + j) = v;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < N) {
-              float v = __uint_as_float(r[j]);
-              if (bias) v += bias[col0 + j];
-              if (rrow) v += rrow[j];
-              orow[j] = v;
-            }
+            float4 pv;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(pv.x), "=f"(pv.y), "=f"(pv.z), "=f"(pv.w)
+                         : "r"(src + (uint32_t)(j * 4))
+                         : "memory");
+            v[j] += pv.x; v[j + 1] += pv.y; v[j + 2] += pv.z; v[j + 3] += pv.w;
           }
         }
+        store_chunk(v, c);
       }
     }
   }
@@ -285,7 +361,7 @@ static bool make_map(CUtensorMap* m, const void* ptr, int rows, int K, int box_r
 
 template <int BLOCK_N, int kStages>
 static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& ml, const CUtensorMap& mw, const float* bias,
-                          const float* residual, float* out, int M, int N, int K, cudaStream_t s) {
+                          const float* residual, float* out, int M, int N, int K, int splits, cudaStream_t s) {
   using S = Smem<BLOCK_N, kStages>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -294,9 +370,25 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& ml, const CU
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + BLOCK_M - 1) / BLOCK_M);
-  gemm_tc_kernel<BLOCK_N, kStages><<<grid, kThreads, S::kTotal, s>>>(ma, ml, mw, bias, residual, out, M, N, K);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((N + BLOCK_N - 1) / BLOCK_N, (M + BLOCK_M - 1) / BLOCK_M, splits);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = splits;
+  cfg.attrs = attr;
+  cfg.numAttrs = splits > 1 ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kStages>, ma, ml, mw, bias, residual, out, M, N, K);
+}
+
+// shared-memory room for the (splits - 1) partial tiles the leader receives (aliases the pipeline stages)
+template <int BLOCK_N, int kStages>
+constexpr bool splits_fit(int splits) {
+  return (splits - 1) * BLOCK_M * (BLOCK_N + 4) * 4 <= kStages * Smem<BLOCK_N, kStages>::kStageBytes;
 }
 
 }  // namespace tc
@@ -309,22 +401,61 @@ void launch_split_bf16(const float* in, int64_t in_stride, void* hi, void* lo, i
                                                                      (__nv_bfloat16*)lo, rows, K);
 }
 
-cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat16* W, const float* bias,
-                           const float* residual, float* out, int M, int N, int K, int num_sms, cudaStream_t s) {
-  if (!gemm_tc_supported(M, N, K)) return cudaErrorInvalidValue;
-  // tile width: fill the machine; wide tiles only when there are plenty of them
+// Tile width and split-K factor from a small cost model: the per-SM TMA fill rate (~80 GB/s) bounds these
+// skinny GEMMs, so the goal is to spread the operand bytes over ~all SMs without re-reading A too often.
+// split-K runs as a thread-block cluster (<= 8 CTAs, BLOCK_N <= 64) reduced over distributed shared memory.
+void gemm_tc_plan(int M, int N, int K, int num_sms, int* bn_out, int* splits_out) {
   const int m_tiles = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
-  int bn = 128;
-  if ((int64_t)m_tiles * ((N + 127) / 128) < num_sms) bn = 64;
-  if ((int64_t)m_tiles * ((N + 63) / 64) < num_sms / 2) bn = 32;
+  const int kb = K / tc::BLOCK_K;
+  double best = 1e30;
+  int best_bn = 64, best_sp = 1;
+  const int bns[3] = {128, 64, 32};
+  const int sps[6] = {1, 2, 3, 4, 6, 8};
+  for (int bi = 0; bi < 3; ++bi) {
+    const int bn = bns[bi];
+    const int n_tiles = (N + bn - 1) / bn;
+    for (int si = 0; si < 6; ++si) {
+      const int sp = sps[si];
+      if (kb % sp) continue;
+      const int kbp = kb / sp;
+      if (sp > 1) {
+        if (kbp < 2 || bn > 64) continue;
+        const bool fit = bn == 64 ? tc::splits_fit<64, 4>(sp) : tc::splits_fit<32, 6>(sp);
+        if (!fit) continue;
+      }
+      const int ctas = m_tiles * n_tiles * sp;
+      const int waves = (ctas + num_sms - 1) / num_sms;
+      const double per_cta_kb = kbp * (2.0 * 16.0 + bn * 0.125);             // KB of smem fill
+      double t = waves * (2.5 + per_cta_kb / 80.0);                          // us
+      if (sp > 1) t += 1.0 + (sp - 1) * (128.0 * bn * 4.0 / 1024.0) / 40.0;  // 2 cluster barriers + DSMEM pushes
+      if (t < best) { best = t; best_bn = bn; best_sp = sp; }
+    }
+  }
+  *bn_out = best_bn;
+  *splits_out = best_sp;
+}
+
+cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat16* W, const float* bias,
+                           const float* residual, float* out, int M, int N, int K, int num_sms, int force_splits,
+                           cudaStream_t s) {
+  if (!gemm_tc_supported(M, N, K)) return cudaErrorInvalidValue;
+  int bn, splits;
+  gemm_tc_plan(M, N, K, num_sms, &bn, &splits);
+  if (force_splits == 1) {            // A/B switch: best tile width without split-K
+    const int m_tiles = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
+    bn = 128;
+    if ((int64_t)m_tiles * ((N + 127) / 128) < num_sms) bn = 64;
+    if ((int64_t)m_tiles * ((N + 63) / 64) < num_sms / 2) bn = 32;
+    splits = 1;
+  }
   CUtensorMap ma, ml, mw;
   if (!tc::make_map(&ma, a_hi, M, K, tc::BLOCK_M) || !tc::make_map(&ml, a_lo, M, K, tc::BLOCK_M) ||
       !tc::make_map(&mw, W, N, K, bn))
     return cudaErrorUnknown;
   switch (bn) {
-    case 128: return tc::launch<128, 4>(ma, ml, mw, bias, residual, out, M, N, K, s);
-    case 64: return tc::launch<64, 4>(ma, ml, mw, bias, residual, out, M, N, K, s);
-    default: return tc::launch<32, 6>(ma, ml, mw, bias, residual, out, M, N, K, s);
+    case 128: return tc::launch<128, 4>(ma, ml, mw, bias, residual, out, M, N, K, 1, s);
+    case 64: return tc::launch<64, 4>(ma, ml, mw, bias, residual, out, M, N, K, splits, s);
+    default: return tc::launch<32, 6>(ma, ml, mw, bias, residual, out, M, N, K, splits, s);
   }
 }
 

@@ -43,7 +43,8 @@ struct ConvQkvParams {
   float* gate_part;     // [M, NCH, 2*NH]  partial gate pre-activations per channel chunk
   int B, T, inner, NH, KS, NCH;
 };
-void launch_conv_qkv_gates(const ConvQkvParams& p, cudaStream_t s);
+// false when (KS, T, NH) has no instantiation
+bool launch_conv_qkv_gates(const ConvQkvParams& p, cudaStream_t s);
 
 // argmax over action logits + inv_tokenize.
 // continuous: logits [B, act_dim*num_actions] -> tokens [B, act_dim], actions = max(tok-shift,0)*bw+min
@@ -99,7 +100,10 @@ void launch_gemm_simple(const float* A, const __nv_bfloat16* W, const float* bia
 // tcgen05 path: A given as bf16 hi/lo planes (A = hi + lo), W bf16, fp32 accumulate in TMEM.
 bool gemm_tc_supported(int M, int N, int K);
 void launch_split_bf16(const float* in, int64_t in_stride, void* hi, void* lo, int rows, int K, cudaStream_t s);
+// split-K is chosen by a cost model (cluster of CTAs reduced over DSMEM); force_splits = 1 disables it.
 cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat16* W, const float* bias,
-                           const float* residual, float* out, int M, int N, int K, int num_sms, cudaStream_t s);
+                           const float* residual, float* out, int M, int N, int K, int num_sms, int force_splits,
+                           cudaStream_t s);
+void gemm_tc_plan(int M, int N, int K, int num_sms, int* bn_out, int* splits_out);
 
 }  // namespace xl

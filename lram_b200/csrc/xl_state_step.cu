@@ -422,101 +422,105 @@ static cudaError_t launch(const StateStepParams& p, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------
 // kernel 2: finalize one (env, head)
+// Latency-bound (a few KB per CTA), so: every global load is issued up front, and the T tokens share each
+// block reduction (3 reductions in total: q.n, mean, variance) instead of doing 3 per token.
 // ------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void block_sum_n(float (&v)[N], float* red /* [N][32] */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
+  __syncthreads();                     // protect `red` from the previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) red[k * 32 + wid] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    float r = (lane < nw) ? red[k * 32 + lane] : 0.f;
+    v[k] = warp_sum(r);
+  }
+}
+
+// blockDim = DH rounded up to a warp multiple (<= 1024): one head channel per thread, all T tokens. Straight
+// and short on purpose: every CTA runs this code once, so its size is what the instruction cache sees.
 template <int T>
-__global__ void __launch_bounds__(256) mlstm_state_finalize_kernel(StateStepParams p) {
+__global__ void __launch_bounds__(1024) mlstm_state_finalize_kernel(StateStepParams p) {
   __shared__ float s_f[T], s_i[T], s_m[T + 1], s_pre[2 * T];
-  __shared__ float s_red[32];
+  __shared__ float s_red[T * 32];
   const int bh = blockIdx.x;
   const int b = bh / p.NH, hd = bh - b * p.NH;
   const int DH = p.DH, inner = p.inner, RS = p.rows_split;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  if (tid < 32) compute_gates<T>(p, b, hd, bh, s_f, s_i, s_m, s_pre);
-  __syncthreads();
-  const float kscale = rsqrtf((float)DH);
-  constexpr int kMaxPerThread = 4;     // DH <= 4 * 256
-  float qn[T];
-  {
-    float nreg[kMaxPerThread];
+  const int a = threadIdx.x;
+  const bool ok = a < DH;
+  const int ch = hd * DH + (ok ? a : 0);
+
+  // ---- all global loads first ---------------------------------------------------------------------
+  float nreg = ok ? p.n[(int64_t)bh * DH + a] : 0.f;
+  const float wn = ok ? p.outnorm_w[ch] : 0.f;
+  const float wskip = (ok && p.skip) ? p.skip[ch] : 0.f;
+  float2 qk[T];
+  float num[T], act[T], zz[T];
 #pragma unroll
-    for (int i = 0; i < kMaxPerThread; ++i) {
-      const int a = tid + i * nthr;
-      nreg[i] = (a < DH) ? p.n[(int64_t)bh * DH + a] : 0.f;
-    }
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const float2* qk = reinterpret_cast<const float2*>(p.qk) + (((int64_t)b * T + t) * p.NH + hd) * DH;
-      const float ft = s_f[t], it = s_i[t] * kscale;
-      float part = 0.f;
-#pragma unroll
-      for (int i = 0; i < kMaxPerThread; ++i) {
-        const int a = tid + i * nthr;
-        if (a < DH) {
-          const float2 q2 = qk[a];
-          nreg[i] = fmaf(ft, nreg[i], it * q2.y);
-          part = fmaf(q2.x, nreg[i], part);
-        }
-      }
-      qn[t] = block_sum(part, s_red);
-    }
-#pragma unroll
-    for (int i = 0; i < kMaxPerThread; ++i) {
-      const int a = tid + i * nthr;
-      if (a < DH) p.n[(int64_t)bh * DH + a] = nreg[i];
-    }
+  for (int t = 0; t < T; ++t) {
+    const int64_t row = (int64_t)b * T + t;
+    qk[t] = ok ? reinterpret_cast<const float2*>(p.qk)[(row * p.NH + hd) * DH + a] : make_float2(0.f, 0.f);
+    float s = 0.f;
+    if (ok)
+      for (int r = 0; r < RS; ++r) s += p.partial[(((int64_t)bh * RS + r) * T + t) * DH + a];   // fixed order
+    num[t] = s;
+    act[t] = (ok && p.skip) ? p.act[row * inner + ch] : 0.f;
+    zz[t] = (ok && p.skip) ? p.u[row * 2 * inner + inner + ch] : 0.f;
   }
+  if (threadIdx.x < 32) compute_gates<T>(p, b, hd, bh, s_f, s_i, s_m, s_pre);
+  __syncthreads();
+
+  // ---- n recurrence and q.n for the T tokens --------------------------------------------------------
+  const float kscale = rsqrtf((float)DH);
+  float qn[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    nreg = fmaf(s_f[t], nreg, s_i[t] * kscale * qk[t].y);
+    qn[t] = qk[t].x * nreg;
+  }
+  block_sum_n<T>(qn, s_red);
+  if (ok) p.n[(int64_t)bh * DH + a] = nreg;
+  // ---- h = num / den, GroupNorm over the head, skip + output gate -----------------------------------
+  float mean[T], var[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const float den = fmaxf(fabsf(qn[t]), expf(-s_m[t + 1])) + p.cell_eps;
-    float hreg[kMaxPerThread];
-    float part = 0.f;
+    num[t] = num[t] / den;                   // h (zero for the padded threads)
+    mean[t] = num[t];
+  }
+  block_sum_n<T>(mean, s_red);
 #pragma unroll
-    for (int i = 0; i < kMaxPerThread; ++i) {
-      const int c = tid + i * nthr;
-      hreg[i] = 0.f;
-      if (c < DH) {
-        float s = 0.f;
-        for (int r = 0; r < RS; ++r) s += p.partial[(((int64_t)bh * RS + r) * T + t) * DH + c];   // fixed order
-        hreg[i] = s / den;
-        part += hreg[i];
-      }
-    }
-    const float mean = block_sum(part, s_red) / (float)DH;
-    float vpart = 0.f;
+  for (int t = 0; t < T; ++t) {
+    mean[t] /= (float)DH;
+    const float dlt = ok ? num[t] - mean[t] : 0.f;
+    var[t] = dlt * dlt;
+  }
+  block_sum_n<T>(var, s_red);
+  if (ok) {
 #pragma unroll
-    for (int i = 0; i < kMaxPerThread; ++i) {
-      const int c = tid + i * nthr;
-      if (c < DH) {
-        const float dlt = hreg[i] - mean;
-        vpart = fmaf(dlt, dlt, vpart);
-      }
-    }
-    const float rstd = rsqrtf(block_sum(vpart, s_red) / (float)DH + p.ln_eps);
-    const int64_t row = (int64_t)b * T + t;
-#pragma unroll
-    for (int i = 0; i < kMaxPerThread; ++i) {
-      const int c = tid + i * nthr;
-      if (c < DH) {
-        const int ch = hd * DH + c;
-        float o = (hreg[i] - mean) * rstd * (1.f + p.outnorm_w[ch]);
-        if (p.h_raw) p.h_raw[row * inner + ch] = hreg[i];
-        if (p.skip) {
-          const float a = p.act[row * inner + ch];
-          const float z = p.u[row * 2 * inner + inner + ch];
-          o = (o + p.skip[ch] * a) * silu(z);
-        }
-        if (p.out) p.out[row * inner + ch] = o;
-        if (p.out_hi) {
-          // A = hi + lo with hi = bf16(A), lo = bf16(A - hi): operand planes of the tcgen05 proj_down
-          const __nv_bfloat16 hi = __float2bfloat16_rn(o);
-          reinterpret_cast<__nv_bfloat16*>(p.out_hi)[row * inner + ch] = hi;
-          reinterpret_cast<__nv_bfloat16*>(p.out_lo)[row * inner + ch] =
-              __float2bfloat16_rn(o - __bfloat162float(hi));
-        }
+    for (int t = 0; t < T; ++t) {
+      const float rstd = rsqrtf(var[t] / (float)DH + p.ln_eps);
+      const int64_t row = (int64_t)b * T + t;
+      float o = (num[t] - mean[t]) * rstd * (1.f + wn);
+      if (p.h_raw) p.h_raw[row * inner + ch] = num[t];
+      if (p.skip) o = (o + wskip * act[t]) * silu_fast(zz[t]);
+      if (p.out) p.out[row * inner + ch] = o;
+      if (p.out_hi) {
+        // A = hi + lo with hi = bf16(A), lo = bf16(A - hi): operand planes of the tcgen05 proj_down
+        const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+        reinterpret_cast<__nv_bfloat16*>(p.out_hi)[row * inner + ch] = hi;
+        reinterpret_cast<__nv_bfloat16*>(p.out_lo)[row * inner + ch] = __float2bfloat16_rn(o - __bfloat162float(hi));
       }
     }
   }
-  if (tid == 0) p.m[bh] = s_m[T];
+  if (threadIdx.x == 0) p.m[bh] = s_m[T];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -575,11 +579,12 @@ static void resolve_tiling(StateStepParams& p, int num_sms) {
 // kernel 2; p must carry the same rows_split the stream kernel ran with (resolved here the same way)
 cudaError_t launch_state_finalize(StateStepParams p, int num_sms, cudaStream_t s) {
   resolve_tiling(p, num_sms);
+  const int thr = ((p.DH + 31) / 32) * 32;
   switch (p.T) {
-    case 1: mlstm_state_finalize_kernel<1><<<p.B * p.NH, 256, 0, s>>>(p); break;
-    case 2: mlstm_state_finalize_kernel<2><<<p.B * p.NH, 256, 0, s>>>(p); break;
-    case 3: mlstm_state_finalize_kernel<3><<<p.B * p.NH, 256, 0, s>>>(p); break;
-    case 4: mlstm_state_finalize_kernel<4><<<p.B * p.NH, 256, 0, s>>>(p); break;
+    case 1: mlstm_state_finalize_kernel<1><<<p.B * p.NH, thr, 0, s>>>(p); break;
+    case 2: mlstm_state_finalize_kernel<2><<<p.B * p.NH, thr, 0, s>>>(p); break;
+    case 3: mlstm_state_finalize_kernel<3><<<p.B * p.NH, thr, 0, s>>>(p); break;
+    case 4: mlstm_state_finalize_kernel<4><<<p.B * p.NH, thr, 0, s>>>(p); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -594,7 +599,7 @@ cudaError_t launch_state_step(StateStepParams p, int num_sms, cudaStream_t s) {
     if (p.cols_per_cta <= 0) p.cols_per_cta = cols;
   }
   if (p.cols_per_cta % 4 || p.DH % p.cols_per_cta || p.cols_per_cta > 256 ||
-      kThreads % (p.cols_per_cta / 4) || p.DH > 4 * 256 || p.NCH > kMaxNCH || p.rows_split > p.DH)
+      kThreads % (p.cols_per_cta / 4) || p.DH > 1024 || p.NCH > kMaxNCH || p.rows_split > p.DH)
     return cudaErrorInvalidValue;
   switch (p.T) {
     case 1: return launch_T<1>(p, s);
