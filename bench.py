@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=5)
+    ap.add_argument("--discrete", action="store_true", help="discrete-action head (argmax over the first 18 logits)")
+    ap.add_argument("--domains", default="metaworld", help="metaworld | dmcontrol | composuite | mimicgen | mixed")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -182,7 +184,7 @@ def main():
     from lram_b200 import _lib as L
     from lram_b200.config import preset
     from lram_b200.engine import XLSTMEngine
-    from lram_b200.rollout import gather_env_results, shard_env_ids
+    from lram_b200.rollout import OverlappedTokenGather, shard_env_ids
     from lram_b200.synth import make_state_dict, make_stream
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -201,13 +203,13 @@ def main():
     env_ids = shard_env_ids(n_envs, rank, world)
     K, W = args.steps, args.warmup
     mode = L.XL_MODE_FUSED if args.mode == "fused" else L.XL_MODE_PER_TOKEN
-    flags = 0 if args.no_graph else L.XL_FLAG_GRAPH
+    flags = (0 if args.no_graph else L.XL_FLAG_GRAPH) | (L.XL_FLAG_DISCRETE if args.discrete else 0)
 
     eng = XLSTMEngine(cfg, sd, max_batch=B, device=dev)
     cache = eng.new_state(B)
     total = K + W
     n_stream = min(total, 64)                    # the synthetic stream is cycled; values don't affect timing
-    states_np, rtg_np, _ = make_stream(cfg, env_ids, n_stream, domains="metaworld")
+    states_np, rtg_np, _ = make_stream(cfg, env_ids, n_stream, domains=args.domains)
     d_states = torch.from_numpy(states_np).to(dev)      # resident in HBM before the timed region
     d_rtg = torch.from_numpy(rtg_np).to(dev)
     s_in = torch.empty(B, cfg.state_dim, device=dev)
@@ -215,6 +217,7 @@ def main():
     out = {"action_tokens": torch.zeros(B, cfg.act_dim, dtype=torch.int32, device=dev),
            "action_preds": torch.zeros(B, cfg.act_dim, dtype=torch.float32, device=dev)}
     stream = torch.cuda.current_stream(dev)
+    gatherer = OverlappedTokenGather(B, cfg.act_dim, world, dev) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -226,7 +229,7 @@ def main():
         r_in.copy_(d_rtg[t % n_stream], non_blocking=True)
         eng.policy_step(cache, s_in, r_in, mode=mode, flags=flags, out=out)
         if world > 1:
-            return gather_env_results(out["action_tokens"], n_envs, rank, world)
+            return gatherer.submit(out["action_tokens"])     # NCCL all-gather on a side stream
         return out["action_tokens"]
 
     # ---------------- device-resident throughput ------------------------------------------------------------
@@ -240,6 +243,8 @@ def main():
     ev0.record(stream)
     for t in range(W, W + K):
         dev_step(t)
+    if gatherer is not None:
+        gatherer.finish()                                    # the last gathers are inside the timed region
     ev1.record(stream)
     barrier()
     clocks = sampler.stop()
@@ -264,7 +269,7 @@ def main():
                              flags=flags)
         if world > 1:
             g_tok.copy_(h_tok, non_blocking=True)
-            gather_env_results(g_tok, n_envs, rank, world)
+            gatherer.submit(g_tok)
 
     for t in range(W):
         host_step(t)
@@ -277,6 +282,8 @@ def main():
         t0 = time.perf_counter()
         host_step(t)
         lat.append((time.perf_counter() - t0) * 1e3)
+    if gatherer is not None:
+        gatherer.finish()
     e1.record(stream)
     torch.cuda.synchronize(dev)
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
@@ -301,7 +308,7 @@ def main():
         for t in range(args.profile_steps):
             s_in.copy_(d_states[t % n_stream])
             r_in.copy_(d_rtg[t % n_stream])
-            eng.policy_step(cache, s_in, r_in, mode=mode, flags=0, out=out)
+            eng.policy_step(cache, s_in, r_in, mode=mode, flags=flags & ~L.XL_FLAG_GRAPH, out=out)
         torch.cuda.synchronize(dev)
         ms_sum, cnt, step_ms = C.c_double(), C.c_int64(), C.c_double()
         eng.lib.xl_profile_end(eng.handle, C.byref(ms_sum), C.byref(cnt), C.byref(step_ms))
@@ -331,9 +338,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"xLSTM {args.model} recurrent step, {B} synthetic Meta-World envs per GPU "
-                                   f"(BASELINE.json configs[1])",
+            "config": {"workload": f"xLSTM {args.model} recurrent step, {B} synthetic {args.domains} envs per GPU"
+                                   + (" (BASELINE.json configs[1])" if (args.model, B) == ("48M", 64) else ""),
                        "model": args.model, "envs_per_gpu": B, "global_envs": n_envs, "tokens_per_step": 3,
+                       "domains": args.domains, "head": "discrete" if args.discrete else "continuous-tokenized",
                        "step_mode": args.mode, "cuda_graph": not args.no_graph, "weights": "bf16 GEMM matrices",
                        "state": "fp32", "parallelism": f"env-sharded x{world}",
                        "l2": f"state stream {cache.nbytes() / 2**20:.0f} MiB per step exceeds the 126 MB L2"},

@@ -47,6 +47,52 @@ def gather_env_results(local: torch.Tensor, n_envs: int, rank: int, world_size: 
     return out
 
 
+class OverlappedTokenGather:
+    """Per-step all-gather of the action tokens, off the critical path.
+
+    Step t's tokens are snapshotted into one of two staging buffers on the compute stream (a 2 KB copy) and
+    all-gathered on a side stream while step t+1 computes; envs never wait for other ranks' actions, so the
+    only ordering needed is "staging buffer k is not overwritten before its gather finished" (2 steps apart).
+    Requires equal shards (B_local * world == n_envs); results are in rank-major order [world, B_local, A] and
+    `global_view()` puts them back in env order (env i lives on rank i % world).
+    """
+
+    def __init__(self, B_local: int, act_dim: int, world_size: int, device, group=None):
+        self.world, self.group = world_size, group
+        self.side = torch.cuda.Stream(device=device)
+        self.stage = [torch.zeros(B_local, act_dim, dtype=torch.int32, device=device) for _ in range(2)]
+        self.out = [torch.zeros(world_size, B_local, act_dim, dtype=torch.int32, device=device) for _ in range(2)]
+        self.done = [None, None]
+        self.k = 0
+
+    def submit(self, tokens: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+        k = self.k
+        cur = torch.cuda.current_stream(tokens.device)
+        if self.done[k] is not None:
+            cur.wait_event(self.done[k])                 # gather of step t-2 read this staging buffer
+        self.stage[k].copy_(tokens, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            dist.all_gather_into_tensor(self.out[k].view(-1, tokens.shape[-1]), self.stage[k], group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[k] = ev
+        self.k ^= 1
+        return self.out[k]
+
+    def finish(self):
+        for ev in self.done:
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+
+    def global_view(self, gathered: torch.Tensor) -> torch.Tensor:
+        # [world, B_local, A] -> [n_envs, A] with env = b * world + r
+        return gathered.permute(1, 0, 2).reshape(-1, gathered.shape[-1])
+
+
 class BatchedRollout:
     """Drives B envs of a `SyntheticEnvBatch`-like object (reset() -> obs[B,204]; step(a) -> obs, reward, done)
     through the CUDA policy, one library call per env step with pinned host buffers."""
