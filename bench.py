@@ -170,6 +170,8 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=5)
     ap.add_argument("--discrete", action="store_true", help="discrete-action head (argmax over the first 18 logits)")
     ap.add_argument("--domains", default="metaworld", help="metaworld | dmcontrol | composuite | mimicgen | mixed")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="xl_set_option passthrough for A/B runs, e.g. --opt microbatches=1 --opt state_impl=1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -206,6 +208,11 @@ def main():
     flags = (0 if args.no_graph else L.XL_FLAG_GRAPH) | (L.XL_FLAG_DISCRETE if args.discrete else 0)
 
     eng = XLSTMEngine(cfg, sd, max_batch=B, device=dev)
+    opts = {}
+    for kv in args.opt:
+        name, val = kv.split("=")
+        eng.set_option(name, int(val))
+        opts[name] = int(val)
     cache = eng.new_state(B)
     total = K + W
     n_stream = min(total, 64)                    # the synthetic stream is cycled; values don't affect timing
@@ -314,6 +321,8 @@ def main():
         eng.lib.xl_profile_end(eng.handle, C.byref(ms_sum), C.byref(cnt), C.byref(step_ms))
         if cnt.value:
             avg_ms = ms_sum.value / cnt.value
+            # one launch covers the envs of one micro-batch (B envs when the step is not split)
+            alg_bytes = alg_bytes * cfg.num_blocks * args.profile_steps // cnt.value
             ach = alg_bytes / (avg_ms / 1e3) / 1e9
             roof = {"bound": "hbm", "kernel": "mlstm_state_step_kernel", "achieved": ach,
                     "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
@@ -342,7 +351,8 @@ def main():
                                    + (" (BASELINE.json configs[1])" if (args.model, B) == ("48M", 64) else ""),
                        "model": args.model, "envs_per_gpu": B, "global_envs": n_envs, "tokens_per_step": 3,
                        "domains": args.domains, "head": "discrete" if args.discrete else "continuous-tokenized",
-                       "step_mode": args.mode, "cuda_graph": not args.no_graph, "weights": "bf16 GEMM matrices",
+                       "step_mode": args.mode, "cuda_graph": not args.no_graph, "options": opts,
+                       "weights": "bf16 GEMM matrices",
                        "state": "fp32", "parallelism": f"env-sharded x{world}",
                        "l2": f"state stream {cache.nbytes() / 2**20:.0f} MiB per step exceeds the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

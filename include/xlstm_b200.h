@@ -98,7 +98,11 @@ typedef enum {
 /* Pieces of the recurrent state (`past_key_values`, src/algos/models/decision_xlstm.py:163,168-169:
  * {"block_i": {"mlstm_state": (C, n, m), "conv_state": (conv,)}}), all fp32, resident in ONE caller-owned
  * buffer, layer-major so that one block's C is a single contiguous stream:
- *   for i in 0..L-1:  C[B,NH,DH,DH] | n[B,NH,DH] | m[B,NH] | conv[B,KS,inner]   (each 256-B aligned) */
+ *   for i in 0..L-1:  C[B,NH,DH/W,DH,W] | n[B,NH,DH] | m[B,NH] | conv[B,KS,inner]   (each 256-B aligned)
+ * C is SLAB-MAJOR: the reference's C[b,h,dk,dv] lives at [b][h][dv / W][dk][dv % W] with W = 128 when
+ * DH % 128 == 0 (else W = DH, i.e. the reference's row-major layout). Every [32 x 128] tile the state kernel
+ * streams is then 16 contiguous KB (measured +4-5 % HBM throughput over row-major tiles). n, m and conv keep
+ * the reference's layouts. lram_b200.engine.c_to_slab / c_from_slab convert. */
 typedef enum { XL_STATE_C = 0, XL_STATE_N = 1, XL_STATE_M = 2, XL_STATE_CONV = 3 } xl_state_part;
 
 /* step modes */
@@ -145,7 +149,8 @@ int xl_encoder_step(xl_handle* h, void* state, const float* x_in, float* x_out, 
 
 /* mLSTMCell.step's recurrent_step_stabilized_simple + MultiHeadLayerNorm alone ([ext-xlstm], reached via
  * decision_xlstm.py:163), for unit parity. qkv: fp32 [B*T, 3, inner] (q | k | v); igate, fgate: fp32
- * [B*T, NH] pre-activations (bias already added). C [B,NH,DH,DH], n [B,NH,DH], m [B,NH] updated in place.
+ * [B*T, NH] pre-activations (bias already added). C (slab-major, see xl_state_part), n [B,NH,DH], m [B,NH]
+ * updated in place.
  * h_norm: fp32 [B*T, inner] = GroupNorm_NH(h) * (1 + outnorm_w[inner]); h_raw (nullable): un-normalised h.
  * rows_split / cols_per_cta: 0 = automatic tiling. */
 int xl_mlstm_cell_step(xl_handle* h, float* C, float* n, float* m, const float* qkv, const float* igate,
@@ -180,9 +185,14 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
               float* out, int M, int N, int K, int impl, void* stream);
 
 /* Implementation switches for A/B measurements (defaults in brackets):
- *   "state_impl": [1] TMA-fed ring for the state stream, 0 register-batched global loads
+ *   "state_impl": [1] one-shot TMA ring, 2 persistent stream-K TMA ring, 0 register-batched global loads
+ *   "state_stages" / "state_ctas_per_sm": ring depth and persistent CTAs per SM of impl 2 (0 = default)
+ *   "state_rows_split": row chunks per (env, head) of impl 0/1 (0 = automatic)
  *   "gemm_impl":  [0] auto (tcgen05 when K % 64 == 0), 1 CUDA-core, 2 tcgen05
- *   "gemm_splitk": [1] cluster split-K (DSMEM reduction) in the tcgen05 Linear when the cost model asks, 0 never */
+ *   "gemm_splitk": [0] cluster split-K (DSMEM reduction) in the tcgen05 Linear when the cost model asks
+ *   "pdl": [1] programmatic dependent launch of every kernel (process-wide)
+ *   "microbatches": [1] env micro-batches of a fused step, pipelined on side streams; "pipeline_order": [1]
+ *                   their state-stream kernels take turns */
 int xl_set_option(xl_handle* h, const char* name, int value);
 
 /* Counters for bench.py: kernels launched by this handle since the last call (reset on read). */

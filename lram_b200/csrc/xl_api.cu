@@ -52,6 +52,8 @@ struct GraphCacheEntry {
 
 }  // namespace
 
+constexpr int kMaxMicro = 8;   // env micro-batches pipelined on side streams
+
 struct xl_handle {
   xl_config cfg;
   int device = 0;
@@ -71,11 +73,19 @@ struct xl_handle {
   int64_t launches = 0;
   std::vector<GraphCacheEntry> graphs;
   size_t a_cap = 0;                    // elements per bf16 hi/lo plane
+  size_t a_env = 0;                    // bf16 elements of a plane owned by one env (micro-batch slicing)
   int num_tickets = 0;
   cudaStream_t cap_stream = nullptr;   // graph capture never happens on the caller's (possibly legacy) stream
-  int state_impl = 1;                  // 1 = TMA ring, 0 = register-batched loads (xl_set_option "state_impl")
+  cudaStream_t side[kMaxMicro - 1] = {};   // micro-batches 1.. run here (forked from / joined to the main stream)
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxMicro - 1] = {}, ev_state[kMaxMicro] = {};
+  int state_impl = 1;                  // 1 = one-shot TMA ring (default), 2 = persistent stream-K TMA ring, 0 = plain loads
+  int state_stages = 0;                // impl 2 ring depth (0 = default)        (xl_set_option "state_stages")
+  int state_ctas_per_sm = 0;           // impl 2 persistent CTAs per SM (0 = 1)  (xl_set_option "state_ctas_per_sm")
+  int state_rows_split = 0;            // 0 = automatic                          (xl_set_option "state_rows_split")
   int gemm_impl = 0;                   // 0 auto, 1 CUDA-core, 2 tcgen05      (xl_set_option "gemm_impl")
   int gemm_splitk = 0;                 // cluster split-K in the tcgen05 Linear (xl_set_option "gemm_splitk")
+  int microbatches = 0;                // 0 = automatic; env micro-batches per fused step ("microbatches")
+  int pipeline_order = 1;              // 1 = state-stream kernels of the micro-batches run one after another
   bool profiling = false;
   std::vector<cudaEvent_t> prof_state;  // start/stop pairs around state-step launches
   std::vector<cudaEvent_t> prof_step;   // start/stop pairs around policy steps
@@ -110,22 +120,47 @@ int check_batch(const xl_handle* h, int B) {
   return XL_OK;
 }
 
+// The slice of the workspace owned by the envs [b0, b0 + Bk) of a step: every array is carved with a fixed
+// per-env stride (room for 4 tokens), so disjoint env ranges never overlap and micro-batches can run
+// concurrently on different streams.
+struct Ws {
+  float *x, *xn, *xtok, *hid, *u, *qkv, *act, *gate_part, *gated, *partial, *s_emb, *states_pad, *logits;
+  __nv_bfloat16 *a_hi, *a_lo;
+  size_t a_cap;
+  int low_smem;     // 1: kernels of this slice run beside other micro-batches' state stream -> small smem footprints
+};
+
+Ws ws_slice(const xl_handle* h, int b0, int Bk) {
+  const xl_config& c = h->cfg;
+  const size_t d = c.embedding_dim, inner = c.inner_dim, e = (size_t)b0;
+  Ws w;
+  w.x = h->x + e * 4 * d; w.xn = h->xn + e * 4 * d; w.xtok = h->xtok + e * 4 * d; w.hid = h->hid + e * 4 * d;
+  w.u = h->u + e * 4 * 2 * inner; w.qkv = h->qkv + e * 4 * 3 * inner; w.act = h->act + e * 4 * inner;
+  w.gate_part = h->gate_part + e * 4 * 16 * 2 * c.num_heads; w.gated = h->gated + e * 4 * inner;
+  w.partial = h->partial + e * c.num_heads * 32 * 4 * h->DH;
+  w.s_emb = h->s_emb + e * d; w.states_pad = h->states_pad + e * h->Kpad; w.logits = h->logits + e * h->head_out;
+  w.a_hi = h->a_hi + e * h->a_env; w.a_lo = h->a_lo + e * h->a_env;
+  w.a_cap = (size_t)Bk * h->a_env;     // a slice may only use its envs' share of the planes
+  w.low_smem = 0;
+  return w;
+}
+
 // Linear layer dispatch. impl: 0 auto, 1 CUDA-core, 2 tensor-core.
-// presplit: the bf16 hi/lo planes of A already sit in h->a_hi / h->a_lo (written by the producing kernel).
-int linear(xl_handle* h, const float* A, const void* W, const float* bias, const float* residual, float* out,
-           int M, int N, int K, int impl, cudaStream_t s, bool presplit = false) {
+// presplit: the bf16 hi/lo planes of A already sit in w.a_hi / w.a_lo (written by the producing kernel).
+int linear(xl_handle* h, const Ws& w, const float* A, const void* W, const float* bias, const float* residual,
+           float* out, int M, int N, int K, int impl, cudaStream_t s, bool presplit = false) {
   if (K % 8 != 0) return fail(XL_ERR_UNSUPPORTED, "linear: K=%d must be a multiple of 8", K);
-  const bool tc_ok = xl::gemm_tc_supported(M, N, K) && (size_t)M * K <= h->a_cap;
+  const bool tc_ok = xl::gemm_tc_supported(M, N, K) && (size_t)M * K <= w.a_cap;
   if (impl == 2 && !tc_ok)
     return fail(XL_ERR_UNSUPPORTED, "linear: tcgen05 path needs K %% 64 == 0 and M*K <= %zu (got M=%d K=%d)",
-                h->a_cap, M, K);
+                w.a_cap, M, K);
   if (impl == 2 || (impl == 0 && tc_ok)) {
     if (!presplit) {
-      xl::launch_split_bf16(A, K, h->a_hi, h->a_lo, M, K, s);
+      xl::launch_split_bf16(A, K, w.a_hi, w.a_lo, M, K, s);
       h->launches += 1;
     }
-    XL_CUDA(xl::launch_gemm_tc(h->a_hi, h->a_lo, (const __nv_bfloat16*)W, bias, residual, out, M, N, K,
-                               h->num_sms, h->gemm_splitk ? 0 : 1, s));
+    XL_CUDA(xl::launch_gemm_tc(w.a_hi, w.a_lo, (const __nv_bfloat16*)W, bias, residual, out, M, N, K,
+                               h->num_sms, h->gemm_splitk ? 0 : 1, w.low_smem, s));
     h->launches += 1;
     return XL_OK;
   }
@@ -135,117 +170,185 @@ int linear(xl_handle* h, const float* A, const void* W, const float* bias, const
   return XL_OK;
 }
 
-// One pass of the block stack over M = B*T rows held in h->x (rows ordered [b][t]).
-int run_blocks(xl_handle* h, void* state, int B, int T, unsigned flags, cudaStream_t s) {
+// One env range of one step: envs [b0, b0 + Bk) of a state buffer laid out for B envs, on stream s.
+struct Slice {
+  int B, b0, Bk;
+  Ws ws;
+  cudaStream_t s;
+};
+
+Slice make_slice(const xl_handle* h, int B, int b0, int Bk, cudaStream_t s) {
+  Slice sl;
+  sl.B = B; sl.b0 = b0; sl.Bk = Bk; sl.s = s;
+  sl.ws = ws_slice(h, b0, Bk);
+  return sl;
+}
+
+struct BlockPlan {
+  bool tc_up, tc_down;
+  int impl;
+};
+
+BlockPlan block_plan(const xl_handle* h, const Slice& sl, int T, unsigned flags) {
+  const xl_config& c = h->cfg;
+  const int M = sl.Bk * T;
+  BlockPlan p;
+  p.impl = (flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
+  // when the tensor-core Linear will run, the producers write its bf16 hi/lo operand planes directly
+  p.tc_up = p.impl != 1 && xl::gemm_tc_supported(M, 2 * c.inner_dim, c.embedding_dim) &&
+            (size_t)M * c.embedding_dim <= sl.ws.a_cap;
+  p.tc_down = p.impl != 1 && xl::gemm_tc_supported(M, c.embedding_dim, c.inner_dim) &&
+              (size_t)M * c.inner_dim <= sl.ws.a_cap;
+  return p;
+}
+
+xl::StateStepParams state_params(const xl_handle* h, void* state, const Slice& sl, int i, int T, bool tc_down) {
+  const xl_config& c = h->cfg;
+  const int inner = c.inner_dim, NH = c.num_heads, DH = h->DH;
+  const StateLayout L = state_layout(h, sl.B);
+  const BlockWeights& w = h->blocks[i];
+  char* base = (char*)state + (size_t)i * L.layer_bytes;
+  const int M = sl.Bk * T;
+  xl::StateStepParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.C = (float*)(base + L.c_off) + (size_t)sl.b0 * NH * DH * DH;
+  sp.n = (float*)(base + L.n_off) + (size_t)sl.b0 * NH * DH;
+  sp.m = (float*)(base + L.m_off) + (size_t)sl.b0 * NH;
+  sp.qk = sl.ws.qkv;
+  sp.v = sl.ws.qkv + (size_t)2 * M * inner;
+  sp.gate_part = sl.ws.gate_part;
+  sp.igate_b = (const float*)w.w[XL_W_IGATE_B];
+  sp.fgate_b = (const float*)w.w[XL_W_FGATE_B];
+  sp.outnorm_w = (const float*)w.w[XL_W_OUTNORM];
+  sp.skip = (const float*)w.w[XL_W_SKIP];
+  sp.act = sl.ws.act;
+  sp.u = sl.ws.u;
+  sp.out = tc_down ? nullptr : sl.ws.gated;
+  sp.out_hi = tc_down ? sl.ws.a_hi : nullptr;
+  sp.out_lo = tc_down ? sl.ws.a_lo : nullptr;
+  sp.partial = sl.ws.partial;
+  sp.B = sl.Bk; sp.T = T; sp.NH = NH; sp.DH = DH; sp.inner = inner; sp.NCH = h->NCH;
+  sp.ln_eps = c.ln_eps; sp.cell_eps = c.cell_eps;
+  sp.impl = h->state_impl; sp.num_layers = c.num_blocks;
+  sp.stages = h->state_stages; sp.ctas_per_sm = h->state_ctas_per_sm; sp.rows_split = h->state_rows_split;
+  if (sl.ws.low_smem) {          // leave shared memory for the co-resident kernels of the other micro-batches
+    if (sp.stages <= 0) sp.stages = 4;
+    sp.meta_slots = 2;
+  }
+  return sp;
+}
+
+// block i, part 1: x_n = LN(x); u = x_n W_up^T; conv + SiLU + q/k/v + gate partials   (rows ordered [b][t])
+int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned flags) {
   const xl_config& c = h->cfg;
   const int d = c.embedding_dim, inner = c.inner_dim, NH = c.num_heads;
-  const int M = B * T;
-  const StateLayout L = state_layout(h, B);
-  const int impl = (flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
-  // when the tensor-core Linear will run, the producers write its bf16 hi/lo operand planes directly
-  const bool tc_up = impl != 1 && xl::gemm_tc_supported(M, 2 * inner, d) && (size_t)M * d <= h->a_cap;
-  const bool tc_down = impl != 1 && xl::gemm_tc_supported(M, d, inner) && (size_t)M * inner <= h->a_cap;
-  for (int i = 0; i < c.num_blocks; ++i) {
-    const BlockWeights& w = h->blocks[i];
-    char* base = (char*)state + (size_t)i * L.layer_bytes;
-    // x_n = LN(x) (gamma = 1 + w)
-    xl::launch_ln_rows(h->x, d, tc_up ? nullptr : h->xn, d, (const float*)w.w[XL_W_XLSTM_NORM], nullptr, 1,
-                       c.ln_eps, M, d, tc_up ? h->a_hi : nullptr, tc_up ? h->a_lo : nullptr, s);
-    h->launches += 1;
-    // u = x_n @ W_up^T   [M, 2*inner]
-    int rc = linear(h, h->xn, w.w[XL_W_PROJ_UP], nullptr, nullptr, h->u, M, 2 * inner, d, impl, s, tc_up);
-    if (rc) return rc;
-    // conv + silu + q/k/v + gate partials
-    xl::ConvQkvParams cp;
-    cp.u = h->u;
-    cp.conv_state = (float*)(base + L.conv_off);
-    cp.conv_w = (const float*)w.w[XL_W_CONV_W];
-    cp.conv_b = (const float*)w.w[XL_W_CONV_B];
-    cp.wq = (const float*)w.w[XL_W_Q_PROJ];
-    cp.wk = (const float*)w.w[XL_W_K_PROJ];
-    cp.wv = (const float*)w.w[XL_W_V_PROJ];
-    cp.wi = (const float*)w.w[XL_W_IGATE_W];
-    cp.wf = (const float*)w.w[XL_W_FGATE_W];
-    cp.qk = h->qkv;
-    cp.v = h->qkv + (size_t)2 * M * inner;
-    cp.act = h->act;
-    cp.gate_part = h->gate_part;
-    cp.B = B; cp.T = T; cp.inner = inner; cp.NH = NH; cp.KS = c.conv_kernel; cp.NCH = h->NCH;
-    if (!xl::launch_conv_qkv_gates(cp, s))
-      return fail(XL_ERR_UNSUPPORTED, "conv/qkv kernel not instantiated for KS=%d T=%d NH=%d", cp.KS, cp.T, cp.NH);
-    h->launches += 1;
-    // state step (+ GroupNorm + skip + output gate)
-    xl::StateStepParams sp;
-    memset(&sp, 0, sizeof(sp));
-    sp.C = (float*)(base + L.c_off);
-    sp.n = (float*)(base + L.n_off);
-    sp.m = (float*)(base + L.m_off);
-    sp.qk = h->qkv;
-    sp.v = h->qkv + (size_t)2 * M * inner;
-    sp.gate_part = h->gate_part;
-    sp.igate_b = (const float*)w.w[XL_W_IGATE_B];
-    sp.fgate_b = (const float*)w.w[XL_W_FGATE_B];
-    sp.outnorm_w = (const float*)w.w[XL_W_OUTNORM];
-    sp.skip = (const float*)w.w[XL_W_SKIP];
-    sp.act = h->act;
-    sp.u = h->u;
-    sp.out = tc_down ? nullptr : h->gated;
-    sp.out_hi = tc_down ? h->a_hi : nullptr;
-    sp.out_lo = tc_down ? h->a_lo : nullptr;
-    sp.partial = h->partial;
-    sp.B = B; sp.T = T; sp.NH = NH; sp.DH = h->DH; sp.inner = inner; sp.NCH = h->NCH;
-    sp.ln_eps = c.ln_eps; sp.cell_eps = c.cell_eps;
-    sp.impl = h->state_impl; sp.num_layers = c.num_blocks;
-    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    if (h->profiling) {
-      XL_CUDA(cudaEventCreate(&pe0));
-      XL_CUDA(cudaEventCreate(&pe1));
-      XL_CUDA(cudaEventRecord(pe0, s));
-    }
-    XL_CUDA(xl::launch_state_step(sp, h->num_sms, s));
-    h->launches += 2;
-    if (h->profiling) {
-      XL_CUDA(cudaEventRecord(pe1, s));
-      h->prof_state.push_back(pe0);
-      h->prof_state.push_back(pe1);
-    }
-    XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, s));
-    // x = x + gated @ W_down^T
-    rc = linear(h, h->gated, w.w[XL_W_PROJ_DOWN], nullptr, h->x, h->x, M, d, inner, impl, s, tc_down);
+  const int M = sl.Bk * T;
+  const StateLayout L = state_layout(h, sl.B);
+  const BlockPlan bp = block_plan(h, sl, T, flags);
+  const BlockWeights& w = h->blocks[i];
+  const Ws& ws = sl.ws;
+  char* base = (char*)state + (size_t)i * L.layer_bytes;
+  xl::launch_ln_rows(ws.x, d, bp.tc_up ? nullptr : ws.xn, d, (const float*)w.w[XL_W_XLSTM_NORM], nullptr, 1,
+                     c.ln_eps, M, d, bp.tc_up ? ws.a_hi : nullptr, bp.tc_up ? ws.a_lo : nullptr, sl.s);
+  h->launches += 1;
+  int rc = linear(h, ws, ws.xn, w.w[XL_W_PROJ_UP], nullptr, nullptr, ws.u, M, 2 * inner, d, bp.impl, sl.s, bp.tc_up);
+  if (rc) return rc;
+  xl::ConvQkvParams cp;
+  cp.u = ws.u;
+  cp.conv_state = (float*)(base + L.conv_off) + (size_t)sl.b0 * c.conv_kernel * inner;
+  cp.conv_w = (const float*)w.w[XL_W_CONV_W];
+  cp.conv_b = (const float*)w.w[XL_W_CONV_B];
+  cp.wq = (const float*)w.w[XL_W_Q_PROJ];
+  cp.wk = (const float*)w.w[XL_W_K_PROJ];
+  cp.wv = (const float*)w.w[XL_W_V_PROJ];
+  cp.wi = (const float*)w.w[XL_W_IGATE_W];
+  cp.wf = (const float*)w.w[XL_W_FGATE_W];
+  cp.qk = ws.qkv;
+  cp.v = ws.qkv + (size_t)2 * M * inner;
+  cp.act = ws.act;
+  cp.gate_part = ws.gate_part;
+  cp.B = sl.Bk; cp.T = T; cp.inner = inner; cp.NH = NH; cp.KS = c.conv_kernel; cp.NCH = h->NCH;
+  if (!xl::launch_conv_qkv_gates(cp, sl.s))
+    return fail(XL_ERR_UNSUPPORTED, "conv/qkv kernel not instantiated for KS=%d T=%d NH=%d", cp.KS, cp.T, cp.NH);
+  h->launches += 1;
+  return XL_OK;
+}
+
+// block i, part 2: the HBM-bound state stream (C update + partial numerators)
+int block_state(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned flags) {
+  const BlockPlan bp = block_plan(h, sl, T, flags);
+  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down);
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  if (h->profiling) {
+    XL_CUDA(cudaEventCreate(&pe0));
+    XL_CUDA(cudaEventCreate(&pe1));
+    XL_CUDA(cudaEventRecord(pe0, sl.s));
+  }
+  XL_CUDA(xl::launch_state_step(sp, h->num_sms, sl.s));
+  h->launches += 1;
+  if (h->profiling) {
+    XL_CUDA(cudaEventRecord(pe1, sl.s));
+    h->prof_state.push_back(pe0);
+    h->prof_state.push_back(pe1);
+  }
+  return XL_OK;
+}
+
+// block i, part 3: n/m update + normalise + skip + output gate; x = x + gated W_down^T
+int block_post(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned flags) {
+  const xl_config& c = h->cfg;
+  const BlockPlan bp = block_plan(h, sl, T, flags);
+  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down);
+  const Ws& ws = sl.ws;
+  XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, sl.s));
+  h->launches += 1;
+  return linear(h, ws, ws.gated, h->blocks[i].w[XL_W_PROJ_DOWN], nullptr, ws.x, ws.x, sl.Bk * T, c.embedding_dim,
+                c.inner_dim, bp.impl, sl.s, bp.tc_down);
+}
+
+// One pass of the block stack over M = Bk*T rows held in ws.x (rows ordered [b][t]).
+int run_blocks(xl_handle* h, void* state, const Slice& sl, int T, unsigned flags) {
+  for (int i = 0; i < h->cfg.num_blocks; ++i) {
+    int rc = block_pre(h, state, sl, i, T, flags);
+    if (!rc) rc = block_state(h, state, sl, i, T, flags);
+    if (!rc) rc = block_post(h, state, sl, i, T, flags);
     if (rc) return rc;
   }
   XL_CUDA(cudaGetLastError());
   return XL_OK;
 }
 
-// Encoder over x_in [B,T,d] -> x_out [B,T,d] (post_blocks_norm applied).
-int run_encoder(xl_handle* h, void* state, const float* x_in, float* x_out, int B, int T, int mode,
-                unsigned flags, cudaStream_t s) {
+// Encoder over x_in [B,T,d] -> x_out [B,T,d] (post_blocks_norm applied), single stream.
+int run_encoder(xl_handle* h, void* state, const Slice& sl, const float* x_in, float* x_out, int T, int mode,
+                unsigned flags) {
   const xl_config& c = h->cfg;
   const int d = c.embedding_dim;
+  const int B = sl.Bk;
+  const Ws& ws = sl.ws;
+  cudaStream_t s = sl.s;
   const float* post_w = (const float*)h->pw[XL_W_POST_NORM - XL_W_POST_NORM];
   if (mode == XL_MODE_FUSED || T == 1) {
-    if (x_in != h->x) {
-      XL_CUDA(cudaMemcpyAsync(h->x, x_in, sizeof(float) * (size_t)B * T * d, cudaMemcpyDeviceToDevice, s));
+    if (x_in != ws.x) {
+      XL_CUDA(cudaMemcpyAsync(ws.x, x_in, sizeof(float) * (size_t)B * T * d, cudaMemcpyDeviceToDevice, s));
     }
-    int rc = run_blocks(h, state, B, T, flags, s);
+    int rc = run_blocks(h, state, sl, T, flags);
     if (rc) return rc;
-    xl::launch_ln_rows(h->x, d, x_out, d, post_w, nullptr, 1, c.ln_eps, B * T, d, nullptr, nullptr, s);
+    xl::launch_ln_rows(ws.x, d, x_out, d, post_w, nullptr, 1, c.ln_eps, B * T, d, nullptr, nullptr, s);
     h->launches += 1;
   } else if (mode == XL_MODE_PER_TOKEN) {
     // reference order: for token: for block  (decision_xlstm.py:161-165). x_in may alias x_out: token t's
     // input row is consumed (gathered) before its output row is written.
     const float* src = x_in;
     if (x_in == x_out) {
-      XL_CUDA(cudaMemcpyAsync(h->xtok, x_in, sizeof(float) * (size_t)B * T * d, cudaMemcpyDeviceToDevice, s));
-      src = h->xtok;
+      XL_CUDA(cudaMemcpyAsync(ws.xtok, x_in, sizeof(float) * (size_t)B * T * d, cudaMemcpyDeviceToDevice, s));
+      src = ws.xtok;
     }
     for (int t = 0; t < T; ++t) {
-      xl::launch_copy_rows(src + (size_t)t * d, (int64_t)T * d, h->x, d, B, d, s);
+      xl::launch_copy_rows(src + (size_t)t * d, (int64_t)T * d, ws.x, d, B, d, s);
       h->launches += 1;
-      int rc = run_blocks(h, state, B, 1, flags, s);
+      int rc = run_blocks(h, state, sl, 1, flags);
       if (rc) return rc;
-      xl::launch_ln_rows(h->x, d, x_out + (size_t)t * d, (int64_t)T * d, post_w, nullptr, 1, c.ln_eps, B, d,
+      xl::launch_ln_rows(ws.x, d, x_out + (size_t)t * d, (int64_t)T * d, post_w, nullptr, 1, c.ln_eps, B, d,
                          nullptr, nullptr, s);
       h->launches += 1;
     }
@@ -256,53 +359,145 @@ int run_encoder(xl_handle* h, void* state, const float* x_in, float* x_out, int 
   return XL_OK;
 }
 
-int run_policy(xl_handle* h, void* state, const float* states, const float* rtg, const float* rewards,
-               int32_t* tokens, float* actions, float* logits, float* hidden, int B, int mode, unsigned flags,
-               cudaStream_t s) {
+// Arguments of one policy step (device pointers for the WHOLE batch of B envs).
+struct StepArgs {
+  void* state;
+  const float *states, *rtg, *rewards;
+  int32_t* tokens;
+  float *actions, *logits, *hidden;
+  int B, mode;
+  unsigned flags;
+};
+
+// embed_state Linear(204 -> d) on zero-padded K, (s, rtg, r) token embedding + embed_ln -> xt [Bk, 3, d]
+int policy_front(xl_handle* h, const StepArgs& a, const Slice& sl, float* xt) {
+  const xl_config& c = h->cfg;
+  const int d = c.embedding_dim;
+  const int impl = (a.flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
+  auto PW = [&](int id) { return h->pw[id - XL_W_POST_NORM]; };
+  const Ws& ws = sl.ws;
+  xl::launch_pad_rows(a.states + (size_t)sl.b0 * c.state_dim, c.state_dim, ws.states_pad, h->Kpad, sl.Bk, sl.s);
+  h->launches += 1;
+  int rc = linear(h, ws, ws.states_pad, PW(XL_W_EMBED_STATE_W), (const float*)PW(XL_W_EMBED_STATE_B), nullptr,
+                  ws.s_emb, sl.Bk, d, h->Kpad, impl, sl.s);
+  if (rc) return rc;
+  xl::launch_embed_tokens(ws.s_emb, a.rtg + sl.b0, a.rewards ? a.rewards + sl.b0 : nullptr,
+                          (const float*)PW(XL_W_EMBED_RETURN_W), (const float*)PW(XL_W_EMBED_RETURN_B),
+                          (const float*)PW(XL_W_EMBED_REWARD_W), (const float*)PW(XL_W_EMBED_REWARD_B),
+                          (const float*)PW(XL_W_EMBED_LN_W), (const float*)PW(XL_W_EMBED_LN_B), c.embed_ln_eps, xt,
+                          sl.Bk, d, sl.s);
+  h->launches += 1;
+  return XL_OK;
+}
+
+// action head on the rtg token of hid [Bk, T, d] -> logits -> argmax / inv_tokenize
+int policy_back(xl_handle* h, const StepArgs& a, const Slice& sl, const float* hid) {
   const xl_config& c = h->cfg;
   const int d = c.embedding_dim, T = c.tokens_per_step;
-  const int impl = (flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
+  const int impl = (a.flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
   auto PW = [&](int id) { return h->pw[id - XL_W_POST_NORM]; };
-  // embed_state: Linear(204 -> d) on zero-padded K
-  xl::launch_pad_rows(states, c.state_dim, h->states_pad, h->Kpad, B, s);
+  const Ws& ws = sl.ws;
+  cudaStream_t s = sl.s;
+  const int Bk = sl.Bk;
+  // gather row b*T + pos to a dense [Bk,d], then Linear(d -> 2192 / 274)
+  float* xa = ws.s_emb;  // reuse [Bk,d]
+  xl::launch_copy_rows(hid + (size_t)c.action_token_pos * d, (int64_t)T * d, xa, d, Bk, d, s);
   h->launches += 1;
-  int rc = linear(h, h->states_pad, PW(XL_W_EMBED_STATE_W), (const float*)PW(XL_W_EMBED_STATE_B), nullptr,
-                  h->s_emb, B, d, h->Kpad, impl, s);
-  if (rc) return rc;
-  float* xt = (mode == XL_MODE_FUSED) ? h->x : h->xtok;
-  xl::launch_embed_tokens(h->s_emb, rtg, rewards, (const float*)PW(XL_W_EMBED_RETURN_W),
-                          (const float*)PW(XL_W_EMBED_RETURN_B), (const float*)PW(XL_W_EMBED_REWARD_W),
-                          (const float*)PW(XL_W_EMBED_REWARD_B), (const float*)PW(XL_W_EMBED_LN_W),
-                          (const float*)PW(XL_W_EMBED_LN_B), c.embed_ln_eps, xt, B, d, s);
-  h->launches += 1;
-  float* hid = hidden ? hidden : h->hid;
-  rc = run_encoder(h, state, xt, hid, B, T, mode, flags, s);
-  if (rc) return rc;
-  // action head on the rtg token (row b*T + pos): gather to a dense [B,d] then Linear(d -> 2192 / 274)
-  float* xa = h->s_emb;  // reuse [B,d]
-  xl::launch_copy_rows(hid + (size_t)c.action_token_pos * d, (int64_t)T * d, xa, d, B, d, s);
-  h->launches += 1;
-  const bool discrete = (flags & XL_FLAG_DISCRETE) != 0;
+  const bool discrete = (a.flags & XL_FLAG_DISCRETE) != 0;
   // discrete branch only needs the first num_actions logits (multi_domain_discrete_dt_model.py:99-101)
   const int n_out = discrete ? h->num_actions : h->head_out;
-  float* lg = logits ? logits : h->logits;
+  int32_t* tokens = a.tokens + (size_t)sl.b0 * c.act_dim;
+  float* actions = a.actions + (size_t)sl.b0 * c.act_dim;
+  float* logits = a.logits ? a.logits + (size_t)sl.b0 * n_out : nullptr;
+  int rc;
   if (discrete) {
-    // keep the row pitch of the full head so both branches share the argmax kernel's addressing
-    rc = linear(h, xa, PW(XL_W_HEAD_W), (const float*)PW(XL_W_HEAD_B), nullptr, h->logits, B, n_out, d, impl, s);
+    rc = linear(h, ws, xa, PW(XL_W_HEAD_W), (const float*)PW(XL_W_HEAD_B), nullptr, ws.logits, Bk, n_out, d, impl, s);
     if (rc) return rc;
     if (logits) {
-      XL_CUDA(cudaMemcpyAsync(logits, h->logits, sizeof(float) * (size_t)B * n_out, cudaMemcpyDeviceToDevice, s));
+      XL_CUDA(cudaMemcpyAsync(logits, ws.logits, sizeof(float) * (size_t)Bk * n_out, cudaMemcpyDeviceToDevice, s));
     }
-    xl::launch_argmax_tokens(h->logits, n_out, B, c.act_dim, n_out, c.discrete_actions, 1, 0.f, 0.f, tokens,
+    xl::launch_argmax_tokens(ws.logits, n_out, Bk, c.act_dim, n_out, c.discrete_actions, 1, 0.f, 0.f, tokens,
                              actions, s);
   } else {
-    rc = linear(h, xa, PW(XL_W_HEAD_W), (const float*)PW(XL_W_HEAD_B), nullptr, lg, B, n_out, d, impl, s);
+    float* lg = logits ? logits : ws.logits;
+    rc = linear(h, ws, xa, PW(XL_W_HEAD_W), (const float*)PW(XL_W_HEAD_B), nullptr, lg, Bk, n_out, d, impl, s);
     if (rc) return rc;
     const float bw = (c.tok_max_val - c.tok_min_val) / (float)c.action_channels;
-    xl::launch_argmax_tokens(lg, h->head_out, B, c.act_dim, h->num_actions, c.discrete_actions, 0, bw,
+    xl::launch_argmax_tokens(lg, h->head_out, Bk, c.act_dim, h->num_actions, c.discrete_actions, 0, bw,
                              c.tok_min_val, tokens, actions, s);
   }
   h->launches += 1;
+  return XL_OK;
+}
+
+// How many env micro-batches a fused step is split into. The state stream of one micro-batch (HBM-bound)
+// overlaps the latency-bound LayerNorm / projection / conv / finalize chain of the others.
+int pick_microbatches(const xl_handle* h, int B, int mode) {
+  if (mode != XL_MODE_FUSED) return 1;
+  // Measured on B200 (profiles/r01_microbatch_pipeline.md): the chain kernels are memory-LATENCY bound and slow
+  // down under a saturated memory system by about what the overlap gains, so the default is one batch.
+  int mb = h->microbatches > 0 ? h->microbatches : 1;
+  if (mb > kMaxMicro) mb = kMaxMicro;
+  if (mb > B) mb = B;
+  return mb < 1 ? 1 : mb;
+}
+
+int run_policy(xl_handle* h, const StepArgs& a, cudaStream_t s) {
+  const xl_config& c = h->cfg;
+  const int d = c.embedding_dim, T = c.tokens_per_step;
+  const float* post_w = (const float*)h->pw[XL_W_POST_NORM - XL_W_POST_NORM];
+  const int MB = pick_microbatches(h, a.B, a.mode);
+  if (MB == 1) {
+    const Slice sl = make_slice(h, a.B, 0, a.B, s);
+    float* xt = (a.mode == XL_MODE_FUSED) ? sl.ws.x : sl.ws.xtok;
+    int rc = policy_front(h, a, sl, xt);
+    if (rc) return rc;
+    float* hid = a.hidden ? a.hidden : sl.ws.hid;
+    rc = run_encoder(h, a.state, sl, xt, hid, T, a.mode, a.flags);
+    if (rc) return rc;
+    rc = policy_back(h, a, sl, hid);
+    if (rc) return rc;
+    XL_CUDA(cudaGetLastError());
+    return XL_OK;
+  }
+  // ---- fused step, MB env micro-batches: slice 0 on the caller's stream, the others on side streams ----
+  Slice sl[kMaxMicro];
+  int b0 = 0;
+  for (int k = 0; k < MB; ++k) {
+    const int Bk = a.B / MB + (k < a.B % MB ? 1 : 0);
+    sl[k] = make_slice(h, a.B, b0, Bk, k == 0 ? s : h->side[k - 1]);
+    sl[k].ws.low_smem = 1;
+    b0 += Bk;
+  }
+  XL_CUDA(cudaEventRecord(h->ev_fork, s));
+  for (int k = 1; k < MB; ++k) XL_CUDA(cudaStreamWaitEvent(sl[k].s, h->ev_fork, 0));
+  int rc = XL_OK;
+  for (int k = 0; k < MB && !rc; ++k) rc = policy_front(h, a, sl[k], sl[k].ws.x);
+  for (int i = 0; i < c.num_blocks && !rc; ++i) {
+    for (int k = 0; k < MB && !rc; ++k) rc = block_pre(h, a.state, sl[k], i, T, a.flags);
+    for (int k = 0; k < MB && !rc; ++k) {
+      if (h->pipeline_order && !(i == 0 && k == 0)) {
+        // the HBM-bound kernels take turns: S(k, i) starts when S(k-1, i) (or S(MB-1, i-1)) has finished
+        XL_CUDA(cudaStreamWaitEvent(sl[k].s, h->ev_state[(k + MB - 1) % MB], 0));
+      }
+      rc = block_state(h, a.state, sl[k], i, T, a.flags);
+      if (!rc && h->pipeline_order) XL_CUDA(cudaEventRecord(h->ev_state[k], sl[k].s));
+    }
+    for (int k = 0; k < MB && !rc; ++k) rc = block_post(h, a.state, sl[k], i, T, a.flags);
+  }
+  for (int k = 0; k < MB && !rc; ++k) {
+    float* hid = a.hidden ? a.hidden + (size_t)sl[k].b0 * T * d : sl[k].ws.hid;
+    xl::launch_ln_rows(sl[k].ws.x, d, hid, d, post_w, nullptr, 1, c.ln_eps, sl[k].Bk * T, d, nullptr, nullptr,
+                       sl[k].s);
+    h->launches += 1;
+    rc = policy_back(h, a, sl[k], hid);
+  }
+  // join (also on the error path, so that a capture never ends with unjoined streams)
+  for (int k = 1; k < MB; ++k) {
+    cudaEventRecord(h->ev_join[k - 1], sl[k].s);
+    cudaStreamWaitEvent(s, h->ev_join[k - 1], 0);
+  }
+  if (rc) return rc;
   XL_CUDA(cudaGetLastError());
   return XL_OK;
 }
@@ -387,6 +582,7 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   if (a_cap < B * (size_t)h->Kpad) a_cap = B * (size_t)h->Kpad;
   if (a_cap < (size_t)1 << 20) a_cap = (size_t)1 << 20;   // room for xl_linear unit tests
   h->a_cap = a_cap;
+  h->a_env = 4 * (inner > d ? inner : d);
   const size_t o_hi = carve(2 * a_cap), o_lo = carve(2 * a_cap);
   h->ws_bytes = off;
   cudaError_t e = cudaMalloc((void**)&h->ws, h->ws_bytes);
@@ -396,6 +592,12 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   }
   cudaMemset(h->ws, 0, h->ws_bytes);
   cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
+  for (int k = 0; k < kMaxMicro - 1; ++k) {
+    cudaStreamCreateWithFlags(&h->side[k], cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming);
+  }
+  for (int k = 0; k < kMaxMicro; ++k) cudaEventCreateWithFlags(&h->ev_state[k], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   h->x = (float*)(h->ws + o_x); h->xn = (float*)(h->ws + o_xn); h->xtok = (float*)(h->ws + o_xtok);
   h->hid = (float*)(h->ws + o_hid);
   h->u = (float*)(h->ws + o_u); h->qkv = (float*)(h->ws + o_qkv); h->act = (float*)(h->ws + o_act);
@@ -417,6 +619,13 @@ void xl_destroy(xl_handle* h) {
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->ws) cudaFree(h->ws);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  for (int k = 0; k < kMaxMicro - 1; ++k) {
+    if (h->side[k]) cudaStreamDestroy(h->side[k]);
+    if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
+  }
+  for (int k = 0; k < kMaxMicro; ++k)
+    if (h->ev_state[k]) cudaEventDestroy(h->ev_state[k]);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
 
@@ -532,7 +741,8 @@ int xl_encoder_step(xl_handle* h, void* state, const float* x_in, float* x_out, 
   if (T < 1 || T > 4) return fail(XL_ERR_UNSUPPORTED, "T=%d outside [1,4]", T);
   rc = xl_weights_ready(h);
   if (rc) return rc;
-  return run_encoder(h, state, x_in, x_out, B, T, mode, flags, (cudaStream_t)stream);
+  const Slice sl = make_slice(h, B, 0, B, (cudaStream_t)stream);
+  return run_encoder(h, state, sl, x_in, x_out, T, mode, flags);
 }
 
 int xl_mlstm_cell_step(xl_handle* h, float* C, float* n, float* m, const float* qkv, const float* igate,
@@ -563,7 +773,19 @@ int xl_mlstm_cell_step(xl_handle* h, float* C, float* n, float* m, const float* 
   sp.rows_split = rows_split; sp.cols_per_cta = cols_per_cta;
   sp.ln_eps = c.ln_eps; sp.cell_eps = c.cell_eps;
   sp.impl = h->state_impl; sp.num_layers = c.num_blocks;
+  sp.stages = h->state_stages; sp.ctas_per_sm = h->state_ctas_per_sm;
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  if (h->profiling) {
+    XL_CUDA(cudaEventCreate(&pe0));
+    XL_CUDA(cudaEventCreate(&pe1));
+    XL_CUDA(cudaEventRecord(pe0, s));
+  }
   XL_CUDA(xl::launch_state_step(sp, h->num_sms, s));
+  if (h->profiling) {
+    XL_CUDA(cudaEventRecord(pe1, s));
+    h->prof_state.push_back(pe0);
+    h->prof_state.push_back(pe1);
+  }
   XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, s));
   h->launches += 3;
   return XL_OK;
@@ -577,6 +799,9 @@ int xl_policy_step(xl_handle* h, void* state, const float* states, const float* 
   if (!state || !states || !rtg || !tokens || !actions) return fail(XL_ERR_INVALID_ARG, "null argument");
   if (mode != XL_MODE_FUSED && mode != XL_MODE_PER_TOKEN) return fail(XL_ERR_INVALID_ARG, "unknown mode %d", mode);
   cudaStream_t s = (cudaStream_t)stream;
+  StepArgs args;
+  args.state = state; args.states = states; args.rtg = rtg; args.rewards = rewards; args.tokens = tokens;
+  args.actions = actions; args.logits = logits; args.hidden = hidden; args.B = B; args.mode = mode; args.flags = flags;
   if (!(flags & XL_FLAG_GRAPH)) {
     rc = xl_weights_ready(h);
     if (rc) return rc;
@@ -586,7 +811,7 @@ int xl_policy_step(xl_handle* h, void* state, const float* states, const float* 
       XL_CUDA(cudaEventCreate(&pe1));
       XL_CUDA(cudaEventRecord(pe0, s));
     }
-    rc = run_policy(h, state, states, rtg, rewards, tokens, actions, logits, hidden, B, mode, flags, s);
+    rc = run_policy(h, args, s);
     if (h->profiling) {
       cudaEventRecord(pe1, s);
       h->prof_step.push_back(pe0);
@@ -615,7 +840,7 @@ int xl_policy_step(xl_handle* h, void* state, const float* states, const float* 
   cudaGraph_t graph = nullptr;
   const int64_t before = h->launches;
   XL_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-  rc = run_policy(h, state, states, rtg, rewards, tokens, actions, logits, hidden, B, mode, flags, h->cap_stream);
+  rc = run_policy(h, args, h->cap_stream);
   cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
   g.launches = h->launches - before;
   h->launches = before;
@@ -661,14 +886,32 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
               float* out, int M, int N, int K, int impl, void* stream) {
   if (!h || !A || !W_bf16 || !out) return fail(XL_ERR_INVALID_ARG, "null argument");
   if (M <= 0 || N <= 0 || K <= 0) return fail(XL_ERR_INVALID_ARG, "bad GEMM shape");
-  return linear(h, A, W_bf16, bias, residual, out, M, N, K, impl, (cudaStream_t)stream);
+  Ws w = ws_slice(h, 0, h->cfg.max_batch);
+  w.a_cap = h->a_cap;                  // a stand-alone Linear may use the whole operand planes
+  return linear(h, w, A, W_bf16, bias, residual, out, M, N, K, impl, (cudaStream_t)stream);
 }
 
 int xl_set_option(xl_handle* h, const char* name, int value) {
   if (!h || !name) return fail(XL_ERR_INVALID_ARG, "null argument");
   if (!strcmp(name, "state_impl")) {
-    if (value != 0 && value != 1) return fail(XL_ERR_INVALID_ARG, "state_impl must be 0 or 1");
+    if (value < 0 || value > 2) return fail(XL_ERR_INVALID_ARG, "state_impl must be 0, 1 or 2");
     h->state_impl = value;
+  } else if (!strcmp(name, "state_stages")) {
+    if (value < 0 || value > 8) return fail(XL_ERR_INVALID_ARG, "state_stages must be in [0, 8]");
+    h->state_stages = value;
+  } else if (!strcmp(name, "state_ctas_per_sm")) {
+    if (value < 0 || value > 2) return fail(XL_ERR_INVALID_ARG, "state_ctas_per_sm must be in [0, 2]");
+    h->state_ctas_per_sm = value;
+  } else if (!strcmp(name, "state_rows_split")) {
+    if (value < 0 || value > 32) return fail(XL_ERR_INVALID_ARG, "state_rows_split must be in [0, 32]");
+    h->state_rows_split = value;
+  } else if (!strcmp(name, "microbatches")) {
+    if (value < 0 || value > kMaxMicro) return fail(XL_ERR_INVALID_ARG, "microbatches must be in [0, %d]", kMaxMicro);
+    h->microbatches = value;
+  } else if (!strcmp(name, "pdl")) {
+    xl::g_use_pdl = value ? 1 : 0;       // process-wide: programmatic dependent launch of every kernel
+  } else if (!strcmp(name, "pipeline_order")) {
+    h->pipeline_order = value ? 1 : 0;
   } else if (!strcmp(name, "gemm_splitk")) {
     h->gemm_splitk = value ? 1 : 0;
   } else if (!strcmp(name, "gemm_impl")) {

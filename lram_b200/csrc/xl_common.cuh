@@ -8,6 +8,37 @@
 
 namespace xl {
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// Every kernel of the step is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may
+// become resident while the previous kernel N of the stream is still running. Every thread of a kernel runs
+//     [prologue]  pdl_wait();  pdl_trigger();  [body]
+// pdl_wait() returns when kernel N has completed and its writes are visible; pdl_trigger() then lets the NEXT
+// kernel start launching. Because the trigger comes after the wait, a kernel's prologue runs only when every
+// kernel up to N-1 is complete: the prologue may read weights and anything written by kernels <= N-1 (the
+// recurrent state of the previous env step, activations two kernels back), set up barriers / TMEM / tensor
+// maps and prefetch; anything kernel N itself writes is read, and every global write is done, after the wait.
+// Both are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_use_pdl;   // xl_set_option("pdl", 0/1); defined in xl_elementwise.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                            Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -9,6 +9,8 @@
 
 namespace xl {
 
+int g_use_pdl = 1;
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm rows: one warp per row, three passes over an L1-resident row (two-pass variance like ATen).
 // xlstm LayerNorm: F.layer_norm(x, weight = 1 + w, bias = None, eps)  (residual_weight = 1)
@@ -23,6 +25,8 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
                                                       __nv_bfloat16* __restrict__ a_lo) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
   if (warp >= rows) return;
   const float* x = in + (int64_t)warp * in_stride;
   const int d4 = d >> 2;
@@ -88,11 +92,13 @@ __global__ void __launch_bounds__(1024) ln_rows_cta_kernel(const float* __restri
   const bool ok = i < (d >> 2);
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 g = v, bb = v;
-  if (ok) {
-    v = reinterpret_cast<const float4*>(in + (int64_t)row * in_stride)[i];
+  if (ok) {                                // weights: before the dependency wait
     g = reinterpret_cast<const float4*>(w)[i];
     if (bias) bb = reinterpret_cast<const float4*>(bias)[i];
   }
+  pdl_wait();
+  pdl_trigger();
+  if (ok) v = reinterpret_cast<const float4*>(in + (int64_t)row * in_stride)[i];
   const float mean = block_sum((v.x + v.y) + (v.z + v.w), red) / (float)d;
   const float a = v.x - mean, b = v.y - mean, c = v.z - mean, e = v.w - mean;
   const float q = ok ? (a * a + b * b) + (c * c + e * e) : 0.f;
@@ -125,15 +131,14 @@ void launch_ln_rows(const float* in, int64_t in_stride, float* out, int64_t out_
   if (rows <= 0) return;
   if (d <= 4096) {
     const int threads = (((d >> 2) + 31) / 32) * 32;
-    ln_rows_cta_kernel<<<rows, threads, 0, s>>>(in, in_stride, out, out_stride, w, bias, residual_weight, eps, d,
-                                                (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo);
+    launch_k(ln_rows_cta_kernel, dim3(rows), dim3(threads), 0, s, in, in_stride, out, out_stride, w, bias,
+             residual_weight, eps, d, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo);
     return;
   }
   const int warps_per_block = 8;
   dim3 grid((rows + warps_per_block - 1) / warps_per_block);
-  ln_rows_kernel<<<grid, warps_per_block * 32, 0, s>>>(in, in_stride, out, out_stride, w, bias,
-                                                       residual_weight, eps, rows, d,
-                                                       (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo);
+  launch_k(ln_rows_kernel, grid, dim3(warps_per_block * 32), 0, s, in, in_stride, out, out_stride, w, bias,
+           residual_weight, eps, rows, d, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -148,6 +153,8 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(
     float eps, float* __restrict__ x, int B, int d) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
   if (row >= 3 * B) return;
   const int b = row / 3, tok = row - 3 * b;
   const float scal = (tok == 1) ? rtg[b] : ((tok == 2 && rew) ? rew[b] : 0.f);
@@ -175,25 +182,29 @@ void launch_embed_tokens(const float* s_emb, const float* rtg, const float* rew,
                          const float* ln_b, float eps, float* x, int B, int d, cudaStream_t s) {
   const int rows = 3 * B;
   dim3 grid((rows + 7) / 8);
-  embed_tokens_kernel<<<grid, 256, 0, s>>>(s_emb, rtg, rew, w_ret, b_ret, w_rew, b_rew, ln_w, ln_b, eps,
-                                           x, B, d);
+  launch_k(embed_tokens_kernel, grid, dim3(256), 0, s, s_emb, rtg, rew, w_ret, b_ret, w_rew, b_rew, ln_w, ln_b, eps,
+           x, B, d);
 }
 
 __global__ void pad_rows_kernel(const float* __restrict__ in, int K, float* __restrict__ out, int Kpad,
                                 int rows) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   if (i >= (int64_t)rows * Kpad) return;
   const int r = (int)(i / Kpad), c = (int)(i - (int64_t)r * Kpad);
   out[i] = c < K ? in[(int64_t)r * K + c] : 0.f;
 }
 void launch_pad_rows(const float* in, int K, float* out, int Kpad, int rows, cudaStream_t s) {
   const int64_t n = (int64_t)rows * Kpad;
-  pad_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, K, out, Kpad, rows);
+  launch_k(pad_rows_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, in, K, out, Kpad, rows);
 }
 
 __global__ void copy_rows_kernel(const float* __restrict__ in, int64_t in_stride, float* __restrict__ out,
                                  int64_t out_stride, int rows, int d) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   if (i >= (int64_t)rows * d) return;
   const int r = (int)(i / d), c = (int)(i - (int64_t)r * d);
   out[(int64_t)r * out_stride + c] = in[(int64_t)r * in_stride + c];
@@ -201,7 +212,8 @@ __global__ void copy_rows_kernel(const float* __restrict__ in, int64_t in_stride
 void launch_copy_rows(const float* in, int64_t in_stride, float* out, int64_t out_stride, int rows, int d,
                       cudaStream_t s) {
   const int64_t n = (int64_t)rows * d;
-  copy_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(in, in_stride, out, out_stride, rows, d);
+  launch_k(copy_rows_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, in, in_stride, out, out_stride,
+           rows, d);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -233,27 +245,26 @@ __global__ void __launch_bounds__(128, 4) conv_qkv_gates_kernel(ConvQkvParams p)
   for (int t = 0; t < kMaxT; ++t)
 #pragma unroll
     for (int o = 0; o < 4; ++o) q[t][o] = k[t][o] = v[t][o] = 0.f;
+  // Everything this thread needs that no kernel of the step writes (weights, and the conv window, which only
+  // this kernel touches) is loaded BEFORE the dependency wait, so it overlaps the tail of proj_up.
+  float win[KS][4];
+  float cw[4][KS];
+  float cbv[4] = {0.f, 0.f, 0.f, 0.f};
+  float wq[16], wk[16], wv[16];
+  float* cs = p.conv_state + (int64_t)b * KS * inner + c;
   if (active) {
     // rows 1..KS-1 of the state are the KS-1 most recent inputs (oldest first); row 0 is shifted out
-    float win[KS][4];
-    float* cs = p.conv_state + (int64_t)b * KS * inner + c;
 #pragma unroll
     for (int r = 0; r < KS; ++r) {
       const float4 w4 = *reinterpret_cast<const float4*>(cs + (int64_t)r * inner);
       win[r][0] = w4.x; win[r][1] = w4.y; win[r][2] = w4.z; win[r][3] = w4.w;
     }
-    float4 xm4[kMaxT];
-#pragma unroll
-    for (int t = 0; t < kMaxT; ++t)
-      if (t < T) xm4[t] = *reinterpret_cast<const float4*>(p.u + ((int64_t)b * T + t) * 2 * inner + c);
-    float cw[4][KS];
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
       for (int r = 0; r < KS; ++r) cw[ch][r] = p.conv_w[(int64_t)(c + ch) * KS + r];
     const float4 cb = *reinterpret_cast<const float4*>(p.conv_b + c);
-    const float cbv[4] = {cb.x, cb.y, cb.z, cb.w};
-    float wq[16], wk[16], wv[16];
+    cbv[0] = cb.x; cbv[1] = cb.y; cbv[2] = cb.z; cbv[3] = cb.w;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 a4 = reinterpret_cast<const float4*>(p.wq + (int64_t)j * 16)[i];
@@ -263,6 +274,14 @@ __global__ void __launch_bounds__(128, 4) conv_qkv_gates_kernel(ConvQkvParams p)
       wk[4 * i] = k4.x; wk[4 * i + 1] = k4.y; wk[4 * i + 2] = k4.z; wk[4 * i + 3] = k4.w;
       wv[4 * i] = v4.x; wv[4 * i + 1] = v4.y; wv[4 * i + 2] = v4.z; wv[4 * i + 3] = v4.w;
     }
+  }
+  pdl_wait();
+  pdl_trigger();
+  if (active) {
+    float4 xm4[kMaxT];
+#pragma unroll
+    for (int t = 0; t < kMaxT; ++t)
+      if (t < T) xm4[t] = *reinterpret_cast<const float4*>(p.u + ((int64_t)b * T + t) * 2 * inner + c);
 #pragma unroll
     for (int t = 0; t < kMaxT; ++t) {
       if (t < T) {
@@ -377,7 +396,7 @@ bool launch_conv_qkv_gates(const ConvQkvParams& p, cudaStream_t s) {
   dim3 grid(p.NCH, p.B);
   // instantiated for the shipped presets (KS = 4, NH = 4; 1..4 tokens per step) plus NH = 1, 2, 8
 #define XL_CONV_CASE(KSV, TV, NHV) \
-  if (p.KS == KSV && p.T == TV && p.NH == NHV) { conv_qkv_gates_kernel<KSV, TV, NHV><<<grid, threads, 0, s>>>(p); return true; }
+  if (p.KS == KSV && p.T == TV && p.NH == NHV) { launch_k(conv_qkv_gates_kernel<KSV, TV, NHV>, grid, dim3(threads), 0, s, p); return true; }
   XL_CONV_CASE(4, 1, 4) XL_CONV_CASE(4, 2, 4) XL_CONV_CASE(4, 3, 4) XL_CONV_CASE(4, 4, 4)
   XL_CONV_CASE(4, 1, 8) XL_CONV_CASE(4, 3, 8) XL_CONV_CASE(4, 1, 2) XL_CONV_CASE(4, 3, 2)
   XL_CONV_CASE(4, 1, 1) XL_CONV_CASE(4, 3, 1) XL_CONV_CASE(2, 1, 4) XL_CONV_CASE(2, 3, 4)
@@ -401,6 +420,8 @@ __global__ void __launch_bounds__(256) argmax_tokens_kernel(const float* __restr
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int nrows = discrete ? B : B * act_dim;
+  pdl_wait();
+  pdl_trigger();
   if (w >= nrows) return;
   const int b = discrete ? w : w / act_dim;
   const int j = discrete ? 0 : w - b * act_dim;
@@ -450,8 +471,8 @@ void launch_argmax_tokens(const float* logits, int64_t row_pitch, int B, int act
                           int32_t* tokens, float* actions, cudaStream_t s) {
   const int rows = discrete ? B : B * act_dim;
   dim3 grid((rows + 7) / 8);
-  argmax_tokens_kernel<<<grid, 256, 0, s>>>(logits, row_pitch, B, act_dim, num_actions, discrete_actions,
-                                            discrete, bin_width, min_val, tokens, actions);
+  launch_k(argmax_tokens_kernel, grid, dim3(256), 0, s, logits, row_pitch, B, act_dim, num_actions,
+           discrete_actions, discrete, bin_width, min_val, tokens, actions);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -462,6 +483,8 @@ __global__ void __launch_bounds__(256) state_reset_kernel(float* C, float* n, fl
                                                           int64_t c_per_env, int64_t n_per_env,
                                                           int64_t m_per_env, int64_t conv_per_env) {
   const int b = blockIdx.y;
+  pdl_wait();
+  pdl_trigger();
   if (mask && mask[b] == 0) return;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(256) gemm_simple_kernel(const float* __restric
   __shared__ __align__(16) float As[2][BK][BM + PAD];
   __shared__ __align__(16) float Ws[2][BK][BN + PAD];
   const int tid = threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int ty = tid >> 4, tx = tid & 15;
 
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(256) gemm_simple_kernel(const float* __restric
 void launch_gemm_simple(const float* A, const __nv_bfloat16* W, const float* bias, const float* residual,
                         float* out, int M, int N, int K, cudaStream_t s) {
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  gemm_simple_kernel<<<grid, 256, 0, s>>>(A, W, bias, residual, out, M, N, K);
+  launch_k(gemm_simple_kernel, grid, dim3(256), 0, s, A, W, bias, residual, out, M, N, K);
 }
 
 }  // namespace xl

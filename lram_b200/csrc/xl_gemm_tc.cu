@@ -140,10 +140,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
+  // The weight tiles of the first ring round are requested BEFORE the dependency wait (weights are never
+  // written by a kernel): they stream in while the kernel that produces the activations is still running.
+  const int pre_kb = num_kb < kStages ? num_kb : kStages;
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < pre_kb; ++kb) {
+      mbar_expect_tx(full_bar(kb), S::kStageBytes);
+      tma_load_2d(base + kb * S::kStageBytes + 2 * S::kABytes, &map_w, full_bar(kb), (kb0 + kb) * BLOCK_K, n0);
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < pre_kb; ++kb) {
+        const uint32_t st = base + kb * S::kStageBytes;
+        tma_load_2d(st, &map_a_hi, full_bar(kb), (kb0 + kb) * BLOCK_K, m0);
+        tma_load_2d(st + S::kABytes, &map_a_lo, full_bar(kb), (kb0 + kb) * BLOCK_K, m0);
+      }
+      for (int kb = pre_kb; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
@@ -316,6 +333,8 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
                                                          __nv_bfloat16* __restrict__ hi,
                                                          __nv_bfloat16* __restrict__ lo, int rows, int K) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  pdl_wait();
+  pdl_trigger();
   if (i >= (int64_t)rows * K) return;
   const int r = (int)(i / K), c = (int)(i - (int64_t)r * K);
   const float4 v = *reinterpret_cast<const float4*>(in + (int64_t)r * in_stride + c);
@@ -375,13 +394,22 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& ml, const CU
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = splits;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (splits > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = splits;
+    ++na;
+  }
+  if (g_use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = splits > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kStages>, ma, ml, mw, bias, residual, out, M, N, K);
 }
 
@@ -397,8 +425,8 @@ bool gemm_tc_supported(int M, int N, int K) { return K % tc::BLOCK_K == 0 && K >
 
 void launch_split_bf16(const float* in, int64_t in_stride, void* hi, void* lo, int rows, int K, cudaStream_t s) {
   const int64_t n4 = (int64_t)rows * K / 4;
-  tc::split_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(in, in_stride, (__nv_bfloat16*)hi,
-                                                                     (__nv_bfloat16*)lo, rows, K);
+  launch_k(tc::split_bf16_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, s, in, in_stride,
+           (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, K);
 }
 
 // Tile width and split-K factor from a small cost model: the per-SM TMA fill rate (~80 GB/s) bounds these
@@ -437,11 +465,11 @@ void gemm_tc_plan(int M, int N, int K, int num_sms, int* bn_out, int* splits_out
 
 cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat16* W, const float* bias,
                            const float* residual, float* out, int M, int N, int K, int num_sms, int force_splits,
-                           cudaStream_t s) {
+                           int low_smem, cudaStream_t s) {
   if (!gemm_tc_supported(M, N, K)) return cudaErrorInvalidValue;
   int bn, splits;
   gemm_tc_plan(M, N, K, num_sms, &bn, &splits);
-  if (force_splits == 1) {            // A/B switch: best tile width without split-K
+  if (force_splits == 1 || low_smem) {   // A/B switch: best tile width without split-K
     const int m_tiles = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
     bn = 128;
     if ((int64_t)m_tiles * ((N + 127) / 128) < num_sms) bn = 64;
@@ -452,6 +480,14 @@ cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat
   if (!tc::make_map(&ma, a_hi, M, K, tc::BLOCK_M) || !tc::make_map(&ml, a_lo, M, K, tc::BLOCK_M) ||
       !tc::make_map(&mw, W, N, K, bn))
     return cudaErrorUnknown;
+  if (low_smem) {
+    // shallow rings (<= 110 KB): the CTA must fit beside a resident state-stream CTA of another micro-batch
+    switch (bn) {
+      case 128: return tc::launch<128, 2>(ma, ml, mw, bias, residual, out, M, N, K, 1, s);
+      case 64: return tc::launch<64, 2>(ma, ml, mw, bias, residual, out, M, N, K, 1, s);
+      default: return tc::launch<32, 3>(ma, ml, mw, bias, residual, out, M, N, K, 1, s);
+    }
+  }
   switch (bn) {
     case 128: return tc::launch<128, 4>(ma, ml, mw, bias, residual, out, M, N, K, 1, s);
     case 64: return tc::launch<64, 4>(ma, ml, mw, bias, residual, out, M, N, K, splits, s);

@@ -6,6 +6,8 @@
 
 namespace xl {
 
+extern int g_use_pdl;   // programmatic dependent launch of every kernel (xl_common.cuh); xl_set_option("pdl")
+
 // ---- xl_elementwise.cu ---------------------------------------------------------------------------
 // LayerNorm over the last dim for `rows` rows. gamma = (residual_weight ? 1 + w : w), optional bias.
 // in row r at in + r*in_stride, out row r at out + r*out_stride. Optional bf16 hi/lo split outputs
@@ -60,7 +62,7 @@ void launch_state_reset(float* C, float* n, float* m, float* conv, const uint8_t
 
 // ---- xl_state_step.cu ----------------------------------------------------------------------------
 struct StateStepParams {
-  float* C;                 // [B, NH, DH, DH]
+  float* C;                 // [B, NH, DH/Wc, DH, Wc] slab-major (Wc = 128 when DH % 128 == 0, else DH)
   float* n;                 // [B, NH, DH]
   float* m;                 // [B, NH]
   const float* qk;          // [M, NH, DH, 2]  (q, k) pairs, unscaled
@@ -80,7 +82,13 @@ struct StateStepParams {
   int B, T, NH, DH, inner, NCH;
   int rows_split;           // RS
   int cols_per_cta;         // multiple of 4, <= 128, divides DH
-  int impl;                 // 1 = TMA ring (default), 0 = register-batched global loads
+  int impl;                 // 2 = persistent TMA ring (default), 1 = one-shot TMA ring, 0 = register-batched loads
+  int stages;               // impl 2: ring depth (0 = default)
+  int ctas_per_sm;          // impl 2: persistent CTAs per SM (0 = 1)
+  int meta_slots;           // impl 2: depth of the segment-metadata ring (0 = 3)
+  // impl 2 stream-K partition (filled by the launchers): grid G, tiles per CTA q (+1 for the first r CTAs),
+  // partial slots per item. sk_grid == 0 -> rows_split layout of impl 0/1.
+  int sk_grid, sk_q, sk_r, sk_smax;
   int num_layers;           // blocks sharing the L2 with this one (cache-policy choice); 0 = 1
   float ln_eps, cell_eps;
 };
@@ -103,7 +111,7 @@ void launch_split_bf16(const float* in, int64_t in_stride, void* hi, void* lo, i
 // split-K is chosen by a cost model (cluster of CTAs reduced over DSMEM); force_splits = 1 disables it.
 cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat16* W, const float* bias,
                            const float* residual, float* out, int M, int N, int K, int num_sms, int force_splits,
-                           cudaStream_t s);
+                           int low_smem, cudaStream_t s);
 void gemm_tc_plan(int M, int N, int K, int num_sms, int* bn_out, int* splits_out);
 
 }  // namespace xl

@@ -37,6 +37,15 @@ constexpr int kThreads = 256;        // consumer threads
 constexpr int kUnroll = 8;
 constexpr int kMaxNCH = 16;
 
+// stream-K partition of N stage tiles over G CTAs (impl 2): CTA c owns [sk_start(c), sk_start(c+1))
+__host__ __device__ __forceinline__ int sk_start(const StateStepParams& p, int c) {
+  return c * p.sk_q + (c < p.sk_r ? c : p.sk_r);
+}
+__host__ __device__ __forceinline__ int sk_cta_of(const StateStepParams& p, int tile) {
+  const int big = p.sk_r * (p.sk_q + 1);
+  return tile < big ? tile / (p.sk_q + 1) : p.sk_r + (tile - big) / p.sk_q;
+}
+
 // Gate recurrence of one (env, head) for the T tokens of the step. Called by one full warp; results in shared
 // memory. Streaming CTAs and the finalize CTA run this same code on the same inputs -> identical f, i, m.
 template <int T>
@@ -88,8 +97,15 @@ __device__ __forceinline__ void row_update(float (&c)[4], const float* __restric
   }
 }
 
+// C is stored SLAB-MAJOR in HBM: [B, NH, DH/Wc, DH (dk rows), Wc (dv cols)] with Wc = 128 when DH % 128 == 0
+// (else Wc = DH, i.e. plain row-major): every [32 rows x 128 cols] tile is 16 contiguous KB, and the slabs of
+// an (env, head) follow each other. Logical element C[bh][r][c] lives at
+//   C + ((bh * (DH/Wc) + c / Wc) * DH + r) * Wc + c % Wc.
+__host__ __device__ __forceinline__ int slab_width(int DH) { return (DH % 128 == 0) ? 128 : DH; }
+
 struct TileCoord {
   int bh, b, hd, rs, cs, r0, nrows, c0, rows_per;
+  int wc, slab_row0, cin;      // slab width, first row of the tile in the [B*NH*CSl*DH, Wc] view, column inside the slab
 };
 __device__ __forceinline__ TileCoord tile_coord(const StateStepParams& p) {
   TileCoord tc;
@@ -105,6 +121,10 @@ __device__ __forceinline__ TileCoord tile_coord(const StateStepParams& p) {
   tc.r0 = tc.rs * tc.rows_per;
   tc.nrows = max(0, min(p.DH, tc.r0 + tc.rows_per) - tc.r0);
   tc.c0 = tc.cs * p.cols_per_cta;
+  tc.wc = slab_width(p.DH);
+  const int slab = tc.c0 / tc.wc;
+  tc.cin = tc.c0 - slab * tc.wc;
+  tc.slab_row0 = (tc.bh * (p.DH / tc.wc) + slab) * p.DH + tc.r0;
   return tc;
 }
 
@@ -142,6 +162,8 @@ __global__ void __launch_bounds__(kThreads, 3) mlstm_state_stream_ldg_kernel(Sta
   float* sqk = smem;                         // [T][rows_per][2]
   float* sacc = smem + T * tstride;          // [TY][T][cols_per_cta]
 
+  pdl_wait();
+  pdl_trigger();
   if (tid < 32) compute_gates<T>(p, tc.b, tc.hd, tc.bh, s_f, s_i, s_m, s_pre);
 #pragma unroll
   for (int t = 0; t < T; ++t) {
@@ -169,8 +191,8 @@ __global__ void __launch_bounds__(kThreads, 3) mlstm_state_stream_ldg_kernel(Sta
 #pragma unroll
   for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
 
-  float4* Cp = reinterpret_cast<float4*>(p.C + ((int64_t)tc.bh * DH + tc.r0) * DH + tc.c0) + tx;
-  const int64_t rs4 = DH >> 2;               // row stride in float4
+  float4* Cp = reinterpret_cast<float4*>(p.C + (int64_t)tc.slab_row0 * tc.wc + tc.cin) + tx;
+  const int64_t rs4 = tc.wc >> 2;            // row stride in float4 (slab-major C)
   int rbase = ty;
   for (; rbase + (kUnroll - 1) * TY < tc.nrows; rbase += TY * kUnroll) {   // full batches: no predicates
     float4 cv[kUnroll];
@@ -273,17 +295,10 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
     // ===== producer warp =====
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
-      // the step's (q, k) pairs of this row chunk: T contiguous runs of nrows*8 bytes
-      mbar_expect_tx(qk_bar, (uint32_t)(T * tc.nrows * 8));
-#pragma unroll
-      for (int t = 0; t < T; ++t)
-        bulk_copy_g2s(smem_u32(sqk + t * tstride),
-                      p.qk + ((((int64_t)tc.b * T + t) * p.NH + tc.hd) * DH + tc.r0) * 2,
-                      (uint32_t)(tc.nrows * 8), qk_bar);
       uint64_t policy = 0;
       if (kStream) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      const int grow0 = tc.bh * DH + tc.r0;
-      for (int i = 0; i < nblk; ++i) {
+      const int grow0 = tc.slab_row0;
+      auto issue = [&](int i) {
         const int s = i % kStages;
         mbar_wait(empty_bar(s), ((i / kStages) & 1) ^ 1);
         mbar_expect_tx(full_bar(s), stage_bytes);
@@ -292,21 +307,39 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
           asm volatile(
               "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
               "[%0], [%1, {%3, %4}], [%2], %5;"
-              ::"r"(dst), "l"(&mapC), "r"(full_bar(s)), "r"(tc.c0), "r"(grow0 + i * kStageRows), "l"(policy)
+              ::"r"(dst), "l"(&mapC), "r"(full_bar(s)), "r"(tc.cin), "r"(grow0 + i * kStageRows), "l"(policy)
               : "memory");
         } else {
           asm volatile(
               "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-              ::"r"(dst), "l"(&mapC), "r"(full_bar(s)), "r"(tc.c0), "r"(grow0 + i * kStageRows)
+              ::"r"(dst), "l"(&mapC), "r"(full_bar(s)), "r"(tc.cin), "r"(grow0 + i * kStageRows)
               : "memory");
         }
-      }
+      };
+      // C was last written by the previous env step: the ring is filled before the dependency wait
+      const int pre = nblk < kStages ? nblk : kStages;
+      for (int i = 0; i < pre; ++i) issue(i);
+      pdl_wait();
+      pdl_trigger();
+      // the step's (q, k) pairs of this row chunk: T contiguous runs of nrows*8 bytes
+      mbar_expect_tx(qk_bar, (uint32_t)(T * tc.nrows * 8));
+#pragma unroll
+      for (int t = 0; t < T; ++t)
+        bulk_copy_g2s(smem_u32(sqk + t * tstride),
+                      p.qk + ((((int64_t)tc.b * T + t) * p.NH + tc.hd) * DH + tc.r0) * 2,
+                      (uint32_t)(tc.nrows * 8), qk_bar);
+      for (int i = pre; i < nblk; ++i) issue(i);
+    } else {
+      pdl_wait();
+      pdl_trigger();
     }
     return;   // consumers only use the named barrier 1 from here on
   }
 
   // ===== consumers =====
   const int tx = tid % TX, ty = tid / TX;
+  pdl_wait();
+  pdl_trigger();
   if (warp == 0) compute_gates<T>(p, tc.b, tc.hd, tc.bh, s_f, s_i, s_m, s_pre);
   float vi[T][4];
 #pragma unroll
@@ -329,8 +362,8 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
 #pragma unroll
   for (int t = 0; t < T; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
 
-  float4* Cp = reinterpret_cast<float4*>(p.C + ((int64_t)tc.bh * DH + tc.r0) * DH + tc.c0) + tx;
-  const int64_t rs4 = DH >> 2;
+  float4* Cp = reinterpret_cast<float4*>(p.C + (int64_t)tc.slab_row0 * tc.wc + tc.cin) + tx;
+  const int64_t rs4 = tc.wc >> 2;
   constexpr int kRowsPerThread = 4;                 // fast path: TY == 8 -> 32 rows / 8 row lanes
   const bool fast = (TY * kRowsPerThread == kStageRows);
   mbar_wait(qk_bar, 0);
@@ -392,8 +425,9 @@ static cudaError_t launch(const StateStepParams& p, cudaStream_t s) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return cudaErrorUnknown;
   CUtensorMap map;
-  cuuint64_t gdim[2] = {(cuuint64_t)p.DH, (cuuint64_t)p.B * p.NH * p.DH};
-  cuuint64_t gstride[1] = {(cuuint64_t)p.DH * sizeof(float)};
+  const int wc = slab_width(p.DH);
+  cuuint64_t gdim[2] = {(cuuint64_t)wc, (cuuint64_t)p.B * p.NH * (p.DH / wc) * p.DH};
+  cuuint64_t gstride[1] = {(cuuint64_t)wc * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)p.cols_per_cta, (cuuint32_t)kStageRows};
   cuuint32_t estr[2] = {1, 1};
   if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.C, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -414,11 +448,312 @@ static cudaError_t launch(const StateStepParams& p, cudaStream_t s) {
   }
   const int CS = p.DH / p.cols_per_cta;
   const int64_t grid = (int64_t)p.B * p.NH * CS * p.rows_split;
-  mlstm_state_stream_tma_kernel<T, kStream><<<(unsigned)grid, kBlock, smem, s>>>(map, p);
-  return cudaGetLastError();
+  return launch_k(mlstm_state_stream_tma_kernel<T, kStream>, dim3((unsigned)grid), dim3(kBlock), smem, s, map, p);
 }
 
 }  // namespace tma
+
+// ------------------------------------------------------------------------------------------------
+// impl 2: persistent TMA-fed ring with a stream-K partition of the state.
+// The state of the launch is a list of N = B*NH*(DH/128)*(DH/32) stage tiles ([32 rows x 128 cols] fp32,
+// 16 KB), ordered (env*head, column slab, row block). CTA c of G (one per SM) owns the contiguous run
+// [c*q + min(c,r), ...) of q or q+1 tiles (q = N/G, r = N%G): every CTA moves the same number of bytes
+// (+-16 KB), the ring of C tiles never drains between items, and there is neither wave quantisation nor a
+// slow tail. A run crosses item = (env*head, column slab) boundaries; each (item, CTA) segment leaves one
+// partial numerator [T, 128] in slot (c - first CTA of the item), and the finalize kernel adds an item's
+// slots in slot order (deterministic; the same integer arithmetic on both sides).
+//   warp 8  (1 thread): C-tile producer — cp.async.bulk.tensor.2d into a `stages`-deep ring, evict-first
+//   warp 9            : segment-metadata producer — bulk copies of the segment's (q,k) pairs and v slab and
+//                       the gate recurrence of its (env, head) into a small ring, ahead of the consumers
+//   warps 0..7        : consumers — 128-bit shared loads, T x (2 FMA + 1 FMA) per element in registers,
+//                       128-bit streaming stores back to C, one cross-warp reduction of q^T C per segment
+// A 1-CTA/SM launch leaves shared memory and ~1700 thread slots per SM for the latency-bound kernels of OTHER
+// env micro-batches (LayerNorm, projections, conv/qkv, finalize) that the step pipeline (xl_api.cu) runs
+// concurrently on side streams.
+// ------------------------------------------------------------------------------------------------
+namespace pers {
+
+using tma::bulk_copy_g2s;
+using tma::mbar_arrive;
+using tma::mbar_expect_tx;
+using tma::mbar_init;
+using tma::mbar_wait;
+using tma::smem_u32;
+
+constexpr int kStageRows = 32;
+constexpr int kW = 128;                       // column slab
+constexpr int kMaxStages = 8;
+constexpr int kMaxMetaSlots = 4;
+constexpr int kConsumerWarps = kThreads / 32;
+constexpr int kBlock = kThreads + 64;         // + C-tile producer warp + metadata producer warp
+constexpr int kStageFloats = kStageRows * kW;
+
+__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__host__ __device__ inline int meta_floats(int T, int DH) { return T * DH * 2 + T * kW + 16; }
+
+template <int T, bool kStream>
+__global__ void __launch_bounds__(kBlock, 2)
+mlstm_state_stream_persistent_kernel(const __grid_constant__ CUtensorMap mapC, StateStepParams p, int stages,
+                                     int meta_slots) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar[2 * kMaxStages + 2 * kMaxMetaSlots];
+
+  const int DH = p.DH, CS = DH / kW, NH = p.NH;
+  const int nblk = DH / kStageRows;                 // stage tiles per item
+  const int mfl = meta_floats(T, DH);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x;
+  const int tile_begin = sk_start(p, cta), tile_end = sk_start(p, cta + 1);
+
+  // dynamic smem: [ring: stages x 32 x 128 fp32 | 128-B aligned][meta ring][red: 2 x 8 x T x 128]
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  float* ring = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)));
+  float* meta = ring + (size_t)stages * kStageFloats;
+  float* red = meta + (size_t)meta_slots * mfl;
+  const uint32_t bar0 = smem_u32(s_bar);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+  auto meta_full = [&](int s) { return bar0 + 8u * (2 * kMaxStages + s); };
+  auto meta_empty = [&](int s) { return bar0 + 8u * (2 * kMaxStages + kMaxMetaSlots + s); };
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), kConsumerWarps);
+    }
+    for (int s = 0; s < meta_slots; ++s) {
+      mbar_init(meta_full(s), 1);
+      mbar_init(meta_empty(s), kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == kConsumerWarps) {
+    // ===== C-tile producer: one TMA per stage tile, straight through the CTA's run =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
+      uint64_t policy = 0;
+      if (kStream) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+      int s = 0;
+      uint32_t ph = 0;
+      int item = tile_begin / nblk;
+      int i = tile_begin - item * nblk;
+      // C was last written by the previous env step: the first `stages` tiles are in flight before the
+      // dependency wait, i.e. while the kernel that produces this step's q/k/v/gates is still running
+      bool waited = false;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        if (!waited && tile - tile_begin == stages) {
+          pdl_wait();
+          pdl_trigger();
+          waited = true;
+        }
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), (uint32_t)(kStageFloats * sizeof(float)));
+        const uint32_t dst = sbase + (uint32_t)(s * kStageFloats * sizeof(float));
+        // slab-major C: tile t of the launch is the 16 KB at C + t * 16 KB
+        const int c0 = 0, r0 = tile * kStageRows;
+        if (kStream) {
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+              "[%0], [%1, {%3, %4}], [%2], %5;"
+              ::"r"(dst), "l"(&mapC), "r"(full_bar(s)), "r"(c0), "r"(r0), "l"(policy)
+              : "memory");
+        } else {
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+              ::"r"(dst), "l"(&mapC), "r"(full_bar(s)), "r"(c0), "r"(r0)
+              : "memory");
+        }
+        if (++s == stages) { s = 0; ph ^= 1; }
+        if (++i == nblk) { i = 0; ++item; }
+      }
+      if (!waited) {
+        pdl_wait();
+        pdl_trigger();
+      }
+    } else {
+      pdl_wait();
+      pdl_trigger();
+    }
+    return;
+  }
+
+  if (warp == kConsumerWarps + 1) {
+    // ===== segment-metadata producer =====
+    pdl_wait();
+    pdl_trigger();
+    int slot = 0;
+    uint32_t ph = 0;
+    for (int tile = tile_begin; tile < tile_end;) {
+      const int item = tile / nblk, i0 = tile - item * nblk;
+      const int cnt = min(nblk - i0, tile_end - tile);
+      const int bh = item / CS, cs = item - bh * CS;
+      const int b = bh / NH, hd = bh - b * NH;
+      const int r0 = i0 * kStageRows, rows = cnt * kStageRows;
+      float* ms = meta + (size_t)slot * mfl;
+      float* s_gate = ms + T * DH * 2 + T * kW;                 // f[0..T) at +0, i[0..T) at +4
+      // gate pre-activations: loads issued before anything waits
+      float pre = 0.f;
+      if (lane < 2 * T) {
+        const int t = lane >> 1, is_f = lane & 1;
+        const float* gp = p.gate_part + ((int64_t)b * T + t) * p.NCH * 2 * NH + (is_f ? NH : 0) + hd;
+        float sum = 0.f;
+        for (int c = 0; c < p.NCH; ++c) sum += gp[c * 2 * NH];   // fixed order, as compute_gates()
+        const float* bias = is_f ? p.fgate_b : p.igate_b;
+        if (bias) sum += bias[hd];
+        pre = sum;
+      }
+      float mprev = p.m[bh];
+      if (lane == 0) {
+        mbar_wait(meta_empty(slot), ph ^ 1);                     // consumers released this slot
+        mbar_expect_tx_only(meta_full(slot), (uint32_t)(T * rows * 8 + T * kW * 4));
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          bulk_copy_g2s(smem_u32(ms + t * DH * 2),
+                        p.qk + ((((int64_t)b * T + t) * NH + hd) * DH + r0) * 2, (uint32_t)(rows * 8),
+                        meta_full(slot));
+          bulk_copy_g2s(smem_u32(ms + T * DH * 2 + t * kW),
+                        p.v + ((int64_t)b * T + t) * p.inner + hd * DH + cs * kW, (uint32_t)(kW * 4),
+                        meta_full(slot));
+        }
+      }
+      // same arithmetic, same order as compute_gates() (the finalize kernel) -> identical f, i
+      float fv[T], iv[T];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const float ig = __shfl_sync(0xffffffffu, pre, 2 * t);
+        const float fg = __shfl_sync(0xffffffffu, pre, 2 * t + 1);
+        const float lf = log_sigmoid(fg);
+        const float mnew = fmaxf(lf + mprev, ig);
+        fv[t] = expf(lf + mprev - mnew);
+        iv[t] = expf(ig - mnew);
+        mprev = mnew;
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          s_gate[t] = fv[t];
+          s_gate[4 + t] = iv[t];
+        }
+        mbar_arrive(meta_full(slot));                            // release: gates visible with the phase
+      }
+      __syncwarp();
+      if (++slot == meta_slots) { slot = 0; ph ^= 1; }
+      tile += cnt;
+    }
+    return;
+  }
+
+  // ===== consumers: warp w owns rows w, w+8, w+16, w+24 of every 32-row tile; lane owns 4 columns =====
+  const int tx = lane, ty = warp;
+  const float kscale = rsqrtf((float)DH);
+  const int64_t rs4 = kW >> 2;
+  const int tstride = 2 * DH;
+  pdl_wait();
+  pdl_trigger();
+  int s = 0, slot = 0, seg = 0;
+  uint32_t ph = 0, mph = 0;
+  for (int tile = tile_begin; tile < tile_end; ++seg) {
+    const int item = tile / nblk, i0 = tile - item * nblk;
+    const int cnt = min(nblk - i0, tile_end - tile);
+    const int bh = item / CS, cs = item - bh * CS;
+    const float* ms = meta + (size_t)slot * mfl;
+    const float* sqk = ms;                                       // [T][rows of this segment][2]
+    const float* sv = ms + T * DH * 2;
+    const float* s_gate = sv + T * kW;
+    mbar_wait(meta_full(slot), mph);
+    float f[T], vi[T][4], acc[T][4];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      f[t] = s_gate[t];
+      const float it_ = s_gate[4 + t] * kscale;
+      const float4 vv = *reinterpret_cast<const float4*>(sv + t * kW + 4 * tx);
+      vi[t][0] = vv.x * it_; vi[t][1] = vv.y * it_; vi[t][2] = vv.z * it_; vi[t][3] = vv.w * it_;
+      acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+    }
+    float4* Cp = reinterpret_cast<float4*>(p.C + (int64_t)tile * kStageFloats) + tx;   // slab-major C
+    for (int i = 0; i < cnt; ++i) {
+      const float* st = ring + (size_t)s * kStageFloats;
+      const int rblk = i * kStageRows;
+      mbar_wait(full_bar(s), ph);
+      float4 cv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) cv[r] = *reinterpret_cast<const float4*>(st + (ty + r * 8) * kW + 4 * tx);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(s));       // the slot is free as soon as it sits in registers
+      if (++s == stages) { s = 0; ph ^= 1; }
+      float4* rp = Cp + (int64_t)(rblk + ty) * rs4;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float c[4] = {cv[r].x, cv[r].y, cv[r].z, cv[r].w};
+        row_update<T>(c, sqk + 2 * (rblk + ty + r * 8), tstride, f, vi, acc);
+        const float4 o = make_float4(c[0], c[1], c[2], c[3]);
+        if (kStream) st_stream(rp + (int64_t)r * 8 * rs4, o);
+        else rp[(int64_t)r * 8 * rs4] = o;
+      }
+    }
+    // q^T C of this segment: cross-warp reduction in a double-buffered scratch (one named barrier per segment)
+    float* rb = red + (seg & 1) * (kConsumerWarps * T * kW);
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      *reinterpret_cast<float4*>(rb + (ty * T + t) * kW + 4 * tx) =
+          make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(meta_empty(slot));     // (q,k), v, gates of this slot are no longer needed
+    if (++slot == meta_slots) { slot = 0; mph ^= 1; }
+    asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+    const int pslot = cta - sk_cta_of(p, item * nblk);
+    float* dst = p.partial + (((int64_t)item * p.sk_smax + pslot) * T) * kW;
+    for (int idx = tid; idx < T * kW; idx += kThreads) {
+      float sum = 0.f;
+      const int t = idx / kW, c = idx - t * kW;
+#pragma unroll
+      for (int y = 0; y < kConsumerWarps; ++y) sum += rb[(y * T + t) * kW + c];
+      dst[idx] = sum;
+    }
+    tile += cnt;
+  }
+}
+
+static size_t smem_bytes(int T, int DH, int stages, int meta_slots) {
+  return 128 + sizeof(float) * ((size_t)stages * kStageFloats + (size_t)meta_slots * meta_floats(T, DH) +
+                                2 * (size_t)kConsumerWarps * T * kW);
+}
+
+template <int T, bool kStream>
+static cudaError_t launch(const StateStepParams& p, cudaStream_t s) {
+  tma::EncodeTiledFn enc = tma::get_encode();
+  if (!enc) return cudaErrorUnknown;
+  CUtensorMap map;
+  cuuint64_t gdim[2] = {(cuuint64_t)kW, (cuuint64_t)p.B * p.NH * p.DH * (p.DH / kW)};
+  cuuint64_t gstride[1] = {(cuuint64_t)kW * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)kW, (cuuint32_t)kStageRows};
+  cuuint32_t estr[2] = {1, 1};
+  if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p.C, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
+      CUDA_SUCCESS)
+    return cudaErrorInvalidValue;
+  int stages = p.stages > 0 ? p.stages : 6;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  const int meta_slots = p.meta_slots >= 2 && p.meta_slots <= kMaxMetaSlots ? p.meta_slots : 3;
+  const size_t smem = smem_bytes(T, p.DH, stages, meta_slots);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(mlstm_state_stream_persistent_kernel<T, kStream>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  return launch_k(mlstm_state_stream_persistent_kernel<T, kStream>, dim3((unsigned)p.sk_grid), dim3(kBlock), smem,
+                  s, map, p, stages, meta_slots);
+}
+
+}  // namespace pers
 
 // ------------------------------------------------------------------------------------------------
 // kernel 2: finalize one (env, head)
@@ -461,20 +796,40 @@ __global__ void __launch_bounds__(1024) mlstm_state_finalize_kernel(StateStepPar
   float nreg = ok ? p.n[(int64_t)bh * DH + a] : 0.f;
   const float wn = ok ? p.outnorm_w[ch] : 0.f;
   const float wskip = (ok && p.skip) ? p.skip[ch] : 0.f;
+  // Only the partial numerators come from the kernel right before this one (the state stream); n, m, the gate
+  // partials, (q,k), a and z were written at least two kernels back, so they are loaded, and the gate
+  // recurrence is computed, BEFORE the dependency wait — i.e. while the state stream is still running.
   float2 qk[T];
   float num[T], act[T], zz[T];
+  int sk_item = 0, sk_nseg = 0;
+  if (p.sk_grid > 0 && ok) {
+    const int nblk = DH >> 5;
+    sk_item = bh * (DH >> 7) + (a >> 7);
+    sk_nseg = sk_cta_of(p, (sk_item + 1) * nblk - 1) - sk_cta_of(p, sk_item * nblk) + 1;
+  }
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const int64_t row = (int64_t)b * T + t;
     qk[t] = ok ? reinterpret_cast<const float2*>(p.qk)[(row * p.NH + hd) * DH + a] : make_float2(0.f, 0.f);
-    float s = 0.f;
-    if (ok)
-      for (int r = 0; r < RS; ++r) s += p.partial[(((int64_t)bh * RS + r) * T + t) * DH + a];   // fixed order
-    num[t] = s;
     act[t] = (ok && p.skip) ? p.act[row * inner + ch] : 0.f;
     zz[t] = (ok && p.skip) ? p.u[row * 2 * inner + inner + ch] : 0.f;
   }
   if (threadIdx.x < 32) compute_gates<T>(p, b, hd, bh, s_f, s_i, s_m, s_pre);
+  pdl_wait();
+  pdl_trigger();
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    float s = 0.f;
+    if (ok) {
+      if (p.sk_grid > 0) {     // stream-K slots of item (bh, column slab), in slot order
+        const float* pp = p.partial + ((int64_t)sk_item * p.sk_smax * T + t) * 128 + (a & 127);
+        for (int r = 0; r < sk_nseg; ++r) s += pp[(int64_t)r * T * 128];
+      } else {
+        for (int r = 0; r < RS; ++r) s += p.partial[(((int64_t)bh * RS + r) * T + t) * DH + a];   // fixed order
+      }
+    }
+    num[t] = s;
+  }
   __syncthreads();
 
   // ---- n recurrence and q.n for the T tokens --------------------------------------------------------
@@ -540,14 +895,20 @@ void state_step_auto_tiling(int B, int NH, int DH, int num_sms, int* rows_split,
   *cols_per_cta = cols;
 }
 
+static bool persistent_ok(const StateStepParams& p) {
+  return p.impl == 2 && p.DH % pers::kW == 0 && p.DH >= pers::kW && p.rows_split <= 0 &&
+         (p.cols_per_cta <= 0 || p.cols_per_cta == pers::kW);
+}
+
 template <int T>
 static cudaError_t launch_T(const StateStepParams& p, cudaStream_t s) {
+  // stream (evict-first) when the stack's C does not fit comfortably in L2; keep it cached when it does
+  const size_t c_bytes = sizeof(float) * (size_t)p.B * p.NH * p.DH * p.DH;
+  const bool stream = c_bytes * (size_t)(p.num_layers > 0 ? p.num_layers : 1) > ((size_t)64 << 20);
+  if (p.sk_grid > 0) return stream ? pers::launch<T, true>(p, s) : pers::launch<T, false>(p, s);
   const int rows_per = (p.DH + p.rows_split - 1) / p.rows_split;
   cudaError_t e;
-  if (p.impl == 1 && rows_per % 4 == 0) {
-    // stream (evict-first) when the stack's C does not fit comfortably in L2; keep it cached when it does
-    const size_t c_bytes = sizeof(float) * (size_t)p.B * p.NH * p.DH * p.DH;
-    const bool stream = c_bytes * (size_t)(p.num_layers > 0 ? p.num_layers : 1) > ((size_t)64 << 20);
+  if (p.impl >= 1 && rows_per % 4 == 0) {
     e = stream ? tma::launch<T, true>(p, s) : tma::launch<T, false>(p, s);
   } else {
     const int TX = p.cols_per_cta / 4, TY = kThreads / TX;
@@ -561,13 +922,29 @@ static cudaError_t launch_T(const StateStepParams& p, cudaStream_t s) {
     }
     const int CS = p.DH / p.cols_per_cta;
     const int64_t grid = (int64_t)p.B * p.NH * CS * p.rows_split;
-    mlstm_state_stream_ldg_kernel<T><<<(unsigned)grid, kThreads, smem, s>>>(p);
-    e = cudaGetLastError();
+    e = launch_k(mlstm_state_stream_ldg_kernel<T>, dim3((unsigned)grid), dim3(kThreads), smem, s, p);
   }
   return e;
 }
 
+// Both kernels of the step resolve the tiling with this function, from the same inputs.
+// rows_split / cols_per_cta given explicitly (> 0) select the rows_split layout of impl 0/1.
 static void resolve_tiling(StateStepParams& p, int num_sms) {
+  p.sk_grid = 0;
+  if (persistent_ok(p)) {
+    const int64_t N = (int64_t)p.B * p.NH * (p.DH / pers::kW) * (p.DH / pers::kStageRows);
+    const int64_t cap = (int64_t)num_sms * (p.ctas_per_sm > 0 ? p.ctas_per_sm : 1);
+    const int G = (int)(N < cap ? N : cap);
+    const int nblk = p.DH / pers::kStageRows;
+    p.sk_grid = G;
+    p.sk_q = (int)(N / G);
+    p.sk_r = (int)(N % G);
+    const int by_q = (nblk + p.sk_q - 1) / p.sk_q + 1;
+    p.sk_smax = by_q < nblk ? by_q : nblk;
+    p.cols_per_cta = pers::kW;
+    p.rows_split = 1;
+    return;
+  }
   if (p.rows_split <= 0 || p.cols_per_cta <= 0) {
     int rs, cols;
     state_step_auto_tiling(p.B, p.NH, p.DH, num_sms, &rs, &cols);
@@ -581,10 +958,10 @@ cudaError_t launch_state_finalize(StateStepParams p, int num_sms, cudaStream_t s
   resolve_tiling(p, num_sms);
   const int thr = ((p.DH + 31) / 32) * 32;
   switch (p.T) {
-    case 1: mlstm_state_finalize_kernel<1><<<p.B * p.NH, thr, 0, s>>>(p); break;
-    case 2: mlstm_state_finalize_kernel<2><<<p.B * p.NH, thr, 0, s>>>(p); break;
-    case 3: mlstm_state_finalize_kernel<3><<<p.B * p.NH, thr, 0, s>>>(p); break;
-    case 4: mlstm_state_finalize_kernel<4><<<p.B * p.NH, thr, 0, s>>>(p); break;
+    case 1: return launch_k(mlstm_state_finalize_kernel<1>, dim3(p.B * p.NH), dim3(thr), 0, s, p);
+    case 2: return launch_k(mlstm_state_finalize_kernel<2>, dim3(p.B * p.NH), dim3(thr), 0, s, p);
+    case 3: return launch_k(mlstm_state_finalize_kernel<3>, dim3(p.B * p.NH), dim3(thr), 0, s, p);
+    case 4: return launch_k(mlstm_state_finalize_kernel<4>, dim3(p.B * p.NH), dim3(thr), 0, s, p);
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -592,13 +969,8 @@ cudaError_t launch_state_finalize(StateStepParams p, int num_sms, cudaStream_t s
 
 // kernel 1
 cudaError_t launch_state_step(StateStepParams p, int num_sms, cudaStream_t s) {
-  if (p.rows_split <= 0 || p.cols_per_cta <= 0) {
-    int rs, cols;
-    state_step_auto_tiling(p.B, p.NH, p.DH, num_sms, &rs, &cols);
-    if (p.rows_split <= 0) p.rows_split = rs;
-    if (p.cols_per_cta <= 0) p.cols_per_cta = cols;
-  }
-  if (p.cols_per_cta % 4 || p.DH % p.cols_per_cta || p.cols_per_cta > 256 ||
+  resolve_tiling(p, num_sms);
+  if (p.cols_per_cta % 4 || p.DH % p.cols_per_cta || slab_width(p.DH) % p.cols_per_cta ||
       kThreads % (p.cols_per_cta / 4) || p.DH > 1024 || p.NCH > kMaxNCH || p.rows_split > p.DH)
     return cudaErrorInvalidValue;
   switch (p.T) {
@@ -614,6 +986,8 @@ cudaError_t launch_state_step(StateStepParams p, int num_sms, cudaStream_t s) {
 __global__ void repack_qkv_kernel(const float* __restrict__ qkv, float* __restrict__ qk, float* __restrict__ v,
                                   int M, int inner) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   if (i >= (int64_t)M * inner) return;
   const int64_t m = i / inner;
   const int c = (int)(i - m * inner);
@@ -623,7 +997,7 @@ __global__ void repack_qkv_kernel(const float* __restrict__ qkv, float* __restri
 }
 void launch_repack_qkv(const float* qkv, float* qk, float* v, int M, int inner, cudaStream_t s) {
   const int64_t n = (int64_t)M * inner;
-  repack_qkv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(qkv, qk, v, M, inner);
+  launch_k(repack_qkv_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, qkv, qk, v, M, inner);
 }
 
 }  // namespace xl

@@ -63,6 +63,24 @@ def strip_checkpoint_prefixes(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Te
     return out
 
 
+def slab_width(DH: int) -> int:
+    """Column-slab width of the C layout in HBM (include/xlstm_b200.h, xl_state_layout)."""
+    return 128 if DH % 128 == 0 else DH
+
+
+def c_to_slab(c: torch.Tensor) -> torch.Tensor:
+    """reference layout C[B,NH,DH(dk),DH(dv)] -> slab-major [B,NH,DH/W,DH,W] (contiguous copy)."""
+    B, NH, DH, _ = c.shape
+    W = slab_width(DH)
+    return c.reshape(B, NH, DH, DH // W, W).permute(0, 1, 3, 2, 4).contiguous()
+
+
+def c_from_slab(p: torch.Tensor) -> torch.Tensor:
+    """slab-major [B,NH,CS,DH,W] -> reference layout [B,NH,DH,DH] (copy)."""
+    B, NH, CS, DH, W = p.shape
+    return p.permute(0, 1, 3, 2, 4).reshape(B, NH, DH, CS * W)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
@@ -82,9 +100,14 @@ class StateCache:
         flat = self.buf[off.value // 4: (off.value + size.value) // 4]
         cfg = self.engine.cfg
         NH, DH = cfg.num_heads, cfg.head_dim
-        shape = {L.XL_STATE_C: (self.B, NH, DH, DH), L.XL_STATE_N: (self.B, NH, DH),
+        W = slab_width(DH)
+        shape = {L.XL_STATE_C: (self.B, NH, DH // W, DH, W), L.XL_STATE_N: (self.B, NH, DH),
                  L.XL_STATE_M: (self.B, NH), L.XL_STATE_CONV: (self.B, cfg.conv1d_kernel_size, cfg.inner)}[part]
         return flat.view(*shape)
+
+    def c_logical(self, layer: int) -> torch.Tensor:
+        """C of one block in the reference's [B, NH, DH(dk), DH(dv)] layout (a copy; the cache itself is slab-major)."""
+        return c_from_slab(self.view(layer, L.XL_STATE_C))
 
     def nbytes(self) -> int:
         return self.buf.numel() * 4
@@ -93,7 +116,7 @@ class StateCache:
     def to_past_key_values(self) -> Dict[str, Dict[str, tuple]]:
         out = {}
         for i in range(self.engine.cfg.num_blocks):
-            c = self.view(i, L.XL_STATE_C).clone()
+            c = self.c_logical(i)
             n = self.view(i, L.XL_STATE_N).clone().unsqueeze(-1)
             m = self.view(i, L.XL_STATE_M).clone().view(self.B, -1, 1, 1)
             conv = self.view(i, L.XL_STATE_CONV).clone()
@@ -104,7 +127,7 @@ class StateCache:
         for i in range(self.engine.cfg.num_blocks):
             st = pkv[f"block_{i}"]
             c, n, m = st["mlstm_state"]
-            self.view(i, L.XL_STATE_C).copy_(c.to(self.buf.device, torch.float32))
+            self.view(i, L.XL_STATE_C).copy_(c_to_slab(c.to(self.buf.device, torch.float32)))
             self.view(i, L.XL_STATE_N).copy_(n.to(self.buf.device, torch.float32).reshape(self.B, -1, n.shape[2]))
             self.view(i, L.XL_STATE_M).copy_(m.to(self.buf.device, torch.float32).reshape(self.B, -1))
             self.view(i, L.XL_STATE_CONV).copy_(st["conv_state"][0].to(self.buf.device, torch.float32))
@@ -225,13 +248,18 @@ class XLSTMEngine:
                                              _ptr(h_tokens), _ptr(h_actions), state.B, mode, flags, self._stream()))
 
     def cell_step(self, Cs, n, m, qkv, igate, fgate, outnorm_w, B: int, T: int, rows_split: int = 0,
-                  cols_per_cta: int = 0, want_raw: bool = True):
+                  cols_per_cta: int = 0, want_raw: bool = True, slab: bool = False):
+        """Unit-parity entry point. `Cs` is given and updated in the REFERENCE layout [B,NH,DH,DH] unless
+        `slab=True` (then it already is the library's slab-major layout and no conversion copies are made)."""
         inner = self.cfg.inner
         h_norm = torch.empty(B * T, inner, dtype=torch.float32, device=self.device)
         h_raw = torch.empty_like(h_norm) if want_raw else None
-        L.check(self.lib.xl_mlstm_cell_step(self.handle, _ptr(Cs), _ptr(n), _ptr(m), _ptr(qkv), _ptr(igate),
+        Cp = Cs if slab else c_to_slab(Cs)
+        L.check(self.lib.xl_mlstm_cell_step(self.handle, _ptr(Cp), _ptr(n), _ptr(m), _ptr(qkv), _ptr(igate),
                                             _ptr(fgate), _ptr(outnorm_w), _ptr(h_norm), _ptr(h_raw), B, T,
                                             rows_split, cols_per_cta, self._stream()))
+        if not slab:
+            Cs.copy_(c_from_slab(Cp))
         return h_norm, h_raw
 
     def linear(self, A: torch.Tensor, W_bf16: torch.Tensor, bias=None, residual=None, impl: int = 0):
