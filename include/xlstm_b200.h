@@ -179,6 +179,21 @@ int xl_policy_step_host(xl_handle* h, void* state, const float* h_states, const 
                         const float* h_rewards, int32_t* h_tokens, float* h_actions, int B, int mode,
                         unsigned flags, void* stream);
 
+/* Context prefill of the encoder: x_in fp32 [B, S, d] (already embedded tokens), y_out fp32 [B, S, d] or NULL
+ * (last_hidden_state of every token). Leaves `state` exactly where S calls of xLSTMBlockStack.step would
+ * (src/algos/models/decision_xlstm.py:161-165; this is what the reference's `chunkwise_step` hook :158-159
+ * asks of layers.step with S > 1). Runs layer-major over chunks of tokens: the projections are tcgen05 GEMMs
+ * over all rows of a chunk, the matrix memory stays on chip for the chunk (xl_prefill.cu). Allocates / grows a
+ * private workspace on first use (synchronises the device then); B <= max_batch. */
+int xl_prefill(xl_handle* h, void* state, const float* x_in, float* y_out, int B, int S, unsigned flags, void* stream);
+
+/* Same for the whole policy: Tn timesteps of context per env, states fp32 [B, Tn, state_dim], rtg fp32 [B, Tn],
+ * rewards fp32 [B, Tn] or NULL (= 0). Embeds every timestep into its (s, rtg, r) tokens
+ * (online_decision_transformer_model.py:522-530,588-612) and prefills the 3*Tn tokens; no action outputs
+ * (a context only warms the state: src/callbacks/evaluation.py:213-237 `persist_context`). */
+int xl_policy_prefill(xl_handle* h, void* state, const float* states, const float* rtg, const float* rewards, int B,
+                      int Tn, unsigned flags, void* stream);
+
 /* out[M,N] = A[M,K] @ W[N,K]^T (+ bias[N]) (+ residual[M,N]); A fp32, W bf16, fp32 accumulate.
  * The nn.Linear of proj_up / proj_down / embed_state / action_net. impl: 0 auto, 1 CUDA-core, 2 tcgen05. */
 int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bias, const float* residual,

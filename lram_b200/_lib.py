@@ -101,6 +101,10 @@ def load():
     lib.xl_policy_step.restype = i32
     lib.xl_policy_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, u32, vp]
     lib.xl_policy_step_host.restype = i32
+    lib.xl_prefill.argtypes = [vp, vp, vp, vp, i32, i32, u32, vp]
+    lib.xl_prefill.restype = i32
+    lib.xl_policy_prefill.argtypes = [vp, vp, vp, vp, vp, i32, i32, u32, vp]
+    lib.xl_policy_prefill.restype = i32
     lib.xl_linear.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.xl_linear.restype = i32
     lib.xl_set_option.argtypes = [vp, C.c_char_p, i32]

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -86,6 +87,13 @@ struct xl_handle {
   int gemm_splitk = 0;                 // cluster split-K in the tcgen05 Linear (xl_set_option "gemm_splitk")
   int microbatches = 0;                // 0 = automatic; env micro-batches per fused step ("microbatches")
   int pipeline_order = 1;              // 1 = state-stream kernels of the micro-batches run one after another
+  // context-prefill workspace (lazily allocated by xl_prefill / xl_policy_prefill, grow-only)
+  char* pf_buf = nullptr;
+  int pf_rows = 0;
+  float *pf_x = nullptr, *pf_xn = nullptr, *pf_u = nullptr, *pf_qkv = nullptr, *pf_act = nullptr, *pf_gp = nullptr,
+        *pf_gated = nullptr, *pf_num = nullptr, *pf_qn = nullptr, *pf_f = nullptr, *pf_i = nullptr, *pf_m = nullptr,
+        *pf_semb = nullptr, *pf_spad = nullptr, *pf_sin = nullptr, *pf_rtg = nullptr, *pf_rew = nullptr;
+  __nv_bfloat16 *pf_hi = nullptr, *pf_lo = nullptr;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_state;  // start/stop pairs around state-step launches
   std::vector<cudaEvent_t> prof_step;   // start/stop pairs around policy steps
@@ -502,6 +510,118 @@ int run_policy(xl_handle* h, const StepArgs& a, cudaStream_t s) {
   return XL_OK;
 }
 
+// ---- context prefill ----------------------------------------------------------------------------------
+int ensure_prefill_ws(xl_handle* h, int rows) {
+  if (rows <= h->pf_rows) return XL_OK;
+  const xl_config& c = h->cfg;
+  const size_t d = c.embedding_dim, inner = c.inner_dim, NH = c.num_heads, R = (size_t)rows;
+  const size_t kmax = std::max(std::max(inner, d), (size_t)h->Kpad);
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  const size_t o_x = carve(4 * R * d), o_xn = carve(4 * R * d), o_u = carve(4 * R * 2 * inner);
+  const size_t o_qkv = carve(4 * R * 3 * inner), o_act = carve(4 * R * inner), o_gp = carve(4 * R * 16 * 2 * NH);
+  const size_t o_gated = carve(4 * R * inner), o_num = carve(4 * R * inner), o_qn = carve(4 * R * NH);
+  const size_t o_f = carve(4 * R * NH), o_i = carve(4 * R * NH), o_m = carve(4 * R * NH);
+  const size_t o_semb = carve(4 * R * d), o_spad = carve(4 * R * h->Kpad), o_sin = carve(4 * R * c.state_dim);
+  const size_t o_rtg = carve(4 * R), o_rew = carve(4 * R);
+  const size_t o_hi = carve(2 * R * kmax), o_lo = carve(2 * R * kmax);
+  XL_CUDA(cudaDeviceSynchronize());            // nothing may still be using the old workspace
+  if (h->pf_buf) cudaFree(h->pf_buf);
+  h->pf_buf = nullptr;
+  h->pf_rows = 0;
+  cudaError_t e = cudaMalloc((void**)&h->pf_buf, off);
+  if (e != cudaSuccess) return fail(XL_ERR_CUDA, "cudaMalloc(prefill workspace %zu B) failed: %s", off, cudaGetErrorString(e));
+  char* b = h->pf_buf;
+  h->pf_x = (float*)(b + o_x); h->pf_xn = (float*)(b + o_xn); h->pf_u = (float*)(b + o_u);
+  h->pf_qkv = (float*)(b + o_qkv); h->pf_act = (float*)(b + o_act); h->pf_gp = (float*)(b + o_gp);
+  h->pf_gated = (float*)(b + o_gated); h->pf_num = (float*)(b + o_num); h->pf_qn = (float*)(b + o_qn);
+  h->pf_f = (float*)(b + o_f); h->pf_i = (float*)(b + o_i); h->pf_m = (float*)(b + o_m);
+  h->pf_semb = (float*)(b + o_semb); h->pf_spad = (float*)(b + o_spad); h->pf_sin = (float*)(b + o_sin);
+  h->pf_rtg = (float*)(b + o_rtg); h->pf_rew = (float*)(b + o_rew);
+  h->pf_hi = (__nv_bfloat16*)(b + o_hi); h->pf_lo = (__nv_bfloat16*)(b + o_lo);
+  h->pf_rows = rows;
+  return XL_OK;
+}
+
+Ws prefill_ws(const xl_handle* h) {
+  Ws w;
+  memset(&w, 0, sizeof(w));
+  w.x = h->pf_x; w.xn = h->pf_xn; w.u = h->pf_u; w.qkv = h->pf_qkv; w.act = h->pf_act; w.gate_part = h->pf_gp;
+  w.gated = h->pf_gated; w.s_emb = h->pf_semb; w.states_pad = h->pf_spad;
+  w.a_hi = h->pf_hi; w.a_lo = h->pf_lo;
+  const size_t kmax = std::max(std::max((size_t)h->cfg.inner_dim, (size_t)h->cfg.embedding_dim), (size_t)h->Kpad);
+  w.a_cap = (size_t)h->pf_rows * kmax;
+  w.low_smem = 0;
+  return w;
+}
+
+// tokens per env in one prefill chunk: ~2048 rows per chunk over all envs, a multiple of 12 (whole (s, rtg, r)
+// timesteps and whole 4-token cell stages)
+int prefill_chunk_tokens(int B) {
+  int sc = 2048 / B;
+  if (sc < 48) sc = 48;
+  return sc / 12 * 12;
+}
+
+// The block stack over the chunk held in pf_x [B*Sc, d] (rows [env][token]), in place; state advanced by Sc tokens.
+int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cudaStream_t s) {
+  const xl_config& c = h->cfg;
+  const int d = c.embedding_dim, inner = c.inner_dim, NH = c.num_heads, DH = h->DH;
+  const int M = B * Sc;
+  const StateLayout L = state_layout(h, B);
+  const Ws ws = prefill_ws(h);
+  const int impl = (flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
+  const bool tc_up = impl != 1 && xl::gemm_tc_supported(M, 2 * inner, d) && (size_t)M * d <= ws.a_cap;
+  const bool tc_down = impl != 1 && xl::gemm_tc_supported(M, d, inner) && (size_t)M * inner <= ws.a_cap;
+  for (int i = 0; i < c.num_blocks; ++i) {
+    const BlockWeights& w = h->blocks[i];
+    char* base = (char*)state + (size_t)i * L.layer_bytes;
+    xl::launch_ln_rows(ws.x, d, tc_up ? nullptr : ws.xn, d, (const float*)w.w[XL_W_XLSTM_NORM], nullptr, 1, c.ln_eps,
+                       M, d, tc_up ? ws.a_hi : nullptr, tc_up ? ws.a_lo : nullptr, s);
+    h->launches += 1;
+    int rc = linear(h, ws, ws.xn, w.w[XL_W_PROJ_UP], nullptr, nullptr, ws.u, M, 2 * inner, d, impl, s, tc_up);
+    if (rc) return rc;
+    xl::ConvQkvParams cp;
+    cp.u = ws.u;
+    cp.conv_state = (float*)(base + L.conv_off);
+    cp.conv_w = (const float*)w.w[XL_W_CONV_W];
+    cp.conv_b = (const float*)w.w[XL_W_CONV_B];
+    cp.wq = (const float*)w.w[XL_W_Q_PROJ];
+    cp.wk = (const float*)w.w[XL_W_K_PROJ];
+    cp.wv = (const float*)w.w[XL_W_V_PROJ];
+    cp.wi = (const float*)w.w[XL_W_IGATE_W];
+    cp.wf = (const float*)w.w[XL_W_FGATE_W];
+    cp.qk = ws.qkv;
+    cp.v = ws.qkv + (size_t)2 * M * inner;
+    cp.act = ws.act;
+    cp.gate_part = ws.gate_part;
+    cp.B = B; cp.T = Sc; cp.inner = inner; cp.NH = NH; cp.KS = c.conv_kernel; cp.NCH = h->NCH;
+    if (!xl::launch_conv_qkv_gates_seq(cp, Sc, s))
+      return fail(XL_ERR_UNSUPPORTED, "sequence conv/qkv kernel not instantiated for KS=%d NH=%d", cp.KS, cp.NH);
+    xl::launch_gate_scan_seq(ws.gate_part, (const float*)w.w[XL_W_IGATE_B], (const float*)w.w[XL_W_FGATE_B],
+                             (float*)(base + L.m_off), h->pf_f, h->pf_i, h->pf_m, B, Sc, NH, h->NCH, s);
+    XL_CUDA(xl::launch_cell_seq((float*)(base + L.c_off), (float*)(base + L.n_off), cp.qk, cp.v, h->pf_f, h->pf_i,
+                                h->pf_num, h->pf_qn, B, Sc, NH, DH, inner, s));
+    XL_CUDA(xl::launch_finalize_seq(h->pf_num, h->pf_qn, h->pf_m, (const float*)w.w[XL_W_OUTNORM],
+                                    (const float*)w.w[XL_W_SKIP], ws.act, ws.u, tc_down ? nullptr : ws.gated,
+                                    tc_down ? ws.a_hi : nullptr, tc_down ? ws.a_lo : nullptr, B, Sc, NH, DH, inner,
+                                    c.ln_eps, c.cell_eps, s));
+    h->launches += 5;
+    rc = linear(h, ws, ws.gated, w.w[XL_W_PROJ_DOWN], nullptr, ws.x, ws.x, M, d, inner, impl, s, tc_down);
+    if (rc) return rc;
+  }
+  XL_CUDA(cudaGetLastError());
+  return XL_OK;
+}
+
+bool prefill_fast_path(const xl_handle* h) {
+  return xl::prefill_cell_supported(h->DH) && h->cfg.conv_kernel == 4;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -618,6 +738,7 @@ void xl_destroy(xl_handle* h) {
   for (auto& g : h->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->ws) cudaFree(h->ws);
+  if (h->pf_buf) cudaFree(h->pf_buf);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (int k = 0; k < kMaxMicro - 1; ++k) {
     if (h->side[k]) cudaStreamDestroy(h->side[k]);
@@ -879,6 +1000,121 @@ int xl_policy_step_host(xl_handle* h, void* state, const float* h_states, const 
   XL_CUDA(cudaMemcpyAsync(h_tokens, h->d_tokens, sizeof(int32_t) * (size_t)B * c.act_dim, cudaMemcpyDeviceToHost, s));
   XL_CUDA(cudaMemcpyAsync(h_actions, h->d_actions, sizeof(float) * (size_t)B * c.act_dim, cudaMemcpyDeviceToHost, s));
   XL_CUDA(cudaStreamSynchronize(s));
+  return XL_OK;
+}
+
+int xl_prefill(xl_handle* h, void* state, const float* x_in, float* y_out, int B, int S, unsigned flags, void* stream) {
+  int rc = check_batch(h, B);
+  if (rc) return rc;
+  if (!state || !x_in) return fail(XL_ERR_INVALID_ARG, "null argument");
+  if (S <= 0) return fail(XL_ERR_INVALID_ARG, "S=%d must be positive", S);
+  rc = xl_weights_ready(h);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const xl_config& c = h->cfg;
+  const int d = c.embedding_dim;
+  const float* post_w = (const float*)h->pw[XL_W_POST_NORM - XL_W_POST_NORM];
+  int pos = 0;
+  if (prefill_fast_path(h)) {
+    const int sc_max = prefill_chunk_tokens(B);
+    while (S - pos >= 8) {
+      const int Sc = std::min(sc_max, (S - pos) / 4 * 4);
+      rc = ensure_prefill_ws(h, B * Sc);
+      if (rc) return rc;
+      XL_CUDA(cudaMemcpy2DAsync(h->pf_x, sizeof(float) * (size_t)Sc * d, x_in + (size_t)pos * d,
+                                sizeof(float) * (size_t)S * d, sizeof(float) * (size_t)Sc * d, B,
+                                cudaMemcpyDeviceToDevice, s));
+      rc = prefill_blocks(h, state, B, Sc, flags, s);
+      if (rc) return rc;
+      if (y_out) {
+        xl::launch_ln_rows(h->pf_x, d, h->pf_xn, d, post_w, nullptr, 1, c.ln_eps, B * Sc, d, nullptr, nullptr, s);
+        h->launches += 1;
+        XL_CUDA(cudaMemcpy2DAsync(y_out + (size_t)pos * d, sizeof(float) * (size_t)S * d, h->pf_xn,
+                                  sizeof(float) * (size_t)Sc * d, sizeof(float) * (size_t)Sc * d, B,
+                                  cudaMemcpyDeviceToDevice, s));
+      }
+      pos += Sc;
+    }
+  }
+  // remaining tokens (and shapes the sequence kernels do not cover): fused recurrent steps of <= 4 tokens
+  const Slice sl = make_slice(h, B, 0, B, s);
+  while (pos < S) {
+    const int T = std::min(4, S - pos);
+    XL_CUDA(cudaMemcpy2DAsync(sl.ws.x, sizeof(float) * (size_t)T * d, x_in + (size_t)pos * d,
+                              sizeof(float) * (size_t)S * d, sizeof(float) * (size_t)T * d, B, cudaMemcpyDeviceToDevice, s));
+    rc = run_encoder(h, state, sl, sl.ws.x, sl.ws.hid, T, XL_MODE_FUSED, flags);
+    if (rc) return rc;
+    if (y_out)
+      XL_CUDA(cudaMemcpy2DAsync(y_out + (size_t)pos * d, sizeof(float) * (size_t)S * d, sl.ws.hid,
+                                sizeof(float) * (size_t)T * d, sizeof(float) * (size_t)T * d, B, cudaMemcpyDeviceToDevice, s));
+    pos += T;
+  }
+  return XL_OK;
+}
+
+int xl_policy_prefill(xl_handle* h, void* state, const float* states, const float* rtg, const float* rewards, int B,
+                      int Tn, unsigned flags, void* stream) {
+  int rc = check_batch(h, B);
+  if (rc) return rc;
+  if (!state || !states || !rtg) return fail(XL_ERR_INVALID_ARG, "null argument");
+  if (Tn <= 0) return fail(XL_ERR_INVALID_ARG, "Tn=%d must be positive", Tn);
+  rc = xl_weights_ready(h);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const xl_config& c = h->cfg;
+  const int d = c.embedding_dim, sd = c.state_dim, T = c.tokens_per_step;
+  const int impl = (flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
+  auto PW = [&](int id) { return h->pw[id - XL_W_POST_NORM]; };
+  int pos = 0;   // timesteps done
+  if (prefill_fast_path(h)) {
+    const int tc_max = prefill_chunk_tokens(B) / T;
+    while (Tn - pos >= 4) {
+      const int Tc = std::min(tc_max, (Tn - pos) / 4 * 4);       // 4 timesteps = 12 tokens = 3 cell stages
+      const int rows = B * Tc;
+      rc = ensure_prefill_ws(h, rows * T);
+      if (rc) return rc;
+      const Ws ws = prefill_ws(h);
+      // gather the chunk's timesteps of every env: [B, Tc, sd], [B, Tc]
+      XL_CUDA(cudaMemcpy2DAsync(h->pf_sin, sizeof(float) * (size_t)Tc * sd, states + (size_t)pos * sd,
+                                sizeof(float) * (size_t)Tn * sd, sizeof(float) * (size_t)Tc * sd, B,
+                                cudaMemcpyDeviceToDevice, s));
+      XL_CUDA(cudaMemcpy2DAsync(h->pf_rtg, sizeof(float) * (size_t)Tc, rtg + pos, sizeof(float) * (size_t)Tn,
+                                sizeof(float) * (size_t)Tc, B, cudaMemcpyDeviceToDevice, s));
+      if (rewards)
+        XL_CUDA(cudaMemcpy2DAsync(h->pf_rew, sizeof(float) * (size_t)Tc, rewards + pos, sizeof(float) * (size_t)Tn,
+                                  sizeof(float) * (size_t)Tc, B, cudaMemcpyDeviceToDevice, s));
+      // embed: rows (env, timestep) -> tokens (env, timestep, {s, rtg, r}) == the env's sequence order
+      xl::launch_pad_rows(h->pf_sin, sd, ws.states_pad, h->Kpad, rows, s);
+      h->launches += 1;
+      rc = linear(h, ws, ws.states_pad, PW(XL_W_EMBED_STATE_W), (const float*)PW(XL_W_EMBED_STATE_B), nullptr, ws.s_emb,
+                  rows, d, h->Kpad, impl, s);
+      if (rc) return rc;
+      xl::launch_embed_tokens(ws.s_emb, h->pf_rtg, rewards ? h->pf_rew : nullptr, (const float*)PW(XL_W_EMBED_RETURN_W),
+                              (const float*)PW(XL_W_EMBED_RETURN_B), (const float*)PW(XL_W_EMBED_REWARD_W),
+                              (const float*)PW(XL_W_EMBED_REWARD_B), (const float*)PW(XL_W_EMBED_LN_W),
+                              (const float*)PW(XL_W_EMBED_LN_B), c.embed_ln_eps, ws.x, rows, d, s);
+      h->launches += 1;
+      rc = prefill_blocks(h, state, B, Tc * T, flags, s);
+      if (rc) return rc;
+      pos += Tc;
+    }
+  }
+  // remaining timesteps: ordinary fused policy steps, outputs discarded
+  for (; pos < Tn; ++pos) {
+    XL_CUDA(cudaMemcpy2DAsync(h->d_states, sizeof(float) * (size_t)sd, states + (size_t)pos * sd,
+                              sizeof(float) * (size_t)Tn * sd, sizeof(float) * (size_t)sd, B, cudaMemcpyDeviceToDevice, s));
+    XL_CUDA(cudaMemcpy2DAsync(h->d_rtg, sizeof(float), rtg + pos, sizeof(float) * (size_t)Tn, sizeof(float), B,
+                              cudaMemcpyDeviceToDevice, s));
+    if (rewards)
+      XL_CUDA(cudaMemcpy2DAsync(h->d_rew, sizeof(float), rewards + pos, sizeof(float) * (size_t)Tn, sizeof(float), B,
+                                cudaMemcpyDeviceToDevice, s));
+    StepArgs a;
+    a.state = state; a.states = h->d_states; a.rtg = h->d_rtg; a.rewards = rewards ? h->d_rew : nullptr;
+    a.tokens = h->d_tokens; a.actions = h->d_actions; a.logits = nullptr; a.hidden = nullptr;
+    a.B = B; a.mode = XL_MODE_FUSED; a.flags = flags & ~(unsigned)XL_FLAG_GRAPH;
+    rc = run_policy(h, a, s);
+    if (rc) return rc;
+  }
   return XL_OK;
 }
 

@@ -73,7 +73,11 @@ class FusedXLSTMEncoder:
         if cache.B != B:
             raise ValueError(f"past_key_values holds {cache.B} envs, inputs have batch {B}")
         x = inputs_embeds.to(self.engine.device, torch.float32)
-        hs = self.engine.encoder_step(cache, x, mode=self.mode)
+        if x.shape[1] > 4:
+            # a whole context at once: what `chunkwise_step` (decision_xlstm.py:158-159) asks of layers.step
+            hs = self.engine.prefill(cache, x)
+        else:
+            hs = self.engine.encoder_step(cache, x, mode=self.mode)
         return _Output(last_hidden_state=hs, past_key_values=cache, hidden_states=None, attentions=None)
 
     __call__ = forward

@@ -214,6 +214,31 @@ class XLSTMEngine:
                                          mode, flags, self._stream()))
         return out
 
+    def prefill(self, state: StateCache, x: torch.Tensor, want_hidden: bool = True, flags: int = 0):
+        """Context prefill of the encoder: x [B,S,d] fp32 cuda (embedded tokens) -> last_hidden_state [B,S,d]
+        (or None); state advanced by S tokens, exactly as S recurrent steps would (xl_prefill)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[0] == state.B
+        x = x.contiguous()
+        out = torch.empty_like(x) if want_hidden else None
+        L.check(self.lib.xl_prefill(self.handle, _ptr(state.buf), _ptr(x), _ptr(out), x.shape[0], x.shape[1], flags,
+                                    self._stream()))
+        return out
+
+    def policy_prefill(self, state: StateCache, states: torch.Tensor, rtg: torch.Tensor,
+                       rewards: Optional[torch.Tensor] = None, flags: int = 0):
+        """Warm the recurrent state with Tn timesteps of context per env: states [B,Tn,state_dim], rtg [B,Tn],
+        rewards [B,Tn] or None (= the 0 placeholder the rollout feeds). No action outputs (xl_policy_prefill)."""
+        cfg = self.cfg
+        B, Tn = state.B, states.shape[1]
+        assert states.is_cuda and states.dtype == torch.float32 and tuple(states.shape) == (B, Tn, cfg.state_dim)
+        assert rtg.is_cuda and rtg.dtype == torch.float32 and rtg.numel() == B * Tn
+        states, rtg = states.contiguous(), rtg.contiguous()
+        if rewards is not None:
+            rewards = rewards.to(self.device, torch.float32).contiguous()
+            assert rewards.numel() == B * Tn
+        L.check(self.lib.xl_policy_prefill(self.handle, _ptr(state.buf), _ptr(states), _ptr(rtg), _ptr(rewards), B, Tn,
+                                           flags, self._stream()))
+
     def policy_step(self, state: StateCache, states: torch.Tensor, rtg: torch.Tensor,
                     rewards: Optional[torch.Tensor] = None, mode: int = L.XL_MODE_FUSED, flags: int = 0,
                     want_logits: bool = False, want_hidden: bool = False, out: Optional[dict] = None):

@@ -315,6 +315,71 @@ def test_microbatch_pipeline_equals_single_stream(name, B):
     eng.close()
 
 
+# ------------------------------------------------------------------------------------------------------------
+# context prefill (SURVEY §8 a11 / BASELINE configs[3])
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,B,S", [("toy128", 3, 50), ("toy128", 2, 7), ("16M", 2, 36), ("toy", 2, 21),
+                                      ("48M", 1, 24)])
+def test_prefill_vs_oracle_steps(name, B, S):
+    """xl_prefill over S tokens == S recurrent oracle steps: hidden states of every token and the state left."""
+    from lram_b200.decision_xlstm import FusedXLSTMEncoder
+    from oracle import xlstm_oracle as O
+    cfg, sd, eng = _engine(name, B)
+    ora = O.OracleEncoder(cfg, sd)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, S, cfg.d, generator=g)
+    # start from a non-trivial state: 2 tokens through the step path on both sides
+    x0 = torch.randn(B, 2, cfg.d, generator=g)
+    enc = FusedXLSTMEncoder(eng, mode=L.XL_MODE_FUSED)
+    out0 = enc(inputs_embeds=x0.cuda(), past_key_values=None, use_cache=True)
+    cache = out0["past_key_values"]
+    _, pkv_o = ora.forward_cached(x0, None)
+    out = enc(inputs_embeds=x.cuda(), past_key_values=cache, use_cache=True)       # S > 4 -> prefill path
+    refs = []
+    for t in range(S):
+        r, pkv_o = ora.forward_cached(x[:, t:t + 1], pkv_o)
+        refs.append(r)
+    ref = torch.cat(refs, dim=1)
+    assert _rel(out["last_hidden_state"].cpu(), ref) < REL_TOL
+    exp = cache.to_past_key_values()
+    for i in range(cfg.num_blocks):
+        c, n, m = pkv_o[f"block_{i}"]["mlstm_state"]
+        ce, ne, me = exp[f"block_{i}"]["mlstm_state"]
+        assert _rel(ce.cpu(), c) < REL_TOL and _rel(ne.cpu(), n) < REL_TOL, f"block {i}"
+        assert (me.cpu() - m).abs().max() < 1e-4
+        assert _rel(exp[f"block_{i}"]["conv_state"][0].cpu(), pkv_o[f"block_{i}"]["conv_state"][0]) < 1e-5
+    # and the rollout continues from the prefilled state exactly like from the stepped one
+    x1 = torch.randn(B, 3, cfg.d, generator=g)
+    o1 = enc(inputs_embeds=x1.cuda(), past_key_values=cache, use_cache=True)
+    r1, _ = ora.forward_cached(x1, pkv_o)
+    assert _rel(o1["last_hidden_state"].cpu(), r1) < REL_TOL
+    eng.close()
+
+
+def test_policy_prefill_equals_stepping():
+    """xl_policy_prefill(context of Tn timesteps) then a rollout == stepping through the context: same action
+    tokens afterwards (needs no oracle: both sides are this library; the step path is oracle-checked above)."""
+    cfg, sd, eng = _engine("16M", 3)
+    Tn, Tr = 23, 4
+    states, rtg, _ = make_stream(cfg, range(3), Tn + Tr, domains="mixed")
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    stepped = eng.new_state(3)
+    for t in range(Tn):
+        eng.policy_step(stepped, dev(states[t]), dev(rtg[t]))
+    pre = eng.new_state(3)
+    eng.policy_prefill(pre, dev(states[:Tn].transpose(1, 0, 2)), dev(rtg[:Tn].T))
+    for i in range(cfg.num_blocks):
+        assert _rel(pre.c_logical(i).cpu(), stepped.c_logical(i).cpu()) < 1e-4, f"block {i}"
+        assert (pre.view(i, L.XL_STATE_M) - stepped.view(i, L.XL_STATE_M)).abs().max().item() < 1e-4
+    for t in range(Tn, Tn + Tr):
+        a = eng.policy_step(stepped, dev(states[t]), dev(rtg[t]), want_hidden=True)
+        b = eng.policy_step(pre, dev(states[t]), dev(rtg[t]), want_hidden=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a["action_tokens"].cpu(), b["action_tokens"].cpu())
+        assert _rel(b["last_hidden_state"].cpu(), a["last_hidden_state"].cpu()) < 1e-4
+    eng.close()
+
+
 def test_per_env_reset_mask():
     """reset of a subset of envs == those envs starting from past_key_values=None; others untouched."""
     cfg, sd, eng = _engine("toy128", 4)
