@@ -559,12 +559,12 @@ Ws prefill_ws(const xl_handle* h) {
   return w;
 }
 
-// tokens per env in one prefill chunk: ~2048 rows per chunk over all envs, a multiple of 12 (whole (s, rtg, r)
-// timesteps and whole 4-token cell stages)
+// tokens per env in one prefill chunk: ~2048 rows per chunk over all envs, a multiple of 24 (whole (s, rtg, r)
+// timesteps and whole 8-token cell stages)
 int prefill_chunk_tokens(int B) {
   int sc = 2048 / B;
   if (sc < 48) sc = 48;
-  return sc / 12 * 12;
+  return sc / 24 * 24;
 }
 
 // The block stack over the chunk held in pf_x [B*Sc, d] (rows [env][token]), in place; state advanced by Sc tokens.
@@ -604,8 +604,8 @@ int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cud
       return fail(XL_ERR_UNSUPPORTED, "sequence conv/qkv kernel not instantiated for KS=%d NH=%d", cp.KS, cp.NH);
     xl::launch_gate_scan_seq(ws.gate_part, (const float*)w.w[XL_W_IGATE_B], (const float*)w.w[XL_W_FGATE_B],
                              (float*)(base + L.m_off), h->pf_f, h->pf_i, h->pf_m, B, Sc, NH, h->NCH, s);
-    XL_CUDA(xl::launch_cell_seq((float*)(base + L.c_off), (float*)(base + L.n_off), cp.qk, cp.v, h->pf_f, h->pf_i,
-                                h->pf_num, h->pf_qn, B, Sc, NH, DH, inner, s));
+    XL_CUDA(xl::launch_cell_seq((float*)(base + L.c_off), (float*)(base + L.n_off), cp.qk, cp.qk + (size_t)M * inner,
+                                cp.v, h->pf_f, h->pf_i, h->pf_num, h->pf_qn, B, Sc, NH, DH, inner, s));
     XL_CUDA(xl::launch_finalize_seq(h->pf_num, h->pf_qn, h->pf_m, (const float*)w.w[XL_W_OUTNORM],
                                     (const float*)w.w[XL_W_SKIP], ws.act, ws.u, tc_down ? nullptr : ws.gated,
                                     tc_down ? ws.a_hi : nullptr, tc_down ? ws.a_lo : nullptr, B, Sc, NH, DH, inner,
@@ -1018,7 +1018,7 @@ int xl_prefill(xl_handle* h, void* state, const float* x_in, float* y_out, int B
   if (prefill_fast_path(h)) {
     const int sc_max = prefill_chunk_tokens(B);
     while (S - pos >= 8) {
-      const int Sc = std::min(sc_max, (S - pos) / 4 * 4);
+      const int Sc = std::min(sc_max, (S - pos) / 8 * 8);
       rc = ensure_prefill_ws(h, B * Sc);
       if (rc) return rc;
       XL_CUDA(cudaMemcpy2DAsync(h->pf_x, sizeof(float) * (size_t)Sc * d, x_in + (size_t)pos * d,
@@ -1068,8 +1068,8 @@ int xl_policy_prefill(xl_handle* h, void* state, const float* states, const floa
   int pos = 0;   // timesteps done
   if (prefill_fast_path(h)) {
     const int tc_max = prefill_chunk_tokens(B) / T;
-    while (Tn - pos >= 4) {
-      const int Tc = std::min(tc_max, (Tn - pos) / 4 * 4);       // 4 timesteps = 12 tokens = 3 cell stages
+    while (Tn - pos >= 8) {
+      const int Tc = std::min(tc_max, (Tn - pos) / 8 * 8);       // 8 timesteps = 24 tokens = 3 cell stages
       const int rows = B * Tc;
       rc = ensure_prefill_ws(h, rows * T);
       if (rc) return rc;

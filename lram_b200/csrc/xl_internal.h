@@ -101,16 +101,18 @@ void launch_repack_qkv(const float* qkv, float* qk, float* v, int M, int inner, 
 
 // ---- xl_prefill.cu -------------------------------------------------------------------------------
 // Sequence (context prefill) versions of the per-block kernels; rows are ordered [env][token] with S tokens
-// per env. S % 4 == 0, S >= KS.
+// per env. S % 8 == 0.
 bool prefill_cell_supported(int DH);
-// conv + SiLU + q/k/v + gate partials over the chunk, then conv_state <- last KS inputs. false: no instantiation
+// conv + SiLU + q/k/v + gate partials over the chunk, then conv_state <- last KS inputs. p.qk receives the q
+// plane [M, inner] followed by the k plane [M, inner] (M = B*S). false: no instantiation
 bool launch_conv_qkv_gates_seq(const ConvQkvParams& p, int S, cudaStream_t s);
 // m/f/i per token ([B*NH][S] each) from the gate partials; m_state [B*NH] in/out
 void launch_gate_scan_seq(const float* gate_part, const float* igate_b, const float* fgate_b, float* m_state,
                           float* fseq, float* iseq, float* mseq, int B, int S, int NH, int NCH, cudaStream_t s);
 // C / n advanced over the S tokens on chip; num [B*S, inner] = q^T C, qn [B*S, NH] = q.n per token
-cudaError_t launch_cell_seq(float* C, float* n, const float* qk, const float* v, const float* fseq, const float* iseq,
-                            float* num, float* qn, int B, int S, int NH, int DH, int inner, cudaStream_t s);
+cudaError_t launch_cell_seq(float* C, float* n, const float* q, const float* k, const float* v, const float* fseq,
+                            const float* iseq, float* num, float* qn, int B, int S, int NH, int DH, int inner,
+                            cudaStream_t s);
 cudaError_t launch_finalize_seq(const float* num, const float* qn, const float* mseq, const float* outnorm_w,
                                 const float* skip, const float* act, const float* u, float* out, void* out_hi,
                                 void* out_lo, int B, int S, int NH, int DH, int inner, float ln_eps, float cell_eps,

@@ -150,9 +150,9 @@ __global__ void __launch_bounds__(128, 2) conv_qkv_gates_seq_kernel(ConvQkvParam
             }
             q[o] = sq; k[o] = sk; v[o] = sv;
           }
-          float* qk = p.qk + (row * inner + c) * 2;
-          *reinterpret_cast<float4*>(qk) = make_float4(q[0], k[0], q[1], k[1]);
-          *reinterpret_cast<float4*>(qk + 4) = make_float4(q[2], k[2], q[3], k[3]);
+          // prefill layout: q plane then k plane ([M, inner] each) instead of the step path's interleaved pairs
+          *reinterpret_cast<float4*>(p.qk + row * inner + c) = make_float4(q[0], q[1], q[2], q[3]);
+          *reinterpret_cast<float4*>(p.qk + ((int64_t)p.B * S + row) * inner + c) = make_float4(k[0], k[1], k[2], k[3]);
           *reinterpret_cast<float4*>(p.v + row * inner + c) = make_float4(v[0], v[1], v[2], v[3]);
           *reinterpret_cast<float4*>(p.act + row * inner + c) = make_float4(a[0], a[1], a[2], a[3]);
 #pragma unroll
@@ -224,105 +224,135 @@ __global__ void __launch_bounds__(256) conv_state_seq_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------
 // Gate scan: per (env, head) the stabiliser recurrence over the chunk's tokens,
 //   lf = logsigmoid(f~);  m' = max(lf + m, i~);  f = exp(lf + m - m');  i = exp(i~ - m')
-// with exactly the arithmetic of compute_gates() (xl_state_step.cu). One warp per (env, head): 32 tokens'
-// pre-activations are summed / log-sigmoided in parallel, the max-plus chain runs over warp shuffles, f and i
-// are again computed in parallel. Outputs are [B*NH][S] so that a (env, head)'s tokens are contiguous.
+// with exactly the arithmetic of compute_gates() (xl_state_step.cu). One CTA per (env, head): the
+// pre-activations of 512 tokens are summed / log-sigmoided in parallel, one warp runs the max-plus chain over
+// shared memory, f and i are again computed in parallel. Outputs are [B*NH][S]: a head's tokens are contiguous.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) gate_scan_seq_kernel(const float* __restrict__ gate_part,
                                                             const float* __restrict__ igate_b,
                                                             const float* __restrict__ fgate_b, float* __restrict__ m_state,
                                                             float* __restrict__ fseq, float* __restrict__ iseq,
                                                             float* __restrict__ mseq, int B, int S, int NH, int NCH) {
+  constexpr int kSuper = 512;                    // tokens per super-chunk (4 per thread)
+  __shared__ float s_ig[kSuper + 32], s_lf[kSuper + 32], s_mp[kSuper], s_mn[kSuper];
   pdl_wait();
   pdl_trigger();
-  const int bh = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (bh >= B * NH) return;
+  const int bh = blockIdx.x;
   const int b = bh / NH, hd = bh - b * NH;
-  float m = m_state[bh];
+  const int tid = threadIdx.x, lane = tid & 31;
+  float m = m_state[bh];                         // carried by warp 0
   const float bi = igate_b ? igate_b[hd] : 0.f, bf = fgate_b ? fgate_b[hd] : 0.f;
-  for (int s0 = 0; s0 < S; s0 += 32) {
-    const int s = s0 + lane;
-    float ig = -INFINITY, lf = 0.f;
-    if (s < S) {
-      const float* gp = gate_part + ((int64_t)b * S + s) * NCH * 2 * NH + hd;
+  for (int s0 = 0; s0 < S; s0 += kSuper) {
+    const int cnt = min(kSuper, S - s0);
+    // (A) pre-activations of all tokens of the super-chunk, in parallel
+    for (int u = tid; u < cnt; u += 128) {
+      const float* gp = gate_part + ((int64_t)b * S + s0 + u) * NCH * 2 * NH + hd;
       float si = 0.f, sf = 0.f;
-      for (int c = 0; c < NCH; ++c) {      // fixed order, as compute_gates()
+      for (int c = 0; c < NCH; ++c) {            // fixed order, as compute_gates()
         si += gp[c * 2 * NH];
         sf += gp[c * 2 * NH + NH];
       }
-      ig = si + bi;
-      lf = log_sigmoid(sf + bf);
+      s_ig[u] = si + bi;
+      s_lf[u] = log_sigmoid(sf + bf);
     }
-    float mprev_mine = 0.f, mnew_mine = 0.f;
-    const int cnt = min(32, S - s0);
-    for (int jj = 0; jj < cnt; ++jj) {
-      const float lfj = __shfl_sync(0xffffffffu, lf, jj);
-      const float igj = __shfl_sync(0xffffffffu, ig, jj);
-      const float mn = fmaxf(lfj + m, igj);
-      if (jj == lane) { mprev_mine = m; mnew_mine = mn; }
-      m = mn;
+    __syncthreads();
+    // (B) the max-plus chain m' = max(lf + m, i~): warp 0, every lane runs it on broadcast values (the loads do
+    //     not depend on the chain, so add + max are the critical path)
+    if (tid < 32) {
+      for (int g0 = 0; g0 < cnt; g0 += 32) {
+        float lfv[32], igv[32];
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {        // broadcast loads, all issued before the chain starts
+          lfv[jj] = s_lf[g0 + jj];
+          igv[jj] = s_ig[g0 + jj];
+        }
+        float mp_mine = 0.f, mn_mine = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          if (g0 + jj < cnt) {                   // warp-uniform
+            const float mn = fmaxf(lfv[jj] + m, igv[jj]);
+            if (jj == lane) { mp_mine = m; mn_mine = mn; }
+            m = mn;
+          }
+        }
+        if (g0 + lane < cnt) { s_mp[g0 + lane] = mp_mine; s_mn[g0 + lane] = mn_mine; }
+      }
     }
-    if (s < S) {
-      const int64_t o = (int64_t)bh * S + s;
-      fseq[o] = expf(lf + mprev_mine - mnew_mine);
-      iseq[o] = expf(ig - mnew_mine);
-      mseq[o] = mnew_mine;
+    __syncthreads();
+    // (C) f, i of all tokens, in parallel
+    for (int u = tid; u < cnt; u += 128) {
+      const float mp = s_mp[u], mn = s_mn[u];
+      const int64_t o = (int64_t)bh * S + s0 + u;
+      fseq[o] = expf(s_lf[u] + mp - mn);
+      iseq[o] = expf(s_ig[u] - mn);
+      mseq[o] = mn;
     }
+    __syncthreads();
   }
-  if (lane == 0) m_state[bh] = m;
+  if (tid == 0) m_state[bh] = m;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sequence cell: CTA = (env*head, 16-column slab of C, or the extra "n slab"); C slab [DH x 16] lives in
-// registers for the whole chunk. 8 consumer warps: thread = (row lane rl in 0..63, column group cg in 0..3),
-// rows rl + 64 r. A producer warp streams the chunk's tokens through a 3-deep ring of 4-token stages
-// ((q,k) pairs of the whole head, the slab's v, f and i) with bulk copies + mbarriers.
+// Sequence cell: CTA = (env*head, w-column slab of C, or the extra "n slab"); the C slab [DH x w] lives in
+// registers for the whole chunk. w = DH/32 for the shipped presets, so that one env is 4 heads x 32 slabs + 4
+// n slabs = 132 CTAs: one CTA per SM, one wave, and 16 consumer warps keep the fp32 pipe busy on their own.
+// Thread = (row lane rl, column group cg in 0..3): rows rl + RL r (r < R), columns CPT cg .. CPT cg + CPT - 1
+// (CPT = w / 4). A warp holds 8 row lanes x 4 column groups, so q/k shared loads are 8-address broadcasts and the
+// row reduction needs 3 shuffle steps. A producer warp streams the chunk's tokens through a 3-deep ring of
+// 8-token stages (q and k of the whole head, the slab's v, f and i) with bulk copies + mbarriers.
+// The fp32 pipe is the bound (3-register FFMA issues every 2nd cycle per SM sub-partition), so the per-element
+// work per token is cut from 3 to 2 operations by deferring the forget gate inside a stage:
+//   with F_t = f_1 ... f_t (stage-local), c^ = c / F_t obeys  c^ <- c^ + k (v i / F_t),  num_t = F_t (q . c^),
+//   and c = F_8 c^ once per stage. When F_8 is too small for that to be safe (a forget gate near 0, i.e. an
+//   input-gate spike) the stage runs the plain recurrence  c <- f c + k v i  instead (CTA-uniform branch).
 // ------------------------------------------------------------------------------------------------
-constexpr int kSlabW = 16;
-constexpr int kTB = 4;          // tokens per stage
+constexpr int kTB = 8;          // tokens per stage
 constexpr int kStages = 3;
-constexpr int kConsumers = 256;
-constexpr int kBlock = kConsumers + 32;
+constexpr float kMinDecay = 1e-12f;
 
 struct CellSeqParams {
   float* C;               // [B, NH, DH/Wc, DH, Wc] slab-major state
   float* n;               // [B, NH, DH]
-  const float* qk;        // [B*S, NH, DH, 2]
+  const float* q;         // [B*S, inner]   (prefill layout: separate q / k planes)
+  const float* k;         // [B*S, inner]
   const float* v;         // [B*S, inner]
   const float* fseq;      // [B*NH, S]
   const float* iseq;      // [B*NH, S]
   float* num;             // [B*S, inner]   q^T C per token (un-normalised)
   float* qn;              // [B*S, NH]      q . n per token
   int B, S, NH, DH, inner;
+  int nw;                 // consumer warps (row lanes RL = 8 * nw, R = DH / RL)
 };
 
-__host__ __device__ inline int cell_stage_floats(int DH) { return kTB * DH * 2 + kTB * kSlabW + 2 * kTB; }
+__host__ __device__ inline int cell_stage_floats(int DH, int w) { return kTB * (2 * DH + w + 2); }
 
-template <int R>
-__global__ void __launch_bounds__(kBlock, (R <= 8 ? 2 : 1)) mlstm_cell_seq_kernel(CellSeqParams p) {
+template <int R, int CPT, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) mlstm_cell_seq_kernel(CellSeqParams p) {
+  constexpr int W = 4 * CPT;
+  constexpr int RL = 8 * NW;                                    // row lanes
+  constexpr int DH = RL * R;                                    // compile-time: shared-memory offsets are immediates
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[2 * kStages];
-  const int DH = p.DH, NH = p.NH, S = p.S;
-  const int nsl = DH / kSlabW;
+  const int NH = p.NH, S = p.S;
+  constexpr int nsl = DH / W;
   const int bh = blockIdx.x / (nsl + 1);
   const int slab = blockIdx.x - bh * (nsl + 1);
   const bool n_slab = slab == nsl;
   const int b = bh / NH, hd = bh - b * NH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int sfl = cell_stage_floats(DH);
+  constexpr int sfl = kTB * (2 * DH + W + 2);
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   float* stage0 = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)));
-  float* red = stage0 + (size_t)kStages * sfl;                  // 2 x [8 warps][kTB][16]
+  float* red = stage0 + (size_t)kStages * sfl;                  // 2 x [NW][kTB][W]
   const uint32_t bar0 = smem_u32(s_bar);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
-  const int nbatch = (S + kTB - 1) / kTB;                       // S % kTB == 0 (host-checked)
+  const int nbatch = S / kTB;                                   // S % kTB == 0 (host-checked)
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), kConsumers / 32);
+      mbar_init(empty_bar(s), NW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -330,27 +360,28 @@ __global__ void __launch_bounds__(kBlock, (R <= 8 ? 2 : 1)) mlstm_cell_seq_kerne
   pdl_wait();
   pdl_trigger();
 
-  if (warp == kConsumers / 32) {
+  if (warp == NW) {
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
       for (int bt = 0; bt < nbatch; ++bt) {
         mbar_wait(empty_bar(s), ph ^ 1);
         float* st = stage0 + (size_t)s * sfl;
-        const uint32_t bytes = (uint32_t)(kTB * DH * 8 + (n_slab ? 0 : kTB * kSlabW * 4) + 2 * kTB * 4);
+        const uint32_t bytes = (uint32_t)(kTB * DH * 8 + (n_slab ? 0 : kTB * W * 4) + 2 * kTB * 4);
         mbar_expect_tx(full_bar(s), bytes);
         const int64_t row0 = (int64_t)b * S + (int64_t)bt * kTB;
 #pragma unroll
         for (int t = 0; t < kTB; ++t) {
-          bulk_copy_g2s(smem_u32(st + t * DH * 2), p.qk + (((row0 + t) * NH + hd) * DH) * 2, (uint32_t)(DH * 8),
+          bulk_copy_g2s(smem_u32(st + t * DH), p.q + (row0 + t) * p.inner + hd * DH, (uint32_t)(DH * 4), full_bar(s));
+          bulk_copy_g2s(smem_u32(st + (kTB + t) * DH), p.k + (row0 + t) * p.inner + hd * DH, (uint32_t)(DH * 4),
                         full_bar(s));
           if (!n_slab)
-            bulk_copy_g2s(smem_u32(st + kTB * DH * 2 + t * kSlabW),
-                          p.v + (row0 + t) * p.inner + hd * DH + slab * kSlabW, (uint32_t)(kSlabW * 4), full_bar(s));
+            bulk_copy_g2s(smem_u32(st + kTB * DH * 2 + t * W), p.v + (row0 + t) * p.inner + hd * DH + slab * W,
+                          (uint32_t)(W * 4), full_bar(s));
         }
-        bulk_copy_g2s(smem_u32(st + kTB * DH * 2 + kTB * kSlabW), p.fseq + (int64_t)bh * S + (int64_t)bt * kTB,
+        bulk_copy_g2s(smem_u32(st + kTB * (2 * DH + W)), p.fseq + (int64_t)bh * S + (int64_t)bt * kTB,
                       (uint32_t)(kTB * 4), full_bar(s));
-        bulk_copy_g2s(smem_u32(st + kTB * DH * 2 + kTB * kSlabW + kTB), p.iseq + (int64_t)bh * S + (int64_t)bt * kTB,
+        bulk_copy_g2s(smem_u32(st + kTB * (2 * DH + W) + kTB), p.iseq + (int64_t)bh * S + (int64_t)bt * kTB,
                       (uint32_t)(kTB * 4), full_bar(s));
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
@@ -359,112 +390,144 @@ __global__ void __launch_bounds__(kBlock, (R <= 8 ? 2 : 1)) mlstm_cell_seq_kerne
   }
 
   // ===== consumers =====
-  const int cg = lane & 3;                      // column group: columns 4 cg .. 4 cg + 3 of the slab
-  const int rl = (warp << 3) + (lane >> 2);     // row lane 0..63
-  const int wc = (DH % 128 == 0) ? 128 : DH;    // slab width of the state layout in HBM
-  const int CSl = DH / wc;
+  const int cg = lane & 3;                      // columns CPT cg .. CPT cg + CPT - 1 of the slab
+  const int rl = (warp << 3) + (lane >> 2);     // row lane 0 .. RL - 1
+  constexpr int wc = (DH % 128 == 0) ? 128 : DH;    // slab width of the state layout in HBM
+  constexpr int CSl = DH / wc;
   const float kscale = rsqrtf((float)DH);
-  float c[R][4];
-  // load the slab (or n in column 0 of the n slab)
-  if (!n_slab) {
-    const int col0 = slab * kSlabW + 4 * cg;
-    const int hs = col0 / wc, cin = col0 - hs * wc;
-    const float* base = p.C + ((int64_t)(bh * CSl + hs) * DH) * wc + cin;
+  // C[bh][row][col] of the slab-major layout
+  auto c_ptr = [&](int row, int col) {
+    const int hs = col / wc;
+    return p.C + ((int64_t)(bh * CSl + hs) * DH + row) * wc + (col - hs * wc);
+  };
+  float c[R][CPT];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float4 v4 = *reinterpret_cast<const float4*>(base + (int64_t)(rl + 64 * r) * wc);
-      c[r][0] = v4.x; c[r][1] = v4.y; c[r][2] = v4.z; c[r][3] = v4.w;
-    }
-  } else {
+  for (int r = 0; r < R; ++r) {
+    const int row = rl + RL * r;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      c[r][0] = (cg == 0) ? p.n[(int64_t)bh * DH + rl + 64 * r] : 0.f;
-      c[r][1] = c[r][2] = c[r][3] = 0.f;
+    for (int j = 0; j < CPT; ++j) {
+      if (!n_slab) c[r][j] = *c_ptr(row, slab * W + CPT * cg + j);
+      else c[r][j] = (cg == 0 && j == 0) ? p.n[(int64_t)bh * DH + row] : 0.f;   // the n slab: n in column 0
     }
   }
   int s = 0;
   uint32_t ph = 0;
   for (int bt = 0; bt < nbatch; ++bt) {
     const float* st = stage0 + (size_t)s * sfl;
-    const float* sqk = st;
-    const float* sv = st + kTB * DH * 2;
-    const float* sf = sv + kTB * kSlabW;
+    const float* sq = st + rl;
+    const float* sk = st + kTB * DH + rl;
+    const float* sv = st + kTB * DH * 2 + CPT * cg;
+    const float* sf = st + kTB * (2 * DH + W);
     const float* si = sf + kTB;
     mbar_wait(full_bar(s), ph);
-    float acc[kTB][4];
+    float F[kTB];                               // stage-local cumulative decay
+    {
+      float a = 1.f;
 #pragma unroll
-    for (int t = 0; t < kTB; ++t) {
-      const float f = sf[t];
-      const float it = si[t] * kscale;
-      float vi[4];
-      if (!n_slab) {
-        const float4 v4 = *reinterpret_cast<const float4*>(sv + t * kSlabW + 4 * cg);
-        vi[0] = v4.x * it; vi[1] = v4.y * it; vi[2] = v4.z * it; vi[3] = v4.w * it;
-      } else {
-        vi[0] = (cg == 0) ? it : 0.f;
-        vi[1] = vi[2] = vi[3] = 0.f;
+      for (int t = 0; t < kTB; ++t) {
+        a *= sf[t];
+        F[t] = a;
       }
-      acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+    }
+    const bool deferred = F[kTB - 1] >= kMinDecay;              // CTA-uniform
+    float* rb = red + (bt & 1) * (NW * kTB * W);
+    // two half-stages of 4 tokens: 4 x CPT accumulators live at a time
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float2 q2 = *reinterpret_cast<const float2*>(sqk + (t * DH + rl + 64 * r) * 2);
+    for (int half = 0; half < 2; ++half) {
+      float acc[4][CPT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          c[r][j] = fmaf(f, c[r][j], q2.y * vi[j]);
-          acc[t][j] = fmaf(q2.x, c[r][j], acc[t][j]);
+      for (int tt = 0; tt < 4; ++tt) {
+        const int t = half * 4 + tt;
+        const float it = si[t] * kscale;
+        float vi[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          if (!n_slab) vi[j] = sv[t * W + j] * it;
+          else vi[j] = (cg == 0 && j == 0) ? it : 0.f;
+          acc[tt][j] = 0.f;
+        }
+        if (deferred) {
+          const float inv = __frcp_rn(F[t]);
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) vi[j] *= inv;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float qv = sq[t * DH + RL * r], kv = sk[t * DH + RL * r];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+              c[r][j] = fmaf(kv, vi[j], c[r][j]);
+              acc[tt][j] = fmaf(qv, c[r][j], acc[tt][j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) acc[tt][j] *= F[t];
+        } else {
+          const float f = sf[t];
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float qv = sq[t * DH + RL * r], kv = sk[t * DH + RL * r];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+              c[r][j] = fmaf(f, c[r][j], kv * vi[j]);
+              acc[tt][j] = fmaf(qv, c[r][j], acc[tt][j]);
+            }
+          }
         }
       }
+      // reduce over the 8 row lanes of the warp (lane bits 2..4); the warps meet in shared memory
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          float v = acc[tt][j];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          acc[tt][j] = v;
+        }
+      if (lane < 4) {
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt)
+#pragma unroll
+          for (int j = 0; j < CPT; ++j) rb[(warp * kTB + half * 4 + tt) * W + CPT * cg + j] = acc[tt][j];
+      }
+    }
+    if (deferred) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) c[r][j] *= F[kTB - 1];
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty_bar(s));
     if (++s == kStages) { s = 0; ph ^= 1; }
-    // reduce over the 8 row lanes of the warp (lane bits 2..4), then over the 8 warps through shared memory
-#pragma unroll
-    for (int t = 0; t < kTB; ++t)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float v = acc[t][j];
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        acc[t][j] = v;
-      }
-    float* rb = red + (bt & 1) * (8 * kTB * kSlabW);
-    if (lane < 4) {
-#pragma unroll
-      for (int t = 0; t < kTB; ++t)
-        *reinterpret_cast<float4*>(rb + (warp * kTB + t) * kSlabW + 4 * cg) =
-            make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
-    if (tid < kTB * kSlabW) {
-      const int t = tid / kSlabW, col = tid - t * kSlabW;
+    asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
+    if (tid < kTB * W) {
+      const int t = tid / W, col = tid - t * W;
       float sum = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) sum += rb[(w * kTB + t) * kSlabW + col];   // fixed order
+      for (int y = 0; y < NW; ++y) sum += rb[(y * kTB + t) * W + col];      // fixed order
       const int64_t row = (int64_t)b * S + (int64_t)bt * kTB + t;
-      if (!n_slab) p.num[row * p.inner + hd * DH + slab * kSlabW + col] = sum;
+      if (!n_slab) p.num[row * p.inner + hd * DH + slab * W + col] = sum;
       else if (col == 0) p.qn[row * NH + hd] = sum;
     }
   }
   // write the slab back
-  if (!n_slab) {
-    const int col0 = slab * kSlabW + 4 * cg;
-    const int hs = col0 / wc, cin = col0 - hs * wc;
-    float* base = p.C + ((int64_t)(bh * CSl + hs) * DH) * wc + cin;
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      *reinterpret_cast<float4*>(base + (int64_t)(rl + 64 * r) * wc) = make_float4(c[r][0], c[r][1], c[r][2], c[r][3]);
-  } else if (cg == 0) {
+  for (int r = 0; r < R; ++r) {
+    const int row = rl + RL * r;
 #pragma unroll
-    for (int r = 0; r < R; ++r) p.n[(int64_t)bh * DH + rl + 64 * r] = c[r][0];
+    for (int j = 0; j < CPT; ++j) {
+      if (!n_slab) *c_ptr(row, slab * W + CPT * cg + j) = c[r][j];
+      else if (cg == 0 && j == 0) p.n[(int64_t)bh * DH + row] = c[r][0];
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // Sequence finalize (token-parallel): h = num / (max(|q.n|, exp(-m)) + eps), MultiHeadLayerNorm over the head,
 // learnable skip and output gate; emits the bf16 hi/lo planes of proj_down's A operand (or fp32).
-// grid = (B*S rows) x NH, blockDim = DH rounded up to a warp multiple.
+// One warp per (row, head).
 // ------------------------------------------------------------------------------------------------
 struct FinalizeSeqParams {
   const float* num;       // [M, inner]
@@ -480,37 +543,65 @@ struct FinalizeSeqParams {
   float ln_eps, cell_eps;
 };
 
-__global__ void __launch_bounds__(1024) mlstm_finalize_seq_kernel(FinalizeSeqParams p) {
-  __shared__ float red[32];
-  const int row = blockIdx.x, hd = blockIdx.y;
-  const int DH = p.DH, inner = p.inner;
-  const int a = threadIdx.x;
-  const bool ok = a < DH;
-  const int ch = hd * DH + (ok ? a : 0);
-  const float wn = ok ? p.outnorm_w[ch] : 0.f;
-  const float wskip = ok ? p.skip[ch] : 0.f;
+// one warp per (row, head): shuffle reductions only, no block barriers
+__global__ void __launch_bounds__(256) mlstm_finalize_seq_kernel(FinalizeSeqParams p) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   pdl_wait();
   pdl_trigger();
-  const int b = row / p.S, s = row - b * p.S;
-  const float qn = p.qn[(int64_t)row * p.NH + hd];
+  if (w >= (int64_t)p.B * p.S * p.NH) return;
+  const int64_t row = w / p.NH;
+  const int hd = (int)(w - row * p.NH);
+  const int DH = p.DH, inner = p.inner;
+  const int b = (int)(row / p.S), s = (int)(row - (int64_t)b * p.S);
+  const float qn = p.qn[row * p.NH + hd];
   const float m = p.mseq[((int64_t)b * p.NH + hd) * p.S + s];
-  const float num = ok ? p.num[(int64_t)row * inner + ch] : 0.f;
-  const float act = ok ? p.act[(int64_t)row * inner + ch] : 0.f;
-  const float zz = ok ? p.u[(int64_t)row * 2 * inner + inner + ch] : 0.f;
   const float den = fmaxf(fabsf(qn), expf(-m)) + p.cell_eps;
-  const float h = num / den;
-  const float mean = block_sum(h, red) / (float)DH;
-  const float dlt = ok ? h - mean : 0.f;
-  const float var = block_sum(dlt * dlt, red) / (float)DH;
-  if (!ok) return;
-  const float rstd = rsqrtf(var + p.ln_eps);
-  float o = (h - mean) * rstd * (1.f + wn);
-  o = (o + wskip * act) * silu_fast(zz);
-  if (p.out) p.out[(int64_t)row * inner + ch] = o;
-  if (p.out_hi) {
-    const __nv_bfloat16 hi = __float2bfloat16_rn(o);
-    p.out_hi[(int64_t)row * inner + ch] = hi;
-    p.out_lo[(int64_t)row * inner + ch] = __float2bfloat16_rn(o - __bfloat162float(hi));
+  const float* num = p.num + row * inner + hd * DH;
+  // up to 32 channels per lane (DH <= 1024) held in registers: every global load is issued up front
+  float hv[32], av[32], zv[32];
+  float sum = 0.f;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    const int a = lane + 32 * e;
+    hv[e] = 0.f; av[e] = 0.f; zv[e] = 0.f;
+    if (a < DH) {
+      hv[e] = num[a];
+      av[e] = p.act[row * inner + hd * DH + a];
+      zv[e] = p.u[row * 2 * inner + inner + hd * DH + a];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    if (lane + 32 * e < DH) {
+      hv[e] = hv[e] / den;
+      sum += hv[e];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)DH;
+  float sq = 0.f;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    if (lane + 32 * e < DH) {
+      const float dlt = hv[e] - mean;
+      sq += dlt * dlt;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)DH + p.ln_eps);
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    const int a = lane + 32 * e;
+    if (a < DH) {
+      const int ch = hd * DH + a;
+      float o = (hv[e] - mean) * rstd * (1.f + p.outnorm_w[ch]);
+      o = (o + p.skip[ch] * av[e]) * silu_fast(zv[e]);
+      if (p.out) p.out[row * inner + ch] = o;
+      if (p.out_hi) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+        p.out_hi[row * inner + ch] = hi;
+        p.out_lo[row * inner + ch] = __float2bfloat16_rn(o - __bfloat162float(hi));
+      }
+    }
   }
 }
 
@@ -519,16 +610,28 @@ __global__ void __launch_bounds__(1024) mlstm_finalize_seq_kernel(FinalizeSeqPar
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+// (R, CPT, NW) instantiations: head dims 640 / 512 / 384 / 256 (the presets: 32 slabs per head -> 132 CTAs per env
+// at NH = 4), 768 and 1024, and the small test heads 128 / 64 / 32
+#define XL_CELL_CASES(X) X(5, 5, 16) X(4, 4, 16) X(3, 3, 16) X(2, 2, 16) X(6, 6, 16) X(8, 8, 16) X(1, 1, 16) X(1, 4, 8) X(1, 4, 4)
+
+static bool cell_plan(int DH, int* R, int* CPT, int* NW) {
+#define XL_CELL_MATCH(r, c, n) \
+  if (DH == 8 * n * r && DH % (4 * c) == 0) { *R = r; *CPT = c; *NW = n; return true; }
+  XL_CELL_CASES(XL_CELL_MATCH)
+#undef XL_CELL_MATCH
+  return false;
+}
+
 bool prefill_cell_supported(int DH) {
-  const int R = DH / 64;
-  return DH % 64 == 0 && (R == 1 || R == 2 || R == 4 || R == 6 || R == 8 || R == 10 || R == 12 || R == 16);
+  int R, CPT, NW;
+  return cell_plan(DH, &R, &CPT, &NW);
 }
 
 bool launch_conv_qkv_gates_seq(const ConvQkvParams& p, int S, cudaStream_t s) {
   const int nblk = p.inner / 4;
   const int per_chunk = (nblk + p.NCH - 1) / p.NCH;
   const int threads = ((per_chunk + 31) / 32) * 32;
-  const int run = 32;                                   // tokens per CTA
+  const int run = 8;                                    // tokens per CTA
   dim3 grid(p.NCH, p.B, (S + run - 1) / run);
   if (p.KS == 4 && p.NH == 4) {
     launch_k(pf::conv_qkv_gates_seq_kernel<4, 4>, grid, dim3(threads), 0, s, p, S, run);
@@ -549,43 +652,39 @@ bool launch_conv_qkv_gates_seq(const ConvQkvParams& p, int S, cudaStream_t s) {
 
 void launch_gate_scan_seq(const float* gate_part, const float* igate_b, const float* fgate_b, float* m_state,
                           float* fseq, float* iseq, float* mseq, int B, int S, int NH, int NCH, cudaStream_t s) {
-  const int warps = B * NH;
-  launch_k(pf::gate_scan_seq_kernel, dim3((warps + 3) / 4), dim3(128), 0, s, gate_part, igate_b, fgate_b, m_state, fseq,
-           iseq, mseq, B, S, NH, NCH);
+  launch_k(pf::gate_scan_seq_kernel, dim3(B * NH), dim3(128), 0, s, gate_part, igate_b, fgate_b, m_state, fseq, iseq,
+           mseq, B, S, NH, NCH);
 }
 
-template <int R>
-static cudaError_t launch_cell_R(const pf::CellSeqParams& p, cudaStream_t s) {
-  const size_t smem = 128 + sizeof(float) * ((size_t)pf::kStages * pf::cell_stage_floats(p.DH) +
-                                             2 * (size_t)8 * pf::kTB * pf::kSlabW);
+template <int R, int CPT, int NW>
+static cudaError_t launch_cell_RC(const pf::CellSeqParams& p, cudaStream_t s) {
+  const int w = 4 * CPT;
+  const size_t smem = 128 + sizeof(float) * ((size_t)pf::kStages * pf::cell_stage_floats(p.DH, w) +
+                                             2 * (size_t)NW * pf::kTB * w);
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(pf::mlstm_cell_seq_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(pf::mlstm_cell_seq_kernel<R, CPT, NW>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_smem = smem;
   }
-  const int grid = p.B * p.NH * (p.DH / pf::kSlabW + 1);
-  return launch_k(pf::mlstm_cell_seq_kernel<R>, dim3(grid), dim3(pf::kBlock), smem, s, p);
+  const int grid = p.B * p.NH * (p.DH / w + 1);
+  return launch_k(pf::mlstm_cell_seq_kernel<R, CPT, NW>, dim3(grid), dim3((NW + 1) * 32), smem, s, p);
 }
 
-cudaError_t launch_cell_seq(float* C, float* n, const float* qk, const float* v, const float* fseq, const float* iseq,
-                            float* num, float* qn, int B, int S, int NH, int DH, int inner, cudaStream_t s) {
-  if (!prefill_cell_supported(DH) || S % pf::kTB != 0) return cudaErrorInvalidValue;
+cudaError_t launch_cell_seq(float* C, float* n, const float* q, const float* k, const float* v, const float* fseq,
+                            const float* iseq, float* num, float* qn, int B, int S, int NH, int DH, int inner,
+                            cudaStream_t s) {
+  int R, CPT, NW;
+  if (!cell_plan(DH, &R, &CPT, &NW) || S % pf::kTB != 0) return cudaErrorInvalidValue;
   pf::CellSeqParams p;
-  p.C = C; p.n = n; p.qk = qk; p.v = v; p.fseq = fseq; p.iseq = iseq; p.num = num; p.qn = qn;
-  p.B = B; p.S = S; p.NH = NH; p.DH = DH; p.inner = inner;
-  switch (DH / 64) {
-    case 1: return launch_cell_R<1>(p, s);
-    case 2: return launch_cell_R<2>(p, s);
-    case 4: return launch_cell_R<4>(p, s);
-    case 6: return launch_cell_R<6>(p, s);
-    case 8: return launch_cell_R<8>(p, s);
-    case 10: return launch_cell_R<10>(p, s);
-    case 12: return launch_cell_R<12>(p, s);
-    case 16: return launch_cell_R<16>(p, s);
-    default: return cudaErrorInvalidValue;
-  }
+  p.C = C; p.n = n; p.q = q; p.k = k; p.v = v; p.fseq = fseq; p.iseq = iseq; p.num = num; p.qn = qn;
+  p.B = B; p.S = S; p.NH = NH; p.DH = DH; p.inner = inner; p.nw = NW;
+#define XL_CELL_LAUNCH(r, c, n) \
+  if (R == r && CPT == c && NW == n) return launch_cell_RC<r, c, n>(p, s);
+  XL_CELL_CASES(XL_CELL_LAUNCH)
+#undef XL_CELL_LAUNCH
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_finalize_seq(const float* num, const float* qn, const float* mseq, const float* outnorm_w,
@@ -596,8 +695,8 @@ cudaError_t launch_finalize_seq(const float* num, const float* qn, const float* 
   p.num = num; p.qn = qn; p.mseq = mseq; p.outnorm_w = outnorm_w; p.skip = skip; p.act = act; p.u = u; p.out = out;
   p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo;
   p.B = B; p.S = S; p.NH = NH; p.DH = DH; p.inner = inner; p.ln_eps = ln_eps; p.cell_eps = cell_eps;
-  const int thr = ((DH + 31) / 32) * 32;
-  return launch_k(pf::mlstm_finalize_seq_kernel, dim3(B * S, NH), dim3(thr), 0, s, p);
+  const int64_t warps = (int64_t)B * S * NH;
+  return launch_k(pf::mlstm_finalize_seq_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, s, p);
 }
 
 }  // namespace xl
