@@ -324,9 +324,16 @@ def main():
             # one launch covers the envs of one micro-batch (B envs when the step is not split)
             alg_bytes = alg_bytes * cfg.num_blocks * args.profile_steps // cnt.value
             ach = alg_bytes / (avg_ms / 1e3) / 1e9
-            roof = {"bound": "hbm", "kernel": "mlstm_state_step_kernel", "achieved": ach,
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r01_state_traffic.json")
+            if os.path.exists(tpath):
+                with open(tpath) as fh:
+                    rec = json.load(fh).get(f"{args.model}:{B}:impl{opts.get('state_impl', 1)}")
+                if rec and opts.get("microbatches", 1) == 1:
+                    traffic = rec["traffic"]      # one ncu --set full capture of this kernel at this shape
+            roof = {"bound": "hbm", "kernel": "mlstm_state_stream_tma_kernel", "achieved": ach,
                     "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "avg_launch_us": avg_ms * 1e3,
+                    "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "avg_launch_us": avg_ms * 1e3,
                     "launches_timed": cnt.value, "algorithmic_bytes_per_launch": alg_bytes,
                     "share_of_step": ms_sum.value / max(step_ms.value, 1e-9)}
     if world > 1:
