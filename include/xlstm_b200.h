@@ -113,6 +113,10 @@ typedef enum { XL_STATE_C = 0, XL_STATE_N = 1, XL_STATE_M = 2, XL_STATE_CONV = 3
 #define XL_FLAG_DISCRETE 1u   /* discrete-action branch: argmax over logits[:discrete_actions]             */
 #define XL_FLAG_GRAPH 2u      /* replay the step from a cached CUDA graph (pointers must stay the same)    */
 #define XL_FLAG_SIMPLE_GEMM 4u/* force the CUDA-core GEMM (debug / small M)                               */
+#define XL_FLAG_STATE_EMBEDS 8u /* xl_policy_step: `states` is fp32 [B, d] = state-token embeddings already
+                                 * computed by the caller (image observations: embed_image / ImpalaCNN,
+                                 * discrete_decision_transformer_model.py:187-203, image_encoders.py:10-66, stays in
+                                 * PyTorch/cuDNN); the embed_state Linear is skipped                          */
 
 int xl_abi_version(void);
 const char* xl_last_error(void);
@@ -163,6 +167,7 @@ int xl_mlstm_cell_step(xl_handle* h, float* C, float* n, float* m, const float* 
  * transformer_model.py:368-383 -> multi_domain_discrete_dt_model.py:83-108) + MinMaxTokenizer.inv_tokenize
  * (src/tokenizers_custom/minmax_tokenizer.py:31-47).
  *   states  fp32 [B, state_dim]  (already zero-padded to 204: src/algos/decision_xlstm.py:16-19)
+ *                                or fp32 [B, d] state embeddings with XL_FLAG_STATE_EMBEDS
  *   rtg     fp32 [B]             returns-to-go of this timestep
  *   rewards fp32 [B] or NULL     reward token input; NULL = 0 (what the reference feeds, evaluation.py:132)
  *   tokens  int32 [B, act_dim]   argmax action tokens (continuous) / [B] first column (discrete)
@@ -204,7 +209,11 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
  *   "state_stages" / "state_ctas_per_sm": ring depth and persistent CTAs per SM of impl 2 (0 = default)
  *   "state_rows_split": row chunks per (env, head) of impl 0/1 (0 = automatic)
  *   "gemm_impl":  [0] auto (tcgen05 when K % 64 == 0), 1 CUDA-core, 2 tcgen05
- *   "gemm_splitk": [0] cluster split-K (DSMEM reduction) in the tcgen05 Linear when the cost model asks
+ *   "gemm_splitk": [8] max split-K planes of proj_up / proj_down (cost model picks <= this; 0/1 = off). Each
+ *                  split CTA writes its partial tile to its own plane; the consumer kernels (LayerNorm,
+ *                  conv/qkv, finalize) add the planes in order: no atomics, bit-reproducible
+ *   "gemm_up_bn" / "gemm_up_splits" / "gemm_down_bn" / "gemm_down_splits": [0 = cost model] force tile width
+ *                  (32/64/128) and split-K factor of the two projections
  *   "pdl": [1] programmatic dependent launch of every kernel (process-wide)
  *   "microbatches": [1] env micro-batches of a fused step, pipelined on side streams; "pipeline_order": [1]
  *                   their state-stream kernels take turns */

@@ -19,7 +19,7 @@ XL_ERR_INVALID_ARG, XL_ERR_UNSUPPORTED, XL_ERR_CUDA, XL_ERR_NOT_READY, XL_ERR_NO
 
 # modes / flags
 XL_MODE_PER_TOKEN, XL_MODE_FUSED = 0, 1
-XL_FLAG_DISCRETE, XL_FLAG_GRAPH, XL_FLAG_SIMPLE_GEMM = 1, 2, 4
+XL_FLAG_DISCRETE, XL_FLAG_GRAPH, XL_FLAG_SIMPLE_GEMM, XL_FLAG_STATE_EMBEDS = 1, 2, 4, 8
 
 # state parts
 XL_STATE_C, XL_STATE_N, XL_STATE_M, XL_STATE_CONV = 0, 1, 2, 3

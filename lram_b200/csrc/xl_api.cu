@@ -54,6 +54,8 @@ struct GraphCacheEntry {
 }  // namespace
 
 constexpr int kMaxMicro = 8;   // env micro-batches pipelined on side streams
+constexpr int kSplitMax = 8;   // split-K planes of the skinny projections
+constexpr size_t kSplitRows = 1024;   // split-K only pays (and has plane storage) up to this many rows
 
 struct xl_handle {
   xl_config cfg;
@@ -84,7 +86,13 @@ struct xl_handle {
   int state_ctas_per_sm = 0;           // impl 2 persistent CTAs per SM (0 = 1)  (xl_set_option "state_ctas_per_sm")
   int state_rows_split = 0;            // 0 = automatic                          (xl_set_option "state_rows_split")
   int gemm_impl = 0;                   // 0 auto, 1 CUDA-core, 2 tcgen05      (xl_set_option "gemm_impl")
-  int gemm_splitk = 0;                 // cluster split-K in the tcgen05 Linear (xl_set_option "gemm_splitk")
+  int gemm_splitk = 8;                 // max split-K planes of proj_up / proj_down, 0/1 = off ("gemm_splitk")
+  int gemm_up_bn = 0, gemm_up_splits = 0, gemm_down_bn = 0, gemm_down_splits = 0;   // 0 = cost model; A/B overrides
+  int debug_skip = 0;                  // measurement aid: bit k set = do not launch kernel class k of every block
+                                       // (1 LN, 2 proj_up, 4 conv/qkv, 8 state stream, 16 finalize, 32 proj_down);
+                                       // results are garbage, only the step time is meaningful ("debug_skip")
+  float *part_up = nullptr, *part_down = nullptr;   // split-K planes [kSplitMax][part_rows][2*inner | d]
+  size_t part_rows = 0;
   int microbatches = 0;                // 0 = automatic; env micro-batches per fused step ("microbatches")
   int pipeline_order = 1;              // 1 = state-stream kernels of the micro-batches run one after another
   // context-prefill workspace (lazily allocated by xl_prefill / xl_policy_prefill, grow-only)
@@ -155,8 +163,10 @@ Ws ws_slice(const xl_handle* h, int b0, int Bk) {
 
 // Linear layer dispatch. impl: 0 auto, 1 CUDA-core, 2 tensor-core.
 // presplit: the bf16 hi/lo planes of A already sit in w.a_hi / w.a_lo (written by the producing kernel).
+// bn / splits / split_stride: tile width and split-K of the tcgen05 kernel (0 / 1 / 0 = planned, no split).
 int linear(xl_handle* h, const Ws& w, const float* A, const void* W, const float* bias, const float* residual,
-           float* out, int M, int N, int K, int impl, cudaStream_t s, bool presplit = false) {
+           float* out, int M, int N, int K, int impl, cudaStream_t s, bool presplit = false, int bn = 0,
+           int splits = 1, long long split_stride = 0) {
   if (K % 8 != 0) return fail(XL_ERR_UNSUPPORTED, "linear: K=%d must be a multiple of 8", K);
   const bool tc_ok = xl::gemm_tc_supported(M, N, K) && (size_t)M * K <= w.a_cap;
   if (impl == 2 && !tc_ok)
@@ -168,10 +178,11 @@ int linear(xl_handle* h, const Ws& w, const float* A, const void* W, const float
       h->launches += 1;
     }
     XL_CUDA(xl::launch_gemm_tc(w.a_hi, w.a_lo, (const __nv_bfloat16*)W, bias, residual, out, M, N, K,
-                               h->num_sms, h->gemm_splitk ? 0 : 1, w.low_smem, s));
+                               h->num_sms, bn, splits, split_stride, w.low_smem, s));
     h->launches += 1;
     return XL_OK;
   }
+  if (splits > 1) return fail(XL_ERR_INVALID_ARG, "linear: split-K needs the tcgen05 path");
   xl::launch_gemm_simple(A, (const __nv_bfloat16*)W, bias, residual, out, M, N, K, s);
   h->launches += 1;
   XL_CUDA(cudaGetLastError());
@@ -195,6 +206,7 @@ Slice make_slice(const xl_handle* h, int B, int b0, int Bk, cudaStream_t s) {
 struct BlockPlan {
   bool tc_up, tc_down;
   int impl;
+  int up_bn, up_sp, down_bn, down_sp;     // tile width / split-K planes of proj_up and proj_down (sp = 1: none)
 };
 
 BlockPlan block_plan(const xl_handle* h, const Slice& sl, int T, unsigned flags) {
@@ -207,10 +219,30 @@ BlockPlan block_plan(const xl_handle* h, const Slice& sl, int T, unsigned flags)
             (size_t)M * c.embedding_dim <= sl.ws.a_cap;
   p.tc_down = p.impl != 1 && xl::gemm_tc_supported(M, c.embedding_dim, c.inner_dim) &&
               (size_t)M * c.inner_dim <= sl.ws.a_cap;
+  // split-K (planes summed by the consumer kernels): whole-batch slices only, rows within the plane storage
+  const bool can_split = !sl.ws.low_smem && sl.b0 == 0 && (size_t)M <= h->part_rows && c.embedding_dim <= 4096;
+  const int max_sp = can_split ? std::min(std::max(h->gemm_splitk, 1), kSplitMax) : 1;
+  p.up_bn = p.down_bn = 0;
+  p.up_sp = p.down_sp = 1;
+  if (p.tc_up) {
+    xl::gemm_tc_plan(M, 2 * c.inner_dim, c.embedding_dim, h->num_sms, max_sp, &p.up_bn, &p.up_sp);
+    if (h->gemm_up_bn) p.up_bn = h->gemm_up_bn;
+    if (h->gemm_up_splits && can_split && (c.embedding_dim / 64) % h->gemm_up_splits == 0 &&
+        h->gemm_up_splits <= kSplitMax)
+      p.up_sp = h->gemm_up_splits;
+  }
+  if (p.tc_down) {
+    xl::gemm_tc_plan(M, c.embedding_dim, c.inner_dim, h->num_sms, max_sp, &p.down_bn, &p.down_sp);
+    if (h->gemm_down_bn) p.down_bn = h->gemm_down_bn;
+    if (h->gemm_down_splits && can_split && (c.inner_dim / 64) % h->gemm_down_splits == 0 &&
+        h->gemm_down_splits <= kSplitMax)
+      p.down_sp = h->gemm_down_splits;
+  }
   return p;
 }
 
-xl::StateStepParams state_params(const xl_handle* h, void* state, const Slice& sl, int i, int T, bool tc_down) {
+xl::StateStepParams state_params(const xl_handle* h, void* state, const Slice& sl, int i, int T, bool tc_down,
+                                 int up_sp = 1) {
   const xl_config& c = h->cfg;
   const int inner = c.inner_dim, NH = c.num_heads, DH = h->DH;
   const StateLayout L = state_layout(h, sl.B);
@@ -230,7 +262,9 @@ xl::StateStepParams state_params(const xl_handle* h, void* state, const Slice& s
   sp.outnorm_w = (const float*)w.w[XL_W_OUTNORM];
   sp.skip = (const float*)w.w[XL_W_SKIP];
   sp.act = sl.ws.act;
-  sp.u = sl.ws.u;
+  sp.u = up_sp > 1 ? h->part_up : sl.ws.u;
+  sp.u_splits = up_sp;
+  sp.u_stride = (int64_t)M * 2 * inner;
   sp.out = tc_down ? nullptr : sl.ws.gated;
   sp.out_hi = tc_down ? sl.ws.a_hi : nullptr;
   sp.out_lo = tc_down ? sl.ws.a_lo : nullptr;
@@ -256,13 +290,26 @@ int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned
   const BlockWeights& w = h->blocks[i];
   const Ws& ws = sl.ws;
   char* base = (char*)state + (size_t)i * L.layer_bytes;
-  xl::launch_ln_rows(ws.x, d, bp.tc_up ? nullptr : ws.xn, d, (const float*)w.w[XL_W_XLSTM_NORM], nullptr, 1,
-                     c.ln_eps, M, d, bp.tc_up ? ws.a_hi : nullptr, bp.tc_up ? ws.a_lo : nullptr, sl.s);
+  if (h->debug_skip & 1) {
+  } else if (i > 0 && bp.down_sp > 1) {
+    // the previous block's proj_down left split-K planes: x += planes, then normalise
+    xl::launch_ln_rows_reduce(ws.x, h->part_down, bp.down_sp, (int64_t)M * d, bp.tc_up ? nullptr : ws.xn, d,
+                              (const float*)w.w[XL_W_XLSTM_NORM], c.ln_eps, M, d, bp.tc_up ? ws.a_hi : nullptr,
+                              bp.tc_up ? ws.a_lo : nullptr, sl.s);
+  } else {
+    xl::launch_ln_rows(ws.x, d, bp.tc_up ? nullptr : ws.xn, d, (const float*)w.w[XL_W_XLSTM_NORM], nullptr, 1,
+                       c.ln_eps, M, d, bp.tc_up ? ws.a_hi : nullptr, bp.tc_up ? ws.a_lo : nullptr, sl.s);
+  }
   h->launches += 1;
-  int rc = linear(h, ws, ws.xn, w.w[XL_W_PROJ_UP], nullptr, nullptr, ws.u, M, 2 * inner, d, bp.impl, sl.s, bp.tc_up);
+  int rc = (h->debug_skip & 2) ? 0 : linear(h, ws, ws.xn, w.w[XL_W_PROJ_UP], nullptr, nullptr,
+                  bp.up_sp > 1 ? h->part_up : ws.u, M, 2 * inner,
+                  d, bp.impl, sl.s, bp.tc_up, bp.up_bn, bp.up_sp, (long long)M * 2 * inner);
   if (rc) return rc;
+  if (h->debug_skip & 4) return XL_OK;
   xl::ConvQkvParams cp;
-  cp.u = ws.u;
+  cp.u = bp.up_sp > 1 ? h->part_up : ws.u;
+  cp.u_splits = bp.up_sp;
+  cp.u_stride = (int64_t)M * 2 * inner;
   cp.conv_state = (float*)(base + L.conv_off) + (size_t)sl.b0 * c.conv_kernel * inner;
   cp.conv_w = (const float*)w.w[XL_W_CONV_W];
   cp.conv_b = (const float*)w.w[XL_W_CONV_B];
@@ -285,14 +332,14 @@ int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned
 // block i, part 2: the HBM-bound state stream (C update + partial numerators)
 int block_state(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned flags) {
   const BlockPlan bp = block_plan(h, sl, T, flags);
-  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down);
+  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp);
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (h->profiling) {
     XL_CUDA(cudaEventCreate(&pe0));
     XL_CUDA(cudaEventCreate(&pe1));
     XL_CUDA(cudaEventRecord(pe0, sl.s));
   }
-  XL_CUDA(xl::launch_state_step(sp, h->num_sms, sl.s));
+  if (!(h->debug_skip & 8)) XL_CUDA(xl::launch_state_step(sp, h->num_sms, sl.s));
   h->launches += 1;
   if (h->profiling) {
     XL_CUDA(cudaEventRecord(pe1, sl.s));
@@ -306,12 +353,32 @@ int block_state(xl_handle* h, void* state, const Slice& sl, int i, int T, unsign
 int block_post(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned flags) {
   const xl_config& c = h->cfg;
   const BlockPlan bp = block_plan(h, sl, T, flags);
-  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down);
+  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp);
   const Ws& ws = sl.ws;
-  XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, sl.s));
+  const int M = sl.Bk * T;
+  if (!(h->debug_skip & 16)) XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, sl.s));
   h->launches += 1;
-  return linear(h, ws, ws.gated, h->blocks[i].w[XL_W_PROJ_DOWN], nullptr, ws.x, ws.x, sl.Bk * T, c.embedding_dim,
-                c.inner_dim, bp.impl, sl.s, bp.tc_down);
+  if (h->debug_skip & 32) return XL_OK;
+  if (bp.down_sp > 1)   // planes; folded into x by the next LayerNorm (block_pre of block i+1 / final_norm)
+    return linear(h, ws, ws.gated, h->blocks[i].w[XL_W_PROJ_DOWN], nullptr, nullptr, h->part_down, M,
+                  c.embedding_dim, c.inner_dim, bp.impl, sl.s, bp.tc_down, bp.down_bn, bp.down_sp,
+                  (long long)M * c.embedding_dim);
+  return linear(h, ws, ws.gated, h->blocks[i].w[XL_W_PROJ_DOWN], nullptr, ws.x, ws.x, M, c.embedding_dim,
+                c.inner_dim, bp.impl, sl.s, bp.tc_down, bp.down_bn);
+}
+
+// post_blocks_norm over the M = Bk*T rows of ws.x left by run_blocks (folds the last block's split-K planes)
+void final_norm(xl_handle* h, const Slice& sl, int T, unsigned flags, float* out, int64_t out_stride) {
+  const xl_config& c = h->cfg;
+  const int d = c.embedding_dim, M = sl.Bk * T;
+  const BlockPlan bp = block_plan(h, sl, T, flags);
+  const float* post_w = (const float*)h->pw[XL_W_POST_NORM - XL_W_POST_NORM];
+  if (bp.down_sp > 1)
+    xl::launch_ln_rows_reduce(sl.ws.x, h->part_down, bp.down_sp, (int64_t)M * d, out, out_stride, post_w, c.ln_eps,
+                              M, d, nullptr, nullptr, sl.s);
+  else
+    xl::launch_ln_rows(sl.ws.x, d, out, out_stride, post_w, nullptr, 1, c.ln_eps, M, d, nullptr, nullptr, sl.s);
+  h->launches += 1;
 }
 
 // One pass of the block stack over M = Bk*T rows held in ws.x (rows ordered [b][t]).
@@ -341,8 +408,7 @@ int run_encoder(xl_handle* h, void* state, const Slice& sl, const float* x_in, f
     }
     int rc = run_blocks(h, state, sl, T, flags);
     if (rc) return rc;
-    xl::launch_ln_rows(ws.x, d, x_out, d, post_w, nullptr, 1, c.ln_eps, B * T, d, nullptr, nullptr, s);
-    h->launches += 1;
+    final_norm(h, sl, T, flags, x_out, d);
   } else if (mode == XL_MODE_PER_TOKEN) {
     // reference order: for token: for block  (decision_xlstm.py:161-165). x_in may alias x_out: token t's
     // input row is consumed (gathered) before its output row is written.
@@ -356,9 +422,7 @@ int run_encoder(xl_handle* h, void* state, const Slice& sl, const float* x_in, f
       h->launches += 1;
       int rc = run_blocks(h, state, sl, 1, flags);
       if (rc) return rc;
-      xl::launch_ln_rows(ws.x, d, x_out + (size_t)t * d, (int64_t)T * d, post_w, nullptr, 1, c.ln_eps, B, d,
-                         nullptr, nullptr, s);
-      h->launches += 1;
+      final_norm(h, sl, 1, flags, x_out + (size_t)t * d, (int64_t)T * d);
     }
   } else {
     return fail(XL_ERR_INVALID_ARG, "unknown mode %d", mode);
@@ -384,12 +448,19 @@ int policy_front(xl_handle* h, const StepArgs& a, const Slice& sl, float* xt) {
   const int impl = (a.flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
   auto PW = [&](int id) { return h->pw[id - XL_W_POST_NORM]; };
   const Ws& ws = sl.ws;
-  xl::launch_pad_rows(a.states + (size_t)sl.b0 * c.state_dim, c.state_dim, ws.states_pad, h->Kpad, sl.Bk, sl.s);
-  h->launches += 1;
-  int rc = linear(h, ws, ws.states_pad, PW(XL_W_EMBED_STATE_W), (const float*)PW(XL_W_EMBED_STATE_B), nullptr,
-                  ws.s_emb, sl.Bk, d, h->Kpad, impl, sl.s);
-  if (rc) return rc;
-  xl::launch_embed_tokens(ws.s_emb, a.rtg + sl.b0, a.rewards ? a.rewards + sl.b0 : nullptr,
+  const float* s_emb = ws.s_emb;
+  if (a.flags & XL_FLAG_STATE_EMBEDS) {
+    // a.states already holds the state-token embeddings [B, d] (image observations: embed_image = ImpalaCNN,
+    // discrete_decision_transformer_model.py:187-203, runs in PyTorch/cuDNN before this call)
+    s_emb = a.states + (size_t)sl.b0 * d;
+  } else {
+    xl::launch_pad_rows(a.states + (size_t)sl.b0 * c.state_dim, c.state_dim, ws.states_pad, h->Kpad, sl.Bk, sl.s);
+    h->launches += 1;
+    int rc = linear(h, ws, ws.states_pad, PW(XL_W_EMBED_STATE_W), (const float*)PW(XL_W_EMBED_STATE_B), nullptr,
+                    ws.s_emb, sl.Bk, d, h->Kpad, impl, sl.s);
+    if (rc) return rc;
+  }
+  xl::launch_embed_tokens(s_emb, a.rtg + sl.b0, a.rewards ? a.rewards + sl.b0 : nullptr,
                           (const float*)PW(XL_W_EMBED_RETURN_W), (const float*)PW(XL_W_EMBED_RETURN_B),
                           (const float*)PW(XL_W_EMBED_REWARD_W), (const float*)PW(XL_W_EMBED_REWARD_B),
                           (const float*)PW(XL_W_EMBED_LN_W), (const float*)PW(XL_W_EMBED_LN_B), c.embed_ln_eps, xt,
@@ -495,9 +566,7 @@ int run_policy(xl_handle* h, const StepArgs& a, cudaStream_t s) {
   }
   for (int k = 0; k < MB && !rc; ++k) {
     float* hid = a.hidden ? a.hidden + (size_t)sl[k].b0 * T * d : sl[k].ws.hid;
-    xl::launch_ln_rows(sl[k].ws.x, d, hid, d, post_w, nullptr, 1, c.ln_eps, sl[k].Bk * T, d, nullptr, nullptr,
-                       sl[k].s);
-    h->launches += 1;
+    final_norm(h, sl[k], T, a.flags, hid, d);
     rc = policy_back(h, a, sl[k], hid);
   }
   // join (also on the error path, so that a capture never ends with unjoined streams)
@@ -587,6 +656,8 @@ int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cud
     if (rc) return rc;
     xl::ConvQkvParams cp;
     cp.u = ws.u;
+    cp.u_splits = 1;
+    cp.u_stride = 0;
     cp.conv_state = (float*)(base + L.conv_off);
     cp.conv_w = (const float*)w.w[XL_W_CONV_W];
     cp.conv_b = (const float*)w.w[XL_W_CONV_B];
@@ -704,6 +775,9 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   h->a_cap = a_cap;
   h->a_env = 4 * (inner > d ? inner : d);
   const size_t o_hi = carve(2 * a_cap), o_lo = carve(2 * a_cap);
+  h->part_rows = M < kSplitRows ? M : kSplitRows;
+  const size_t o_pu = carve(4 * (size_t)kSplitMax * h->part_rows * 2 * inner);
+  const size_t o_pd = carve(4 * (size_t)kSplitMax * h->part_rows * d);
   h->ws_bytes = off;
   cudaError_t e = cudaMalloc((void**)&h->ws, h->ws_bytes);
   if (e != cudaSuccess) {
@@ -729,6 +803,7 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   h->counters = (unsigned int*)(h->ws + o_cnt);
 
   h->a_hi = (__nv_bfloat16*)(h->ws + o_hi); h->a_lo = (__nv_bfloat16*)(h->ws + o_lo);
+  h->part_up = (float*)(h->ws + o_pu); h->part_down = (float*)(h->ws + o_pd);
   *out = h;
   return XL_OK;
 }
@@ -989,6 +1064,9 @@ int xl_policy_step_host(xl_handle* h, void* state, const float* h_states, const 
   int rc = check_batch(h, B);
   if (rc) return rc;
   if (!state || !h_states || !h_rtg || !h_tokens || !h_actions) return fail(XL_ERR_INVALID_ARG, "null argument");
+  if (flags & XL_FLAG_STATE_EMBEDS)
+    return fail(XL_ERR_UNSUPPORTED, "xl_policy_step_host takes raw states; state embeddings are device tensors "
+                                    "(use xl_policy_step with XL_FLAG_STATE_EMBEDS)");
   cudaStream_t s = (cudaStream_t)stream;
   const xl_config& c = h->cfg;
   XL_CUDA(cudaMemcpyAsync(h->d_states, h_states, sizeof(float) * (size_t)B * c.state_dim, cudaMemcpyHostToDevice, s));
@@ -1149,7 +1227,17 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "pipeline_order")) {
     h->pipeline_order = value ? 1 : 0;
   } else if (!strcmp(name, "gemm_splitk")) {
-    h->gemm_splitk = value ? 1 : 0;
+    if (value < 0 || value > kSplitMax) return fail(XL_ERR_INVALID_ARG, "gemm_splitk must be in [0, %d]", kSplitMax);
+    h->gemm_splitk = value;
+  } else if (!strcmp(name, "gemm_up_bn") || !strcmp(name, "gemm_down_bn")) {
+    if (value != 0 && value != 32 && value != 64 && value != 128)
+      return fail(XL_ERR_INVALID_ARG, "%s must be 0, 32, 64 or 128", name);
+    (name[5] == 'u' ? h->gemm_up_bn : h->gemm_down_bn) = value;
+  } else if (!strcmp(name, "gemm_up_splits") || !strcmp(name, "gemm_down_splits")) {
+    if (value < 0 || value > kSplitMax) return fail(XL_ERR_INVALID_ARG, "%s must be in [0, %d]", name, kSplitMax);
+    (name[5] == 'u' ? h->gemm_up_splits : h->gemm_down_splits) = value;
+  } else if (!strcmp(name, "debug_skip")) {
+    h->debug_skip = value;
   } else if (!strcmp(name, "gemm_impl")) {
     if (value < 0 || value > 2) return fail(XL_ERR_INVALID_ARG, "gemm_impl must be 0, 1 or 2");
     h->gemm_impl = value;

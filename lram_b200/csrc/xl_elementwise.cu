@@ -85,7 +85,9 @@ __global__ void __launch_bounds__(1024) ln_rows_cta_kernel(const float* __restri
                                                            const float* __restrict__ w,
                                                            const float* __restrict__ bias, int residual_weight,
                                                            float eps, int d, __nv_bfloat16* __restrict__ a_hi,
-                                                           __nv_bfloat16* __restrict__ a_lo) {
+                                                           __nv_bfloat16* __restrict__ a_lo,
+                                                           const float* __restrict__ part, int splits,
+                                                           int64_t part_stride, float* __restrict__ x_out) {
   __shared__ float red[32];
   const int row = blockIdx.x;
   const int i = threadIdx.x;
@@ -98,7 +100,18 @@ __global__ void __launch_bounds__(1024) ln_rows_cta_kernel(const float* __restri
   }
   pdl_wait();
   pdl_trigger();
-  if (ok) v = reinterpret_cast<const float4*>(in + (int64_t)row * in_stride)[i];
+  if (ok) {
+    v = reinterpret_cast<const float4*>(in + (int64_t)row * in_stride)[i];
+    if (part) {
+      // residual stream += split-K planes of proj_down, in plane order (deterministic); written back in place
+      const float4* pp = reinterpret_cast<const float4*>(part + (int64_t)row * d) + i;
+      for (int z = 0; z < splits; ++z) {
+        const float4 a4 = pp[(z * part_stride) >> 2];
+        v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+      }
+      reinterpret_cast<float4*>(x_out + (int64_t)row * in_stride)[i] = v;
+    }
+  }
   const float mean = block_sum((v.x + v.y) + (v.z + v.w), red) / (float)d;
   const float a = v.x - mean, b = v.y - mean, c = v.z - mean, e = v.w - mean;
   const float q = ok ? (a * a + b * b) + (c * c + e * e) : 0.f;
@@ -132,13 +145,24 @@ void launch_ln_rows(const float* in, int64_t in_stride, float* out, int64_t out_
   if (d <= 4096) {
     const int threads = (((d >> 2) + 31) / 32) * 32;
     launch_k(ln_rows_cta_kernel, dim3(rows), dim3(threads), 0, s, in, in_stride, out, out_stride, w, bias,
-             residual_weight, eps, d, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo);
+             residual_weight, eps, d, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, (const float*)nullptr, 0,
+             (int64_t)0, (float*)nullptr);
     return;
   }
   const int warps_per_block = 8;
   dim3 grid((rows + warps_per_block - 1) / warps_per_block);
   launch_k(ln_rows_kernel, grid, dim3(warps_per_block * 32), 0, s, in, in_stride, out, out_stride, w, bias,
            residual_weight, eps, rows, d, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo);
+}
+
+void launch_ln_rows_reduce(float* x, const float* part, int splits, int64_t part_stride, float* out,
+                           int64_t out_stride, const float* w, float eps, int rows, int d, void* a_hi, void* a_lo,
+                           cudaStream_t s) {
+  if (rows <= 0) return;
+  const int threads = (((d >> 2) + 31) / 32) * 32;     // d <= 4096 (checked where the split is planned)
+  launch_k(ln_rows_cta_kernel, dim3(rows), dim3(threads), 0, s, (const float*)x, (int64_t)d, out, out_stride, w,
+           (const float*)nullptr, 1, eps, d, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, part, splits, part_stride,
+           x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -281,7 +305,14 @@ __global__ void __launch_bounds__(128, 4) conv_qkv_gates_kernel(ConvQkvParams p)
     float4 xm4[kMaxT];
 #pragma unroll
     for (int t = 0; t < kMaxT; ++t)
-      if (t < T) xm4[t] = *reinterpret_cast<const float4*>(p.u + ((int64_t)b * T + t) * 2 * inner + c);
+      if (t < T) {
+        const float* up = p.u + ((int64_t)b * T + t) * 2 * inner + c;
+        xm4[t] = *reinterpret_cast<const float4*>(up);
+        for (int z = 1; z < p.u_splits; ++z) {          // split-K planes of proj_up, added in plane order
+          const float4 a4 = *reinterpret_cast<const float4*>(up + z * p.u_stride);
+          xm4[t].x += a4.x; xm4[t].y += a4.y; xm4[t].z += a4.z; xm4[t].w += a4.w;
+        }
+      }
 #pragma unroll
     for (int t = 0; t < kMaxT; ++t) {
       if (t < T) {

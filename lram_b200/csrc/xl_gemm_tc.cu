@@ -98,7 +98,8 @@ template <int BLOCK_N, int kStages>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
-               const float* __restrict__ residual, float* __restrict__ out, int M, int N, int K) {
+               const float* __restrict__ residual, float* __restrict__ out, int M, int N, int K,
+               long long split_stride) {
   using S = Smem<BLOCK_N, kStages>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -110,7 +111,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * BLOCK_M;
-  // split-K: blockIdx.z (== rank in the (1,1,splits) cluster) owns k-blocks [kb0, kb0 + num_kb)
+  // split-K: blockIdx.z owns k-blocks [kb0, kb0 + num_kb) and writes its raw partial tile to the plane
+  // out + blockIdx.z * split_stride; the CONSUMER kernels (LayerNorm, conv/qkv, finalize) add the planes in
+  // plane order, so there is no reduction step, no atomics and no inter-CTA synchronisation here.
   const int splits = gridDim.z;
   const int kb_total = K / BLOCK_K;
   const int kb_per = (kb_total + splits - 1) / splits;
@@ -197,17 +200,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
 
   // ===== epilogue: warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====================
-  // splits == 1: TMEM -> registers -> bias/residual -> global, 32 columns at a time.
-  // splits  > 1: the CTAs of a cluster hold partial sums of the same tile (split-K). Ranks > 0 push their
-  //   accumulators into the leader's shared memory over DSMEM (the pipeline stages are idle by then), the
-  //   leader adds them in rank order (deterministic) and runs the epilogue. Two cluster barriers, no global
-  //   round trip.
+  // TMEM -> registers -> (bias, residual: only when splits == 1, host-enforced) -> global, 32 columns at a time.
   const bool is_epi = warp >= 2;
   const int q = warp & 3;
   const int row = m0 + q * 32 + lane;
-  constexpr int kPitch = BLOCK_N + 4;                         // floats; +4 breaks the bank alignment of rows
-  uint32_t rank = 0;
-  if (splits > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  out += (long long)blockIdx.z * split_stride;
 
   auto store_chunk = [&](const float (&v)[32], int c) {       // bias + residual + store of 32 columns
     if (row >= M) return;
@@ -259,63 +256,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   };
 
-  if (splits == 1) {
-    if (is_epi) {
-      mbar_wait(tmem_full_bar, 0);
-      tcgen05_fence_after();
+  if (is_epi) {
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    if (num_kb > 0) {
 #pragma unroll
       for (int c = 0; c < BLOCK_N; c += 32) {
         float v[32];
         tmem_load_chunk(v, c);
-        store_chunk(v, c);
-      }
-    }
-  } else {
-    if (is_epi) {
-      mbar_wait(tmem_full_bar, 0);          // this CTA's MMAs are complete -> its smem stages are idle
-      tcgen05_fence_after();
-    }
-    __syncwarp();
-    // (1) every CTA of the cluster is done with its main loop
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    if (is_epi && rank > 0) {
-      // push my partial tile row into the leader's staging area: [rank-1][128 rows][kPitch]
-      const uint32_t local = base + (uint32_t)(((rank - 1) * BLOCK_M + q * 32 + lane) * kPitch * 4);
-      uint32_t remote;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
-#pragma unroll
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        float v[32];
-        tmem_load_chunk(v, c);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote + (uint32_t)((c + j) * 4)),
-                       "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3])
-                       : "memory");
-      }
-    }
-    __syncwarp();
-    // (2) all partials have landed in the leader's shared memory
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    if (is_epi && rank == 0) {
-#pragma unroll
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        float v[32];
-        tmem_load_chunk(v, c);
-        for (int r = 1; r < splits; ++r) {                     // fixed order: rank 1, 2, ...
-          const uint32_t src = base + (uint32_t)((((r - 1) * BLOCK_M + q * 32 + lane) * kPitch + c) * 4);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 pv;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(pv.x), "=f"(pv.y), "=f"(pv.z), "=f"(pv.w)
-                         : "r"(src + (uint32_t)(j * 4))
-                         : "memory");
-            v[j] += pv.x; v[j + 1] += pv.y; v[j + 2] += pv.z; v[j + 3] += pv.w;
-          }
-        }
         store_chunk(v, c);
       }
     }
@@ -380,7 +328,8 @@ static bool make_map(CUtensorMap* m, const void* ptr, int rows, int K, int box_r
 
 template <int BLOCK_N, int kStages>
 static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& ml, const CUtensorMap& mw, const float* bias,
-                          const float* residual, float* out, int M, int N, int K, int splits, cudaStream_t s) {
+                          const float* residual, float* out, int M, int N, int K, int splits, long long split_stride,
+                          cudaStream_t s) {
   using S = Smem<BLOCK_N, kStages>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -394,15 +343,8 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& ml, const CU
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = s;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   int na = 0;
-  if (splits > 1) {
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 1;
-    attr[na].val.clusterDim.y = 1;
-    attr[na].val.clusterDim.z = splits;
-    ++na;
-  }
   if (g_use_pdl) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
@@ -410,13 +352,8 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& ml, const CU
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kStages>, ma, ml, mw, bias, residual, out, M, N, K);
-}
-
-// shared-memory room for the (splits - 1) partial tiles the leader receives (aliases the pipeline stages)
-template <int BLOCK_N, int kStages>
-constexpr bool splits_fit(int splits) {
-  return (splits - 1) * BLOCK_M * (BLOCK_N + 4) * 4 <= kStages * Smem<BLOCK_N, kStages>::kStageBytes;
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kStages>, ma, ml, mw, bias, residual, out, M, N, K,
+                            split_stride);
 }
 
 }  // namespace tc
@@ -429,33 +366,32 @@ void launch_split_bf16(const float* in, int64_t in_stride, void* hi, void* lo, i
            (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, rows, K);
 }
 
-// Tile width and split-K factor from a small cost model: the per-SM TMA fill rate (~80 GB/s) bounds these
-// skinny GEMMs, so the goal is to spread the operand bytes over ~all SMs without re-reading A too often.
-// split-K runs as a thread-block cluster (<= 8 CTAs, BLOCK_N <= 64) reduced over distributed shared memory.
-void gemm_tc_plan(int M, int N, int K, int num_sms, int* bn_out, int* splits_out) {
+// Tile width and split-K factor from a small cost model. These skinny GEMMs (M = envs x tokens, a few hundred
+// rows) are bound by the rate at which ONE SM can pull operand tiles out of L2 (~80 GB/s per SM through TMA,
+// ~6.3 KB/clk chip-wide), not by the tensor pipe and not by L2 bandwidth: every CTA re-reads the A planes of
+// its row tile. So the goal is to put ~one CTA on every SM with as few operand bytes per CTA as possible:
+// wide tiles (fewer A re-reads) x split-K (more CTAs). A split-K CTA writes its partial tile to its own
+// plane; the consumer kernels add the planes (costed below at L2 speed).
+void gemm_tc_plan(int M, int N, int K, int num_sms, int max_splits, int* bn_out, int* splits_out) {
   const int m_tiles = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
   const int kb = K / tc::BLOCK_K;
   double best = 1e30;
   int best_bn = 64, best_sp = 1;
   const int bns[3] = {128, 64, 32};
-  const int sps[6] = {1, 2, 3, 4, 6, 8};
   for (int bi = 0; bi < 3; ++bi) {
     const int bn = bns[bi];
     const int n_tiles = (N + bn - 1) / bn;
-    for (int si = 0; si < 6; ++si) {
-      const int sp = sps[si];
+    for (int sp = 1; sp <= (max_splits < 1 ? 1 : max_splits); ++sp) {
       if (kb % sp) continue;
       const int kbp = kb / sp;
-      if (sp > 1) {
-        if (kbp < 2 || bn > 64) continue;
-        const bool fit = bn == 64 ? tc::splits_fit<64, 4>(sp) : tc::splits_fit<32, 6>(sp);
-        if (!fit) continue;
-      }
       const int ctas = m_tiles * n_tiles * sp;
       const int waves = (ctas + num_sms - 1) / num_sms;
-      const double per_cta_kb = kbp * (2.0 * 16.0 + bn * 0.125);             // KB of smem fill
-      double t = waves * (2.5 + per_cta_kb / 80.0);                          // us
-      if (sp > 1) t += 1.0 + (sp - 1) * (128.0 * bn * 4.0 / 1024.0) / 40.0;  // 2 cluster barriers + DSMEM pushes
+      const double fill_kb = kbp * (2.0 * 16.0 + bn * 0.125);                // operand KB through TMA per CTA
+      const double store_kb = 128.0 * bn * 4.0 / 1024.0;                     // output tile written per CTA
+      double t = waves * (2.5 + fill_kb / 80.0 + store_kb / 80.0);           // us
+      // consumers re-read sp planes; they are latency-bound kernels, so the extra loads cost as if at ~1.5 TB/s
+      // (fitted to the B200 sweep in profiles/r01_gemm_splitk.md)
+      if (sp > 1) t += 0.6 + (double)(sp - 1) * M * N * 4.0 / 1.5e6;
       if (t < best) { best = t; best_bn = bn; best_sp = sp; }
     }
   }
@@ -463,18 +399,17 @@ void gemm_tc_plan(int M, int N, int K, int num_sms, int* bn_out, int* splits_out
   *splits_out = best_sp;
 }
 
+// bn: 128 / 64 / 32 (0 = plan it, without split-K). splits > 1: raw partial tiles go to out + z * split_stride
+// (bias and residual must be null; the consumer adds the planes).
 cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat16* W, const float* bias,
-                           const float* residual, float* out, int M, int N, int K, int num_sms, int force_splits,
-                           int low_smem, cudaStream_t s) {
+                           const float* residual, float* out, int M, int N, int K, int num_sms, int bn, int splits,
+                           long long split_stride, int low_smem, cudaStream_t s) {
   if (!gemm_tc_supported(M, N, K)) return cudaErrorInvalidValue;
-  int bn, splits;
-  gemm_tc_plan(M, N, K, num_sms, &bn, &splits);
-  if (force_splits == 1 || low_smem) {   // A/B switch: best tile width without split-K
-    const int m_tiles = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
-    bn = 128;
-    if ((int64_t)m_tiles * ((N + 127) / 128) < num_sms) bn = 64;
-    if ((int64_t)m_tiles * ((N + 63) / 64) < num_sms / 2) bn = 32;
-    splits = 1;
+  if (splits < 1) splits = 1;
+  if (splits > 1 && (bias || residual || (K / tc::BLOCK_K) % splits)) return cudaErrorInvalidValue;
+  if (bn != 128 && bn != 64 && bn != 32) {
+    int sp;
+    gemm_tc_plan(M, N, K, num_sms, 1, &bn, &sp);
   }
   CUtensorMap ma, ml, mw;
   if (!tc::make_map(&ma, a_hi, M, K, tc::BLOCK_M) || !tc::make_map(&ml, a_lo, M, K, tc::BLOCK_M) ||
@@ -483,15 +418,15 @@ cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat
   if (low_smem) {
     // shallow rings (<= 110 KB): the CTA must fit beside a resident state-stream CTA of another micro-batch
     switch (bn) {
-      case 128: return tc::launch<128, 2>(ma, ml, mw, bias, residual, out, M, N, K, 1, s);
-      case 64: return tc::launch<64, 2>(ma, ml, mw, bias, residual, out, M, N, K, 1, s);
-      default: return tc::launch<32, 3>(ma, ml, mw, bias, residual, out, M, N, K, 1, s);
+      case 128: return tc::launch<128, 2>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
+      case 64: return tc::launch<64, 2>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
+      default: return tc::launch<32, 3>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
     }
   }
   switch (bn) {
-    case 128: return tc::launch<128, 4>(ma, ml, mw, bias, residual, out, M, N, K, 1, s);
-    case 64: return tc::launch<64, 4>(ma, ml, mw, bias, residual, out, M, N, K, splits, s);
-    default: return tc::launch<32, 6>(ma, ml, mw, bias, residual, out, M, N, K, splits, s);
+    case 128: return tc::launch<128, 4>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
+    case 64: return tc::launch<64, 4>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
+    default: return tc::launch<32, 6>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
   }
 }
 

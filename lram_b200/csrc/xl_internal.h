@@ -15,6 +15,11 @@ extern int g_use_pdl;   // programmatic dependent launch of every kernel (xl_com
 void launch_ln_rows(const float* in, int64_t in_stride, float* out, int64_t out_stride, const float* w,
                     const float* bias, int residual_weight, float eps, int rows, int d, void* a_hi,
                     void* a_lo, cudaStream_t s);
+// Same, but first folds a split-K proj_down into the residual stream: x[r] += sum_z part[z*part_stride + r*d]
+// (planes added in order z = 0..splits-1; x dense [rows, d], updated in place), then normalises x. d <= 4096.
+void launch_ln_rows_reduce(float* x, const float* part, int splits, int64_t part_stride, float* out,
+                           int64_t out_stride, const float* w, float eps, int rows, int d, void* a_hi, void* a_lo,
+                           cudaStream_t s);
 
 // Token embedding of one timestep: rows (b, tok) of [B,3,d]:
 //   tok 0 = s_emb[b] (state Linear output incl. bias), tok 1 = rtg[b]*w_ret + b_ret,
@@ -30,7 +35,9 @@ void launch_copy_rows(const float* in, int64_t in_stride, float* out, int64_t ou
                       cudaStream_t s);
 
 struct ConvQkvParams {
-  const float* u;       // [M, 2*inner]  (x_m | z) from proj_up
+  const float* u;       // [M, 2*inner]  (x_m | z) from proj_up; u_splits > 1: sum of that many split-K planes
+  int u_splits;         // 0/1 = one plane
+  int64_t u_stride;     // elements between planes
   float* conv_state;    // [B, KS, inner] in/out
   const float* conv_w;  // [inner, KS]
   const float* conv_b;  // [inner]
@@ -74,6 +81,8 @@ struct StateStepParams {
   const float* skip;        // [inner] or nullptr  -> out = h_norm when nullptr
   const float* act;         // [M, inner]   (used when skip != nullptr)
   const float* u;           // [M, 2*inner] (z = u[:, inner:]) (used when skip != nullptr)
+  int u_splits;             // split-K planes of u to add (0/1 = one plane), u_stride elements apart
+  int64_t u_stride;
   float* out;               // [M, inner]  (h_norm + skip*a) * silu(z), or h_norm
   void* out_hi;             // optional bf16 hi/lo split of `out`
   void* out_lo;
@@ -127,10 +136,12 @@ void launch_gemm_simple(const float* A, const __nv_bfloat16* W, const float* bia
 // tcgen05 path: A given as bf16 hi/lo planes (A = hi + lo), W bf16, fp32 accumulate in TMEM.
 bool gemm_tc_supported(int M, int N, int K);
 void launch_split_bf16(const float* in, int64_t in_stride, void* hi, void* lo, int rows, int K, cudaStream_t s);
-// split-K is chosen by a cost model (cluster of CTAs reduced over DSMEM); force_splits = 1 disables it.
+// bn = tile width (128/64/32, 0 = planned). splits > 1 = split-K: CTA z writes its raw partial tile to the plane
+// out + z*split_stride (bias/residual must be null); the consumer kernels add the planes in order.
 cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat16* W, const float* bias,
-                           const float* residual, float* out, int M, int N, int K, int num_sms, int force_splits,
-                           int low_smem, cudaStream_t s);
-void gemm_tc_plan(int M, int N, int K, int num_sms, int* bn_out, int* splits_out);
+                           const float* residual, float* out, int M, int N, int K, int num_sms, int bn, int splits,
+                           long long split_stride, int low_smem, cudaStream_t s);
+// cost model: tile width and split-K factor (<= max_splits, dividing K/64)
+void gemm_tc_plan(int M, int N, int K, int num_sms, int max_splits, int* bn_out, int* splits_out);
 
 }  // namespace xl

@@ -813,6 +813,8 @@ __global__ void __launch_bounds__(1024) mlstm_state_finalize_kernel(StateStepPar
     qk[t] = ok ? reinterpret_cast<const float2*>(p.qk)[(row * p.NH + hd) * DH + a] : make_float2(0.f, 0.f);
     act[t] = (ok && p.skip) ? p.act[row * inner + ch] : 0.f;
     zz[t] = (ok && p.skip) ? p.u[row * 2 * inner + inner + ch] : 0.f;
+    if (ok && p.skip)
+      for (int z = 1; z < p.u_splits; ++z) zz[t] += p.u[z * p.u_stride + row * 2 * inner + inner + ch];
   }
   if (threadIdx.x < 32) compute_gates<T>(p, b, hd, bh, s_f, s_i, s_m, s_pre);
   pdl_wait();

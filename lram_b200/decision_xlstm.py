@@ -8,8 +8,9 @@
                                               discrete_decision_transformer_sb3.py:13-72
 
 Same names, argument meaning and error behaviour as the reference for this path; everything that is not on
-the inference-cache rollout path (training, losses, prompts, autoregressive per-dimension decoding, image
-encoders) is out of scope and raises NotImplementedError instead of silently doing something else.
+the inference-cache rollout path (training, losses, prompts, autoregressive per-dimension decoding) is out of
+scope and raises NotImplementedError instead of silently doing something else. Image observations run the
+reference's ImpalaCNN in PyTorch/cuDNN (image_encoder.py) and enter the CUDA path as state embeddings.
 All arithmetic runs in libxlstm_b200.so; there is no PyTorch fallback.
 """
 from __future__ import annotations
@@ -21,7 +22,8 @@ import torch
 
 from . import _lib as L
 from .config import XLSTMPolicyConfig
-from .engine import StateCache, XLSTMEngine
+from .engine import StateCache, XLSTMEngine, strip_checkpoint_prefixes
+from .image_encoder import ImpalaCNN, split_image_weights
 from .tokenizers import make_tokenizer
 
 
@@ -95,9 +97,18 @@ class MultiDomainDiscreteDecisionXLSTMModel:
     """
 
     def __init__(self, config: XLSTMPolicyConfig, state_dict: Dict[str, torch.Tensor], max_batch: int = 1,
-                 device=None, mode: int = L.XL_MODE_FUSED, use_graph: bool = False):
+                 device=None, mode: int = L.XL_MODE_FUSED, use_graph: bool = False, image_shape=(3, 64, 64),
+                 img_is_encoded: bool = False):
         self.config = config
         self.engine = XLSTMEngine(config, state_dict, max_batch=max_batch, device=device)
+        # embed_image (ImpalaCNN, multi_domain_discrete_dt_model.py:38-46) exists when the checkpoint carries it;
+        # it stays a PyTorch/cuDNN module feeding the CUDA path with state embeddings
+        self.embed_image = None
+        self.img_is_encoded = img_is_encoded
+        img_sd = split_image_weights(strip_checkpoint_prefixes(state_dict))
+        if img_sd:
+            self.embed_image = ImpalaCNN(image_shape, config.d).to(self.engine.device).eval()
+            self.embed_image.load_state_dict(img_sd)
         self.encoder = FusedXLSTMEncoder(self.engine, mode=mode)
         self.mode = mode
         self.use_graph = use_graph
@@ -119,11 +130,21 @@ class MultiDomainDiscreteDecisionXLSTMModel:
             raise NotImplementedError("only the inference-cache (recurrent) path is implemented")
         if prompt is not None or context_trjs is not None:
             raise NotImplementedError("prompts / retrieval contexts are out of scope")
-        if states.dim() != 3:
-            raise NotImplementedError("image observations go through the PyTorch ImpalaCNN; out of scope here")
         cfg = self.config
         B = states.shape[0]
-        if states.shape[-1] != cfg.state_dim:
+        state_embeds = False
+        if states.dim() == 5:
+            # image observations [B, T, C, H, W]: /255 + embed_image on the newest frame
+            # (online_decision_transformer_model.py:522-526, discrete_decision_transformer_model.py:187-203)
+            if self.embed_image is None:
+                raise ValueError("image observations need embed_image.* weights in the state_dict")
+            states = self.embed_image(states[:, -1].to(self.device)).unsqueeze(1)
+            state_embeds = True
+        elif states.dim() == 3 and self.img_is_encoded and states.shape[-1] == cfg.d:
+            state_embeds = True                     # discrete_decision_transformer_model.py:185-186
+        elif states.dim() != 3:
+            raise ValueError(f"states must be [B,T,{cfg.state_dim}] or [B,T,C,H,W], got {tuple(states.shape)}")
+        elif states.shape[-1] != cfg.state_dim:
             raise ValueError(f"states must be padded to {cfg.state_dim} (DecisionXLSTM.pad_inputs)")
         # is_discrete passed to the head = not actions.is_floating_point(); actions become int64 only for 1-D
         # action envs (online_decision_transformer_model.py:350-352,364)
@@ -142,7 +163,7 @@ class MultiDomainDiscreteDecisionXLSTMModel:
             cache.load_past_key_values(past_key_values)
         flags = (L.XL_FLAG_DISCRETE if discrete else 0) | (L.XL_FLAG_GRAPH if self.use_graph else 0)
         out = self.engine.policy_step(cache, s_last, g_last, r_last, mode=self.mode, flags=flags,
-                                      want_logits=True, want_hidden=True)
+                                      want_logits=True, want_hidden=True, state_embeds=state_embeds)
         tokens = out["action_tokens"].to(torch.long)
         if discrete:
             action_preds = tokens[:, :1].view(B, 1, 1)

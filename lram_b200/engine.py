@@ -241,10 +241,18 @@ class XLSTMEngine:
 
     def policy_step(self, state: StateCache, states: torch.Tensor, rtg: torch.Tensor,
                     rewards: Optional[torch.Tensor] = None, mode: int = L.XL_MODE_FUSED, flags: int = 0,
-                    want_logits: bool = False, want_hidden: bool = False, out: Optional[dict] = None):
+                    want_logits: bool = False, want_hidden: bool = False, out: Optional[dict] = None,
+                    state_embeds: bool = False):
+        """One env step of the policy. `states` [B, state_dim]; with `state_embeds=True` it is instead the
+        state-token embedding [B, d] computed by the caller (image observations -> ImpalaCNN, or the reference's
+        `img_is_encoded` inputs, discrete_decision_transformer_model.py:185-186) and embed_state is skipped."""
         cfg = self.cfg
         B = state.B
-        assert states.is_cuda and states.dtype == torch.float32 and tuple(states.shape) == (B, cfg.state_dim)
+        if state_embeds:
+            flags |= L.XL_FLAG_STATE_EMBEDS
+        want = (B, cfg.d) if (flags & L.XL_FLAG_STATE_EMBEDS) else (B, cfg.state_dim)
+        assert states.is_cuda and states.dtype == torch.float32 and tuple(states.shape) == want, \
+            f"states must be a cuda fp32 tensor of shape {want}, got {tuple(states.shape)}"
         assert rtg.is_cuda and rtg.dtype == torch.float32 and rtg.numel() == B
         states, rtg = states.contiguous(), rtg.contiguous()
         if rewards is not None:
