@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define XL_ABI_VERSION 1
+#define XL_ABI_VERSION 2
 
 typedef enum {
   XL_OK = 0,
@@ -43,7 +43,7 @@ typedef struct xl_handle xl_handle;
  * (configs/agent_params/model_kwargs/multi_domain.yaml:1-11). */
 typedef struct {
   int32_t embedding_dim;      /* d                                              */
-  int32_t num_blocks;         /* L (all mLSTM blocks)                           */
+  int32_t num_blocks;         /* L (mLSTM blocks unless listed in slstm_mask)   */
   int32_t num_heads;          /* NH                                             */
   int32_t inner_dim;          /* ceil(2d/64)*64                                 */
   int32_t conv_kernel;        /* KS = 4                                         */
@@ -60,6 +60,11 @@ typedef struct {
   float embed_ln_eps;         /* 1e-5 nn.LayerNorm                              */
   float tok_min_val;          /* -1 MinMaxTokenizer                             */
   float tok_max_val;          /* +1                                             */
+  /* xLSTM[a:b] stacks (xlstm_config.slstm_at, configs/agent_params/huggingface/xlstm_ms_mediumplus.yaml:27;
+   * README.md:188-190): bit i set = block i is an sLSTM block (sLSTM layer + gated feed-forward).          */
+  uint32_t slstm_mask_lo;     /* blocks 0..31                                   */
+  uint32_t slstm_mask_hi;     /* blocks 32..63                                  */
+  int32_t ffn_dim;            /* ceil(1.3 d / 64) * 64 (slstm_block.feedforward.proj_factor); 0 = no sLSTM */
 } xl_config;
 
 /* Weight slots. Names in comments are the reference's state_dict keys. `layer` = block index, or -1 for
@@ -80,7 +85,19 @@ typedef enum {
   XL_W_OUTNORM = 11,       /* xlstm.mlstm_cell.outnorm.weight (gamma = 1 + w)           fp32 [inner]          */
   XL_W_SKIP = 12,          /* xlstm.learnable_skip                                      fp32 [inner]          */
   XL_W_PROJ_DOWN = 13,     /* xlstm.proj_down.weight                                    bf16 [d, inner]       */
-  XL_W_PER_BLOCK_COUNT = 14,
+  /* sLSTM block (blocks in slstm_mask): encoder.layers.blocks.{i}.*; shares XL_W_XLSTM_NORM, XL_W_CONV_W
+   * ([d,1,KS]) and XL_W_CONV_B ([d]) with the mLSTM slots. DHs = d / NH.                                     */
+  XL_W_S_GATE_I = 14,      /* xlstm.fgate.weight  -> INPUT-gate pre-activation (sic, see oracle) fp32 [NH, DHs, DHs] */
+  XL_W_S_GATE_F = 15,      /* xlstm.igate.weight  -> FORGET-gate pre-activation (sic)       fp32 [NH, DHs, DHs] */
+  XL_W_S_GATE_Z = 16,      /* xlstm.zgate.weight                                        fp32 [NH, DHs, DHs]   */
+  XL_W_S_GATE_O = 17,      /* xlstm.ogate.weight                                        fp32 [NH, DHs, DHs]   */
+  XL_W_S_RECURRENT = 18,   /* xlstm.slstm_cell._recurrent_kernel_  [head, in, gate, out] fp32 [NH, DHs, 4, DHs] */
+  XL_W_S_BIAS = 19,        /* xlstm.slstm_cell._bias_                                   fp32 [NH, 4, DHs]     */
+  XL_W_S_GROUP_NORM = 20,  /* xlstm.group_norm.weight (gamma = 1 + w)                   fp32 [d]              */
+  XL_W_FFN_NORM = 21,      /* ffn_norm.weight (gamma = 1 + w)                           fp32 [d]              */
+  XL_W_FFN_UP = 22,        /* ffn.proj_up.weight                                        bf16 [2*ffn_dim, d]   */
+  XL_W_FFN_DOWN = 23,      /* ffn.proj_down.weight                                      bf16 [d, ffn_dim]     */
+  XL_W_PER_BLOCK_COUNT = 24,
   /* policy level (layer = -1) */
   XL_W_POST_NORM = 32,     /* encoder.layers.post_blocks_norm.weight (gamma = 1 + w)    fp32 [d]              */
   XL_W_EMBED_STATE_W = 33, /* embed_state.weight, K zero-padded to xl_state_dim_padded() bf16 [d, Kpad]       */
@@ -103,7 +120,10 @@ typedef enum {
  * DH % 128 == 0 (else W = DH, i.e. the reference's row-major layout). Every [32 x 128] tile the state kernel
  * streams is then 16 contiguous KB (measured +4-5 % HBM throughput over row-major tiles). n, m and conv keep
  * the reference's layouts. lram_b200.engine.c_to_slab / c_from_slab convert. */
-typedef enum { XL_STATE_C = 0, XL_STATE_N = 1, XL_STATE_M = 2, XL_STATE_CONV = 3 } xl_state_part;
+/* An sLSTM block's slot holds  slstm[4,B,d] = (y, c, n, m) | conv[B,KS,d]  instead (the reference's
+ * {"slstm_state": [4,B,d], "conv_state": (conv,)}); blocks are packed back to back, so the offset of a block
+ * depends on the kinds of the blocks before it — always ask xl_state_layout(). */
+typedef enum { XL_STATE_C = 0, XL_STATE_N = 1, XL_STATE_M = 2, XL_STATE_CONV = 3, XL_STATE_SLSTM = 4 } xl_state_part;
 
 /* step modes */
 #define XL_MODE_PER_TOKEN 0 /* reference order: for token: for block (decision_xlstm.py:161-165)          */

@@ -22,12 +22,15 @@ XL_MODE_PER_TOKEN, XL_MODE_FUSED = 0, 1
 XL_FLAG_DISCRETE, XL_FLAG_GRAPH, XL_FLAG_SIMPLE_GEMM, XL_FLAG_STATE_EMBEDS = 1, 2, 4, 8
 
 # state parts
-XL_STATE_C, XL_STATE_N, XL_STATE_M, XL_STATE_CONV = 0, 1, 2, 3
+XL_STATE_C, XL_STATE_N, XL_STATE_M, XL_STATE_CONV, XL_STATE_SLSTM = 0, 1, 2, 3, 4
+XL_ABI_VERSION = 2
 
 # weight ids (xl_weight_id)
 W = dict(
     XLSTM_NORM=0, PROJ_UP=1, Q_PROJ=2, K_PROJ=3, V_PROJ=4, CONV_W=5, CONV_B=6, IGATE_W=7, IGATE_B=8,
     FGATE_W=9, FGATE_B=10, OUTNORM=11, SKIP=12, PROJ_DOWN=13,
+    S_GATE_I=14, S_GATE_F=15, S_GATE_Z=16, S_GATE_O=17, S_RECURRENT=18, S_BIAS=19, S_GROUP_NORM=20,
+    FFN_NORM=21, FFN_UP=22, FFN_DOWN=23,
     POST_NORM=32, EMBED_STATE_W=33, EMBED_STATE_B=34, EMBED_RETURN_W=35, EMBED_RETURN_B=36,
     EMBED_REWARD_W=37, EMBED_REWARD_B=38, EMBED_LN_W=39, EMBED_LN_B=40, HEAD_W=41, HEAD_B=42,
 )
@@ -42,6 +45,7 @@ class XLConfig(C.Structure):
         ("max_batch", C.c_int32),
         ("ln_eps", C.c_float), ("cell_eps", C.c_float), ("embed_ln_eps", C.c_float),
         ("tok_min_val", C.c_float), ("tok_max_val", C.c_float),
+        ("slstm_mask_lo", C.c_uint32), ("slstm_mask_hi", C.c_uint32), ("ffn_dim", C.c_int32),
     ]
 
 

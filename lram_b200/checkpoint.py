@@ -122,17 +122,23 @@ _BLOCK_RE = re.compile(r"^encoder\.layers\.blocks\.(\d+)\.")
 
 
 def infer_config(sd: Dict[str, torch.Tensor], name: str = "checkpoint") -> XLSTMPolicyConfig:
-    """Shapes -> XLSTMPolicyConfig. Refuses checkpoints this path does not cover (sLSTM blocks, ln_bias, RMSNorm,
-    image-only policies), naming the offending key."""
+    """Shapes -> XLSTMPolicyConfig (sLSTM blocks of xLSTM[a:b] stacks are recognised by their
+    `xlstm.slstm_cell._recurrent_kernel_` entry). Refuses checkpoints this path does not cover (ln_bias, RMSNorm,
+    image-only policies, stacks without any mLSTM block), naming the offending key."""
     blocks = sorted({int(m.group(1)) for k in sd for m in [_BLOCK_RE.match(k)] if m})
     if not blocks or blocks != list(range(len(blocks))):
         raise ValueError("state_dict has no contiguous encoder.layers.blocks.{i}.* entries (not an xLSTM policy?)")
+    slstm_at = tuple(i for i in blocks if f"encoder.layers.blocks.{i}.xlstm.slstm_cell._recurrent_kernel_" in sd)
+    mlstm = [i for i in blocks if i not in slstm_at]
+    if not mlstm:
+        raise NotImplementedError("a stack of sLSTM blocks only is not on this path (no mLSTM block found)")
     for k in sd:
-        if ".slstm_cell." in k or ".ffn." in k:
-            raise NotImplementedError(f"{k}: sLSTM / feed-forward blocks (xLSTM[7:1]) are not on this path")
+        m = _BLOCK_RE.match(k)
+        if m and ".ffn." in k and int(m.group(1)) not in slstm_at:
+            raise NotImplementedError(f"{k}: feed-forward sub-layer on an mLSTM block is not on this path")
         if k.endswith("xlstm_norm.bias") or k.endswith("outnorm.bias") or k.endswith("post_blocks_norm.bias"):
             raise NotImplementedError(f"{k}: ln_bias=True variants are not supported")
-    b0 = "encoder.layers.blocks.0.xlstm."
+    b0 = f"encoder.layers.blocks.{mlstm[0]}.xlstm."
     up = sd[b0 + "proj_up.weight"]
     d = up.shape[1]
     inner = up.shape[0] // 2
@@ -151,6 +157,15 @@ def infer_config(sd: Dict[str, torch.Tensor], name: str = "checkpoint") -> XLSTM
     head = sd["action_net.0.weight"] if "action_net.0.weight" in sd else None
     cfg_kw = dict(embedding_dim=d, num_blocks=len(blocks), num_heads=nh, conv1d_kernel_size=ks,
                   qkv_proj_blocksize=bs, proj_factor=inner / d, state_dim=state_dim, name=name)
+    if slstm_at:
+        s0 = f"encoder.layers.blocks.{slstm_at[0]}."
+        rk = sd[s0 + "xlstm.slstm_cell._recurrent_kernel_"]
+        if tuple(rk.shape) != (nh, d // nh, 4, d // nh):
+            raise ValueError(f"_recurrent_kernel_ {tuple(rk.shape)} is not [NH, d/NH, 4, d/NH] for d={d}, NH={nh}")
+        ff = sd[s0 + "ffn.proj_down.weight"].shape[1]
+        cfg_kw.update(slstm_at=slstm_at, ffn_proj_factor=ff / d)
+        if XLSTMPolicyConfig(**cfg_kw).ffn_dim != ff:
+            raise ValueError(f"ffn dim {ff} is not proj_factor*d rounded up to 64 (d={d})")
     cfg = XLSTMPolicyConfig(**cfg_kw)
     if cfg.inner != inner:
         raise ValueError(f"inner={inner} is not proj_factor*d rounded up to 64 (d={d})")

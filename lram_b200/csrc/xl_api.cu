@@ -62,6 +62,7 @@ struct xl_handle {
   int device = 0;
   int num_sms = 148;
   int DH = 0, NCH = 0, Kpad = 0, head_out = 0, num_actions = 0;
+  uint64_t slstm_mask = 0;             // bit i: block i is an sLSTM block (+ gated feed-forward)
   std::vector<BlockWeights> blocks;
   const void* pw[16];  // policy-level weights, index = id - XL_W_POST_NORM
   // workspace (device)
@@ -95,6 +96,8 @@ struct xl_handle {
   size_t part_rows = 0;
   int microbatches = 0;                // 0 = automatic; env micro-batches per fused step ("microbatches")
   int pipeline_order = 1;              // 1 = state-stream kernels of the micro-batches run one after another
+  int l2_prefetch_mb = 0;              // MiB of the NEXT block's C warmed into L2 on a side stream while the chain
+                                       // of the current block runs (0 = off)            ("l2_prefetch_mb")
   // context-prefill workspace (lazily allocated by xl_prefill / xl_policy_prefill, grow-only)
   char* pf_buf = nullptr;
   int pf_rows = 0;
@@ -110,8 +113,11 @@ struct xl_handle {
 namespace {
 
 struct StateLayout {
-  size_t c_off, n_off, m_off, conv_off, layer_bytes;
+  size_t c_off, n_off, m_off, conv_off, layer_bytes;      // mLSTM block slot
+  size_t s_off, sconv_off, slayer_bytes;                   // sLSTM block slot: (y,c,n,m) [4,B,d] | conv [B,KS,d]
 };
+
+inline bool is_slstm(const xl_handle* h, int i) { return (h->slstm_mask >> i) & 1ull; }
 
 StateLayout state_layout(const xl_handle* h, int B) {
   const xl_config& c = h->cfg;
@@ -126,7 +132,20 @@ StateLayout state_layout(const xl_handle* h, int B) {
   L.conv_off = off;
   off = align_up(off + sizeof(float) * (size_t)B * c.conv_kernel * c.inner_dim, 256);
   L.layer_bytes = off;
+  off = 0;
+  L.s_off = off;
+  off = align_up(off + sizeof(float) * (size_t)4 * B * c.embedding_dim, 256);
+  L.sconv_off = off;
+  off = align_up(off + sizeof(float) * (size_t)B * c.conv_kernel * c.embedding_dim, 256);
+  L.slayer_bytes = off;
   return L;
+}
+
+// byte offset of block i's slot: blocks are packed back to back, each with the size of its kind
+size_t layer_base(const xl_handle* h, const StateLayout& L, int i) {
+  const uint64_t below = i >= 64 ? ~0ull : ((1ull << i) - 1ull);
+  const int ns = __builtin_popcountll(h->slstm_mask & below);
+  return (size_t)(i - ns) * L.layer_bytes + (size_t)ns * L.slayer_bytes;
 }
 
 int check_batch(const xl_handle* h, int B) {
@@ -247,7 +266,7 @@ xl::StateStepParams state_params(const xl_handle* h, void* state, const Slice& s
   const int inner = c.inner_dim, NH = c.num_heads, DH = h->DH;
   const StateLayout L = state_layout(h, sl.B);
   const BlockWeights& w = h->blocks[i];
-  char* base = (char*)state + (size_t)i * L.layer_bytes;
+  char* base = (char*)state + layer_base(h, L, i);
   const int M = sl.Bk * T;
   xl::StateStepParams sp;
   memset(&sp, 0, sizeof(sp));
@@ -289,10 +308,10 @@ int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned
   const BlockPlan bp = block_plan(h, sl, T, flags);
   const BlockWeights& w = h->blocks[i];
   const Ws& ws = sl.ws;
-  char* base = (char*)state + (size_t)i * L.layer_bytes;
+  char* base = (char*)state + layer_base(h, L, i);
   if (h->debug_skip & 1) {
-  } else if (i > 0 && bp.down_sp > 1) {
-    // the previous block's proj_down left split-K planes: x += planes, then normalise
+  } else if (i > 0 && bp.down_sp > 1 && !is_slstm(h, i - 1)) {
+    // the previous (mLSTM) block's proj_down left split-K planes: x += planes, then normalise
     xl::launch_ln_rows_reduce(ws.x, h->part_down, bp.down_sp, (int64_t)M * d, bp.tc_up ? nullptr : ws.xn, d,
                               (const float*)w.w[XL_W_XLSTM_NORM], c.ln_eps, M, d, bp.tc_up ? ws.a_hi : nullptr,
                               bp.tc_up ? ws.a_lo : nullptr, sl.s);
@@ -367,13 +386,62 @@ int block_post(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigne
                 c.inner_dim, bp.impl, sl.s, bp.tc_down, bp.down_bn);
 }
 
+// sLSTM block i (sLSTM layer + gated feed-forward) over the M = Bk*T rows of ws.x (rows [env][token]), envs
+// [b0, b0+Bk) of a state holding Btot envs. pend_sp > 1: the previous mLSTM block left that many split-K
+// proj_down planes, folded into x by this block's first LayerNorm. Workspace reuse: xn = LN(x), act = swish(conv),
+// u = gate pre-activations [M,4,d], gated = y [M,d], qkv = feed-forward up projection [M,2ff].
+int slstm_block(xl_handle* h, void* state, const Ws& ws, int Btot, int b0, int Bk, int i, int T, unsigned flags,
+                int pend_sp, cudaStream_t s) {
+  const xl_config& c = h->cfg;
+  const int d = c.embedding_dim, NH = c.num_heads, ff = c.ffn_dim, KS = c.conv_kernel, M = Bk * T;
+  const StateLayout L = state_layout(h, Btot);
+  const BlockWeights& w = h->blocks[i];
+  char* base = (char*)state + layer_base(h, L, i);
+  float* st = (float*)(base + L.s_off) + (size_t)b0 * d;                   // (y,c,n,m), part stride Btot*d
+  float* conv = (float*)(base + L.sconv_off) + (size_t)b0 * KS * d;
+  const int impl = (flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
+  const bool tc_up = impl != 1 && xl::gemm_tc_supported(M, 2 * ff, d) && (size_t)M * d <= ws.a_cap;
+  const bool tc_down = impl != 1 && xl::gemm_tc_supported(M, d, ff) && (size_t)M * ff <= ws.a_cap;
+  auto F = [&](int id) { return (const float*)w.w[id]; };
+  if (pend_sp > 1)
+    xl::launch_ln_rows_reduce(ws.x, h->part_down, pend_sp, (int64_t)M * d, ws.xn, d, F(XL_W_XLSTM_NORM), c.ln_eps, M,
+                              d, nullptr, nullptr, s);
+  else
+    xl::launch_ln_rows(ws.x, d, ws.xn, d, F(XL_W_XLSTM_NORM), nullptr, 1, c.ln_eps, M, d, nullptr, nullptr, s);
+  if (!xl::launch_slstm_conv(ws.xn, conv, F(XL_W_CONV_W), F(XL_W_CONV_B), ws.act, Bk, T, d, KS, s))
+    return fail(XL_ERR_UNSUPPORTED, "sLSTM conv kernel not instantiated for KS=%d", KS);
+  xl::launch_slstm_gates(ws.act, ws.xn, F(XL_W_S_GATE_I), F(XL_W_S_GATE_F), F(XL_W_S_GATE_Z), F(XL_W_S_GATE_O),
+                         F(XL_W_S_BIAS), ws.u, M, d, NH, s);
+  for (int t = 0; t < T; ++t)
+    XL_CUDA(xl::launch_slstm_cell(ws.u, F(XL_W_S_RECURRENT), st, ws.gated, Bk, Btot, T, t, d, NH, s));
+  xl::launch_slstm_out(ws.gated, F(XL_W_S_GROUP_NORM), ws.x, st, M, T, d, NH, c.ln_eps, s);
+  xl::launch_ln_rows(ws.x, d, tc_up ? nullptr : ws.xn, d, F(XL_W_FFN_NORM), nullptr, 1, c.ln_eps, M, d,
+                     tc_up ? ws.a_hi : nullptr, tc_up ? ws.a_lo : nullptr, s);
+  h->launches += 5 + T;
+  int rc = linear(h, ws, ws.xn, w.w[XL_W_FFN_UP], nullptr, nullptr, ws.qkv, M, 2 * ff, d, impl, s, tc_up);
+  if (rc) return rc;
+  xl::launch_ffn_gate(ws.qkv, tc_down ? nullptr : ws.gated, tc_down ? ws.a_hi : nullptr, tc_down ? ws.a_lo : nullptr,
+                      M, ff, s);
+  h->launches += 1;
+  rc = linear(h, ws, ws.gated, w.w[XL_W_FFN_DOWN], nullptr, ws.x, ws.x, M, d, ff, impl, s, tc_down);
+  if (rc) return rc;
+  XL_CUDA(cudaGetLastError());
+  return XL_OK;
+}
+
+// split-K planes the block before i leaves for i's first LayerNorm (1 = none)
+int pending_planes(const xl_handle* h, const Slice& sl, int i, int T, unsigned flags) {
+  if (i == 0 || is_slstm(h, i - 1)) return 1;
+  return block_plan(h, sl, T, flags).down_sp;
+}
+
 // post_blocks_norm over the M = Bk*T rows of ws.x left by run_blocks (folds the last block's split-K planes)
 void final_norm(xl_handle* h, const Slice& sl, int T, unsigned flags, float* out, int64_t out_stride) {
   const xl_config& c = h->cfg;
   const int d = c.embedding_dim, M = sl.Bk * T;
   const BlockPlan bp = block_plan(h, sl, T, flags);
   const float* post_w = (const float*)h->pw[XL_W_POST_NORM - XL_W_POST_NORM];
-  if (bp.down_sp > 1)
+  if (bp.down_sp > 1 && !is_slstm(h, c.num_blocks - 1))
     xl::launch_ln_rows_reduce(sl.ws.x, h->part_down, bp.down_sp, (int64_t)M * d, out, out_stride, post_w, c.ln_eps,
                               M, d, nullptr, nullptr, sl.s);
   else
@@ -383,12 +451,37 @@ void final_norm(xl_handle* h, const Slice& sl, int T, unsigned flags, float* out
 
 // One pass of the block stack over M = Bk*T rows held in ws.x (rows ordered [b][t]).
 int run_blocks(xl_handle* h, void* state, const Slice& sl, int T, unsigned flags) {
-  for (int i = 0; i < h->cfg.num_blocks; ++i) {
-    int rc = block_pre(h, state, sl, i, T, flags);
+  const int L = h->cfg.num_blocks;
+  // L2 warm-up of the next block's C on side stream 0 (whole-batch slices only; side streams belong to the
+  // micro-batches otherwise). Block 0 of the NEXT env step is warmed after the last block's state kernel.
+  const bool warm = h->l2_prefetch_mb > 0 && sl.b0 == 0 && sl.Bk == sl.B && L > 1;
+  const StateLayout lay = state_layout(h, sl.B);
+  const size_t c_bytes = sizeof(float) * (size_t)sl.B * h->cfg.num_heads * h->DH * h->DH;
+  const size_t warm_bytes = std::min(c_bytes, (size_t)h->l2_prefetch_mb << 20);
+  int rc = XL_OK;
+  for (int i = 0; i < L && !rc; ++i) {
+    if (is_slstm(h, i)) {
+      rc = slstm_block(h, state, sl.ws, sl.B, sl.b0, sl.Bk, i, T, flags, pending_planes(h, sl, i, T, flags), sl.s);
+      continue;
+    }
+    rc = block_pre(h, state, sl, i, T, flags);
     if (!rc) rc = block_state(h, state, sl, i, T, flags);
+    if (!rc && warm) {
+      XL_CUDA(cudaEventRecord(h->ev_state[0], sl.s));
+      XL_CUDA(cudaStreamWaitEvent(h->side[0], h->ev_state[0], 0));
+      int nx = (i + 1) % L;
+      while (is_slstm(h, nx) && nx != i) nx = (nx + 1) % L;        // next mLSTM block
+      const char* next_c = (const char*)state + layer_base(h, lay, nx) + lay.c_off;
+      xl::launch_l2_prefetch(next_c, warm_bytes, h->num_sms, h->side[0]);
+      h->launches += 1;
+    }
     if (!rc) rc = block_post(h, state, sl, i, T, flags);
-    if (rc) return rc;
   }
+  if (warm) {   // join (also on the error path: a capture must not end with an unjoined stream)
+    cudaEventRecord(h->ev_join[0], h->side[0]);
+    cudaStreamWaitEvent(sl.s, h->ev_join[0], 0);
+  }
+  if (rc) return rc;
   XL_CUDA(cudaGetLastError());
   return XL_OK;
 }
@@ -553,6 +646,12 @@ int run_policy(xl_handle* h, const StepArgs& a, cudaStream_t s) {
   int rc = XL_OK;
   for (int k = 0; k < MB && !rc; ++k) rc = policy_front(h, a, sl[k], sl[k].ws.x);
   for (int i = 0; i < c.num_blocks && !rc; ++i) {
+    if (is_slstm(h, i)) {
+      for (int k = 0; k < MB && !rc; ++k)
+        rc = slstm_block(h, a.state, sl[k].ws, a.B, sl[k].b0, sl[k].Bk, i, T, a.flags,
+                         pending_planes(h, sl[k], i, T, a.flags), sl[k].s);
+      continue;
+    }
     for (int k = 0; k < MB && !rc; ++k) rc = block_pre(h, a.state, sl[k], i, T, a.flags);
     for (int k = 0; k < MB && !rc; ++k) {
       if (h->pipeline_order && !(i == 0 && k == 0)) {
@@ -647,8 +746,15 @@ int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cud
   const bool tc_up = impl != 1 && xl::gemm_tc_supported(M, 2 * inner, d) && (size_t)M * d <= ws.a_cap;
   const bool tc_down = impl != 1 && xl::gemm_tc_supported(M, d, inner) && (size_t)M * inner <= ws.a_cap;
   for (int i = 0; i < c.num_blocks; ++i) {
+    if (is_slstm(h, i)) {
+      // no parallel form exists for the sLSTM: its cell runs token by token (Sc launches of a tiny kernel), the
+      // rest of the block (conv, gate projections, GroupNorm, feed-forward) over the whole chunk
+      int rcs = slstm_block(h, state, ws, B, 0, B, i, Sc, flags, 1, s);
+      if (rcs) return rcs;
+      continue;
+    }
     const BlockWeights& w = h->blocks[i];
-    char* base = (char*)state + (size_t)i * L.layer_bytes;
+    char* base = (char*)state + layer_base(h, L, i);
     xl::launch_ln_rows(ws.x, d, tc_up ? nullptr : ws.xn, d, (const float*)w.w[XL_W_XLSTM_NORM], nullptr, 1, c.ln_eps,
                        M, d, tc_up ? ws.a_hi : nullptr, tc_up ? ws.a_lo : nullptr, s);
     h->launches += 1;
@@ -719,6 +825,18 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
     return fail(XL_ERR_UNSUPPORTED, "policy token layout is (s, rtg, r): tokens_per_step must be 3");
   const int DH = c.inner_dim / c.num_heads;
   if (DH > 1024) return fail(XL_ERR_UNSUPPORTED, "head_dim > 1024");
+  const uint64_t smask = ((uint64_t)c.slstm_mask_hi << 32) | c.slstm_mask_lo;
+  if (smask) {
+    if (c.num_blocks < 64 && (smask >> c.num_blocks)) return fail(XL_ERR_INVALID_ARG, "slstm_mask names a block >= num_blocks");
+    if (c.num_blocks > 64) return fail(XL_ERR_UNSUPPORTED, "sLSTM stacks: num_blocks <= 64");
+    if (c.embedding_dim % c.num_heads) return fail(XL_ERR_UNSUPPORTED, "sLSTM: embedding_dim %% num_heads != 0");
+    if (c.ffn_dim <= 0 || c.ffn_dim % 8) return fail(XL_ERR_UNSUPPORTED, "sLSTM: ffn_dim must be a positive multiple of 8");
+    if (2 * c.ffn_dim > 3 * c.inner_dim || c.ffn_dim > c.inner_dim || 4 * c.embedding_dim > 2 * c.inner_dim)
+      return fail(XL_ERR_UNSUPPORTED, "sLSTM: ffn_dim %d / d %d do not fit the workspace of inner_dim %d", c.ffn_dim,
+                  c.embedding_dim, c.inner_dim);
+    if ((size_t)8 * (c.embedding_dim / c.num_heads) * 4 + 8 * 8 * 4 * 32 * 4 > 200 * 1024)
+      return fail(XL_ERR_UNSUPPORTED, "sLSTM: head_dim too large for the cell kernel");
+  }
 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -729,6 +847,7 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   if (!h) return fail(XL_ERR_INVALID_ARG, "out of host memory");
   h->cfg = c;
   h->DH = DH;
+  h->slstm_mask = smask;
   {
     // gate pre-activations are produced as NCH partial sums (64 four-channel blocks per chunk), summed in
     // fixed order by the state kernels
@@ -835,7 +954,18 @@ int xl_bind_weight(xl_handle* h, int layer, int which, const void* dev_ptr, int 
   int want_dtype = 0;
   if (layer >= 0) {
     if (layer >= c.num_blocks) return fail(XL_ERR_INVALID_ARG, "layer %d >= num_blocks", layer);
-    switch (which) {
+    const int64_t DHs = d / NH, ff = c.ffn_dim;
+    if (is_slstm(h, layer)) switch (which) {
+      case XL_W_XLSTM_NORM: case XL_W_CONV_B: case XL_W_S_GROUP_NORM: case XL_W_FFN_NORM: want = d; break;
+      case XL_W_CONV_W: want = d * KS; break;
+      case XL_W_S_GATE_I: case XL_W_S_GATE_F: case XL_W_S_GATE_Z: case XL_W_S_GATE_O: want = NH * DHs * DHs; break;
+      case XL_W_S_RECURRENT: want = NH * DHs * 4 * DHs; break;
+      case XL_W_S_BIAS: want = NH * 4 * DHs; break;
+      case XL_W_FFN_UP: want = 2 * ff * d; want_dtype = 1; break;
+      case XL_W_FFN_DOWN: want = d * ff; want_dtype = 1; break;
+      default: return fail(XL_ERR_INVALID_ARG, "weight id %d does not belong to an sLSTM block (layer %d)", which, layer);
+    }
+    else switch (which) {
       case XL_W_XLSTM_NORM: want = d; break;
       case XL_W_PROJ_UP: want = 2 * inner * d; want_dtype = 1; break;
       case XL_W_Q_PROJ: case XL_W_K_PROJ: case XL_W_V_PROJ: want = inner * 4; break;
@@ -876,9 +1006,18 @@ int xl_bind_weight(xl_handle* h, int layer, int which, const void* dev_ptr, int 
 
 int xl_weights_ready(const xl_handle* h) {
   if (!h) return fail(XL_ERR_INVALID_ARG, "null handle");
-  for (int i = 0; i < h->cfg.num_blocks; ++i)
-    for (int k = 0; k < XL_W_PER_BLOCK_COUNT; ++k)
+  static const int s_ids[] = {XL_W_XLSTM_NORM, XL_W_CONV_W, XL_W_CONV_B, XL_W_S_GATE_I, XL_W_S_GATE_F, XL_W_S_GATE_Z,
+                              XL_W_S_GATE_O, XL_W_S_RECURRENT, XL_W_S_BIAS, XL_W_S_GROUP_NORM, XL_W_FFN_NORM,
+                              XL_W_FFN_UP, XL_W_FFN_DOWN};
+  for (int i = 0; i < h->cfg.num_blocks; ++i) {
+    if (is_slstm(h, i)) {
+      for (int k : s_ids)
+        if (!h->blocks[i].w[k]) return fail(XL_ERR_NOT_READY, "sLSTM block %d weight id %d not bound", i, k);
+      continue;
+    }
+    for (int k = 0; k <= XL_W_PROJ_DOWN; ++k)
       if (!h->blocks[i].w[k]) return fail(XL_ERR_NOT_READY, "block %d weight id %d not bound", i, k);
+  }
   for (int id = XL_W_POST_NORM; id <= XL_W_HEAD_B; ++id)
     if (!h->pw[id - XL_W_POST_NORM]) return fail(XL_ERR_NOT_READY, "policy weight id %d not bound", id);
   return XL_OK;
@@ -886,7 +1025,7 @@ int xl_weights_ready(const xl_handle* h) {
 
 size_t xl_state_bytes(const xl_handle* h, int B) {
   if (!h || B <= 0) return 0;
-  return state_layout(h, B).layer_bytes * (size_t)h->cfg.num_blocks;
+  return layer_base(h, state_layout(h, B), h->cfg.num_blocks);
 }
 
 int xl_state_layout(const xl_handle* h, int B, int layer, int part, size_t* offset_bytes, size_t* size_bytes) {
@@ -895,6 +1034,16 @@ int xl_state_layout(const xl_handle* h, int B, int layer, int part, size_t* offs
   const StateLayout L = state_layout(h, B);
   const xl_config& c = h->cfg;
   size_t o, sz;
+  if (is_slstm(h, layer)) {
+    switch (part) {
+      case XL_STATE_SLSTM: o = L.s_off; sz = sizeof(float) * (size_t)4 * B * c.embedding_dim; break;
+      case XL_STATE_CONV: o = L.sconv_off; sz = sizeof(float) * (size_t)B * c.conv_kernel * c.embedding_dim; break;
+      default: return fail(XL_ERR_INVALID_ARG, "state part %d does not exist in sLSTM block %d", part, layer);
+    }
+    *offset_bytes = layer_base(h, L, layer) + o;
+    *size_bytes = sz;
+    return XL_OK;
+  }
   switch (part) {
     case XL_STATE_C: o = L.c_off; sz = sizeof(float) * (size_t)B * c.num_heads * h->DH * h->DH; break;
     case XL_STATE_N: o = L.n_off; sz = sizeof(float) * (size_t)B * c.num_heads * h->DH; break;
@@ -902,7 +1051,7 @@ int xl_state_layout(const xl_handle* h, int B, int layer, int part, size_t* offs
     case XL_STATE_CONV: o = L.conv_off; sz = sizeof(float) * (size_t)B * c.conv_kernel * c.inner_dim; break;
     default: return fail(XL_ERR_INVALID_ARG, "bad state part %d", part);
   }
-  *offset_bytes = (size_t)layer * L.layer_bytes + o;
+  *offset_bytes = layer_base(h, L, layer) + o;
   *size_bytes = sz;
   return XL_OK;
 }
@@ -915,11 +1064,20 @@ int xl_state_reset(xl_handle* h, void* state, const uint8_t* env_mask, int B, vo
   const StateLayout L = state_layout(h, B);
   const xl_config& c = h->cfg;
   if (!env_mask) {
-    XL_CUDA(cudaMemsetAsync(state, 0, L.layer_bytes * (size_t)c.num_blocks, s));
+    XL_CUDA(cudaMemsetAsync(state, 0, layer_base(h, L, c.num_blocks), s));
     return XL_OK;
   }
   for (int i = 0; i < c.num_blocks; ++i) {
-    char* base = (char*)state + (size_t)i * L.layer_bytes;
+    char* base = (char*)state + layer_base(h, L, i);
+    if (is_slstm(h, i)) {
+      const int64_t d = c.embedding_dim, Bd = (int64_t)B * d;
+      float* st = (float*)(base + L.s_off);
+      xl::launch_state_reset((float*)(base + L.sconv_off), st, st + Bd, st + 2 * Bd, env_mask, B,
+                             (int64_t)c.conv_kernel * d, d, d, d, s);
+      xl::launch_state_reset(nullptr, st + 3 * Bd, nullptr, nullptr, env_mask, B, 0, d, 0, 0, s);
+      h->launches += 2;
+      continue;
+    }
     xl::launch_state_reset((float*)(base + L.c_off), (float*)(base + L.n_off), (float*)(base + L.m_off),
                            (float*)(base + L.conv_off), env_mask, B, (int64_t)c.num_heads * h->DH * h->DH,
                            (int64_t)c.num_heads * h->DH, c.num_heads, (int64_t)c.conv_kernel * c.inner_dim, s);
@@ -1224,6 +1382,9 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
     h->microbatches = value;
   } else if (!strcmp(name, "pdl")) {
     xl::g_use_pdl = value ? 1 : 0;       // process-wide: programmatic dependent launch of every kernel
+  } else if (!strcmp(name, "l2_prefetch_mb")) {
+    if (value < 0 || value > 4096) return fail(XL_ERR_INVALID_ARG, "l2_prefetch_mb must be in [0, 4096]");
+    h->l2_prefetch_mb = value;
   } else if (!strcmp(name, "pipeline_order")) {
     h->pipeline_order = value ? 1 : 0;
   } else if (!strcmp(name, "gemm_splitk")) {

@@ -67,6 +67,9 @@ void launch_state_reset(float* C, float* n, float* m, float* conv, const uint8_t
                         int64_t c_per_env, int64_t n_per_env, int64_t m_per_env, int64_t conv_per_env,
                         cudaStream_t s);
 
+// bulk L2 prefetch of [base, base+bytes) (side stream, plain launch; see xl_elementwise.cu)
+void launch_l2_prefetch(const void* base, size_t bytes, int num_sms, cudaStream_t s);
+
 // ---- xl_state_step.cu ----------------------------------------------------------------------------
 struct StateStepParams {
   float* C;                 // [B, NH, DH/Wc, DH, Wc] slab-major (Wc = 128 when DH % 128 == 0, else DH)
@@ -107,6 +110,25 @@ cudaError_t launch_state_step(StateStepParams p, int num_sms, cudaStream_t s);
 cudaError_t launch_state_finalize(StateStepParams p, int num_sms, cudaStream_t s);
 void state_step_auto_tiling(int B, int NH, int DH, int num_sms, int* rows_split, int* cols_per_cta);
 void launch_repack_qkv(const float* qkv, float* qk, float* v, int M, int inner, cudaStream_t s);
+
+// ---- xl_slstm.cu ---------------------------------------------------------------------------------
+// sLSTM block (xLSTM[a:b] stacks). Rows ordered [env][token], T tokens per env; DHs = d / NH.
+// conv step over the T tokens + swish: xc [M,d]; conv_state [B,KS,d] in/out. false: KS not instantiated
+bool launch_slstm_conv(const float* xn, float* conv_state, const float* cw, const float* cb, float* xc, int B,
+                       int T, int d, int KS, cudaStream_t s);
+// pre [M,4,d] (gate-major i,f,z,o) = bias + headwise projections (i,f from xc; z,o from xn); W_* [NH,DHs,DHs],
+// bias [NH,4,DHs]
+void launch_slstm_gates(const float* xc, const float* xn, const float* w_i, const float* w_f, const float* w_z,
+                        const float* w_o, const float* bias, float* pre, int M, int d, int NH, cudaStream_t s);
+// token t of every env: raw = pre + R y_{t-1}, pointwise update of (c,n,m) in st [4,stB,d] (st points at the
+// slice's first env, B envs processed); y -> y_out [M,d]
+cudaError_t launch_slstm_cell(const float* pre, const float* R, float* st, float* y_out, int B, int stB, int T, int t,
+                              int d, int NH, cudaStream_t s);
+// x += MultiHeadLayerNorm(y_out) (gamma = 1 + w); st_y [B,d] <- y of each env's last token
+void launch_slstm_out(const float* y_out, const float* gn_w, float* x, float* st_y, int M, int T, int d, int NH,
+                      float eps, cudaStream_t s);
+// gated feed-forward middle: gelu(up[:, :ff]) * up[:, ff:] -> fp32 out and/or bf16 hi/lo planes [M, ff]
+void launch_ffn_gate(const float* up, float* out, void* hi, void* lo, int M, int ff, cudaStream_t s);
 
 // ---- xl_prefill.cu -------------------------------------------------------------------------------
 // Sequence (context prefill) versions of the per-block kernels; rows are ordered [env][token] with S tokens

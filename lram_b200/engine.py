@@ -36,6 +36,23 @@ _BLOCK_KEYS = {
     "xlstm.learnable_skip": "SKIP",
     "xlstm.proj_down.weight": "PROJ_DOWN",
 }
+# sLSTM block of an xLSTM[a:b] stack (xlstm v1.0.x sLSTMLayer + GatedFeedForward state_dict names). NB the module
+# named `fgate` feeds the INPUT gate and `igate` the FORGET gate (quirk of sLSTMLayer.forward, see the oracle).
+_SLSTM_BLOCK_KEYS = {
+    "xlstm_norm.weight": "XLSTM_NORM",
+    "xlstm.conv1d.conv.weight": "CONV_W",
+    "xlstm.conv1d.conv.bias": "CONV_B",
+    "xlstm.fgate.weight": "S_GATE_I",
+    "xlstm.igate.weight": "S_GATE_F",
+    "xlstm.zgate.weight": "S_GATE_Z",
+    "xlstm.ogate.weight": "S_GATE_O",
+    "xlstm.slstm_cell._recurrent_kernel_": "S_RECURRENT",
+    "xlstm.slstm_cell._bias_": "S_BIAS",
+    "xlstm.group_norm.weight": "S_GROUP_NORM",
+    "ffn_norm.weight": "FFN_NORM",
+    "ffn.proj_up.weight": "FFN_UP",
+    "ffn.proj_down.weight": "FFN_DOWN",
+}
 _POLICY_KEYS = {
     "encoder.layers.post_blocks_norm.weight": "POST_NORM",
     "embed_state.weight": "EMBED_STATE_W",
@@ -101,8 +118,12 @@ class StateCache:
         cfg = self.engine.cfg
         NH, DH = cfg.num_heads, cfg.head_dim
         W = slab_width(DH)
-        shape = {L.XL_STATE_C: (self.B, NH, DH // W, DH, W), L.XL_STATE_N: (self.B, NH, DH),
-                 L.XL_STATE_M: (self.B, NH), L.XL_STATE_CONV: (self.B, cfg.conv1d_kernel_size, cfg.inner)}[part]
+        if cfg.is_slstm(layer):
+            shape = {L.XL_STATE_SLSTM: (4, self.B, cfg.d),
+                     L.XL_STATE_CONV: (self.B, cfg.conv1d_kernel_size, cfg.d)}[part]
+        else:
+            shape = {L.XL_STATE_C: (self.B, NH, DH // W, DH, W), L.XL_STATE_N: (self.B, NH, DH),
+                     L.XL_STATE_M: (self.B, NH), L.XL_STATE_CONV: (self.B, cfg.conv1d_kernel_size, cfg.inner)}[part]
         return flat.view(*shape)
 
     def c_logical(self, layer: int) -> torch.Tensor:
@@ -116,6 +137,10 @@ class StateCache:
     def to_past_key_values(self) -> Dict[str, Dict[str, tuple]]:
         out = {}
         for i in range(self.engine.cfg.num_blocks):
+            if self.engine.cfg.is_slstm(i):
+                out[f"block_{i}"] = {"slstm_state": self.view(i, L.XL_STATE_SLSTM).clone(),
+                                     "conv_state": (self.view(i, L.XL_STATE_CONV).clone(),)}
+                continue
             c = self.c_logical(i)
             n = self.view(i, L.XL_STATE_N).clone().unsqueeze(-1)
             m = self.view(i, L.XL_STATE_M).clone().view(self.B, -1, 1, 1)
@@ -126,6 +151,10 @@ class StateCache:
     def load_past_key_values(self, pkv: Dict[str, Dict[str, tuple]]) -> None:
         for i in range(self.engine.cfg.num_blocks):
             st = pkv[f"block_{i}"]
+            if self.engine.cfg.is_slstm(i):
+                self.view(i, L.XL_STATE_SLSTM).copy_(st["slstm_state"].to(self.buf.device, torch.float32))
+                self.view(i, L.XL_STATE_CONV).copy_(st["conv_state"][0].to(self.buf.device, torch.float32))
+                continue
             c, n, m = st["mlstm_state"]
             self.view(i, L.XL_STATE_C).copy_(c_to_slab(c.to(self.buf.device, torch.float32)))
             self.view(i, L.XL_STATE_N).copy_(n.to(self.buf.device, torch.float32).reshape(self.B, -1, n.shape[2]))
@@ -143,7 +172,7 @@ class XLSTMEngine:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.max_batch = int(max_batch)
         self.lib = L.load()
-        if self.lib.xl_abi_version() != 1:
+        if self.lib.xl_abi_version() != L.XL_ABI_VERSION:
             raise RuntimeError("libxlstm_b200.so ABI mismatch")
         c = L.XLConfig(
             embedding_dim=cfg.d, num_blocks=cfg.num_blocks, num_heads=cfg.num_heads, inner_dim=cfg.inner,
@@ -151,7 +180,8 @@ class XLSTMEngine:
             act_dim=cfg.act_dim, action_channels=cfg.action_channels, discrete_actions=cfg.discrete_actions,
             tokens_per_step=cfg.tokens_per_step, action_token_pos=cfg.action_token_pos, max_batch=self.max_batch,
             ln_eps=cfg.ln_eps, cell_eps=cfg.cell_eps, embed_ln_eps=cfg.embed_ln_eps, tok_min_val=-1.0,
-            tok_max_val=1.0)
+            tok_max_val=1.0, slstm_mask_lo=cfg.slstm_mask & 0xFFFFFFFF, slstm_mask_hi=cfg.slstm_mask >> 32,
+            ffn_dim=cfg.ffn_dim if cfg.slstm_at else 0)
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):
             L.check(self.lib.xl_create(C.byref(c), C.byref(self.handle)))
@@ -168,13 +198,14 @@ class XLSTMEngine:
     def _bind_all(self, sd):
         cfg = self.cfg
         for i in range(cfg.num_blocks):
-            for key, slot in _BLOCK_KEYS.items():
+            slstm = cfg.is_slstm(i)
+            for key, slot in (_SLSTM_BLOCK_KEYS if slstm else _BLOCK_KEYS).items():
                 name = f"encoder.layers.blocks.{i}.{key}"
                 if name not in sd:
                     raise KeyError(f"state_dict is missing {name}")
                 t = sd[name]
                 if slot == "CONV_W":
-                    t = t.reshape(cfg.inner, cfg.conv1d_kernel_size)
+                    t = t.reshape(cfg.d if slstm else cfg.inner, cfg.conv1d_kernel_size)
                 self._bind(i, slot, t, is_bf16_weight(name))
         kpad = self.lib.xl_state_dim_padded(self.handle)
         for name, slot in _POLICY_KEYS.items():

@@ -30,6 +30,8 @@ BF16_WEIGHT_SUFFIXES = (
     "xlstm.proj_down.weight",
     "embed_state.weight",
     "action_net.0.weight",
+    "ffn.proj_up.weight",        # sLSTM block's gated feed-forward
+    "ffn.proj_down.weight",
 )
 
 
@@ -82,6 +84,24 @@ def make_state_dict(cfg: XLSTMPolicyConfig, seed: int = 0, gate_std: float = 0.0
     wang = 2.0 / (L * math.sqrt(d))
     for i in range(L):
         p = f"encoder.layers.blocks.{i}."
+        if cfg.is_slstm(i):
+            # sLSTM block (xlstm v1.0.x sLSTMLayer + GatedFeedForward; names as in its state_dict)
+            dh, ff = d // nh, cfg.ffn_dim
+            cb = 1.0 / math.sqrt(ks)
+            sd[p + "xlstm_norm.weight"] = normal(d, std=0.05)
+            sd[p + "xlstm.conv1d.conv.weight"] = uniform(d, 1, ks, bound=cb)
+            sd[p + "xlstm.conv1d.conv.bias"] = uniform(d, bound=cb)
+            for gname in ("fgate", "igate", "zgate", "ogate"):
+                sd[p + f"xlstm.{gname}.weight"] = normal(nh, dh, dh, std=small * math.sqrt(nh))
+            sd[p + "xlstm.slstm_cell._recurrent_kernel_"] = normal(nh, dh, 4, dh, std=1.0 / math.sqrt(dh) * 0.5)
+            bias = normal(nh, 4, dh, std=0.1)
+            bias[:, 1, :] += torch.linspace(3.0, 6.0, dh)          # forget-gate bias (powerlaw-like, positive)
+            sd[p + "xlstm.slstm_cell._bias_"] = bias
+            sd[p + "xlstm.group_norm.weight"] = normal(d, std=0.05)
+            sd[p + "ffn_norm.weight"] = normal(d, std=0.05)
+            sd[p + "ffn.proj_up.weight"] = normal(2 * ff, d, std=small)
+            sd[p + "ffn.proj_down.weight"] = normal(d, ff, std=max(wang, small * 0.5))
+            continue
         sd[p + "xlstm_norm.weight"] = normal(d, std=0.05)                 # gamma = 1 + w
         sd[p + "xlstm.proj_up.weight"] = normal(2 * inner, d, std=small)
         sd[p + "xlstm.q_proj.weight"] = normal(inner // bs, bs, bs, std=small * 4)

@@ -74,12 +74,47 @@ def make_state_dict_meta(cfg):
     return sd
 
 
+@pytest.mark.parametrize("name", ["toy-ms", "toy128-ms", "48M-ms"])
+def test_infer_config_recognises_slstm_blocks(name):
+    """xLSTM[a:b] checkpoints: sLSTM positions and the feed-forward width come back from the key set / shapes."""
+    cfg = preset(name)
+    sd = make_state_dict(cfg, seed=0) if name != "48M-ms" else _meta_state_dict(cfg)
+    got = infer_config(sd)
+    assert got.slstm_at == cfg.slstm_at and got.ffn_dim == cfg.ffn_dim
+    assert (got.d, got.num_blocks, got.num_heads, got.inner) == (cfg.d, cfg.num_blocks, cfg.num_heads, cfg.inner)
+
+
+def _meta_state_dict(cfg):
+    """shapes only (no 48M of random numbers on the CPU test path)"""
+    sd = make_state_dict(preset("toy-ms"), seed=0)
+    out = {}
+    d, inner, nh, ks, bs, ff = cfg.d, cfg.inner, cfg.num_heads, cfg.conv1d_kernel_size, cfg.qkv_proj_blocksize, cfg.ffn_dim
+    e = lambda *s: torch.empty(*s)
+    for k, v in sd.items():
+        if not k.startswith("encoder.layers.blocks."):
+            out[k] = v
+    out["embed_state.weight"] = e(d, cfg.state_dim)
+    out["action_net.0.weight"] = e(cfg.head_out, d)
+    for i in range(cfg.num_blocks):
+        p = f"encoder.layers.blocks.{i}."
+        if cfg.is_slstm(i):
+            out[p + "xlstm.slstm_cell._recurrent_kernel_"] = e(nh, d // nh, 4, d // nh)
+            out[p + "ffn.proj_down.weight"] = e(d, ff)
+            out[p + "ffn.proj_up.weight"] = e(2 * ff, d)
+            continue
+        out[p + "xlstm.proj_up.weight"] = e(2 * inner, d)
+        out[p + "xlstm.mlstm_cell.igate.weight"] = e(nh, 3 * inner)
+        out[p + "xlstm.conv1d.conv.weight"] = e(inner, 1, ks)
+        out[p + "xlstm.q_proj.weight"] = e(inner // bs, bs, bs)
+    return out
+
+
 def test_infer_config_rejects_uncovered_variants():
     cfg = preset("toy")
     sd = make_state_dict(cfg, seed=0)
     bad = dict(sd)
-    bad["encoder.layers.blocks.1.xlstm.slstm_cell._recurrent_kernel_"] = torch.zeros(1)
-    with pytest.raises(NotImplementedError, match="sLSTM"):
+    bad["encoder.layers.blocks.1.ffn.proj_up.weight"] = torch.zeros(1)
+    with pytest.raises(NotImplementedError, match="feed-forward"):
         infer_config(bad)
     bad = dict(sd)
     bad["encoder.layers.blocks.0.xlstm_norm.bias"] = torch.zeros(cfg.d)

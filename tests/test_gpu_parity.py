@@ -469,3 +469,133 @@ def test_long_horizon_drift_and_rollout_driver():
     assert mism == 0, f"{mism} token mismatches over {steps * B * cfg.act_dim}"
     assert len(res["episode_returns"][0]) == steps // ep_len
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# xLSTM[a:b] stacks: sLSTM blocks (xlstm_ms_mediumplus.yaml:27 slstm_at: [1])
+# ------------------------------------------------------------------------------------------------------------
+def _assert_states_match(cfg, exp, pkv_o, tol=REL_TOL):
+    for i in range(cfg.num_blocks):
+        eo, oo = exp[f"block_{i}"], pkv_o[f"block_{i}"]
+        assert _rel(eo["conv_state"][0].cpu(), oo["conv_state"][0]) < 1e-5, f"block {i} conv"
+        if cfg.is_slstm(i):
+            se, so = eo["slstm_state"].cpu(), oo["slstm_state"]
+            for part, nm in enumerate("ycnm"):
+                assert _rel(se[part], so[part]) < tol, f"block {i} sLSTM {nm}"
+            continue
+        c, n, m = oo["mlstm_state"]
+        ce, ne, me = eo["mlstm_state"]
+        assert _rel(ce.cpu(), c) < tol and _rel(ne.cpu(), n) < tol, f"block {i}"
+        assert (me.cpu() - m).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("name,B,mode", [("toy-ms", 4, L.XL_MODE_PER_TOKEN), ("toy-ms", 4, L.XL_MODE_FUSED),
+                                         ("toy128-ms", 11, L.XL_MODE_FUSED), ("48M-ms", 2, L.XL_MODE_FUSED)])
+def test_slstm_encoder_step_vs_oracle(name, B, mode):
+    from lram_b200.decision_xlstm import FusedXLSTMEncoder
+    from oracle import xlstm_oracle as O
+    cfg, sd, eng = _engine(name, B)
+    enc = FusedXLSTMEncoder(eng, mode=mode)
+    ora = O.OracleEncoder(cfg, sd)
+    g = torch.Generator().manual_seed(19)
+    pkv_o, pkv = None, None
+    for step in range(4):
+        x = torch.randn(B, 3, cfg.d, generator=g)
+        out = enc(inputs_embeds=x.cuda(), past_key_values=pkv, use_cache=True)
+        pkv = out["past_key_values"]
+        ref, pkv_o = ora.forward_cached(x, pkv_o)
+        assert _rel(out["last_hidden_state"].cpu(), ref) < REL_TOL, f"step {step}"
+    _assert_states_match(cfg, pkv.to_past_key_values(), pkv_o)
+    # import the ORACLE's state (reference past_key_values format incl. "slstm_state") and continue
+    x = torch.randn(B, 3, cfg.d, generator=g)
+    out = enc(inputs_embeds=x.cuda(), past_key_values=pkv_o, use_cache=True)
+    ref, _ = ora.forward_cached(x, pkv_o)
+    assert _rel(out["last_hidden_state"].cpu(), ref) < REL_TOL
+    eng.close()
+
+
+@pytest.mark.parametrize("name,B,steps", [("toy128-ms", 6, 5), ("48M-ms", 3, 3)])
+def test_slstm_policy_step_tokens_bit_exact(name, B, steps):
+    from oracle import xlstm_oracle as O
+    cfg, sd, eng = _engine(name, B)
+    ora = O.OraclePolicy(cfg, sd)
+    states, rtg, _ = make_stream(cfg, range(B), steps, domains="mixed")
+    cache, cache_g, pkv = eng.new_state(B), eng.new_state(B), None
+    for t in range(steps):
+        s_t, r_t = torch.from_numpy(states[t]).cuda(), torch.from_numpy(rtg[t]).cuda()
+        out = eng.policy_step(cache, s_t, r_t, mode=L.XL_MODE_FUSED, want_hidden=True, want_logits=True)
+        ref = ora.step(torch.from_numpy(states[t]), torch.from_numpy(rtg[t]), past_key_values=pkv)
+        pkv = ref["past_key_values"]
+        tok = out["action_tokens"].cpu().long()
+        margins = _margin_ok(ref["action_logits"], tok, ref["action_tokens"])
+        assert not margins, f"token mismatches at t={t}, oracle top-2 relative margins {margins}"
+        assert _rel(out["last_hidden_state"].cpu(), ref["last_hidden_state"]) < REL_TOL
+        assert torch.equal(out["action_preds"].cpu(), ref["action_preds"])
+        # CUDA-graph replay of the same step on a second cache: identical bits
+        out_g = eng.policy_step(cache_g, s_t, r_t, mode=L.XL_MODE_FUSED, flags=L.XL_FLAG_GRAPH, want_hidden=True)
+        torch.cuda.synchronize()
+        assert torch.equal(out_g["action_tokens"].cpu(), out["action_tokens"].cpu())
+        assert torch.equal(out_g["last_hidden_state"].cpu(), out["last_hidden_state"].cpu())
+    eng.close()
+
+
+def test_slstm_prefill_reset_and_microbatches():
+    """sLSTM stacks through the other entry points: context prefill == stepping, per-env reset == fresh state,
+    env micro-batches == single stream."""
+    from lram_b200.decision_xlstm import FusedXLSTMEncoder
+    from oracle import xlstm_oracle as O
+    cfg, sd, eng = _engine("toy128-ms", 4)
+    B, S = 4, 30
+    ora = O.OracleEncoder(cfg, sd)
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(B, S, cfg.d, generator=g)
+    enc = FusedXLSTMEncoder(eng, mode=L.XL_MODE_FUSED)
+    out = enc(inputs_embeds=x.cuda(), past_key_values=None, use_cache=True)          # S > 4 -> prefill path
+    refs, pkv_o = [], None
+    for t in range(S):
+        r, pkv_o = ora.forward_cached(x[:, t:t + 1], pkv_o)
+        refs.append(r)
+    assert _rel(out["last_hidden_state"].cpu(), torch.cat(refs, dim=1)) < REL_TOL
+    cache = out["past_key_values"]
+    _assert_states_match(cfg, cache.to_past_key_values(), pkv_o)
+    # per-env reset
+    states, rtg, _ = make_stream(cfg, range(B), 3, domains="mixed")
+    dev = lambda a: torch.from_numpy(a).cuda()
+    c1 = eng.new_state(B)
+    for t in range(2):
+        eng.policy_step(c1, dev(states[t]), dev(rtg[t]))
+    eng.reset(c1, torch.tensor([1, 0, 0, 1], dtype=torch.uint8))
+    o1 = eng.policy_step(c1, dev(states[2]), dev(rtg[2]), want_hidden=True)
+    of = eng.policy_step(eng.new_state(B), dev(states[2]), dev(rtg[2]), want_hidden=True)
+    torch.cuda.synchronize()
+    assert torch.equal(o1["last_hidden_state"].cpu()[[0, 3]], of["last_hidden_state"].cpu()[[0, 3]])
+    # micro-batches
+    ca, cb = eng.new_state(B), eng.new_state(B)
+    for t in range(3):
+        eng.set_option("microbatches", 1)
+        a = eng.policy_step(ca, dev(states[t]), dev(rtg[t]), want_hidden=True)
+        eng.set_option("microbatches", 2)
+        b = eng.policy_step(cb, dev(states[t]), dev(rtg[t]), want_hidden=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a["action_tokens"].cpu(), b["action_tokens"].cpu())
+        assert _rel(b["last_hidden_state"].cpu(), a["last_hidden_state"].cpu()) < 1e-5
+    eng.set_option("microbatches", 0)
+    eng.close()
+
+
+def test_l2_warm_option_is_value_neutral():
+    """xl_set_option("l2_prefetch_mb"): the side-stream L2 warm-up only reads; results are bit-identical."""
+    cfg, sd, eng = _engine("16M", 3)
+    states, rtg, _ = make_stream(cfg, range(3), 3, domains="mixed")
+    dev = lambda a: torch.from_numpy(a).cuda()
+    ca, cb = eng.new_state(3), eng.new_state(3)
+    for t in range(3):
+        eng.set_option("l2_prefetch_mb", 0)
+        a = eng.policy_step(ca, dev(states[t]), dev(rtg[t]), flags=L.XL_FLAG_GRAPH, want_hidden=True)
+        a = {k: v.clone() for k, v in a.items()}
+        eng.set_option("l2_prefetch_mb", 8)
+        b = eng.policy_step(cb, dev(states[t]), dev(rtg[t]), flags=L.XL_FLAG_GRAPH, want_hidden=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a["action_tokens"].cpu(), b["action_tokens"].cpu())
+        assert torch.equal(a["last_hidden_state"].cpu(), b["last_hidden_state"].cpu())
+    eng.close()

@@ -172,3 +172,67 @@ def test_discrete_head_branch():
     o = pol.step(torch.from_numpy(states[0]), torch.from_numpy(rtg[0]), discrete=True)
     assert o["action_tokens"].shape == (3, 1) and int(o["action_tokens"].max()) < cfg.discrete_actions
     assert o["action_logits"].shape == (3, 1, cfg.num_actions)
+
+
+# ---- sLSTM block (xLSTM[7:1] stacks): no external vectors exist ("parity unpinned"); internal pins only -------
+def test_slstm_first_step_closed_form():
+    """From the zero state the sLSTM update has a closed form: m' = i~ (n == 0 branch), i = 1, f = min(exp(logsig(f~)
+    - i~), 1), c' = tanh(z~), n' = 1, y' = sigmoid(o~) tanh(z~) — checks gate order (i, f, z, o) and the branch."""
+    from oracle.xlstm_oracle import slstm_pointwise
+    g = torch.Generator().manual_seed(3)
+    raw = torch.randn(5, 4, 16, generator=g)
+    st = slstm_pointwise(raw, torch.zeros(4, 5, 16))
+    assert torch.allclose(st[3], raw[:, 0])
+    assert torch.allclose(st[1], torch.tanh(raw[:, 2]), atol=1e-7)
+    assert torch.allclose(st[2], torch.ones(5, 16))
+    assert torch.allclose(st[0], torch.sigmoid(raw[:, 3]) * torch.tanh(raw[:, 2]), atol=1e-7)
+    # second step: stabilised form == unstabilised exponential-gate recurrence (eqs. 8-17) where that is finite
+    raw2 = torch.randn(5, 4, 16, generator=g)
+    st2 = slstm_pointwise(raw2, st)
+    i1, i2 = torch.exp(raw[:, 0].double()), torch.exp(raw2[:, 0].double())
+    f2 = torch.sigmoid(raw2[:, 1].double())
+    c_true = f2 * (i1 * torch.tanh(raw[:, 2].double())) + i2 * torch.tanh(raw2[:, 2].double())
+    n_true = f2 * i1 + i2
+    y_true = torch.sigmoid(raw2[:, 3].double()) * c_true / n_true
+    assert torch.allclose(st2[0].double(), y_true, atol=1e-5)
+    # the stabiliser only rescales c and n by exp(-m)
+    assert torch.allclose((st2[1] * torch.exp(st2[3])).double(), c_true, rtol=1e-4, atol=1e-5)
+
+
+def test_slstm_stack_batched_equals_single_env_and_reset():
+    from oracle.xlstm_oracle import OraclePolicy, reset_state_rows
+    cfg = preset("toy128-ms")
+    sd = make_state_dict(cfg, seed=2)
+    pol = OraclePolicy(cfg, sd)
+    states, rtg, _ = make_stream(cfg, range(3), 4, domains="mixed")
+    pkv, single = None, [None] * 3
+    for t in range(3):
+        o = pol.step(torch.from_numpy(states[t]), torch.from_numpy(rtg[t]), past_key_values=pkv)
+        pkv = o["past_key_values"]
+        for b in range(3):
+            ob = pol.step(torch.from_numpy(states[t, b:b + 1]), torch.from_numpy(rtg[t, b:b + 1]),
+                          past_key_values=single[b])
+            single[b] = ob["past_key_values"]
+            assert torch.equal(ob["action_tokens"][0], o["action_tokens"][b])
+            assert torch.allclose(ob["last_hidden_state"][0], o["last_hidden_state"][b], atol=2e-5)
+    assert set(pkv["block_0"]) == {"slstm_state", "conv_state"} and pkv["block_0"]["slstm_state"].shape == (4, 3, cfg.d)
+    assert set(pkv["block_1"]) == {"mlstm_state", "conv_state"}
+    # reset of env 1 == env 1 starting from None
+    r = reset_state_rows(pkv, torch.tensor([False, True, False]))
+    o = pol.step(torch.from_numpy(states[3]), torch.from_numpy(rtg[3]), past_key_values=r)
+    f = pol.step(torch.from_numpy(states[3, 1:2]), torch.from_numpy(rtg[3, 1:2]), past_key_values=None)
+    assert torch.allclose(o["last_hidden_state"][1], f["last_hidden_state"][0], atol=2e-5)
+
+
+def test_slstm_param_count():
+    """xlstm_ms_mediumplus (d=768, 12 blocks, sLSTM at 1): per sLSTM block 2 d^2 (gates + recurrent kernel) +
+    3 * 1024 * d (feed-forward) + small terms."""
+    cfg = preset("48M-ms")
+    sd = make_state_dict(preset("toy-ms"), seed=0)
+    toy = preset("toy-ms")
+    n_enc = sum(v.numel() for k, v in sd.items() if k.startswith("encoder."))
+    assert n_enc == toy.encoder_params()
+    assert cfg.ffn_dim == 1024 and preset("206M", slstm_at=(1,)).ffn_dim == 1664
+    d = 768
+    per_slstm = 2 * d * d + 3 * 1024 * d + d * 4 + d + 4 * d + 3 * d
+    assert cfg.encoder_params() == 11 * (preset("48M").encoder_params() - d) // 12 + per_slstm + d
