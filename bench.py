@@ -99,19 +99,28 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def time_oracle(cfg, sd, B, n_steps, warmup, threads, budget_s=None):
+def workload_config(args, world):
+    """The workload both arms are measured on (BASELINE.json configs[1] by default)."""
+    B = args.envs
+    return {"workload": f"xLSTM {args.model} recurrent step, {B} synthetic {args.domains} envs per GPU"
+                        + (" (BASELINE.json configs[1])" if (args.model, B) == ("48M", 64) else ""),
+            "model": args.model, "envs_per_gpu": B, "global_envs": B * world, "tokens_per_step": 3,
+            "domains": args.domains, "head": "discrete" if args.discrete else "continuous-tokenized"}
+
+
+def time_oracle(cfg, sd, B, n_steps, warmup, threads, budget_s=None, domains="metaworld", discrete=False):
     """Oracle env steps on the host cores. Returns (env_steps_per_s, ms list, steps actually timed)."""
     from lram_b200.synth import make_stream
     from oracle.xlstm_oracle import OraclePolicy
     torch.set_num_threads(threads)
     pol = OraclePolicy(cfg, sd)
-    states, rtg, _ = make_stream(cfg, range(B), n_steps + warmup, domains="metaworld")
+    states, rtg, _ = make_stream(cfg, range(B), n_steps + warmup, domains=domains)
     pkv = None
     ms = []
     t_begin = time.perf_counter()
     for t in range(n_steps + warmup):
         t0 = time.perf_counter()
-        o = pol.step(torch.from_numpy(states[t]), torch.from_numpy(rtg[t]), past_key_values=pkv)
+        o = pol.step(torch.from_numpy(states[t]), torch.from_numpy(rtg[t]), past_key_values=pkv, discrete=discrete)
         pkv = o["past_key_values"]
         dt = time.perf_counter() - t0
         if t >= warmup:
@@ -136,17 +145,18 @@ def run_reference(args):
     # bounded sample: B_ref envs of the workload's args.envs, chosen from one calibration step so that
     # K steps end within ~2 minutes
     b_ref = min(args.envs, 8)
-    v, ms, _ = time_oracle(cfg, sd, b_ref, 1, 1, cores)
+    kw = dict(domains=args.domains, discrete=args.discrete)
+    v, ms, _ = time_oracle(cfg, sd, b_ref, 1, 1, cores, **kw)
     per_env_ms = ms[0] / b_ref
     budget_ms = 120e3
     b_ref = int(max(1, min(args.envs, budget_ms / max(per_env_ms * (args.steps + args.warmup), 1e-9))))
-    value, ms, timed = time_oracle(cfg, sd, b_ref, args.steps, args.warmup, cores, budget_s=240)
+    value, ms, timed = time_oracle(cfg, sd, b_ref, args.steps, args.warmup, cores, budget_s=240, **kw)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": timed, "warmup": args.warmup, "ms_per_step": statistics.mean(ms), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"xLSTM {args.model} recurrent step, {args.envs} synthetic Meta-World envs",
-                   "model": args.model, "envs_per_gpu": args.envs, "tokens_per_step": 3},
+        "config": dict(workload_config(args, max(args.gpus, 1)), backend="oracle port of the xlstm native PyTorch "
+                       "ops, CPU fp32, rank 0 only", sampled_envs=b_ref),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{b_ref} of {args.envs} envs x {timed} env steps, oracle port of the xlstm "
                                    f"native PyTorch backend (xlstm package absent), fp32, {cores} threads"},
@@ -170,6 +180,8 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=5)
     ap.add_argument("--discrete", action="store_true", help="discrete-action head (argmax over the first 18 logits)")
     ap.add_argument("--domains", default="metaworld", help="metaworld | dmcontrol | composuite | mimicgen | mixed")
+    ap.add_argument("--gather-every", type=int, default=16,
+                    help="N > 1: all-gather the action tokens of this many env steps in one collective (1 = per step)")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="xl_set_option passthrough for A/B runs, e.g. --opt microbatches=1 --opt state_impl=1")
     args = ap.parse_args()
@@ -224,7 +236,7 @@ def main():
     out = {"action_tokens": torch.zeros(B, cfg.act_dim, dtype=torch.int32, device=dev),
            "action_preds": torch.zeros(B, cfg.act_dim, dtype=torch.float32, device=dev)}
     stream = torch.cuda.current_stream(dev)
-    gatherer = OverlappedTokenGather(B, cfg.act_dim, world, dev) if world > 1 else None
+    gatherer = OverlappedTokenGather(B, cfg.act_dim, world, dev, every=args.gather_every) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -344,7 +356,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         b_cpu = min(B, 8)
-        v, ms, timed = time_oracle(cfg, sd, b_cpu, 1000, 2, cores, budget_s=20)
+        v, ms, timed = time_oracle(cfg, sd, b_cpu, 1000, 2, cores, budget_s=20, domains=args.domains,
+                                   discrete=args.discrete)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{b_cpu} of {B} envs x {timed} env steps (~20 s), oracle port of the xlstm native "
                          f"PyTorch backend, fp32, {cores} threads", "p50_ms_per_step": statistics.median(ms)}
@@ -354,14 +367,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"xLSTM {args.model} recurrent step, {B} synthetic {args.domains} envs per GPU"
-                                   + (" (BASELINE.json configs[1])" if (args.model, B) == ("48M", 64) else ""),
-                       "model": args.model, "envs_per_gpu": B, "global_envs": n_envs, "tokens_per_step": 3,
-                       "domains": args.domains, "head": "discrete" if args.discrete else "continuous-tokenized",
-                       "step_mode": args.mode, "cuda_graph": not args.no_graph, "options": opts,
-                       "weights": "bf16 GEMM matrices",
-                       "state": "fp32", "parallelism": f"env-sharded x{world}",
-                       "l2": f"state stream {cache.nbytes() / 2**20:.0f} MiB per step exceeds the 126 MB L2"},
+            "config": dict(workload_config(args, world),
+                           step_mode=args.mode, cuda_graph=not args.no_graph, options=opts,
+                           weights="bf16 GEMM matrices", state="fp32", parallelism=f"env-sharded x{world}",
+                           gather=(f"one NCCL all_gather of int32 action tokens per {args.gather_every} env steps, "
+                                   "side stream") if world > 1 else "none (1 GPU)",
+                           l2=f"state stream {cache.nbytes() / 2**20:.0f} MiB per step exceeds the 126 MB L2"),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K, "p50_ms": statistics.median(lat),
                     "p90_ms": sorted(lat)[int(0.9 * (len(lat) - 1))]},

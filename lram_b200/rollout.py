@@ -48,48 +48,91 @@ def gather_env_results(local: torch.Tensor, n_envs: int, rank: int, world_size: 
 
 
 class OverlappedTokenGather:
-    """Per-step all-gather of the action tokens, off the critical path.
+    """All-gather of the action tokens, off the critical path and batched over `every` env steps.
 
-    Step t's tokens are snapshotted into one of two staging buffers on the compute stream (a 2 KB copy) and
-    all-gathered on a side stream while step t+1 computes; envs never wait for other ranks' actions, so the
-    only ordering needed is "staging buffer k is not overwritten before its gather finished" (2 steps apart).
-    Requires equal shards (B_local * world == n_envs); results are in rank-major order [world, B_local, A] and
-    `global_view()` puts them back in env order (env i lives on rank i % world).
+    Step t's tokens are snapshotted into row t % every of one of two staging rings on the compute stream (a 2 KB
+    copy); every `every` steps the ring is all-gathered on a side stream while the following steps compute. Envs
+    never wait for other ranks' actions, so the only ordering needed is "ring k is not overwritten before its
+    gather finished" (the gather of ring k overlaps the `every` steps that fill ring k ^ 1). `every = 1` is a
+    gather per step; larger values amortise the collective's launch + SM footprint (the reference gathers
+    results once, at the end of evaluation: src/utils/misc.py:159-191). `finish()` flushes a partly filled ring.
+    Requires equal shards (B_local * world == n_envs). `results` collects, per flush, a [world, n_steps, B_local, A]
+    tensor when `keep=True` (tests / callers that consume the gathered tokens); `global_view()` puts one step back
+    in env order (env i lives on rank i % world). On CPU tensors (gloo) the same logic runs without streams.
     """
 
-    def __init__(self, B_local: int, act_dim: int, world_size: int, device, group=None):
-        self.world, self.group = world_size, group
-        self.side = torch.cuda.Stream(device=device)
-        self.stage = [torch.zeros(B_local, act_dim, dtype=torch.int32, device=device) for _ in range(2)]
-        self.out = [torch.zeros(world_size, B_local, act_dim, dtype=torch.int32, device=device) for _ in range(2)]
+    def __init__(self, B_local: int, act_dim: int, world_size: int, device, group=None, every: int = 1,
+                 keep: bool = False):
+        assert every >= 1
+        self.world, self.group, self.every, self.keep = world_size, group, int(every), keep
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.side = torch.cuda.Stream(device=self.device) if self.cuda else None
+        mk = lambda *shape: torch.zeros(*shape, dtype=torch.int32, device=self.device)  # noqa: E731
+        self.stage = [mk(self.every, B_local, act_dim) for _ in range(2)]
+        self.out = [mk(world_size, self.every, B_local, act_dim) for _ in range(2)]
         self.done = [None, None]
-        self.k = 0
+        self.k = 0            # ring being filled
+        self.j = 0            # rows filled in ring k
+        self.flushes = 0
+        self.results: List[torch.Tensor] = []
 
-    def submit(self, tokens: torch.Tensor) -> torch.Tensor:
-        import torch.distributed as dist
+    def submit(self, tokens: torch.Tensor) -> Optional[torch.Tensor]:
+        """Queue one step's local tokens [B_local, A]. Returns the gathered [world, n, B_local, A] tensor of the
+        flush this call triggered (valid on the compute stream after `finish()` or an event wait), else None."""
         k = self.k
-        cur = torch.cuda.current_stream(tokens.device)
-        if self.done[k] is not None:
-            cur.wait_event(self.done[k])                 # gather of step t-2 read this staging buffer
-        self.stage[k].copy_(tokens, non_blocking=True)
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        with torch.cuda.stream(self.side):
-            self.side.wait_event(ready)
-            dist.all_gather_into_tensor(self.out[k].view(-1, tokens.shape[-1]), self.stage[k], group=self.group)
-            ev = torch.cuda.Event()
-            ev.record(self.side)
-        self.done[k] = ev
+        if self.cuda:
+            cur = torch.cuda.current_stream(self.device)
+            if self.j == 0 and self.done[k] is not None:
+                cur.wait_event(self.done[k])             # the previous gather of ring k still reads it
+        self.stage[k][self.j].copy_(tokens, non_blocking=True)
+        self.j += 1
+        if self.j == self.every:
+            return self._flush()
+        return None
+
+    def _flush(self) -> Optional[torch.Tensor]:
+        import torch.distributed as dist
+        k, n = self.k, self.j
+        if n == 0:
+            return None
+        src = self.stage[k][:n]
+        dst = self.out[k].view(-1)[: self.world * src.numel()].view(self.world, n, *src.shape[1:])
+        if self.cuda:
+            cur = torch.cuda.current_stream(self.device)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(ready)
+                dist.all_gather_into_tensor(dst.view(-1, src.shape[-1]), src.view(-1, src.shape[-1]),
+                                            group=self.group)
+                if self.keep:
+                    self.results.append(dst.clone())
+                ev = torch.cuda.Event()
+                ev.record(self.side)
+            self.done[k] = ev
+        else:
+            dist.all_gather_into_tensor(dst.view(-1, src.shape[-1]), src.reshape(-1, src.shape[-1]),
+                                        group=self.group)
+            if self.keep:
+                self.results.append(dst.clone())
+        self.flushes += 1
         self.k ^= 1
-        return self.out[k]
+        self.j = 0
+        return dst
 
     def finish(self):
-        for ev in self.done:
-            if ev is not None:
-                torch.cuda.current_stream().wait_event(ev)
+        """Flush a partly filled ring and make the compute stream wait for every outstanding gather."""
+        self._flush()
+        if self.cuda:
+            for ev in self.done:
+                if ev is not None:
+                    torch.cuda.current_stream(self.device).wait_event(ev)
 
     def global_view(self, gathered: torch.Tensor) -> torch.Tensor:
-        # [world, B_local, A] -> [n_envs, A] with env = b * world + r
+        # [world, B_local, A] -> [n_envs, A]  (or [world, n, B_local, A] -> [n, n_envs, A]) with env = b * world + r
+        if gathered.dim() == 4:
+            return gathered.permute(1, 2, 0, 3).reshape(gathered.shape[1], -1, gathered.shape[-1])
         return gathered.permute(1, 0, 2).reshape(-1, gathered.shape[-1])
 
 

@@ -106,6 +106,22 @@ want = torch.tensor([[e * 10 + j for j in range(8)] for e in range(n_envs)], dty
 assert torch.equal(full, want), (rank, full)
 ret = gather_env_results(torch.tensor([float(e) for e in ids]), n_envs, rank, world)
 assert torch.equal(ret, torch.arange(n_envs, dtype=torch.float32))
+# batched / deferred token gather: 7 steps, flush every 3 (two full rings + a partial one at finish())
+from lram_b200.rollout import OverlappedTokenGather
+B_local, A, steps = 4, 8, 7
+for every in (1, 3, 16):
+    g = OverlappedTokenGather(B_local, A, world, "cpu", every=every, keep=True)
+    def tok(r, t):
+        return torch.tensor([[1000 * t + 10 * (b * world + r) + j for j in range(A)] for b in range(B_local)],
+                            dtype=torch.int32)
+    for t in range(steps):
+        g.submit(tok(rank, t))
+    g.finish()
+    assert g.flushes == -(-steps // every), (every, g.flushes)
+    allsteps = torch.cat([g.global_view(r) for r in g.results], dim=0)        # [steps, n_envs, A]
+    want = torch.stack([torch.tensor([[1000 * t + 10 * e + j for j in range(A)] for e in range(B_local * world)],
+                                     dtype=torch.int32) for t in range(steps)])
+    assert torch.equal(allsteps, want), (rank, every)
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 """
