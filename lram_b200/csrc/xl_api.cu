@@ -105,6 +105,8 @@ struct xl_handle {
         *pf_gated = nullptr, *pf_num = nullptr, *pf_qn = nullptr, *pf_f = nullptr, *pf_i = nullptr, *pf_m = nullptr,
         *pf_semb = nullptr, *pf_spad = nullptr, *pf_sin = nullptr, *pf_rtg = nullptr, *pf_rew = nullptr;
   __nv_bfloat16 *pf_hi = nullptr, *pf_lo = nullptr;
+  uint8_t *pf_pc = nullptr, *pf_pv = nullptr;   // prepared operands of the chunkwise tensor-core cell
+  int prefill_cell = 1;                         // 1: chunkwise mma.sync cell (xl_prefill_mma.cu), 0: fp32 sequence cell
   bool profiling = false;
   std::vector<cudaEvent_t> prof_state;  // start/stop pairs around state-step launches
   std::vector<cudaEvent_t> prof_step;   // start/stop pairs around policy steps
@@ -697,6 +699,9 @@ int ensure_prefill_ws(xl_handle* h, int rows) {
   const size_t o_semb = carve(4 * R * d), o_spad = carve(4 * R * h->Kpad), o_sin = carve(4 * R * c.state_dim);
   const size_t o_rtg = carve(4 * R), o_rew = carve(4 * R);
   const size_t o_hi = carve(2 * R * kmax), o_lo = carve(2 * R * kmax);
+  size_t pc_bytes = 0, pv_bytes = 0;
+  if (xl::prefill_cell_mma_supported(h->DH)) xl::prefill_cell_mma_ws(rows, (int)NH, h->DH, &pc_bytes, &pv_bytes);
+  const size_t o_pc = carve(pc_bytes), o_pv = carve(pv_bytes);
   XL_CUDA(cudaDeviceSynchronize());            // nothing may still be using the old workspace
   if (h->pf_buf) cudaFree(h->pf_buf);
   h->pf_buf = nullptr;
@@ -711,6 +716,7 @@ int ensure_prefill_ws(xl_handle* h, int rows) {
   h->pf_semb = (float*)(b + o_semb); h->pf_spad = (float*)(b + o_spad); h->pf_sin = (float*)(b + o_sin);
   h->pf_rtg = (float*)(b + o_rtg); h->pf_rew = (float*)(b + o_rew);
   h->pf_hi = (__nv_bfloat16*)(b + o_hi); h->pf_lo = (__nv_bfloat16*)(b + o_lo);
+  h->pf_pc = (uint8_t*)(b + o_pc); h->pf_pv = (uint8_t*)(b + o_pv);
   h->pf_rows = rows;
   return XL_OK;
 }
@@ -727,12 +733,12 @@ Ws prefill_ws(const xl_handle* h) {
   return w;
 }
 
-// tokens per env in one prefill chunk: ~2048 rows per chunk over all envs, a multiple of 24 (whole (s, rtg, r)
-// timesteps and whole 8-token cell stages)
+// tokens per env in one prefill chunk: ~2048 rows per chunk over all envs, a multiple of 48 (whole (s, rtg, r)
+// timesteps, whole 8-token stages of the fp32 cell and whole 16-token chunks of the tensor-core cell)
 int prefill_chunk_tokens(int B) {
   int sc = 2048 / B;
   if (sc < 48) sc = 48;
-  return sc / 24 * 24;
+  return sc / 48 * 48;
 }
 
 // The block stack over the chunk held in pf_x [B*Sc, d] (rows [env][token]), in place; state advanced by Sc tokens.
@@ -781,8 +787,16 @@ int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cud
       return fail(XL_ERR_UNSUPPORTED, "sequence conv/qkv kernel not instantiated for KS=%d NH=%d", cp.KS, cp.NH);
     xl::launch_gate_scan_seq(ws.gate_part, (const float*)w.w[XL_W_IGATE_B], (const float*)w.w[XL_W_FGATE_B],
                              (float*)(base + L.m_off), h->pf_f, h->pf_i, h->pf_m, B, Sc, NH, h->NCH, s);
-    XL_CUDA(xl::launch_cell_seq((float*)(base + L.c_off), (float*)(base + L.n_off), cp.qk, cp.qk + (size_t)M * inner,
-                                cp.v, h->pf_f, h->pf_i, h->pf_num, h->pf_qn, B, Sc, NH, DH, inner, s));
+    if (h->prefill_cell == 1 && xl::prefill_cell_mma_supported(DH) && Sc % xl::prefill_cell_mma_chunk() == 0) {
+      XL_CUDA(xl::launch_cell_mma((float*)(base + L.c_off), (float*)(base + L.n_off), cp.qk,
+                                  cp.qk + (size_t)M * inner, cp.v, h->pf_f, h->pf_i, h->pf_num, h->pf_qn, h->pf_pc,
+                                  h->pf_pv, B, Sc, NH, DH, inner, s));
+      h->launches += 1;
+    } else {
+      XL_CUDA(xl::launch_cell_seq((float*)(base + L.c_off), (float*)(base + L.n_off), cp.qk,
+                                  cp.qk + (size_t)M * inner, cp.v, h->pf_f, h->pf_i, h->pf_num, h->pf_qn, B, Sc, NH,
+                                  DH, inner, s));
+    }
     XL_CUDA(xl::launch_finalize_seq(h->pf_num, h->pf_qn, h->pf_m, (const float*)w.w[XL_W_OUTNORM],
                                     (const float*)w.w[XL_W_SKIP], ws.act, ws.u, tc_down ? nullptr : ws.gated,
                                     tc_down ? ws.a_hi : nullptr, tc_down ? ws.a_lo : nullptr, B, Sc, NH, DH, inner,
@@ -1254,7 +1268,9 @@ int xl_prefill(xl_handle* h, void* state, const float* x_in, float* y_out, int B
   if (prefill_fast_path(h)) {
     const int sc_max = prefill_chunk_tokens(B);
     while (S - pos >= 8) {
-      const int Sc = std::min(sc_max, (S - pos) / 8 * 8);
+      int Sc = std::min(sc_max, (S - pos) / 8 * 8);
+      // whole 16-token chunks go to the tensor-core cell; an 8-token remainder takes the fp32 cell next round
+      if (h->prefill_cell == 1 && xl::prefill_cell_mma_supported(h->DH) && Sc >= 16) Sc = Sc / 16 * 16;
       rc = ensure_prefill_ws(h, B * Sc);
       if (rc) return rc;
       XL_CUDA(cudaMemcpy2DAsync(h->pf_x, sizeof(float) * (size_t)Sc * d, x_in + (size_t)pos * d,
@@ -1305,7 +1321,9 @@ int xl_policy_prefill(xl_handle* h, void* state, const float* states, const floa
   if (prefill_fast_path(h)) {
     const int tc_max = prefill_chunk_tokens(B) / T;
     while (Tn - pos >= 8) {
-      const int Tc = std::min(tc_max, (Tn - pos) / 8 * 8);       // 8 timesteps = 24 tokens = 3 cell stages
+      int Tc = std::min(tc_max, (Tn - pos) / 8 * 8);             // 8 timesteps = 24 tokens = 3 cell stages
+      // 16 timesteps = 48 tokens = 3 chunks of the tensor-core cell; an 8-timestep remainder takes the fp32 cell
+      if (h->prefill_cell == 1 && xl::prefill_cell_mma_supported(h->DH) && Tc >= 16) Tc = Tc / 16 * 16;
       const int rows = B * Tc;
       rc = ensure_prefill_ws(h, rows * T);
       if (rc) return rc;
@@ -1380,6 +1398,9 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "microbatches")) {
     if (value < 0 || value > kMaxMicro) return fail(XL_ERR_INVALID_ARG, "microbatches must be in [0, %d]", kMaxMicro);
     h->microbatches = value;
+  } else if (!strcmp(name, "prefill_cell")) {
+    if (value < 0 || value > 1) return fail(XL_ERR_INVALID_ARG, "prefill_cell must be 0 (fp32 sequence cell) or 1 (chunkwise mma)");
+    h->prefill_cell = (int)value;
   } else if (!strcmp(name, "pdl")) {
     xl::g_use_pdl = value ? 1 : 0;       // process-wide: programmatic dependent launch of every kernel
   } else if (!strcmp(name, "l2_prefetch_mb")) {

@@ -144,6 +144,13 @@ void launch_gate_scan_seq(const float* gate_part, const float* igate_b, const fl
 cudaError_t launch_cell_seq(float* C, float* n, const float* q, const float* k, const float* v, const float* fseq,
                             const float* iseq, float* num, float* qn, int B, int S, int NH, int DH, int inner,
                             cudaStream_t s);
+// chunkwise tensor-core sequence cell (xl_prefill_mma.cu): prep kernel + mma.sync cell kernel; S % 16 == 0
+bool prefill_cell_mma_supported(int DH);
+int prefill_cell_mma_chunk();
+void prefill_cell_mma_ws(int rows, int NH, int DH, size_t* common_bytes, size_t* vblk_bytes);
+cudaError_t launch_cell_mma(float* C, float* n, const float* q, const float* k, const float* v, const float* fseq,
+                            const float* iseq, float* num, float* qn, void* common, void* vblk, int B, int S, int NH,
+                            int DH, int inner, cudaStream_t s);
 cudaError_t launch_finalize_seq(const float* num, const float* qn, const float* mseq, const float* outnorm_w,
                                 const float* skip, const float* act, const float* u, float* out, void* out_hi,
                                 void* out_lo, int B, int S, int NH, int DH, int inner, float ln_eps, float cell_eps,

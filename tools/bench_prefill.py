@@ -23,6 +23,7 @@ ap.add_argument("--rollout", type=int, default=1000)
 ap.add_argument("--check", type=int, default=64, help="timesteps of the prefix checked against stepping (0 = skip)")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--out", default=None)
+ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE", help="xl_set_option passthrough, e.g. prefill_cell=0")
 args = ap.parse_args()
 
 cfg = preset(args.model)
@@ -31,12 +32,15 @@ B = args.envs
 Tn = args.tokens // 3
 dev = torch.device("cuda", 0)
 eng = XLSTMEngine(cfg, sd, max_batch=B, device=dev)
+for kv in args.opt:
+    name, val = kv.split("=")
+    eng.set_option(name, int(val))
 n_stream = 256
 st_np, rtg_np, _ = make_stream(cfg, range(B), n_stream, domains="mixed")
 reps = (Tn + n_stream - 1) // n_stream
 states = torch.from_numpy(np.ascontiguousarray(np.tile(st_np, (reps, 1, 1))[:Tn].transpose(1, 0, 2))).to(dev)
 rtg = torch.from_numpy(np.ascontiguousarray(np.tile(rtg_np, (reps, 1))[:Tn].T)).to(dev)
-res = {"model": args.model, "envs": B, "context_tokens": Tn * 3, "context_timesteps": Tn}
+res = {"model": args.model, "envs": B, "options": args.opt, "context_tokens": Tn * 3, "context_timesteps": Tn}
 
 if args.check:
     n = min(args.check, Tn)
