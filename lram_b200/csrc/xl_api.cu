@@ -117,6 +117,8 @@ struct xl_handle {
   float *ll_z = nullptr, *ll_q = nullptr, *ll_k = nullptr, *ll_v = nullptr, *ll_act = nullptr, *ll_g = nullptr,
         *ll_gate_part = nullptr, *ll_gates = nullptr, *ll_partial = nullptr;
   unsigned* ll_bar = nullptr;
+  long long* ll_dbg = nullptr;
+  int lowlat_debug = 0;                         // stamp per-phase clocks of CTA 0 ("lowlat_debug"), print with "lowlat_dump"
   size_t ll_smem_limit = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_state;  // start/stop pairs around state-step launches
@@ -491,6 +493,7 @@ int lowlat_prepare(xl_handle* h) {
     const size_t o_v = carve(4 * 16 * inner), o_a = carve(4 * 16 * inner), o_g = carve(4 * 16 * inner);
     const size_t o_gp = carve(4 * (size_t)256 * 16 * 16), o_gt = carve(4 * (size_t)16 * 8 * 16);
     const size_t o_pt = carve(4 * 16 * inner * (DH / 16 + 1)), o_bar = carve(64);
+    const size_t o_dbg = carve(8 * 9 * L);
     XL_CUDA(cudaMalloc((void**)&h->ll_buf, off));
     XL_CUDA(cudaMemset(h->ll_buf, 0, off));
     h->ll_layers = (xl::LowLatLayer*)(h->ll_buf + o_lay);
@@ -498,6 +501,7 @@ int lowlat_prepare(xl_handle* h) {
     h->ll_v = (float*)(h->ll_buf + o_v); h->ll_act = (float*)(h->ll_buf + o_a); h->ll_g = (float*)(h->ll_buf + o_g);
     h->ll_gate_part = (float*)(h->ll_buf + o_gp); h->ll_gates = (float*)(h->ll_buf + o_gt);
     h->ll_partial = (float*)(h->ll_buf + o_pt); h->ll_bar = (unsigned*)(h->ll_buf + o_bar);
+    h->ll_dbg = (long long*)(h->ll_buf + o_dbg);
   }
   std::vector<xl::LowLatLayer> tab(L);
   for (size_t i = 0; i < L; ++i) {
@@ -532,6 +536,7 @@ int lowlat_stack(xl_handle* h, void* state, const Slice& sl, int T, size_t smem,
   p.post_w = (const float*)h->pw[XL_W_POST_NORM - XL_W_POST_NORM];
   p.z = h->ll_z; p.q = h->ll_q; p.k = h->ll_k; p.v = h->ll_v; p.act = h->ll_act; p.g = h->ll_g;
   p.gate_part = h->ll_gate_part; p.gates = h->ll_gates; p.partial = h->ll_partial; p.bar = h->ll_bar;
+  p.dbg = h->lowlat_debug ? h->ll_dbg : nullptr;
   p.L = c.num_blocks; p.B = sl.Bk; p.T = T; p.M = sl.Bk * T; p.d = c.embedding_dim; p.inner = c.inner_dim;
   p.NH = c.num_heads; p.DH = h->DH; p.G = h->num_sms < 256 ? h->num_sms : 256;
   xl::lowlat_plan_state(p.B, p.NH, p.DH, p.G, &p.rpu, &p.RS);
@@ -1532,6 +1537,24 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
     h->lowlat = value ? 1 : 0;
   } else if (!strcmp(name, "lowlat_coop")) {
     h->lowlat_coop = value ? 1 : 0;
+  } else if (!strcmp(name, "lowlat_debug")) {
+    h->lowlat_debug = value ? 1 : 0;
+  } else if (!strcmp(name, "lowlat_dump")) {
+    // prints the per-phase SM-clock breakdown of the LAST latency-kernel launch (CTA 0's view) to stderr
+    if (h->ll_dbg) {
+      const int L = h->cfg.num_blocks;
+      std::vector<long long> st((size_t)9 * L);
+      XL_CUDA(cudaDeviceSynchronize());
+      XL_CUDA(cudaMemcpy(st.data(), h->ll_dbg, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost));
+      double acc[8] = {0};
+      for (int l = 0; l < L; ++l)
+        for (int k = 0; k < 8; ++k) acc[k] += (double)(st[l * 9 + k + 1] - st[l * 9 + k]);
+      static const char* nm[8] = {"A work", "A barrier", "C work", "C barrier", "D1 work", "D1 barrier", "D2 work", "D2 barrier"};
+      fprintf(stderr, "lowlat phases (avg SM clocks per block over %d blocks; whole stack %lld clocks):\n", L,
+              st[(size_t)9 * L - 1] - st[0]);
+      for (int k = 0; k < 8; ++k) fprintf(stderr, "  %-10s %9.0f\n", nm[k], acc[k] / L);
+    }
+    return XL_OK;
   } else if (!strcmp(name, "lowlat_check")) {
     // synchronises the device, reads and clears the latency kernel's barrier words; error if a grid barrier
     // ever timed out (the kernel then fell through with garbage instead of hanging)

@@ -178,6 +178,7 @@ struct LowLatParams {
   float* gates;                 // [B*NH, 3T+1]
   float* partial;               // [strips, RS, T, 128]
   unsigned* bar;                // arrivals, generation, abort flag
+  long long* dbg;               // nullable: clock64 stamps of CTA 0, [L][9] (measurement aid)
   int L, B, T, M, d, inner, NH, DH, G;
   int rpu, RS;                  // phase C: rows per unit, row chunks per strip
   float ln_eps, cell_eps;

@@ -63,28 +63,29 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& gen, int G
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    if (!ld_acquire(bar + 2)) {
-      const unsigned arrived = atomicAdd(bar, 1u);
-      if (arrived == (unsigned)G - 1u) {
-        bar[0] = 0u;
-        __threadfence();
-        atomicAdd(bar + 1, 1u);
-      } else {
-        unsigned spins = 0;
-        while (ld_acquire(bar + 1) == gen) {
-          if (++spins > kSpinLimit) {
-            atomicExch(bar + 2, 1u);
-            break;
-          }
-          if ((spins & 1023u) == 0u && ld_acquire(bar + 2)) break;
+    const unsigned arrived = atomicAdd(bar, 1u);
+    if (arrived == (unsigned)G - 1u) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      unsigned spins = 0;
+      while (ld_acquire(bar + 1) == gen) {
+        if (++spins > kSpinLimit) {
+          atomicExch(bar + 2, 1u);
+          break;
         }
+        if ((spins & 255u) == 0u && ld_acquire(bar + 2)) break;
       }
     }
-    __threadfence();
   }
   gen += 1u;
   __syncthreads();
 }
+
+// per-phase clock stamps of CTA 0 (measurement aid, p.dbg nullable): [layer][9]
+#define XL_LL_STAMP(k) \
+  do { if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[layer * 9 + (k)] = clock64(); } while (0)
 
 // xs stores a row of K floats so that the 8 consecutive k a lane multiplies with one 16-byte weight load sit as
 // two float4 that are bank-conflict free across the warp: float4 group at k (k % 4 == 0) lives at perm4(k).
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) lowlat_stack_kernel(const LowLatP
     float* mst = reinterpret_cast<float*>(sbase + p.m_off);
     float* cvst = reinterpret_cast<float*>(sbase + p.conv_off);
 
+    XL_LL_STAMP(0);
     // =========================== phase A: LN, proj_up, conv / q k v / gate partials =====================
     {
       if (warp < M) {                         // warp w normalises row w (xlstm LayerNorm: gamma = 1 + w, no bias)
@@ -270,71 +272,65 @@ __global__ void __launch_bounds__(kThreads, 1) lowlat_stack_kernel(const LowLatP
           // z half of u: rows of 4 consecutive floats
           for (int idx = lane; idx < M * 4; idx += 32)
             p.z[(size_t)(idx >> 2) * inner + (col0 - inner) + (idx & 3)] = wsc[idx];
-        } else if (lane < B) {
-          const int b = lane, c = col0;
-          float win[4][4];
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            win[0][ch] = 0.f;
-#pragma unroll
-            for (int r = 1; r < 4; ++r) win[r][ch] = wsm[cofs + (b * 3 + r - 1) * 4 + ch];
-          }
+        } else {
+          // conv + SiLU + headwise q/k/v + gate partials: lane = (row m, output channel o) of this 4-channel block.
+          // Token t's conv window is the last 4 of [old rows 1..3, x_0 .. x_t]: no dependency between tokens.
+          const int c = col0;
           const float* cw = wsm;          // [ch][r]
           const float* cb = wsm + 16;
           const float* wq = wsm + 20;
           const float* wk = wsm + 36;
           const float* wv = wsm + 52;
-#pragma unroll
-          for (int t = 0; t < T; ++t) {
-            const int m = b * T + t;
-            float xm[4], a[4], qv[4], kv[4], vv[4];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) xm[ch] = wsc[m * 4 + ch];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch) win[r][ch] = win[r + 1][ch];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) win[3][ch] = xm[ch];
+          for (int base = 0; base < M * 4; base += 32) {
+            const int idx = base + lane;
+            const bool on = idx < M * 4;
+            const int m = on ? (idx >> 2) : 0, o = idx & 3;
+            const int b = m / T, t = m - b * T;
+            float a[4], xm[4];
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
               float acc = 0.f;
 #pragma unroll
-              for (int r = 0; r < 4; ++r) acc = fmaf(win[r][ch], cw[ch * 4 + r], acc);
-              a[ch] = silu(acc + cb[ch]);
-            }
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              float sq = 0.f, sk = 0.f, sv = 0.f;
-#pragma unroll
-              for (int dd = 0; dd < 4; ++dd) {
-                sq = fmaf(a[dd], wq[4 * o + dd], sq);
-                sk = fmaf(a[dd], wk[4 * o + dd], sk);
-                sv = fmaf(xm[dd], wv[4 * o + dd], sv);
+              for (int r = 0; r < 4; ++r) {
+                const int j = t + r;
+                const float wv_ = (j < 3) ? wsm[cofs + (b * 3 + j) * 4 + ch] : wsc[(b * T + j - 3) * 4 + ch];
+                acc = fmaf(wv_, cw[ch * 4 + r], acc);
               }
-              qv[o] = sq; kv[o] = sk; vv[o] = sv;
+              a[ch] = silu(acc + cb[ch]);
+              xm[ch] = wsc[m * 4 + ch];
             }
-            const size_t o4 = (size_t)m * inner + c;
-            *reinterpret_cast<float4*>(p.q + o4) = make_float4(qv[0], qv[1], qv[2], qv[3]);
-            *reinterpret_cast<float4*>(p.k + o4) = make_float4(kv[0], kv[1], kv[2], kv[3]);
-            *reinterpret_cast<float4*>(p.v + o4) = make_float4(vv[0], vv[1], vv[2], vv[3]);
-            *reinterpret_cast<float4*>(p.act + o4) = make_float4(a[0], a[1], a[2], a[3]);
+            float sq = 0.f, sk = 0.f, sv = 0.f;
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) {
+              sq = fmaf(a[dd], wq[4 * o + dd], sq);
+              sk = fmaf(a[dd], wk[4 * o + dd], sk);
+              sv = fmaf(xm[dd], wv[4 * o + dd], sv);
+            }
+            if (on) {
+              const size_t o1 = (size_t)m * inner + c + o;
+              p.q[o1] = sq; p.k[o1] = sk; p.v[o1] = sv;
+              p.act[o1] = (o == 0) ? a[0] : ((o == 1) ? a[1] : ((o == 2) ? a[2] : a[3]));
+            }
             for (int hh = 0; hh < NH; ++hh) {
               const float* g6 = wsm + gofs + hh * 24;
-              float si = 0.f, sf = 0.f;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                si += qv[j] * g6[j] + kv[j] * g6[4 + j] + vv[j] * g6[8 + j];
-                sf += qv[j] * g6[12 + j] + kv[j] * g6[16 + j] + vv[j] * g6[20 + j];
+              float si = on ? (sq * g6[o] + sk * g6[4 + o] + sv * g6[8 + o]) : 0.f;
+              float sf = on ? (sq * g6[12 + o] + sk * g6[16 + o] + sv * g6[20 + o]) : 0.f;
+              si += __shfl_xor_sync(0xffffffffu, si, 1);
+              sf += __shfl_xor_sync(0xffffffffu, sf, 1);
+              si += __shfl_xor_sync(0xffffffffu, si, 2);
+              sf += __shfl_xor_sync(0xffffffffu, sf, 2);
+              if (on && o == 0) {
+                wgs[m * kGateSlots + hh] += si;
+                wgs[m * kGateSlots + NH + hh] += sf;
               }
-              wgs[m * kGateSlots + hh] += si;
-              wgs[m * kGateSlots + NH + hh] += sf;
             }
           }
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-            *reinterpret_cast<float4*>(cvst + ((size_t)b * 4 + r) * inner + c) =
-                make_float4(win[r][0], win[r][1], win[r][2], win[r][3]);
+          // conv window after the T tokens: last 4 of [old rows 1..3, x_0 .. x_{T-1}], oldest first
+          for (int idx = lane; idx < B * 4; idx += 32) {
+            const int b = idx >> 2, r = idx & 3, j = T - 1 + r;
+            const float* src = (j < 3) ? wsm + cofs + (b * 3 + j) * 4 : wsc + (b * T + j - 3) * 4;
+            *reinterpret_cast<float4*>(cvst + ((size_t)b * 4 + r) * inner + c) = make_float4(src[0], src[1], src[2], src[3]);
+          }
         }
         __syncwarp();
       }
@@ -346,7 +342,9 @@ __global__ void __launch_bounds__(kThreads, 1) lowlat_stack_kernel(const LowLatP
         p.gate_part[((size_t)blockIdx.x * MR + m) * kGateSlots + g] = s;
       }
     }
+    XL_LL_STAMP(1);
     grid_barrier(p.bar, gen, G);
+    XL_LL_STAMP(2);
 
     // =========================== phase C: gates, matrix-memory update, partial numerators ===============
     {
@@ -462,7 +460,9 @@ __global__ void __launch_bounds__(kThreads, 1) lowlat_stack_kernel(const LowLatP
         __syncthreads();
       }
     }
+    XL_LL_STAMP(3);
     grid_barrier(p.bar, gen, G);
+    XL_LL_STAMP(4);
 
     // =========================== phase D1: n, q.n, h, MultiHeadLayerNorm, skip, output gate =============
     {
@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) lowlat_stack_kernel(const LowLatP
             zv[e][t] = ok ? __ldcg(p.z + off) : 0.f;
             float s = 0.f;
             if (ok)
+#pragma unroll 8
               for (int rs = 0; rs < p.RS; ++rs)
                 s += __ldcg(p.partial + ((size_t)(strip * p.RS + rs) * T + t) * 128 + col);
             num[e][t] = s;
@@ -556,7 +557,9 @@ __global__ void __launch_bounds__(kThreads, 1) lowlat_stack_kernel(const LowLatP
         __syncthreads();
       }
     }
+    XL_LL_STAMP(5);
     grid_barrier(p.bar, gen, G);
+    XL_LL_STAMP(6);
 
     // =========================== phase D2: x += g W_down^T ==============================================
     {
@@ -588,7 +591,9 @@ __global__ void __launch_bounds__(kThreads, 1) lowlat_stack_kernel(const LowLatP
         __syncwarp();
       }
     }
+    XL_LL_STAMP(7);
     grid_barrier(p.bar, gen, G);
+    XL_LL_STAMP(8);
   }
 
   // =========================== post_blocks_norm ==========================================================

@@ -59,6 +59,8 @@ for name in args.models.split(","):
             print(json.dumps(rows[-1]), flush=True)
         if ll:
             eng.set_option("lowlat_check", 0)
+            if any(kv.startswith("lowlat_debug=1") for kv in args.opt):
+                eng.set_option("lowlat_dump", 0)      # per-phase SM clocks of the last launch -> stderr
         same = bool(torch.equal(toks[0], toks[1]))
         print(json.dumps({"model": name, "envs": B, "tokens_equal_first_40_steps": same}), flush=True)
         rows.append({"model": name, "envs": B, "tokens_equal_first_40_steps": same})
