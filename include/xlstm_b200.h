@@ -235,6 +235,10 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
  *   "gemm_up_bn" / "gemm_up_splits" / "gemm_down_bn" / "gemm_down_splits": [0 = cost model] force tile width
  *                  (32/64/128) and split-K factor of the two projections
  *   "pdl": [1] programmatic dependent launch of every kernel (process-wide)
+ *   "l2_prefetch_mb": [-1 = automatic] MiB of the next block's C warmed into L2 on a side stream while the current
+ *                   block's latency-bound chain runs (0 = off; automatic = 48 when a block's C is 100..300 MB)
+ *   "lowlat": [0] small-batch path: whole block stack as one persistent cooperative kernel for B*T <= 16 rows
+ *                   (parity-tested; measured slower than the default on B200, see profiles/r01_lowlat_persistent.md)
  *   "microbatches": [1] env micro-batches of a fused step, pipelined on side streams; "pipeline_order": [1]
  *                   their state-stream kernels take turns */
 int xl_set_option(xl_handle* h, const char* name, int value);
