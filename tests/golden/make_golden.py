@@ -9,6 +9,8 @@ Sources of truth:
                         (transformers 5.5.0 in this image): an independent implementation of the mLSTM
                         recurrent step by the xlstm authors. Convention differs (q scaled instead of k):
                         h equal, C_hf = sqrt(DH)*C, n_hf = sqrt(DH)*n.
+  hf_mlstm_chunkwise.npz — ``mlstm_chunkwise_fw`` (48 tokens, chunk 16, non-zero initial (C, n, m)) and
+                        ``xLSTMMultiHeadLayerNorm`` from the same transformers module.
   oracle_toy.npz      — produced by oracle/xlstm_oracle.py itself (regression pin + the vectors the GPU
                         parity tests re-check on the box, where /root/reference does not exist).
 
@@ -98,6 +100,42 @@ def make_hf_step():
     print("hf_mlstm_step.npz", {k_: v_.shape for k_, v_ in out.items()})
 
 
+def make_hf_chunkwise_and_norm():
+    """Two more vectors from transformers' xlstm code (same authors as the pip `xlstm` the reference calls):
+    the chunkwise-parallel forward over a sequence STARTING FROM A NON-ZERO STATE (pins the recurrence across many
+    steps and the state hand-over the prefill relies on) and the multi-head LayerNorm (pins the GroupNorm form)."""
+    from transformers.models.xlstm import modeling_xlstm as hf
+    g = torch.Generator().manual_seed(23)
+    B, NH, DH, S = 2, 4, 32, 48
+    q = torch.randn(B, NH, S, DH, generator=g)
+    k = torch.randn(B, NH, S, DH, generator=g)
+    v = torch.randn(B, NH, S, DH, generator=g)
+    ig = torch.randn(B, NH, S, generator=g) * 2.0
+    fg = torch.randn(B, NH, S, generator=g) * 2.0 + 2.0
+    c0 = torch.randn(B, NH, DH, DH, generator=g) * 0.3
+    n0 = torch.randn(B, NH, DH, generator=g) * 0.3
+    m0 = torch.randn(B, NH, 1, generator=g)
+    # transformers 5.5.0 writes `fgate.logsigmoid(vecF)` (no such Tensor method): give it the obvious meaning for
+    # the duration of the call; every other line executed is transformers' own
+    torch.Tensor.logsigmoid = lambda self, x: torch.nn.functional.logsigmoid(x)
+    try:
+        H, _, _, last, _ = hf.mlstm_chunkwise_fw(q, k, v, ig, fg, cstate=c0, nstate=n0, mstate=m0,
+                                                 return_last_states=True, chunk_size=16, eps=1e-6)
+    finally:
+        del torch.Tensor.logsigmoid
+    out = dict(q=q.numpy(), k=k.numpy(), v=v.numpy(), ig=ig.numpy(), fg=fg.numpy(), c0=c0.numpy(), n0=n0.numpy(),
+               m0=m0.numpy(), h=H.numpy(), c_final=last[0].numpy(), n_final=last[1].numpy(), m_final=last[2].numpy())
+    ln = hf.xLSTMMultiHeadLayerNorm(num_heads=NH, head_dim=DH, eps=1e-5, use_weight=True, use_bias=False)
+    w_res = torch.randn(NH * DH, generator=g) * 0.1          # xlstm 1.0.x stores the residual: gamma = 1 + w
+    with torch.no_grad():
+        ln.weight.copy_(1.0 + w_res)
+        x = torch.randn(B, 5, NH, DH, generator=g) * 3.0 + 0.5
+        y = ln(x)
+    out.update(ln_x=x.numpy(), ln_w_residual=w_res.numpy(), ln_y=y.numpy())
+    np.savez_compressed(os.path.join(HERE, "hf_mlstm_chunkwise.npz"), **out)
+    print("hf_mlstm_chunkwise.npz", {k_: v_.shape for k_, v_ in out.items()})
+
+
 def make_oracle_toy():
     from lram_b200.config import preset
     from lram_b200.synth import make_state_dict, make_stream
@@ -135,4 +173,5 @@ if __name__ == "__main__":
     torch.set_num_threads(1)
     make_tokenizer_kat()
     make_hf_step()
+    make_hf_chunkwise_and_norm()
     make_oracle_toy()

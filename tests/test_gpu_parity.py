@@ -70,6 +70,33 @@ def test_cell_step_vs_hf_golden(golden_dir):
     eng.close()
 
 
+def test_cell_steps_from_nonzero_state_vs_hf_chunkwise_golden(golden_dir):
+    """fused-T kernel, 48 tokens as 12 launches of T = 4 from a NON-ZERO (C, n, m), vs vectors from transformers'
+    chunkwise-parallel forward started from the same state (independent implementation, different algorithm)."""
+    g = np.load(os.path.join(golden_dir, "hf_mlstm_chunkwise.npz"))
+    B, NH, S, DH = g["q"].shape
+    cfg, sd, eng = _engine("toy", B)
+    assert (cfg.num_heads, cfg.head_dim) == (NH, DH)
+    dev, s, T = eng.device, math.sqrt(DH), 4
+    C = (torch.from_numpy(g["c0"]) / s).to(dev)
+    n = (torch.from_numpy(g["n0"]) / s).to(dev)
+    m = torch.from_numpy(g["m0"]).reshape(B, NH).to(dev)
+    w0 = torch.zeros(cfg.inner, device=dev)
+    q, k, v = (torch.from_numpy(g[x]) for x in ("q", "k", "v"))          # [B,NH,S,DH]
+    for t0 in range(0, S, T):
+        rows = [torch.stack([x[:, :, t0 + t].reshape(B, NH * DH) for x in (q, k, v)], dim=1) for t in range(T)]
+        qkv = torch.stack(rows, dim=1).reshape(B * T, 3, NH * DH).to(dev)            # row = b*T + t
+        ig = torch.from_numpy(g["ig"][:, :, t0:t0 + T]).permute(0, 2, 1).reshape(B * T, NH).to(dev)
+        fg = torch.from_numpy(g["fg"][:, :, t0:t0 + T]).permute(0, 2, 1).reshape(B * T, NH).to(dev)
+        _, h_raw = eng.cell_step(C, n, m, qkv.contiguous(), ig.contiguous(), fg.contiguous(), w0, B, T)
+        ref = torch.from_numpy(g["h"][:, :, t0:t0 + T]).permute(0, 2, 1, 3).reshape(B * T, NH * DH)
+        assert _rel(h_raw.cpu(), ref) < REL_TOL, f"tokens {t0}..{t0 + T - 1}"
+    assert _rel(C.cpu() * s, torch.from_numpy(g["c_final"])) < 1e-4
+    assert _rel(n.cpu() * s, torch.from_numpy(g["n_final"])) < 1e-4
+    assert (m.cpu().view(B, NH, 1) - torch.from_numpy(g["m_final"])).abs().max() < 1e-5
+    eng.close()
+
+
 @pytest.mark.parametrize("name,B,T,rs,cols", [("toy", 3, 1, 0, 0), ("toy", 3, 3, 0, 0), ("toy", 2, 4, 2, 16),
                                               ("toy128", 2, 3, 4, 32), ("16M", 2, 3, 0, 0), ("16M", 1, 1, 8, 64),
                                               ("48M", 2, 3, 0, 0), ("206M", 1, 3, 0, 0), ("206M", 1, 2, 5, 128)])

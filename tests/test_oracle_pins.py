@@ -91,6 +91,35 @@ def test_cell_step_matches_hf_native(golden_dir):
     np.testing.assert_allclose(m.view(B, NH, 1).numpy(), g["m_final"], rtol=0, atol=1e-6)
 
 
+def test_recurrence_from_nonzero_state_matches_hf_chunkwise(golden_dir):
+    """48 oracle steps from a NON-ZERO (C, n, m) == transformers' chunkwise-parallel forward (chunk 16) started from the
+    same state: pins the recurrence over a sequence, the stabiliser carry and the state hand-over (prefill <-> stepping)."""
+    g = _npz(golden_dir, "hf_mlstm_chunkwise.npz")
+    q, k, v, ig, fg = (torch.from_numpy(g[n]) for n in ("q", "k", "v", "ig", "fg"))
+    B, NH, S, DH = q.shape
+    s = math.sqrt(DH)
+    c = torch.from_numpy(g["c0"]) / s                       # C_hf = sqrt(DH) C (q scaled instead of k)
+    n = (torch.from_numpy(g["n0"]) / s).unsqueeze(-1)
+    m = torch.from_numpy(g["m0"]).unsqueeze(-1)
+    for t in range(S):
+        h, (c, n, m) = O.recurrent_step_stabilized_simple(
+            c, n, m, q[:, :, t:t + 1], k[:, :, t:t + 1], v[:, :, t:t + 1], ig[:, :, t].view(B, NH, 1, 1),
+            fg[:, :, t].view(B, NH, 1, 1))
+        np.testing.assert_allclose(h.squeeze(2).numpy(), g["h"][:, :, t], rtol=5e-4, atol=1e-4)
+    np.testing.assert_allclose((c * s).numpy(), g["c_final"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose((n.squeeze(-1) * s).numpy(), g["n_final"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(m.view(B, NH, 1).numpy(), g["m_final"], rtol=0, atol=1e-5)
+
+
+def test_multihead_layer_norm_matches_hf(golden_dir):
+    """oracle MultiHeadLayerNorm (group_norm, gamma = 1 + w) == transformers' xLSTMMultiHeadLayerNorm with weight 1 + w."""
+    g = _npz(golden_dir, "hf_mlstm_chunkwise.npz")
+    x = torch.from_numpy(g["ln_x"])                         # [B, S, NH, DH]
+    B, S, NH, DH = x.shape
+    y = O.multihead_layer_norm(x.permute(0, 2, 1, 3).contiguous(), torch.from_numpy(g["ln_w_residual"]), eps=1e-5)
+    np.testing.assert_allclose(y.permute(0, 2, 1, 3).reshape(B, S, NH * DH).numpy(), g["ln_y"], rtol=1e-5, atol=2e-6)
+
+
 # ---- (ii) recurrent == parallel -----------------------------------------------------------------------------
 @pytest.mark.parametrize("name,S", [("toy", 24), ("toy128", 9)])
 def test_recurrent_equals_parallel(name, S):
