@@ -163,7 +163,29 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_JSON_FD = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner from C), so
+    fd 1 is pointed at stderr for the whole run and the JSON line goes to a duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -185,6 +207,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="xl_set_option passthrough for A/B runs, e.g. --opt microbatches=1 --opt state_impl=1")
     args = ap.parse_args()
+    _quiet_stdout()
     args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
@@ -387,7 +410,7 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
