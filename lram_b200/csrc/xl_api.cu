@@ -94,6 +94,7 @@ struct xl_handle {
                                        // results are garbage, only the step time is meaningful ("debug_skip")
   float *part_up = nullptr, *part_down = nullptr;   // split-K planes [kSplitMax][part_rows][2*inner | d]
   size_t part_rows = 0;
+  int l2_prefetch_policy = 0;          // 1: warm with an L2 evict_last policy ("l2_prefetch_policy")
   int microbatches = 0;                // 0 = automatic; env micro-batches per fused step ("microbatches")
   int pipeline_order = 1;              // 1 = state-stream kernels of the micro-batches run one after another
   int l2_prefetch_mb = -1;             // MiB of the NEXT block's C warmed into L2 on a side stream while the chain
@@ -573,7 +574,7 @@ int run_blocks(xl_handle* h, void* state, const Slice& sl, int T, unsigned flags
       int nx = (i + 1) % L;
       while (is_slstm(h, nx) && nx != i) nx = (nx + 1) % L;        // next mLSTM block
       const char* next_c = (const char*)state + layer_base(h, lay, nx) + lay.c_off;
-      xl::launch_l2_prefetch(next_c, warm_bytes, h->num_sms, h->side[0]);
+      xl::launch_l2_prefetch(next_c, warm_bytes, h->num_sms, h->l2_prefetch_policy, h->side[0]);
       h->launches += 1;
     }
     if (!rc) rc = block_post(h, state, sl, i, T, flags);
@@ -1525,6 +1526,8 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "l2_prefetch_mb")) {
     if (value < -1 || value > 4096) return fail(XL_ERR_INVALID_ARG, "l2_prefetch_mb must be in [-1, 4096] (-1 = automatic)");
     h->l2_prefetch_mb = value;
+  } else if (!strcmp(name, "l2_prefetch_policy")) {
+    h->l2_prefetch_policy = value ? 1 : 0;
   } else if (!strcmp(name, "pipeline_order")) {
     h->pipeline_order = value ? 1 : 0;
   } else if (!strcmp(name, "gemm_splitk")) {

@@ -540,20 +540,27 @@ void launch_state_reset(float* C, float* n, float* m, float* conv, const uint8_t
 // Runs on a side stream while the latency-bound chain (finalize / proj_down / LN / proj_up / conv) of the
 // current block leaves HBM idle: bulk L2 prefetches of the first `bytes` of the next block's C, so that the
 // next state-stream launch finds part of its read stream in L2. Reads only; no ordering needed against it.
-__global__ void l2_prefetch_kernel(const char* base, unsigned long long bytes, unsigned chunk) {
+__global__ void l2_prefetch_kernel(const char* base, unsigned long long bytes, unsigned chunk, int evict_last) {
   const unsigned long long nchunks = (bytes + chunk - 1) / chunk;
+  unsigned long long policy = 0;
+  if (evict_last) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nchunks;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long off = i * chunk;
     const unsigned sz = (unsigned)((bytes - off) < chunk ? (bytes - off) : chunk) & ~15u;
-    if (sz) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(sz) : "memory");
+    if (!sz) continue;
+    if (evict_last)   // keep the warmed lines resident until the state stream consumes them (its loads are evict_first)
+      asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(base + off), "r"(sz), "l"(policy)
+                   : "memory");
+    else
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(sz) : "memory");
   }
 }
 
-void launch_l2_prefetch(const void* base, size_t bytes, int num_sms, cudaStream_t s) {
+void launch_l2_prefetch(const void* base, size_t bytes, int num_sms, int evict_last, cudaStream_t s) {
   if (!bytes) return;
   const unsigned chunk = 4096;
-  l2_prefetch_kernel<<<num_sms, 64, 0, s>>>((const char*)base, (unsigned long long)bytes, chunk);
+  l2_prefetch_kernel<<<num_sms, 64, 0, s>>>((const char*)base, (unsigned long long)bytes, chunk, evict_last);
 }
 
 }  // namespace xl

@@ -68,7 +68,7 @@ void launch_state_reset(float* C, float* n, float* m, float* conv, const uint8_t
                         cudaStream_t s);
 
 // bulk L2 prefetch of [base, base+bytes) (side stream, plain launch; see xl_elementwise.cu)
-void launch_l2_prefetch(const void* base, size_t bytes, int num_sms, cudaStream_t s);
+void launch_l2_prefetch(const void* base, size_t bytes, int num_sms, int evict_last, cudaStream_t s);
 
 // ---- xl_state_step.cu ----------------------------------------------------------------------------
 struct StateStepParams {
