@@ -110,6 +110,10 @@ struct xl_handle {
   __nv_bfloat16 *pf_hi = nullptr, *pf_lo = nullptr;
   uint8_t *pf_pc = nullptr, *pf_pv = nullptr;   // prepared operands of the chunkwise tensor-core cell
   int prefill_cell = 1;                         // 1: chunkwise mma.sync cell (xl_prefill_mma.cu), 0: fp32 sequence cell
+  int smallm = 0;                               // 1: GEMV-style front (LN + proj_up + conv/qkv) and back (proj_down) kernels for
+                                                // B*T <= 16 rows ("smallm"); measured -3 % latency at B = 1 (16M / 48M), slower
+                                                // elsewhere (profiles/r01_lowlat_persistent.md): off by default
+  float* gp_small = nullptr;                    // its gate partials [16 rows][256 chunks][2 NH]
   // small-batch latency path (xl_lowlat.cu): device table of per-block weight pointers + private workspace,
   // built lazily (outside any capture) by lowlat_prepare
   int lowlat = 0;                               // 1: use the persistent-kernel stack when B*T <= 16 ("lowlat")
@@ -240,6 +244,14 @@ Slice make_slice(const xl_handle* h, int B, int b0, int Bk, cudaStream_t s) {
   return sl;
 }
 
+// Gate-partial chunks of the small-batch front kernel (xl_smallm.cu) when it will run for this slice, else 0.
+int smallm_chunks(const xl_handle* h, const Slice& sl, int T, unsigned flags) {
+  const xl_config& c = h->cfg;
+  if (!h->smallm || h->debug_skip || (flags & XL_FLAG_SIMPLE_GEMM) || h->state_impl == 2) return 0;
+  if (sl.b0 != 0 || sl.Bk != sl.B || sl.ws.low_smem) return 0;
+  return xl::smallm_pre_chunks(sl.Bk, T, c.embedding_dim, c.inner_dim, c.num_heads, c.conv_kernel);
+}
+
 struct BlockPlan {
   bool tc_up, tc_down;
   int impl;
@@ -257,7 +269,8 @@ BlockPlan block_plan(const xl_handle* h, const Slice& sl, int T, unsigned flags)
   p.tc_down = p.impl != 1 && xl::gemm_tc_supported(M, c.embedding_dim, c.inner_dim) &&
               (size_t)M * c.inner_dim <= sl.ws.a_cap;
   // split-K (planes summed by the consumer kernels): whole-batch slices only, rows within the plane storage
-  const bool can_split = !sl.ws.low_smem && sl.b0 == 0 && (size_t)M <= h->part_rows && c.embedding_dim <= 4096;
+  const bool can_split = !sl.ws.low_smem && sl.b0 == 0 && (size_t)M <= h->part_rows && c.embedding_dim <= 4096 &&
+                         !smallm_chunks(h, sl, T, flags);   // the fused front kernel reads a complete x
   const int max_sp = can_split ? std::min(std::max(h->gemm_splitk, 1), kSplitMax) : 1;
   p.up_bn = p.down_bn = 0;
   p.up_sp = p.down_sp = 1;
@@ -279,7 +292,7 @@ BlockPlan block_plan(const xl_handle* h, const Slice& sl, int T, unsigned flags)
 }
 
 xl::StateStepParams state_params(const xl_handle* h, void* state, const Slice& sl, int i, int T, bool tc_down,
-                                 int up_sp = 1) {
+                                 int up_sp = 1, int small_nch = 0) {
   const xl_config& c = h->cfg;
   const int inner = c.inner_dim, NH = c.num_heads, DH = h->DH;
   const StateLayout L = state_layout(h, sl.B);
@@ -307,6 +320,7 @@ xl::StateStepParams state_params(const xl_handle* h, void* state, const Slice& s
   sp.out_lo = tc_down ? sl.ws.a_lo : nullptr;
   sp.partial = sl.ws.partial;
   sp.B = sl.Bk; sp.T = T; sp.NH = NH; sp.DH = DH; sp.inner = inner; sp.NCH = h->NCH;
+  if (small_nch) { sp.gate_part = h->gp_small; sp.NCH = small_nch; }
   sp.ln_eps = c.ln_eps; sp.cell_eps = c.cell_eps;
   sp.impl = h->state_impl; sp.num_layers = c.num_blocks;
   sp.stages = h->state_stages; sp.ctas_per_sm = h->state_ctas_per_sm; sp.rows_split = h->state_rows_split;
@@ -327,6 +341,25 @@ int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned
   const BlockWeights& w = h->blocks[i];
   const Ws& ws = sl.ws;
   char* base = (char*)state + layer_base(h, L, i);
+  if (const int nch = smallm_chunks(h, sl, T, flags)) {
+    // M <= 16 rows: LN + proj_up + conv / q k v / gate partials as ONE GEMV-style kernel (xl_smallm.cu)
+    xl::SmallPreParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.x = ws.x;
+    sp.norm_w = (const float*)w.w[XL_W_XLSTM_NORM];
+    sp.w_up = (const __nv_bfloat16*)w.w[XL_W_PROJ_UP];
+    sp.conv_w = (const float*)w.w[XL_W_CONV_W]; sp.conv_b = (const float*)w.w[XL_W_CONV_B];
+    sp.wq = (const float*)w.w[XL_W_Q_PROJ]; sp.wk = (const float*)w.w[XL_W_K_PROJ]; sp.wv = (const float*)w.w[XL_W_V_PROJ];
+    sp.wi = (const float*)w.w[XL_W_IGATE_W]; sp.wf = (const float*)w.w[XL_W_FGATE_W];
+    sp.conv_state = (float*)(base + L.conv_off);
+    sp.u = ws.u; sp.qk = ws.qkv; sp.v = ws.qkv + (size_t)2 * M * inner; sp.act = ws.act;
+    sp.gate_part = h->gp_small;
+    sp.B = sl.Bk; sp.T = T; sp.d = d; sp.inner = inner; sp.NH = NH; sp.NCH = nch;
+    sp.ln_eps = c.ln_eps;
+    XL_CUDA(xl::launch_smallm_pre(sp, sl.s));
+    h->launches += 1;
+    return XL_OK;
+  }
   if (h->debug_skip & 1) {
   } else if (i > 0 && bp.down_sp > 1 && !is_slstm(h, i - 1)) {
     // the previous (mLSTM) block's proj_down left split-K planes: x += planes, then normalise
@@ -369,7 +402,7 @@ int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned
 // block i, part 2: the HBM-bound state stream (C update + partial numerators)
 int block_state(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned flags) {
   const BlockPlan bp = block_plan(h, sl, T, flags);
-  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp);
+  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp, smallm_chunks(h, sl, T, flags));
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (h->profiling) {
     XL_CUDA(cudaEventCreate(&pe0));
@@ -390,9 +423,21 @@ int block_state(xl_handle* h, void* state, const Slice& sl, int i, int T, unsign
 int block_post(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned flags) {
   const xl_config& c = h->cfg;
   const BlockPlan bp = block_plan(h, sl, T, flags);
-  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp);
+  const int small_nch = smallm_chunks(h, sl, T, flags);
   const Ws& ws = sl.ws;
   const int M = sl.Bk * T;
+  if (small_nch) {
+    // M <= 16 rows: finalize emits fp32 g, then x += g W_down^T as warp GEMVs (xl_smallm.cu)
+    const xl::StateStepParams sp = state_params(h, state, sl, i, T, /*tc_down=*/false, 1, small_nch);
+    XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, sl.s));
+    xl::SmallDownParams dp;
+    dp.g = ws.gated; dp.w_down = (const __nv_bfloat16*)h->blocks[i].w[XL_W_PROJ_DOWN]; dp.x = ws.x;
+    dp.M = M; dp.d = c.embedding_dim; dp.inner = c.inner_dim;
+    XL_CUDA(xl::launch_smallm_down(dp, sl.s));
+    h->launches += 2;
+    return XL_OK;
+  }
+  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp, small_nch);
   if (!(h->debug_skip & 16)) XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, sl.s));
   h->launches += 1;
   if (h->debug_skip & 32) return XL_OK;
@@ -1024,6 +1069,7 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   h->part_rows = M < kSplitRows ? M : kSplitRows;
   const size_t o_pu = carve(4 * (size_t)kSplitMax * h->part_rows * 2 * inner);
   const size_t o_pd = carve(4 * (size_t)kSplitMax * h->part_rows * d);
+  const size_t o_gps = carve(4 * (size_t)16 * 256 * 2 * c.num_heads);
   h->ws_bytes = off;
   cudaError_t e = cudaMalloc((void**)&h->ws, h->ws_bytes);
   if (e != cudaSuccess) {
@@ -1050,6 +1096,7 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
 
   h->a_hi = (__nv_bfloat16*)(h->ws + o_hi); h->a_lo = (__nv_bfloat16*)(h->ws + o_lo);
   h->part_up = (float*)(h->ws + o_pu); h->part_down = (float*)(h->ws + o_pd);
+  h->gp_small = (float*)(h->ws + o_gps);
   *out = h;
   return XL_OK;
 }
@@ -1540,6 +1587,8 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "gemm_up_splits") || !strcmp(name, "gemm_down_splits")) {
     if (value < 0 || value > kSplitMax) return fail(XL_ERR_INVALID_ARG, "%s must be in [0, %d]", name, kSplitMax);
     (name[5] == 'u' ? h->gemm_up_splits : h->gemm_down_splits) = value;
+  } else if (!strcmp(name, "smallm")) {
+    h->smallm = value ? 1 : 0;
   } else if (!strcmp(name, "lowlat")) {
     h->lowlat = value ? 1 : 0;
   } else if (!strcmp(name, "lowlat_coop")) {

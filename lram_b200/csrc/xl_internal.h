@@ -188,6 +188,35 @@ bool lowlat_supported(int B, int T, int d, int inner, int NH, int DH, int KS, si
 void lowlat_plan_state(int B, int NH, int DH, int G, int* rpu_out, int* rs_out);
 cudaError_t launch_lowlat_stack(const LowLatParams& p, size_t smem, int coop, cudaStream_t s);
 
+// ---- xl_smallm.cu --------------------------------------------------------------------------------
+// Front half of an mLSTM block for M = B*T <= 16 rows as one GEMV-style kernel: LN + proj_up + conv/SiLU +
+// headwise q/k/v + gate partials (one chunk per CTA that owns x_m columns). Outputs in the layouts the state-stream
+// and finalize kernels read.
+struct SmallPreParams {
+  const float* x;               // [M, d] residual stream
+  const float* norm_w;          // [d] (gamma = 1 + w)
+  const __nv_bfloat16* w_up;    // [2*inner, d]
+  const float *conv_w, *conv_b, *wq, *wk, *wv, *wi, *wf;
+  float* conv_state;            // [B, 4, inner] in/out
+  float* u;                     // [M, 2*inner]: only the z half is written
+  float* qk;                    // [M, inner, 2]
+  float* v;                     // [M, inner]
+  float* act;                   // [M, inner]
+  float* gate_part;             // [M, NCH, 2*NH]
+  int B, T, d, inner, NH, NCH;
+  float ln_eps;
+};
+int smallm_pre_chunks(int B, int T, int d, int inner, int NH, int KS);   // 0 = shape not supported
+cudaError_t launch_smallm_pre(const SmallPreParams& p, cudaStream_t s);
+// Back half: x[M,d] += g[M,inner] W_down[d,inner]^T as warp GEMVs (no split-K planes, x complete on exit).
+struct SmallDownParams {
+  const float* g;               // [M, inner] fp32 (finalize kernel output)
+  const __nv_bfloat16* w_down;  // [d, inner]
+  float* x;                     // [M, d] in/out
+  int M, d, inner;
+};
+cudaError_t launch_smallm_down(const SmallDownParams& p, cudaStream_t s);
+
 // ---- xl_gemm.cu ----------------------------------------------------------------------------------
 // out[M,N] = A[M,K] W[N,K]^T (+bias) (+residual), A fp32, W bf16, CUDA cores, fp32 accumulate.
 void launch_gemm_simple(const float* A, const __nv_bfloat16* W, const float* bias, const float* residual,

@@ -25,6 +25,7 @@
 
 #include "xl_common.cuh"
 #include "xl_internal.h"
+#include "xl_gemv.cuh"
 
 #ifndef XL_LL_KBA4
 #define XL_LL_KBA4 2
@@ -37,6 +38,8 @@ namespace xl {
 
 namespace ll {
 
+using namespace gv;
+
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kGateSlots = 16;      // 2 * NH <= 16
@@ -48,14 +51,6 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
 // Grid barrier, self re-arming across launches: bar[0] = arrivals, bar[1] = generation, bar[2] = abort flag.
 // Every CTA is resident (cooperative launch, one CTA per SM). A CTA that spins for seconds raises the abort
 // flag, after which every barrier falls through: a bug ends as wrong numbers + a flag, never as a hung GPU.
@@ -86,59 +81,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& gen, int G
 // per-phase clock stamps of CTA 0 (measurement aid, p.dbg nullable): [layer][9]
 #define XL_LL_STAMP(k) \
   do { if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[layer * 9 + (k)] = clock64(); } while (0)
-
-// xs stores a row of K floats so that the 8 consecutive k a lane multiplies with one 16-byte weight load sit as
-// two float4 that are bank-conflict free across the warp: float4 group at k (k % 4 == 0) lives at perm4(k).
-__device__ __forceinline__ int perm4(int k) { return (k & ~255) + (((k >> 2) & 1) << 7) + (((k & 255) >> 3) << 2); }
-
-__device__ __forceinline__ float bf_lo(unsigned w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf_hi(unsigned w) { return __uint_as_float(w & 0xffff0000u); }
-
-// acc[c][m] = sum over this lane's k of W[col0 + c][k] * xs[m][k]  (lane owns k = 256 j + 8 lane .. + 7)
-template <int CG, int MR, int KB>
-__device__ __forceinline__ void gemv_cols(const __nv_bfloat16* __restrict__ W, int K, int col0, const float* xs,
-                                          int ld, int M, float (&acc)[CG][MR], int lane) {
-#pragma unroll
-  for (int c = 0; c < CG; ++c)
-#pragma unroll
-    for (int m = 0; m < MR; ++m) acc[c][m] = 0.f;
-  const int iters = K >> 8;
-  const int rowq = K >> 3;
-  const uint4* Wp = reinterpret_cast<const uint4*>(W + (size_t)col0 * K) + lane;
-  for (int j0 = 0; j0 < iters; j0 += KB) {
-    uint4 w[KB][CG];
-#pragma unroll
-    for (int jj = 0; jj < KB; ++jj)
-      if (j0 + jj < iters) {
-#pragma unroll
-        for (int c = 0; c < CG; ++c) w[jj][c] = __ldg(Wp + (size_t)c * rowq + (j0 + jj) * 32);
-      }
-#pragma unroll
-    for (int jj = 0; jj < KB; ++jj)
-      if (j0 + jj < iters) {
-        const float* xb = xs + (j0 + jj) * 256 + lane * 4;
-#pragma unroll
-        for (int m = 0; m < MR; ++m)
-          if (m < M) {
-            const float4 xa = *reinterpret_cast<const float4*>(xb + m * ld);
-            const float4 xc = *reinterpret_cast<const float4*>(xb + m * ld + 128);
-#pragma unroll
-            for (int c = 0; c < CG; ++c) {
-              float a = acc[c][m];
-              a = fmaf(bf_lo(w[jj][c].x), xa.x, a);
-              a = fmaf(bf_hi(w[jj][c].x), xa.y, a);
-              a = fmaf(bf_lo(w[jj][c].y), xa.z, a);
-              a = fmaf(bf_hi(w[jj][c].y), xa.w, a);
-              a = fmaf(bf_lo(w[jj][c].z), xc.x, a);
-              a = fmaf(bf_hi(w[jj][c].z), xc.y, a);
-              a = fmaf(bf_lo(w[jj][c].w), xc.z, a);
-              a = fmaf(bf_hi(w[jj][c].w), xc.w, a);
-              acc[c][m] = a;
-            }
-          }
-      }
-  }
-}
 
 // sum over the CTA of N values per thread; result in every thread. red: N*32 floats of shared memory.
 template <int N>

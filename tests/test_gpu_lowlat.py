@@ -125,3 +125,39 @@ def test_lowlat_falls_back_when_not_eligible():
     eng.encoder_step(cache, x)
     assert eng.launch_count() >= 6 * cfg.num_blocks
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GEMV-style small-batch kernels (xl_smallm.cu: LN + proj_up + conv/qkv/gate partials in one launch, proj_down in
+# another; option "smallm", B*T <= 16 rows): equality with the multi-kernel path they replace (itself oracle-checked
+# in test_gpu_parity.py), and proof that they ran.
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,B,mode", [("16M", 1, L.XL_MODE_FUSED), ("48M", 2, L.XL_MODE_FUSED),
+                                         ("110M", 5, L.XL_MODE_FUSED), ("16M", 7, L.XL_MODE_PER_TOKEN)])
+def test_smallm_front_kernel_equals_three_kernel_path(name, B, mode):
+    cfg, sd, eng = _engine(name, B)
+    steps = 4
+    states, rtg, _ = make_stream(cfg, range(B), steps, domains="mixed")
+    res, launches = {}, {}
+    for on in (0, 1):
+        eng.set_option("smallm", on)
+        cache = eng.new_state(B)
+        toks, hids = [], []
+        eng.launch_count()
+        for t in range(steps):
+            out = eng.policy_step(cache, torch.from_numpy(states[t]).cuda(), torch.from_numpy(rtg[t]).cuda(), mode=mode,
+                                  want_hidden=True)
+            toks.append(out["action_tokens"].cpu().clone())
+            hids.append(out["last_hidden_state"].cpu().clone())
+        launches[on] = eng.launch_count() / steps
+        res[on] = (torch.stack(toks), torch.stack(hids), cache.to_past_key_values())
+    assert torch.equal(res[1][0], res[0][0])
+    assert _rel(res[1][1], res[0][1]) < 1e-4
+    for i in range(cfg.num_blocks):
+        for a, b in zip(res[1][2][f"block_{i}"]["mlstm_state"], res[0][2][f"block_{i}"]["mlstm_state"]):
+            assert _rel(a.cpu(), b.cpu()) < 1e-4
+        assert _rel(res[1][2][f"block_{i}"]["conv_state"][0].cpu(), res[0][2][f"block_{i}"]["conv_state"][0].cpu()) < 1e-5
+    # two launches fewer per block and token pass (LN and conv/qkv folded into the GEMV kernel)
+    passes = 1 if mode == L.XL_MODE_FUSED else cfg.tokens_per_step
+    assert launches[0] - launches[1] >= 2 * cfg.num_blocks * passes, launches
+    eng.close()
