@@ -239,8 +239,9 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
  *                   block's latency-bound chain runs (0 = off; automatic = 48 when a block's C is 100..300 MB)
  *   "lowlat": [0] small-batch path: whole block stack as one persistent cooperative kernel for B*T <= 16 rows
  *                   (parity-tested; measured slower than the default on B200, see profiles/r01_lowlat_persistent.md)
- *   "smallm": [0] B*T <= 16 rows: LN + proj_up + conv/qkv as one GEMV-style kernel and proj_down as another (4 kernels
- *                   per block instead of 6; parity-tested; -3 % latency at B = 1 for 16M / 48M, slower for more rows)
+ *   "smallm": [-1 = automatic] LN + proj_up + conv/qkv as one GEMV-style kernel and proj_down as another (4 kernels
+ *                   per block instead of 6, fp32 activations against bf16 weights on CUDA cores). 1 = whenever
+ *                   B*T <= 16 rows, 0 = never, automatic = B*T <= 4 rows and d <= 1024 (one env: -14 % step latency)
  *   "microbatches": [1] env micro-batches of a fused step, pipelined on side streams; "pipeline_order": [1]
  *                   their state-stream kernels take turns */
 int xl_set_option(xl_handle* h, const char* name, int value);

@@ -110,9 +110,11 @@ struct xl_handle {
   __nv_bfloat16 *pf_hi = nullptr, *pf_lo = nullptr;
   uint8_t *pf_pc = nullptr, *pf_pv = nullptr;   // prepared operands of the chunkwise tensor-core cell
   int prefill_cell = 1;                         // 1: chunkwise mma.sync cell (xl_prefill_mma.cu), 0: fp32 sequence cell
-  int smallm = 0;                               // 1: GEMV-style front (LN + proj_up + conv/qkv) and back (proj_down) kernels for
-                                                // B*T <= 16 rows ("smallm"); measured -3 % latency at B = 1 (16M / 48M), slower
-                                                // elsewhere (profiles/r01_lowlat_persistent.md): off by default
+  int smallm = -1;                              // GEMV-style front (LN + proj_up + conv/qkv) and back (proj_down) kernels
+                                                // ("smallm"): 1 = whenever B*T <= 16 rows, 0 = never, -1 = automatic: B*T <= 4
+                                                // rows and d <= 1024, where they are measured faster (16M x 1 env: 168 vs 196 us,
+                                                // 48M: 312 vs 359, 110M: 481 vs 506; 206M equal; slower from 2 envs on —
+                                                // profiles/r01_lowlat_persistent.md)
   float* gp_small = nullptr;                    // its gate partials [16 rows][256 chunks][2 NH]
   // small-batch latency path (xl_lowlat.cu): device table of per-block weight pointers + private workspace,
   // built lazily (outside any capture) by lowlat_prepare
@@ -247,7 +249,8 @@ Slice make_slice(const xl_handle* h, int B, int b0, int Bk, cudaStream_t s) {
 // Gate-partial chunks of the small-batch front kernel (xl_smallm.cu) when it will run for this slice, else 0.
 int smallm_chunks(const xl_handle* h, const Slice& sl, int T, unsigned flags) {
   const xl_config& c = h->cfg;
-  if (!h->smallm || h->debug_skip || (flags & XL_FLAG_SIMPLE_GEMM) || h->state_impl == 2) return 0;
+  if (!h->smallm || h->debug_skip || (flags & XL_FLAG_SIMPLE_GEMM)) return 0;
+  if (h->smallm < 0 && (sl.Bk * T > 4 || c.embedding_dim > 1024)) return 0;
   if (sl.b0 != 0 || sl.Bk != sl.B || sl.ws.low_smem) return 0;
   return xl::smallm_pre_chunks(sl.Bk, T, c.embedding_dim, c.inner_dim, c.num_heads, c.conv_kernel);
 }
@@ -320,7 +323,7 @@ xl::StateStepParams state_params(const xl_handle* h, void* state, const Slice& s
   sp.out_lo = tc_down ? sl.ws.a_lo : nullptr;
   sp.partial = sl.ws.partial;
   sp.B = sl.Bk; sp.T = T; sp.NH = NH; sp.DH = DH; sp.inner = inner; sp.NCH = h->NCH;
-  if (small_nch) { sp.gate_part = h->gp_small; sp.NCH = small_nch; }
+  if (small_nch) sp.NCH = 1;      // the small-batch front kernel leaves ONE reduced chunk in ws.gate_part
   sp.ln_eps = c.ln_eps; sp.cell_eps = c.cell_eps;
   sp.impl = h->state_impl; sp.num_layers = c.num_blocks;
   sp.stages = h->state_stages; sp.ctas_per_sm = h->state_ctas_per_sm; sp.rows_split = h->state_rows_split;
@@ -353,7 +356,7 @@ int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned
     sp.wi = (const float*)w.w[XL_W_IGATE_W]; sp.wf = (const float*)w.w[XL_W_FGATE_W];
     sp.conv_state = (float*)(base + L.conv_off);
     sp.u = ws.u; sp.qk = ws.qkv; sp.v = ws.qkv + (size_t)2 * M * inner; sp.act = ws.act;
-    sp.gate_part = h->gp_small;
+    sp.gate_part = ws.gate_part; sp.gate_scratch = h->gp_small; sp.ticket = h->counters;
     sp.B = sl.Bk; sp.T = T; sp.d = d; sp.inner = inner; sp.NH = NH; sp.NCH = nch;
     sp.ln_eps = c.ln_eps;
     XL_CUDA(xl::launch_smallm_pre(sp, sl.s));
@@ -1588,7 +1591,8 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
     if (value < 0 || value > kSplitMax) return fail(XL_ERR_INVALID_ARG, "%s must be in [0, %d]", name, kSplitMax);
     (name[5] == 'u' ? h->gemm_up_splits : h->gemm_down_splits) = value;
   } else if (!strcmp(name, "smallm")) {
-    h->smallm = value ? 1 : 0;
+    if (value < -1 || value > 1) return fail(XL_ERR_INVALID_ARG, "smallm must be -1 (automatic), 0 or 1");
+    h->smallm = value;
   } else if (!strcmp(name, "lowlat")) {
     h->lowlat = value ? 1 : 0;
   } else if (!strcmp(name, "lowlat_coop")) {

@@ -9,7 +9,7 @@
 // activations stay fp32 — no hi/lo planes needed), and a warp that owns an x_m group finishes conv / q / k / v / gate
 // partials for those 4 channels in its epilogue. Outputs are exactly what the state-stream and finalize kernels read:
 // (q,k) pairs [M, inner, 2], v [M, inner], a [M, inner], z in u[:, inner:], the conv window, and gate partials
-// [M, NCH, 2 NH] with one chunk per CTA (summed in chunk order by compute_gates: deterministic).
+// [M, 1, 2 NH] (the per-CTA shares are added in CTA order by the last CTA to finish: deterministic).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -191,13 +191,29 @@ __global__ void __launch_bounds__(kThreads) smallm_pre_kernel(const SmallPrePara
     }
   }
   __syncthreads();
-  // gate partials of this CTA = chunk blockIdx.x (only CTAs that own x_m groups are chunks)
+  // Gate partials: every CTA that owns x_m groups leaves its share in the scratch; the LAST of them to finish adds the
+  // shares in CTA order (deterministic) into the single chunk [M, 1, 2 NH] the state-stream / finalize kernels read.
   if ((int)blockIdx.x < p.NCH) {
+    __shared__ int s_last;
     for (int idx = tid; idx < M * 2 * NH; idx += kThreads) {
       const int m = idx / (2 * NH), g = idx - m * 2 * NH;
       float s = 0.f;
       for (int w = 0; w < kWarps; ++w) s += gs_all[(w * MR + m) * 2 * NH + g];
-      p.gate_part[((size_t)m * p.NCH + blockIdx.x) * 2 * NH + g] = s;
+      p.gate_scratch[((size_t)blockIdx.x * MR + m) * 2 * NH + g] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(p.ticket, 1u) == (unsigned)p.NCH - 1u);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      for (int idx = tid; idx < M * 2 * NH; idx += kThreads) {
+        const int m = idx / (2 * NH), g = idx - m * 2 * NH;
+        float s = 0.f;
+        for (int c = 0; c < p.NCH; ++c) s += __ldcg(p.gate_scratch + ((size_t)c * MR + m) * 2 * NH + g);
+        p.gate_part[(size_t)m * 2 * NH + g] = s;
+      }
+      if (tid == 0) *p.ticket = 0u;          // re-armed for the next launch (stream ordered)
     }
   }
 }

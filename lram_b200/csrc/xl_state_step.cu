@@ -35,7 +35,7 @@ namespace xl {
 
 constexpr int kThreads = 256;        // consumer threads
 constexpr int kUnroll = 8;
-constexpr int kMaxNCH = 256;   // > 16 chunks: lane-parallel sum in compute_gates (small-batch front kernel)
+constexpr int kMaxNCH = 16;
 
 // stream-K partition of N stage tiles over G CTAs (impl 2): CTA c owns [sk_start(c), sk_start(c+1))
 __host__ __device__ __forceinline__ int sk_start(const StateStepParams& p, int c) {
@@ -53,21 +53,7 @@ __device__ __forceinline__ void compute_gates(const StateStepParams& p, int b, i
                                               float* s_i, float* s_m, float* s_pre) {
   const int lane = threadIdx.x & 31;
   const int NH = p.NH;
-  if (p.NCH > 16) {
-    // many chunks (small-batch front kernel, xl_smallm.cu: one chunk per CTA): the lanes share the chunks of each
-    // value, then a fixed-shape shuffle tree — still deterministic
-#pragma unroll
-    for (int vv = 0; vv < 2 * T; ++vv) {
-      const int t = vv >> 1, is_f = vv & 1;
-      const float* gp = p.gate_part + ((int64_t)b * T + t) * p.NCH * 2 * NH + (is_f ? NH : 0) + hd;
-      float s = 0.f;
-      for (int c = lane; c < p.NCH; c += 32) s += gp[c * 2 * NH];
-      s = warp_sum(s);
-      const float* bias = is_f ? p.fgate_b : p.igate_b;
-      if (bias) s += bias[hd];
-      if (lane == 0) s_pre[vv] = s;
-    }
-  } else if (lane < 2 * T) {
+  if (lane < 2 * T) {
     const int t = lane >> 1, is_f = lane & 1;
     const float* gp = p.gate_part + ((int64_t)b * T + t) * p.NCH * 2 * NH + (is_f ? NH : 0) + hd;
     float s = 0.f;
