@@ -323,7 +323,7 @@ xl::StateStepParams state_params(const xl_handle* h, void* state, const Slice& s
   sp.out_lo = tc_down ? sl.ws.a_lo : nullptr;
   sp.partial = sl.ws.partial;
   sp.B = sl.Bk; sp.T = T; sp.NH = NH; sp.DH = DH; sp.inner = inner; sp.NCH = h->NCH;
-  if (small_nch) sp.NCH = 1;      // the small-batch front kernel leaves ONE reduced chunk in ws.gate_part
+  if (small_nch) sp.NCH = small_nch;   // chunks of the small-batch front kernel (one per CTA cluster, <= 16)
   sp.ln_eps = c.ln_eps; sp.cell_eps = c.cell_eps;
   sp.impl = h->state_impl; sp.num_layers = c.num_blocks;
   sp.stages = h->state_stages; sp.ctas_per_sm = h->state_ctas_per_sm; sp.rows_split = h->state_rows_split;
@@ -356,7 +356,7 @@ int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned
     sp.wi = (const float*)w.w[XL_W_IGATE_W]; sp.wf = (const float*)w.w[XL_W_FGATE_W];
     sp.conv_state = (float*)(base + L.conv_off);
     sp.u = ws.u; sp.qk = ws.qkv; sp.v = ws.qkv + (size_t)2 * M * inner; sp.act = ws.act;
-    sp.gate_part = ws.gate_part; sp.gate_scratch = h->gp_small; sp.ticket = h->counters;
+    sp.gate_part = ws.gate_part;
     sp.B = sl.Bk; sp.T = T; sp.d = d; sp.inner = inner; sp.NH = NH; sp.NCH = nch;
     sp.ln_eps = c.ln_eps;
     XL_CUDA(xl::launch_smallm_pre(sp, sl.s));

@@ -202,10 +202,8 @@ struct SmallPreParams {
   float* qk;                    // [M, inner, 2]
   float* v;                     // [M, inner]
   float* act;                   // [M, inner]
-  float* gate_part;             // [M, 1, 2*NH]: ONE chunk, reduced in-kernel
-  float* gate_scratch;          // [NCH, 16, 2*NH] per-CTA shares
-  unsigned* ticket;             // zero between launches
-  int B, T, d, inner, NH, NCH;  // NCH = CTAs that own x_m groups
+  float* gate_part;             // [M, NCH, 2*NH], one chunk per cluster of CTAs
+  int B, T, d, inner, NH, NCH;  // NCH = smallm_pre_chunks() <= 16
   float ln_eps;
 };
 int smallm_pre_chunks(int B, int T, int d, int inner, int NH, int KS);   // 0 = shape not supported

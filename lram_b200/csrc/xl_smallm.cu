@@ -9,7 +9,8 @@
 // activations stay fp32 — no hi/lo planes needed), and a warp that owns an x_m group finishes conv / q / k / v / gate
 // partials for those 4 channels in its epilogue. Outputs are exactly what the state-stream and finalize kernels read:
 // (q,k) pairs [M, inner, 2], v [M, inner], a [M, inner], z in u[:, inner:], the conv window, and gate partials
-// [M, 1, 2 NH] (the per-CTA shares are added in CTA order by the last CTA to finish: deterministic).
+// [M, NCH, 2 NH], one chunk per cluster of 4 CTAs (shares added in rank order over distributed shared memory).
+#include <cooperative_groups.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -22,7 +23,9 @@ namespace xl {
 namespace sm {
 
 using namespace gv;
+namespace cg = cooperative_groups;
 
+constexpr int kCluster = 4;        // CTAs per cluster: gate shares meet over distributed shared memory
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kSmallFloats = 512;   // per-warp staging: conv taps, headwise blocks, gate columns, conv window
@@ -191,31 +194,28 @@ __global__ void __launch_bounds__(kThreads) smallm_pre_kernel(const SmallPrePara
     }
   }
   __syncthreads();
-  // Gate partials: every CTA that owns x_m groups leaves its share in the scratch; the LAST of them to finish adds the
-  // shares in CTA order (deterministic) into the single chunk [M, 1, 2 NH] the state-stream / finalize kernels read.
-  if ((int)blockIdx.x < p.NCH) {
-    __shared__ int s_last;
-    for (int idx = tid; idx < M * 2 * NH; idx += kThreads) {
-      const int m = idx / (2 * NH), g = idx - m * 2 * NH;
-      float s = 0.f;
-      for (int w = 0; w < kWarps; ++w) s += gs_all[(w * MR + m) * 2 * NH + g];
-      p.gate_scratch[((size_t)blockIdx.x * MR + m) * 2 * NH + g] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(p.ticket, 1u) == (unsigned)p.NCH - 1u);
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      for (int idx = tid; idx < M * 2 * NH; idx += kThreads) {
-        const int m = idx / (2 * NH), g = idx - m * 2 * NH;
-        float s = 0.f;
-        for (int c = 0; c < p.NCH; ++c) s += __ldcg(p.gate_scratch + ((size_t)c * MR + m) * 2 * NH + g);
-        p.gate_part[(size_t)m * 2 * NH + g] = s;
-      }
-      if (tid == 0) *p.ticket = 0u;          // re-armed for the next launch (stream ordered)
-    }
+  // Gate partials: the CTAs run in clusters of kCluster; each CTA leaves its share in its own shared memory and the
+  // cluster's rank-0 CTA adds the shares in rank order over distributed shared memory (deterministic) into chunk
+  // blockIdx.x / kCluster of [M, NCH, 2 NH] — NCH <= 16 chunks for the state-stream / finalize kernels to add up.
+  cg::cluster_group cluster = cg::this_cluster();
+  float* share = gs_all;                      // [M][2 NH], reuses the start of the per-warp slots after the sum below
+  const bool xm_cta = (int)blockIdx.x < p.NCH * kCluster;
+  float mine = 0.f;
+  if (xm_cta && tid < M * 2 * NH) {
+    const int m = tid / (2 * NH), g = tid - m * 2 * NH;
+    for (int w = 0; w < kWarps; ++w) mine += gs_all[(w * MR + m) * 2 * NH + g];
   }
+  __syncthreads();
+  if (xm_cta && tid < M * 2 * NH) share[tid] = mine;
+  cluster.sync();
+  if (xm_cta && cluster.block_rank() == 0 && tid < M * 2 * NH) {
+    const int m = tid / (2 * NH), g = tid - m * 2 * NH;
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < kCluster; ++r) s += cluster.map_shared_rank(share, r)[tid];
+    p.gate_part[((size_t)m * p.NCH + blockIdx.x / kCluster) * 2 * NH + g] = s;
+  }
+  cluster.sync();                             // remote shared memory stays valid until rank 0 has read it
 }
 
 size_t smem_floats(int MR, int d, int NH) {
@@ -231,8 +231,22 @@ cudaError_t launch(const SmallPreParams& p, size_t smem, cudaStream_t s) {
     configured = smem;
   }
   const int nblk = p.inner >> 2;
-  const int grid = (2 * nblk + kWarps - 1) / kWarps;
-  return launch_k(smallm_pre_kernel<MR, T>, dim3(grid), dim3(kThreads), smem, s, p);
+  const int grid = (2 * nblk + kWarps - 1) / kWarps;          // multiple of kCluster (host-checked)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, smallm_pre_kernel<MR, T>, p);
 }
 
 // ---- back half: x += g W_down^T for M <= 16 rows ------------------------------------------------------------
@@ -305,9 +319,9 @@ int smallm_pre_chunks(int B, int T, int d, int inner, int NH, int KS) {
   if (d % 256 || inner % 256 || KS != 4 || NH < 1 || NH > 8 || d > 4096) return 0;
   if (17 + 6 * NH + 3 * B > sm::kSmallFloats / 4) return 0;
   const int nblk = inner >> 2;
-  if (nblk % sm::kWarps) return 0;
-  const int nch = nblk / sm::kWarps;
-  return nch <= 256 ? nch : 0;
+  if (nblk % (sm::kWarps * sm::kCluster)) return 0;
+  const int nch = nblk / (sm::kWarps * sm::kCluster);       // one chunk per cluster of CTAs that own x_m groups
+  return nch <= 16 ? nch : 0;
 }
 
 cudaError_t launch_smallm_pre(const SmallPreParams& p, cudaStream_t s) {
