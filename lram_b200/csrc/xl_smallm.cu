@@ -9,7 +9,7 @@
 // activations stay fp32 — no hi/lo planes needed), and a warp that owns an x_m group finishes conv / q / k / v / gate
 // partials for those 4 channels in its epilogue. Outputs are exactly what the state-stream and finalize kernels read:
 // (q,k) pairs [M, inner, 2], v [M, inner], a [M, inner], z in u[:, inner:], the conv window, and gate partials
-// [M, NCH, 2 NH], one chunk per cluster of 4 CTAs (shares added in rank order over distributed shared memory).
+// [M, NCH, 2 NH], one chunk per cluster of 4 or 8 CTAs (shares added in rank order over distributed shared memory).
 #include <cooperative_groups.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -25,7 +25,7 @@ namespace sm {
 using namespace gv;
 namespace cg = cooperative_groups;
 
-constexpr int kCluster = 4;        // CTAs per cluster: gate shares meet over distributed shared memory
+constexpr int kMaxChunks = 16;     // gate-partial chunks the state-stream / finalize kernels add up (xl_state_step.cu)
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kSmallFloats = 512;   // per-warp staging: conv taps, headwise blocks, gate columns, conv window
@@ -194,12 +194,13 @@ __global__ void __launch_bounds__(kThreads) smallm_pre_kernel(const SmallPrePara
     }
   }
   __syncthreads();
-  // Gate partials: the CTAs run in clusters of kCluster; each CTA leaves its share in its own shared memory and the
+  // Gate partials: the CTAs run in clusters of CL = 4 or 8; each CTA leaves its share in its own shared memory and the
   // cluster's rank-0 CTA adds the shares in rank order over distributed shared memory (deterministic) into chunk
-  // blockIdx.x / kCluster of [M, NCH, 2 NH] — NCH <= 16 chunks for the state-stream / finalize kernels to add up.
+  // blockIdx.x / CL of [M, NCH, 2 NH] — NCH <= 16 chunks for the state-stream / finalize kernels to add up.
   cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks();
   float* share = gs_all;                      // [M][2 NH], reuses the start of the per-warp slots after the sum below
-  const bool xm_cta = (int)blockIdx.x < p.NCH * kCluster;
+  const bool xm_cta = (int)blockIdx.x < p.NCH * CL;
   float mine = 0.f;
   if (xm_cta && tid < M * 2 * NH) {
     const int m = tid / (2 * NH), g = tid - m * 2 * NH;
@@ -211,9 +212,8 @@ __global__ void __launch_bounds__(kThreads) smallm_pre_kernel(const SmallPrePara
   if (xm_cta && cluster.block_rank() == 0 && tid < M * 2 * NH) {
     const int m = tid / (2 * NH), g = tid - m * 2 * NH;
     float s = 0.f;
-#pragma unroll
-    for (int r = 0; r < kCluster; ++r) s += cluster.map_shared_rank(share, r)[tid];
-    p.gate_part[((size_t)m * p.NCH + blockIdx.x / kCluster) * 2 * NH + g] = s;
+    for (int r = 0; r < CL; ++r) s += cluster.map_shared_rank(share, r)[tid];
+    p.gate_part[((size_t)m * p.NCH + blockIdx.x / CL) * 2 * NH + g] = s;
   }
   cluster.sync();                             // remote shared memory stays valid until rank 0 has read it
 }
@@ -231,7 +231,8 @@ cudaError_t launch(const SmallPreParams& p, size_t smem, cudaStream_t s) {
     configured = smem;
   }
   const int nblk = p.inner >> 2;
-  const int grid = (2 * nblk + kWarps - 1) / kWarps;          // multiple of kCluster (host-checked)
+  const int grid = (2 * nblk + kWarps - 1) / kWarps;          // multiple of the cluster size (host-checked)
+  const int cl = (nblk / kWarps) / p.NCH;                      // CTAs per cluster: 4 or 8
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
@@ -239,7 +240,7 @@ cudaError_t launch(const SmallPreParams& p, size_t smem, cudaStream_t s) {
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.x = cl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -319,9 +320,12 @@ int smallm_pre_chunks(int B, int T, int d, int inner, int NH, int KS) {
   if (d % 256 || inner % 256 || KS != 4 || NH < 1 || NH > 8 || d > 4096) return 0;
   if (17 + 6 * NH + 3 * B > sm::kSmallFloats / 4) return 0;
   const int nblk = inner >> 2;
-  if (nblk % (sm::kWarps * sm::kCluster)) return 0;
-  const int nch = nblk / (sm::kWarps * sm::kCluster);       // one chunk per cluster of CTAs that own x_m groups
-  return nch <= 16 ? nch : 0;
+  for (int cl = 4; cl <= 8; cl *= 2) {                       // one chunk per cluster of CTAs that own x_m groups
+    if (nblk % (sm::kWarps * cl)) continue;
+    const int nch = nblk / (sm::kWarps * cl);
+    if (nch <= sm::kMaxChunks) return nch;
+  }
+  return 0;
 }
 
 cudaError_t launch_smallm_pre(const SmallPreParams& p, cudaStream_t s) {
