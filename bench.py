@@ -72,6 +72,10 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def mark(self):
+        """samples read from here on belong to the measured window"""
+        self.lines = []
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -275,12 +279,14 @@ def main():
         return out["action_tokens"]
 
     # ---------------- device-resident throughput ------------------------------------------------------------
+    # nvidia-smi needs a few hundred ms to start (longer when 8 ranks start one each): start it before the warm-up
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for t in range(W):
         dev_step(t)
     barrier()
     eng.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for t in range(W, W + K):
@@ -289,13 +295,27 @@ def main():
         gatherer.finish()                                    # the last gathers are inside the timed region
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
     launches = eng.launch_count()
     ms_total = ev0.elapsed_time(ev1)
     if world > 1:
         tt = torch.tensor([ms_total], device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = tt.item()
+    # A timed region shorter than ~1 s can fall between two nvidia-smi samples: keep the SAME steps running (untimed,
+    # same count on every rank: derived from the all-reduced time) until the window under load is ~1.2 s long.
+    extra = 0
+    if ms_total < 1000.0:
+        extra = int((1200.0 - ms_total) / max(ms_total / K, 1e-3))
+        for t in range(W + K, W + K + extra):
+            dev_step(t)
+        if gatherer is not None:
+            gatherer.finish()
+        torch.cuda.synchronize(dev)
+        barrier()
+        eng.launch_count()
+    clocks = sampler.stop()
+    clocks["window"] = (f"the {K} timed steps + {extra} untimed steps of the same workload right after them"
+                        if extra else f"the {K} timed steps")
     value = n_envs * K / (ms_total / 1e3)
 
     # ---------------- end to end through the host-buffer C-ABI call ------------------------------------------
