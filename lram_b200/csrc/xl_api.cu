@@ -115,7 +115,6 @@ struct xl_handle {
                                                 // rows and d <= 1024, where they are measured faster (16M x 1 env: 168 vs 196 us,
                                                 // 48M: 312 vs 359, 110M: 481 vs 506; 206M equal; slower from 2 envs on —
                                                 // profiles/r01_lowlat_persistent.md)
-  float* gp_small = nullptr;                    // its gate partials [16 rows][256 chunks][2 NH]
   // small-batch latency path (xl_lowlat.cu): device table of per-block weight pointers + private workspace,
   // built lazily (outside any capture) by lowlat_prepare
   int lowlat = 0;                               // 1: use the persistent-kernel stack when B*T <= 16 ("lowlat")
@@ -1072,7 +1071,6 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   h->part_rows = M < kSplitRows ? M : kSplitRows;
   const size_t o_pu = carve(4 * (size_t)kSplitMax * h->part_rows * 2 * inner);
   const size_t o_pd = carve(4 * (size_t)kSplitMax * h->part_rows * d);
-  const size_t o_gps = carve(4 * (size_t)16 * 256 * 2 * c.num_heads);
   h->ws_bytes = off;
   cudaError_t e = cudaMalloc((void**)&h->ws, h->ws_bytes);
   if (e != cudaSuccess) {
@@ -1099,7 +1097,6 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
 
   h->a_hi = (__nv_bfloat16*)(h->ws + o_hi); h->a_lo = (__nv_bfloat16*)(h->ws + o_lo);
   h->part_up = (float*)(h->ws + o_pu); h->part_down = (float*)(h->ws + o_pd);
-  h->gp_small = (float*)(h->ws + o_gps);
   *out = h;
   return XL_OK;
 }
