@@ -239,6 +239,9 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
  *                   block's latency-bound chain runs (0 = off; automatic = 48 when a block's C is 100..300 MB)
  *   "lowlat": [0] small-batch path: whole block stack as one persistent cooperative kernel for B*T <= 16 rows
  *                   (parity-tested; measured slower than the default on B200, see profiles/r01_lowlat_persistent.md)
+ *   "conv_impl": [0] pre-cell kernel (conv + SiLU + q/k/v + gate partials): 0 = one thread per 4-channel block walking
+ *                   the step's tokens in sequence, 1 = one thread per (4-channel block, token); bit-identical outputs, measured 5 %
+ *                   slower on the 48M x 64 step (3x the per-thread weight loads), kept for A/B
  *   "smallm": [-1 = automatic] LN + proj_up + conv/qkv as one GEMV-style kernel and proj_down as another (4 kernels
  *                   per block instead of 6, fp32 activations against bf16 weights on CUDA cores). 1 = whenever
  *                   B*T <= 16 rows, 0 = never, automatic = B*T <= 4 rows and d <= 1024 (one env: -14 % step latency)

@@ -95,6 +95,7 @@ struct xl_handle {
   float *part_up = nullptr, *part_down = nullptr;   // split-K planes [kSplitMax][part_rows][2*inner | d]
   size_t part_rows = 0;
   int l2_prefetch_policy = 0;          // 1: warm with an L2 evict_last policy ("l2_prefetch_policy")
+  int conv_impl = 0;                   // pre-cell kernel: 0 = thread per 4-channel block, 1 = thread per (block, token)
   int microbatches = 0;                // 0 = automatic; env micro-batches per fused step ("microbatches")
   int pipeline_order = 1;              // 1 = state-stream kernels of the micro-batches run one after another
   int l2_prefetch_mb = -1;             // MiB of the NEXT block's C warmed into L2 on a side stream while the chain
@@ -395,6 +396,7 @@ int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned
   cp.act = ws.act;
   cp.gate_part = ws.gate_part;
   cp.B = sl.Bk; cp.T = T; cp.inner = inner; cp.NH = NH; cp.KS = c.conv_kernel; cp.NCH = h->NCH;
+  cp.impl = h->conv_impl;
   if (!xl::launch_conv_qkv_gates(cp, sl.s))
     return fail(XL_ERR_UNSUPPORTED, "conv/qkv kernel not instantiated for KS=%d T=%d NH=%d", cp.KS, cp.T, cp.NH);
   h->launches += 1;
@@ -943,6 +945,7 @@ int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cud
     cp.act = ws.act;
     cp.gate_part = ws.gate_part;
     cp.B = B; cp.T = Sc; cp.inner = inner; cp.NH = NH; cp.KS = c.conv_kernel; cp.NCH = h->NCH;
+    cp.impl = 0;
     if (!xl::launch_conv_qkv_gates_seq(cp, Sc, s))
       return fail(XL_ERR_UNSUPPORTED, "sequence conv/qkv kernel not instantiated for KS=%d NH=%d", cp.KS, cp.NH);
     xl::launch_gate_scan_seq(ws.gate_part, (const float*)w.w[XL_W_IGATE_B], (const float*)w.w[XL_W_FGATE_B],
@@ -1587,6 +1590,9 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "gemm_up_splits") || !strcmp(name, "gemm_down_splits")) {
     if (value < 0 || value > kSplitMax) return fail(XL_ERR_INVALID_ARG, "%s must be in [0, %d]", name, kSplitMax);
     (name[5] == 'u' ? h->gemm_up_splits : h->gemm_down_splits) = value;
+  } else if (!strcmp(name, "conv_impl")) {
+    if (value < 0 || value > 1) return fail(XL_ERR_INVALID_ARG, "conv_impl must be 0 or 1");
+    h->conv_impl = value;
   } else if (!strcmp(name, "smallm")) {
     if (value < -1 || value > 1) return fail(XL_ERR_INVALID_ARG, "smallm must be -1 (automatic), 0 or 1");
     h->smallm = value;

@@ -51,6 +51,8 @@ struct ConvQkvParams {
   float* act;           // [M, inner]   a = silu(conv)
   float* gate_part;     // [M, NCH, 2*NH]  partial gate pre-activations per channel chunk
   int B, T, inner, NH, KS, NCH;
+  int impl;             // step path only: 0 = one thread per 4-channel block (tokens in sequence), 1 = one thread per
+                        // (4-channel block, token)
 };
 // false when (KS, T, NH) has no instantiation
 bool launch_conv_qkv_gates(const ConvQkvParams& p, cudaStream_t s);
