@@ -155,6 +155,10 @@ int xl_state_dim_padded(const xl_handle* h);
 int xl_bind_weight(xl_handle* h, int layer, int which, const void* dev_ptr, int dtype, int64_t numel);
 /* 0 when every slot is bound, XL_ERR_NOT_READY (+message naming the first missing slot) otherwise. */
 int xl_weights_ready(const xl_handle* h);
+/* Same, but only for what xl_encoder_step / xl_prefill read: every block + post_blocks_norm. This is the state of a
+ * handle that replaces ONLY `self.encoder` (the swap at decision_xlstm.py:188-189) while the reference policy keeps
+ * its own embeddings and action head. */
+int xl_encoder_weights_ready(const xl_handle* h);
 
 /* Size / layout of the state buffer for B envs. */
 size_t xl_state_bytes(const xl_handle* h, int B);

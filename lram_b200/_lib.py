@@ -91,6 +91,8 @@ def load():
     lib.xl_bind_weight.restype = i32
     lib.xl_weights_ready.argtypes = [vp]
     lib.xl_weights_ready.restype = i32
+    lib.xl_encoder_weights_ready.argtypes = [vp]
+    lib.xl_encoder_weights_ready.restype = i32
     lib.xl_state_bytes.argtypes = [vp, i32]
     lib.xl_state_bytes.restype = sz
     lib.xl_state_layout.argtypes = [vp, i32, i32, i32, C.POINTER(sz), C.POINTER(sz)]

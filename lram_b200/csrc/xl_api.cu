@@ -1182,7 +1182,9 @@ int xl_bind_weight(xl_handle* h, int layer, int which, const void* dev_ptr, int 
   return XL_OK;
 }
 
-int xl_weights_ready(const xl_handle* h) {
+// encoder_only: the block stack + post_blocks_norm (what xl_encoder_step / xl_prefill read); otherwise also the
+// policy-level embeddings and the action head (xl_policy_*).
+static int weights_ready(const xl_handle* h, bool encoder_only) {
   if (!h) return fail(XL_ERR_INVALID_ARG, "null handle");
   static const int s_ids[] = {XL_W_XLSTM_NORM, XL_W_CONV_W, XL_W_CONV_B, XL_W_S_GATE_I, XL_W_S_GATE_F, XL_W_S_GATE_Z,
                               XL_W_S_GATE_O, XL_W_S_RECURRENT, XL_W_S_BIAS, XL_W_S_GROUP_NORM, XL_W_FFN_NORM,
@@ -1196,10 +1198,15 @@ int xl_weights_ready(const xl_handle* h) {
     for (int k = 0; k <= XL_W_PROJ_DOWN; ++k)
       if (!h->blocks[i].w[k]) return fail(XL_ERR_NOT_READY, "block %d weight id %d not bound", i, k);
   }
-  for (int id = XL_W_POST_NORM; id <= XL_W_HEAD_B; ++id)
+  const int last = encoder_only ? XL_W_POST_NORM : XL_W_HEAD_B;
+  for (int id = XL_W_POST_NORM; id <= last; ++id)
     if (!h->pw[id - XL_W_POST_NORM]) return fail(XL_ERR_NOT_READY, "policy weight id %d not bound", id);
   return XL_OK;
 }
+
+int xl_weights_ready(const xl_handle* h) { return weights_ready(h, false); }
+
+int xl_encoder_weights_ready(const xl_handle* h) { return weights_ready(h, true); }
 
 size_t xl_state_bytes(const xl_handle* h, int B) {
   if (!h || B <= 0) return 0;
@@ -1271,7 +1278,7 @@ int xl_encoder_step(xl_handle* h, void* state, const float* x_in, float* x_out, 
   if (rc) return rc;
   if (!state || !x_in || !x_out) return fail(XL_ERR_INVALID_ARG, "null argument");
   if (T < 1 || T > 4) return fail(XL_ERR_UNSUPPORTED, "T=%d outside [1,4]", T);
-  rc = xl_weights_ready(h);
+  rc = weights_ready(h, true);
   if (rc) return rc;
   rc = lowlat_prepare(h);
   if (rc) return rc;
@@ -1428,7 +1435,7 @@ int xl_prefill(xl_handle* h, void* state, const float* x_in, float* y_out, int B
   if (rc) return rc;
   if (!state || !x_in) return fail(XL_ERR_INVALID_ARG, "null argument");
   if (S <= 0) return fail(XL_ERR_INVALID_ARG, "S=%d must be positive", S);
-  rc = xl_weights_ready(h);
+  rc = weights_ready(h, true);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const xl_config& c = h->cfg;

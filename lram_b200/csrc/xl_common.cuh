@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #define XL_WARP 32
 
 namespace xl {
@@ -37,6 +39,30 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   cfg.attrs = attr;
   cfg.numAttrs = g_use_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Opt a kernel in to `smem` bytes of dynamic shared memory (> 48 KB needs cudaFuncAttributeMaxDynamicSharedMemorySize).
+// The attribute belongs to (kernel, device/context): the "already configured" high-water mark is kept per kernel
+// instantiation (the kernel is a template argument) AND per device, and updated atomically, so several handles on
+// different GPUs or threads of one process all get their opt-in.
+constexpr int kMaxDevices = 64;
+template <auto Kernel>
+inline cudaError_t ensure_dyn_smem(size_t smem) {
+  static std::atomic<size_t> configured[kMaxDevices];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool tracked = dev >= 0 && dev < kMaxDevices;
+  if (tracked && smem <= configured[dev].load(std::memory_order_acquire)) return cudaSuccess;
+  if (smem <= 48 * 1024 && tracked && configured[dev].load(std::memory_order_acquire) == 0) return cudaSuccess;
+  e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (tracked) {
+    size_t cur = configured[dev].load(std::memory_order_relaxed);
+    while (cur < smem && !configured[dev].compare_exchange_weak(cur, smem, std::memory_order_release)) {
+    }
+  }
+  return cudaSuccess;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -302,14 +302,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
+  // function-local static: initialised once, thread-safe (C++11); the driver entry point is process-wide
+  static const EncodeTiledFn fn = [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
+      return (EncodeTiledFn)p;
+    return (EncodeTiledFn) nullptr;
+  }();
   return fn;
 }
 
@@ -331,13 +332,7 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& ml, const CU
                           const float* residual, float* out, int M, int N, int K, int splits, long long split_stride,
                           cudaStream_t s) {
   using S = Smem<BLOCK_N, kStages>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, kStages>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (cudaError_t e = ensure_dyn_smem<&gemm_tc_kernel<BLOCK_N, kStages>>(S::kTotal); e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((N + BLOCK_N - 1) / BLOCK_N, (M + BLOCK_M - 1) / BLOCK_M, splits);
   cfg.blockDim = dim3(kThreads);

@@ -569,12 +569,7 @@ size_t scratch_floats(int MR, int T, int DH) {
 
 template <int MR, int T>
 cudaError_t launch(const LowLatParams& p, size_t smem, int coop, cudaStream_t s) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(lowlat_stack_kernel<MR, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  if (cudaError_t e = ensure_dyn_smem<&lowlat_stack_kernel<MR, T>>(smem); e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.G);
   cfg.blockDim = dim3(kThreads);

@@ -661,13 +661,7 @@ static cudaError_t launch_cell_RC(const pf::CellSeqParams& p, cudaStream_t s) {
   const int w = 4 * CPT;
   const size_t smem = 128 + sizeof(float) * ((size_t)pf::kStages * pf::cell_stage_floats(p.DH, w) +
                                              2 * (size_t)NW * pf::kTB * w);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(pf::mlstm_cell_seq_kernel<R, CPT, NW>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_smem = smem;
-  }
+  if (cudaError_t e = ensure_dyn_smem<&pf::mlstm_cell_seq_kernel<R, CPT, NW>>(smem); e != cudaSuccess) return e;
   const int grid = p.B * p.NH * (p.DH / w + 1);
   return launch_k(pf::mlstm_cell_seq_kernel<R, CPT, NW>, dim3(grid), dim3((NW + 1) * 32), smem, s, p);
 }

@@ -534,13 +534,7 @@ static cudaError_t launch_cell_mma_T(const pfm::CellMmaParams& p, cudaStream_t s
   constexpr int DH = DKW * NW;
   const size_t smem = 128 + (size_t)pfm::kStg * (pfm::common_bytes(DH) + pfm::VB) + pfm::VB +
                       sizeof(float) * 2 * (size_t)NW * pfm::LC * 33;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pfm::mlstm_cell_mma_kernel<DKW, NW>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (cudaError_t e = ensure_dyn_smem<&pfm::mlstm_cell_mma_kernel<DKW, NW>>(smem); e != cudaSuccess) return e;
   const int grid = p.B * p.NH * (DH / pfm::WS + 1);
   return launch_k(pfm::mlstm_cell_mma_kernel<DKW, NW>, dim3(grid), dim3((NW + 1) * 32), smem, s, p);
 }

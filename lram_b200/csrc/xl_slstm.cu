@@ -198,12 +198,7 @@ cudaError_t launch_slstm_cell(const float* pre, const float* R, float* st, float
                               int d, int NH, cudaStream_t s) {
   const int DH = d / NH;
   const size_t smem = sizeof(float) * ((size_t)kCE * DH + (size_t)kCS * kCE * 4 * kCO);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(slstm_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr = smem;
-  }
+  if (cudaError_t e = ensure_dyn_smem<&slstm_cell_kernel>(smem); e != cudaSuccess) return e;
   dim3 grid((DH + kCO - 1) / kCO, NH, (B + kCE - 1) / kCE);
   return launch_k(slstm_cell_kernel, grid, dim3(256), smem, s, pre, R, st, y_out, B, stB, T, t, d, NH, DH);
 }

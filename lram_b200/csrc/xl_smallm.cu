@@ -224,12 +224,7 @@ size_t smem_floats(int MR, int d, int NH) {
 
 template <int MR, int T>
 cudaError_t launch(const SmallPreParams& p, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(smallm_pre_kernel<MR, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  if (cudaError_t e = ensure_dyn_smem<&smallm_pre_kernel<MR, T>>(smem); e != cudaSuccess) return e;
   const int nblk = p.inner >> 2;
   const int grid = (2 * nblk + kWarps - 1) / kWarps;          // multiple of the cluster size (host-checked)
   const int cl = (nblk / kWarps) / p.NCH;                      // CTAs per cluster: 4 or 8
@@ -299,12 +294,7 @@ template <int MR>
 cudaError_t launch_down(const SmallDownParams& p, cudaStream_t s) {
   constexpr int CGD = (MR == 4) ? 1 : 2;
   const size_t smem = sizeof(float) * ((size_t)MR * p.inner + (size_t)kWarps * MR * 2);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(smallm_down_kernel<MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  if (cudaError_t e = ensure_dyn_smem<&smallm_down_kernel<MR>>(smem); e != cudaSuccess) return e;
   const int items = p.d / CGD;
   return launch_k(smallm_down_kernel<MR>, dim3((items + kWarps - 1) / kWarps), dim3(kThreads), smem, s, p);
 }

@@ -409,14 +409,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* q = nullptr;
-    cudaDriverEntryPointQueryResult r;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &r) == cudaSuccess &&
-        r == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)q;
-  }
+  // function-local static: initialised once, thread-safe (C++11); the driver entry point is process-wide
+  static const EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      return (EncodeTiledFn)p;
+    return (EncodeTiledFn) nullptr;
+  }();
   return fn;
 }
 
@@ -439,13 +440,7 @@ static cudaError_t launch(const StateStepParams& p, cudaStream_t s) {
   const int TY = kThreads / (p.cols_per_cta / 4);
   const size_t red = sizeof(float) * (size_t)TY * T * p.cols_per_cta;       // aliases the ring
   const size_t smem = 128 + (ring > red ? ring : red) + sizeof(float) * (size_t)2 * T * rows_per;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(mlstm_state_stream_tma_kernel<T, kStream>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_smem = smem;
-  }
+  if (cudaError_t e = ensure_dyn_smem<&mlstm_state_stream_tma_kernel<T, kStream>>(smem); e != cudaSuccess) return e;
   const int CS = p.DH / p.cols_per_cta;
   const int64_t grid = (int64_t)p.B * p.NH * CS * p.rows_split;
   return launch_k(mlstm_state_stream_tma_kernel<T, kStream>, dim3((unsigned)grid), dim3(kBlock), smem, s, map, p);
@@ -742,13 +737,8 @@ static cudaError_t launch(const StateStepParams& p, cudaStream_t s) {
   if (stages < 2) stages = 2;
   const int meta_slots = p.meta_slots >= 2 && p.meta_slots <= kMaxMetaSlots ? p.meta_slots : 3;
   const size_t smem = smem_bytes(T, p.DH, stages, meta_slots);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(mlstm_state_stream_persistent_kernel<T, kStream>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_smem = smem;
-  }
+  if (cudaError_t e = ensure_dyn_smem<&mlstm_state_stream_persistent_kernel<T, kStream>>(smem); e != cudaSuccess)
+    return e;
   return launch_k(mlstm_state_stream_persistent_kernel<T, kStream>, dim3((unsigned)p.sk_grid), dim3(kBlock), smem,
                   s, map, p, stages, meta_slots);
 }
@@ -915,13 +905,8 @@ static cudaError_t launch_T(const StateStepParams& p, cudaStream_t s) {
   } else {
     const int TX = p.cols_per_cta / 4, TY = kThreads / TX;
     const size_t smem = sizeof(float) * ((size_t)2 * T * rows_per + (size_t)TY * T * p.cols_per_cta);
-    static size_t attr_smem = 48 * 1024;
-    if (smem > attr_smem) {
-      e = cudaFuncSetAttribute(mlstm_state_stream_ldg_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem);
-      if (e != cudaSuccess) return e;
-      attr_smem = smem;
-    }
+    e = ensure_dyn_smem<&mlstm_state_stream_ldg_kernel<T>>(smem);
+    if (e != cudaSuccess) return e;
     const int CS = p.DH / p.cols_per_cta;
     const int64_t grid = (int64_t)p.B * p.NH * CS * p.rows_split;
     e = launch_k(mlstm_state_stream_ldg_kernel<T>, dim3((unsigned)grid), dim3(kThreads), smem, s, p);

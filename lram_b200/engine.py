@@ -12,6 +12,7 @@ Reference counterparts: `xLSTMEncoder` (src/algos/models/decision_xlstm.py:119-1
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Dict, Optional
 
 import torch
@@ -162,14 +163,35 @@ class StateCache:
             self.view(i, L.XL_STATE_CONV).copy_(st["conv_state"][0].to(self.buf.device, torch.float32))
 
 
+def _on_device(fn):
+    """Run an engine method with the engine's GPU as the current CUDA device: the handle, its workspace, its streams
+    and the per-device kernel attributes all belong to `self.device`, whatever device the caller has current."""
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapped
+
+
 class XLSTMEngine:
+    """`encoder_only=True` binds the block stack + post_blocks_norm only: the engine behind a `FusedXLSTMEncoder`
+    that replaces just `self.encoder` of a reference policy (decision_xlstm.py:188-189); `policy_step*` then raise
+    XL_ERR_NOT_READY, `encoder_step` / `prefill` work."""
+
     def __init__(self, cfg: XLSTMPolicyConfig, state_dict: Dict[str, torch.Tensor], max_batch: int,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, encoder_only: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("XLSTMEngine needs a CUDA device: the xlstm_b200 path has no CPU fallback")
         cfg.validate()
         self.cfg = cfg
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"XLSTMEngine needs a CUDA device, got {self.device}: there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.encoder_only = bool(encoder_only)
         self.max_batch = int(max_batch)
         self.lib = L.load()
         if self.lib.xl_abi_version() != L.XL_ABI_VERSION:
@@ -186,8 +208,9 @@ class XLSTMEngine:
         with torch.cuda.device(self.device):
             L.check(self.lib.xl_create(C.byref(c), C.byref(self.handle)))
         self._weights = []          # keep device tensors alive
-        self._bind_all(strip_checkpoint_prefixes(state_dict))
-        L.check(self.lib.xl_weights_ready(self.handle))
+        with torch.cuda.device(self.device):
+            self._bind_all(strip_checkpoint_prefixes(state_dict))
+            L.check((self.lib.xl_encoder_weights_ready if self.encoder_only else self.lib.xl_weights_ready)(self.handle))
 
     # ---- weights ----------------------------------------------------------------------------------
     def _bind(self, layer: int, slot: str, t: torch.Tensor, bf16: bool):
@@ -209,6 +232,8 @@ class XLSTMEngine:
                 self._bind(i, slot, t, is_bf16_weight(name))
         kpad = self.lib.xl_state_dim_padded(self.handle)
         for name, slot in _POLICY_KEYS.items():
+            if self.encoder_only and slot != "POST_NORM":
+                continue
             if name not in sd:
                 raise KeyError(f"state_dict is missing {name}")
             t = sd[name]
@@ -229,6 +254,7 @@ class XLSTMEngine:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    @_on_device
     def reset(self, state: StateCache, mask: Optional[torch.Tensor] = None):
         if mask is not None:
             mask = mask.to(self.device, torch.uint8).contiguous()
@@ -236,6 +262,7 @@ class XLSTMEngine:
         L.check(self.lib.xl_state_reset(self.handle, _ptr(state.buf), _ptr(mask), state.B, self._stream()))
 
     # ---- compute ----------------------------------------------------------------------------------
+    @_on_device
     def encoder_step(self, state: StateCache, x: torch.Tensor, mode: int = L.XL_MODE_FUSED, flags: int = 0):
         """x [B,T,d] fp32 cuda -> last_hidden_state [B,T,d]; state advanced in place."""
         assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[0] == state.B
@@ -245,6 +272,7 @@ class XLSTMEngine:
                                          mode, flags, self._stream()))
         return out
 
+    @_on_device
     def prefill(self, state: StateCache, x: torch.Tensor, want_hidden: bool = True, flags: int = 0):
         """Context prefill of the encoder: x [B,S,d] fp32 cuda (embedded tokens) -> last_hidden_state [B,S,d]
         (or None); state advanced by S tokens, exactly as S recurrent steps would (xl_prefill)."""
@@ -255,6 +283,7 @@ class XLSTMEngine:
                                     self._stream()))
         return out
 
+    @_on_device
     def policy_prefill(self, state: StateCache, states: torch.Tensor, rtg: torch.Tensor,
                        rewards: Optional[torch.Tensor] = None, flags: int = 0):
         """Warm the recurrent state with Tn timesteps of context per env: states [B,Tn,state_dim], rtg [B,Tn],
@@ -270,6 +299,7 @@ class XLSTMEngine:
         L.check(self.lib.xl_policy_prefill(self.handle, _ptr(state.buf), _ptr(states), _ptr(rtg), _ptr(rewards), B, Tn,
                                            flags, self._stream()))
 
+    @_on_device
     def policy_step(self, state: StateCache, states: torch.Tensor, rtg: torch.Tensor,
                     rewards: Optional[torch.Tensor] = None, mode: int = L.XL_MODE_FUSED, flags: int = 0,
                     want_logits: bool = False, want_hidden: bool = False, out: Optional[dict] = None,
@@ -303,6 +333,7 @@ class XLSTMEngine:
             mode, flags, self._stream()))
         return out
 
+    @_on_device
     def policy_step_host(self, state: StateCache, h_states: torch.Tensor, h_rtg: torch.Tensor,
                          h_tokens: torch.Tensor, h_actions: torch.Tensor, mode: int = L.XL_MODE_FUSED,
                          flags: int = 0):
@@ -311,6 +342,7 @@ class XLSTMEngine:
         L.check(self.lib.xl_policy_step_host(self.handle, _ptr(state.buf), _ptr(h_states), _ptr(h_rtg), _ptr(None),
                                              _ptr(h_tokens), _ptr(h_actions), state.B, mode, flags, self._stream()))
 
+    @_on_device
     def cell_step(self, Cs, n, m, qkv, igate, fgate, outnorm_w, B: int, T: int, rows_split: int = 0,
                   cols_per_cta: int = 0, want_raw: bool = True, slab: bool = False):
         """Unit-parity entry point. `Cs` is given and updated in the REFERENCE layout [B,NH,DH,DH] unless
@@ -326,6 +358,7 @@ class XLSTMEngine:
             Cs.copy_(c_from_slab(Cp))
         return h_norm, h_raw
 
+    @_on_device
     def linear(self, A: torch.Tensor, W_bf16: torch.Tensor, bias=None, residual=None, impl: int = 0):
         M, K = A.shape
         N = W_bf16.shape[0]
@@ -335,12 +368,14 @@ class XLSTMEngine:
                                    _ptr(residual), _ptr(out), M, N, K, impl, self._stream()))
         return out
 
+    @_on_device
     def set_option(self, name: str, value: int):
         L.check(self.lib.xl_set_option(self.handle, name.encode(), int(value)))
 
     def launch_count(self) -> int:
         return int(self.lib.xl_launch_count(self.handle))
 
+    @_on_device
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
             torch.cuda.synchronize(self.device)

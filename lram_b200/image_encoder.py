@@ -61,12 +61,21 @@ class ImpalaCNN(nn.Module):
         self.linear = nn.Sequential(nn.Linear(self.n_flatten, features_dim), nn.ReLU() if out_relu else nn.Identity())
 
     @torch.no_grad()
-    def forward(self, frames: torch.Tensor) -> torch.Tensor:
-        """frames [N, C, H, W], uint8 (raw 0..255, scaled here like embed_inputs) or float (already / 255)."""
-        x = frames.float() / 255.0 if not frames.is_floating_point() else frames
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x [N, C, H, W] float, ALREADY scaled to 0..1: the caller divides raw frames by 255 exactly once, as the
+        reference's `embed_inputs` does before `embed_image` (online_decision_transformer_model.py:522-526)."""
+        if not x.is_floating_point():
+            raise TypeError("ImpalaCNN takes float frames already scaled by 1/255 (see scale_frames)")
         for stage in self.cnn:
             x = stage(x)
         return self.linear(torch.flatten(F.relu(x), 1))
+
+
+def scale_frames(frames: torch.Tensor) -> torch.Tensor:
+    """`states.float() / 255.0` (online_decision_transformer_model.py:523-525), unconditionally: image observations
+    reach the policy as raw 0..255 values whether their dtype is uint8 or — after `pad_inputs` returned
+    `states.float()` (src/algos/decision_xlstm.py:25) — float."""
+    return frames.float() / 255.0
 
 
 def make_impala_state_dict(features_dim: int, image_shape: Sequence[int] = (3, 64, 64), seed: int = 0,

@@ -14,7 +14,8 @@ action tokens / returns (the reference pickles dicts through gather_object, src/
 from __future__ import annotations
 
 import time
-from typing import Dict, List, Optional
+import warnings
+from typing import Any, Callable, Dict, List, Optional
 
 import numpy as np
 import torch
@@ -195,3 +196,89 @@ class BatchedRollout:
             out["tokens"] = np.stack(toks)
             out["actions"] = np.stack(acts)
         return out
+
+
+def _action_dim(space) -> int:
+    """stable_baselines3.common.preprocessing.get_action_dim for Box / Discrete spaces."""
+    if hasattr(space, "n"):
+        return 1
+    return int(np.prod(space.shape))
+
+
+def custom_evaluate_policy(model, env, n_eval_episodes: int = 10, deterministic: bool = True, render: bool = False,
+                           callback: Optional[Callable[[Dict[str, Any], Dict[str, Any]], None]] = None,
+                           reward_threshold: Optional[float] = None, return_episode_rewards: bool = False,
+                           warn: bool = True, task_id: int = 0):
+    """`custom_evaluate_policy` (src/callbacks/evaluation.py:14-271) with the reference's signature and return values,
+    for `env.num_envs >= 1` (the reference asserts == 1 at :80): all envs of the VecEnv step through ONE batched policy
+    call per env step, each env keeping its own recurrent state in the agent's `past_key_values` (a `StateCache`).
+
+    `model` is the agent (`lram_b200.decision_xlstm.DiscreteDecisionXLSTM`): the loop reads `model.policy`,
+    `model.device`, `model.compute_target_return_val`, `model.get_reward_scale_for_env`, `model.persist_context`,
+    `model.past_key_values`, exactly the attributes the reference loop reads. Per env, in inference-cache mode:
+      * the policy sees (state_t, rtg_t, reward placeholder 0) of the newest timestep (:130-139, 172-177),
+      * rtg_{t+1} = rtg_t - r_t / reward_scale in fp32 (:152-168),
+      * on done: rtg <- target return; the recurrent state is reset (`past_key_values = None`, :238-251) UNLESS
+        `model.persist_context` (:213-237), where the context — here the recurrent state — carries over episodes,
+      * episodes are divided among the envs as SB3 does (:87-89); episode reward / length bookkeeping follows
+        :199-211 (Monitor `info["episode"]` when present; otherwise the reference appends the LAST step's reward).
+    """
+    n_envs = int(env.num_envs)
+    action_dim = _action_dim(env.action_space)
+    discrete_env = hasattr(env.action_space, "n")
+    if warn and not getattr(env, "is_monitor_wrapped", False):
+        warnings.warn("Evaluation environment is not wrapped with a ``Monitor`` wrapper.", UserWarning)
+    episode_rewards, episode_lengths, episode_times = [], [], []
+    episode_counts = np.zeros(n_envs, dtype="int")
+    episode_count_targets = np.array([(n_eval_episodes + i) // n_envs for i in range(n_envs)], dtype="int")
+    current_rewards = np.zeros(n_envs)
+    current_lengths = np.zeros(n_envs, dtype="int")
+    observations = np.asarray(env.reset())
+    target = np.float32(model.compute_target_return_val(env=env, task_id=task_id))
+    rtg = np.full(n_envs, target, dtype=np.float32)
+    env_name = getattr(getattr(env, "envs", [None])[0], "name", None)
+    reward_scale = np.float32(model.get_reward_scale_for_env(envid=env_name))
+    model.past_key_values = None                                   # :120-124
+    persist = bool(getattr(model, "persist_context", False))
+    start_time = [time.time()] * n_envs
+    while (episode_counts < episode_count_targets).any():
+        obs_t = torch.from_numpy(observations)
+        actions = model.predict_batch(model.policy, obs_t, torch.from_numpy(rtg), action_dim,
+                                      env_act_dim=action_dim)
+        a_np = actions.detach().cpu().numpy()
+        if discrete_env:
+            a_np = a_np.astype(int).reshape(n_envs)                # :142-143
+        observations, reward, done, infos = env.step(a_np if n_envs > 1 or discrete_env else [a_np[0]])
+        observations = np.asarray(observations)
+        reward = np.asarray(reward)
+        done = np.asarray(done).astype(bool).reshape(n_envs)
+        current_rewards += reward
+        current_lengths += 1
+        rtg = np.where(done, target, rtg - reward.astype(np.float32) / reward_scale).astype(np.float32)
+        for i in range(n_envs):
+            if episode_counts[i] < episode_count_targets[i]:
+                info = infos[i] if infos is not None else {}
+                if callback is not None:
+                    callback(locals(), globals())
+                if done[i]:
+                    episode_times.append(time.time() - start_time[i])
+                    start_time[i] = time.time()
+                    if "episode" in info:
+                        episode_rewards.append(info["episode"]["r"])
+                        episode_lengths.append(info["episode"]["l"])
+                    else:
+                        episode_rewards.append(reward[i:i + 1] if n_envs > 1 else reward)   # :208 (sic)
+                        episode_lengths.append(current_lengths[i] if n_envs > 1 else current_lengths[0])
+                    episode_counts[i] += 1
+        if done.any() and not persist and model.past_key_values is not None:
+            cache = model.past_key_values
+            cache.engine.reset(cache, torch.from_numpy(done.astype(np.uint8)))
+        if render:
+            env.render()
+    model.past_key_values = None                                   # :259-262
+    mean_reward, std_reward = np.mean(episode_rewards), np.std(episode_rewards)
+    if reward_threshold is not None:
+        assert mean_reward > reward_threshold, f"Mean reward below threshold: {mean_reward:.2f} < {reward_threshold:.2f}"
+    if return_episode_rewards:
+        return episode_rewards, episode_lengths, episode_times
+    return mean_reward, std_reward, np.mean(episode_times)

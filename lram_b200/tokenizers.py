@@ -4,7 +4,7 @@
 Same class names, constructor keywords (`vocab_size`, `shift`, `min_val`, `max_val`, `one_hot`) and
 `tokenize` / `inv_tokenize` methods, so a policy written against the reference can import these instead.
 On the rollout hot path the inverse of `MinMaxTokenizer` is additionally fused into the CUDA argmax
-kernel (lram_b200/csrc/xl_elementwise.cu: argmax_tokens_kernel); `tests/test_tokenizers.py` pins both to
+kernel (lram_b200/csrc/xl_elementwise.cu: argmax_tokens_kernel); `tests/test_oracle_pins.py` pins both to
 known answers produced by the reference's own code (tests/golden/tokenizer_kat.npz).
 """
 from __future__ import annotations

@@ -136,10 +136,13 @@ def test_impala_module_matches_oracle_restatement():
     net = ImpalaCNN((3, 64, 64), cfg.d).eval()
     net.load_state_dict(split_image_weights(sd))
     frames = torch.from_numpy(np.random.default_rng(0).integers(0, 256, (3, 3, 64, 64), dtype=np.uint8))
-    a = net(frames)
+    from lram_b200.image_encoder import scale_frames
+    a = net(scale_frames(frames))
     b = OraclePolicy(cfg, sd).embed_image(frames)
     assert a.shape == (3, cfg.d) and torch.allclose(a, b, rtol=1e-5, atol=1e-6)
-    assert torch.allclose(net(frames.float() / 255.0), a)                    # float input = already scaled
+    assert torch.equal(net(scale_frames(frames.float())), a)                 # raw 0..255 floats scale the same way
+    with pytest.raises(TypeError):
+        net(frames)                                                          # the module never guesses the scaling
     assert (a >= 0).all() and a.abs().max() > 0                              # out_relu
 
 
