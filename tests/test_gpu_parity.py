@@ -654,3 +654,100 @@ def test_conv_impl_token_parallel_is_bit_identical(name, B, mode):
         assert torch.equal(a, b)
     assert torch.equal(res[1][3], res[0][3])
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# every BASELINE.json config at its REAL batch size, against the oracle on a row subsample
+# ------------------------------------------------------------------------------------------------------------
+def _subsample_rows(B, n=8):
+    return sorted({int(round(i * (B - 1) / (n - 1))) for i in range(n)}) if B > n else list(range(B))
+
+
+@pytest.mark.parametrize("name,B,discrete,domains,steps", [
+    ("16M", 1, False, "dmcontrol", 4),       # configs[0]: 16M, one env, DMControl-like stream
+    ("48M", 64, False, "metaworld", 3),      # configs[1]: the headline bench workload
+    ("206M", 128, False, "mixed", 3),        # configs[2]: one GPU's shard (128 envs) of the 1024-env job
+    ("110M", 256, True, "mixed", 3),         # configs[4]: Atari-style discrete head, 256 envs
+])
+def test_baseline_config_real_batch_vs_oracle_rows(name, B, discrete, domains, steps):
+    """The bench path itself (fused 3-token step replayed from a CUDA graph, real batch => real tilings, split-K plans
+    and L2 warm-up choices) for >= 3 env steps; batch rows are independent, so the fp32 oracle runs on <= 8 rows.
+    Tokens / argmax actions bit-exact, hidden states and logits within REL_TOL, recurrent state of the sampled envs too."""
+    from oracle import xlstm_oracle as O
+    cfg, sd, eng = _engine(name, B, seed=3)
+    rows = _subsample_rows(B)
+    ora = O.OraclePolicy(cfg, sd)
+    states, rtg, _ = make_stream(cfg, range(B), steps, domains=domains, seed=777)
+    if discrete:      # Atari observations are frames; their embeddings enter as state tokens (SURVEY §8d config 5)
+        gen = torch.Generator().manual_seed(5)
+        emb = torch.randn(steps, B, cfg.d, generator=gen).clamp_min(0)           # post-ReLU like embed_image output
+    flags = L.XL_FLAG_GRAPH | (L.XL_FLAG_DISCRETE if discrete else 0)
+    cache, pkv, out = eng.new_state(B), None, None
+    s_dev = torch.empty(B, cfg.d if discrete else cfg.state_dim, device="cuda")
+    r_dev = torch.empty(B, device="cuda")
+    for t in range(steps):
+        s_cpu = emb[t] if discrete else torch.from_numpy(states[t])
+        s_dev.copy_(s_cpu)
+        r_dev.copy_(torch.from_numpy(rtg[t]))
+        out = eng.policy_step(cache, s_dev, r_dev, mode=L.XL_MODE_FUSED, flags=flags, want_hidden=True,
+                              want_logits=True, out=out, state_embeds=discrete)
+        torch.cuda.synchronize()
+        ref = ora.step(s_cpu[rows], torch.from_numpy(rtg[t][rows]), past_key_values=pkv, discrete=discrete,
+                       state_embeds=discrete)
+        pkv = ref["past_key_values"]
+        tok = out["action_tokens"].cpu().long()[rows]
+        if discrete:
+            tok = tok[:, :1]
+        lg_ref = ref["action_logits"].reshape(len(rows), -1, cfg.num_actions)
+        margins = _margin_ok(lg_ref[..., :cfg.discrete_actions] if discrete else lg_ref,
+                             tok.view(len(rows), -1), ref["action_tokens"].view(len(rows), -1))
+        assert not margins, f"{name} x {B}: token mismatches at t={t}, oracle top-2 relative margins {margins}"
+        assert _rel(out["last_hidden_state"].cpu()[rows], ref["last_hidden_state"]) < REL_TOL
+        assert _rel(out["action_logits"].cpu()[rows].reshape(len(rows), -1),
+                    ref["action_logits"].reshape(len(rows), -1)) < REL_TOL
+        if not discrete:
+            assert torch.equal(out["action_preds"].cpu()[rows], ref["action_preds"])
+    for bi in (0, cfg.num_blocks - 1):
+        c_ref, n_ref, m_ref = pkv[f"block_{bi}"]["mlstm_state"]
+        idx = torch.tensor(rows, device="cuda")
+        c_gpu = torch.index_select(cache.view(bi, L.XL_STATE_C), 0, idx)
+        from lram_b200.engine import c_from_slab
+        assert _rel(c_from_slab(c_gpu).cpu(), c_ref) < REL_TOL
+        assert _rel(cache.view(bi, L.XL_STATE_N)[rows].cpu(), n_ref.squeeze(-1)) < REL_TOL
+        assert _rel(cache.view(bi, L.XL_STATE_M)[rows].cpu(), m_ref.view(len(rows), -1)) < REL_TOL
+    eng.close()
+
+
+def test_fp32_checkpoint_weights_error_bound(capsys):
+    """A real LRAM checkpoint holds fp32 weights; the engine rounds the four GEMM matrix families to bf16
+    (north_star: "bf16 weights, fp32 state"). Against the fp32 oracle on the UNROUNDED weights this measures what that
+    rounding costs over 12 blocks and 6 env steps: hidden-state error and argmax-token agreement. The bound asserted is
+    loose (bf16 has 8 mantissa bits: ~4e-3 per weight, averaging down over K); INTEGRATION.md quotes the measured value."""
+    from lram_b200.engine import XLSTMEngine
+    from oracle import xlstm_oracle as O
+    B, steps = 16, 6
+    cfg = preset("48M")
+    sd32 = make_state_dict(cfg, seed=9, round_bf16=False)
+    eng = XLSTMEngine(cfg, sd32, max_batch=B)
+    ora = O.OraclePolicy(cfg, sd32)
+    states, rtg, _ = make_stream(cfg, range(B), steps, domains="mixed", seed=99)
+    cache, pkv = eng.new_state(B), None
+    worst_h, agree, total, flipped_margin = 0.0, 0, 0, []
+    for t in range(steps):
+        out = eng.policy_step(cache, torch.from_numpy(states[t]).cuda(), torch.from_numpy(rtg[t]).cuda(),
+                              want_hidden=True, want_logits=True)
+        ref = ora.step(torch.from_numpy(states[t]), torch.from_numpy(rtg[t]), past_key_values=pkv)
+        pkv = ref["past_key_values"]
+        worst_h = max(worst_h, _rel(out["last_hidden_state"].cpu(), ref["last_hidden_state"]))
+        tok = out["action_tokens"].cpu().long()
+        agree += int((tok == ref["action_tokens"]).sum())
+        total += tok.numel()
+        flipped_margin += _margin_ok(ref["action_logits"], tok, ref["action_tokens"])
+    with capsys.disabled():
+        print(f"\n[fp32-checkpoint] 48M x {B} envs x {steps} steps: max rel hidden error {worst_h:.3e}; "
+              f"argmax tokens equal {agree}/{total}; oracle top-2 margins at the flips "
+              f"{[round(m, 5) for m in flipped_margin]}")
+    assert worst_h < 2e-2
+    assert agree / total > 0.97
+    assert all(m < 2e-2 for m in flipped_margin)        # only near-ties may flip
+    eng.close()

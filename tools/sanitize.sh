@@ -1,0 +1,26 @@
+#!/bin/bash
+# compute-sanitizer over the hot path (SURVEY.md §5 "race detection"): memcheck, racecheck, synccheck and initcheck on
+# tools/sanitize_step.py. Run on the GPU box:   gpurun --timeout 1500 -- bash tools/sanitize.sh
+# Logs land in gpurun_out/sanitize_<tool>.log; copy the summaries to profiles/.
+# racecheck tracks shared-memory hazards only and is ~50x slower: it gets the cases whose kernels hand data between
+# warps through shared memory + mbarriers (state stream ring, tcgen05 Linear pipeline, prefill cell).
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+CS=${CS:-/usr/local/cuda/bin/compute-sanitizer}
+run() { # tool, per-case timeout, cases...
+  local tool=$1 tmo=$2; shift 2
+  local log=gpurun_out/sanitize_${tool}.log
+  : > "$log"
+  for c in "$@"; do
+    echo "=== $tool :: $c" >> "$log"
+    timeout "$tmo" "$CS" --tool "$tool" --error-exitcode 9 --print-limit 20 \
+      python tools/sanitize_step.py "$c" >> "$log" 2>&1
+    echo "=== exit $? ($c)" >> "$log"
+  done
+  echo "--- $tool"; grep -E "=== exit|ERROR SUMMARY|RACECHECK SUMMARY|sanitize_step" "$log"
+}
+run memcheck 600 fused_eager fused_graph per_token one_env discrete real_16M slstm prefill
+run synccheck 600 fused_eager per_token one_env real_16M slstm prefill
+run initcheck 600 fused_eager one_env real_16M prefill
+run racecheck 900 fused_eager one_env real_16M prefill
