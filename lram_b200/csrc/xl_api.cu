@@ -86,6 +86,19 @@ struct xl_handle {
   int state_stages = 0;                // impl 2 ring depth (0 = default)        (xl_set_option "state_stages")
   int state_ctas_per_sm = 0;           // impl 2 persistent CTAs per SM (0 = 1)  (xl_set_option "state_ctas_per_sm")
   int state_rows_split = 0;            // 0 = automatic                          (xl_set_option "state_rows_split")
+  int up_fuse = 0;                     // 1: conv / q k v / gate partials run in the proj_up epilogue (fused 3-token step,
+                                       // tcgen05 path, no split-K); 0: separate pre-cell kernel ("up_fuse"). Measured on
+                                       // B200 (profiles/r02_chain_fusion.md): one launch fewer per block but 3 % SLOWER at
+                                       // 48M x 64 envs and 9 % slower at 206M x 128 -- the 32-wide x_m tiles make 1.5x more
+                                       // CTAs re-read the A planes from L2, which is what bounds these skinny GEMMs
+  int gp_chunks = 16;                  // gate-partial chunks the workspace holds per row (>= NCH and >= inner/64)
+  int state_fuse = 0;                  // finalize inside the state stream kernel, one thread-block cluster per (env, head):
+                                       // 1 = every CTA normalises its 128 columns, GroupNorm statistics meet over DSMEM;
+                                       // 2 = numerators are pushed to rank 0, which finalizes the head; 3 = measurement aid
+                                       // (unfused kernel under the cluster shape); 0 = separate finalize kernel (default).
+                                       // Measured (profiles/r02_chain_fusion.md): variant 2 wins 1-2 % at 206M x 128 and
+                                       // 48M x 256, loses 5 % at 48M x 64 and 2 % at 110M x 256: cluster co-scheduling alone
+                                       // costs 1.4 us per launch there, and the tails no longer overlap ("state_fuse")
   int gemm_impl = 0;                   // 0 auto, 1 CUDA-core, 2 tcgen05      (xl_set_option "gemm_impl")
   int gemm_splitk = 8;                 // max split-K planes of proj_up / proj_down, 0/1 = off ("gemm_splitk")
   int gemm_up_bn = 0, gemm_up_splits = 0, gemm_down_bn = 0, gemm_down_splits = 0;   // 0 = cost model; A/B overrides
@@ -195,7 +208,7 @@ Ws ws_slice(const xl_handle* h, int b0, int Bk) {
   Ws w;
   w.x = h->x + e * 4 * d; w.xn = h->xn + e * 4 * d; w.xtok = h->xtok + e * 4 * d; w.hid = h->hid + e * 4 * d;
   w.u = h->u + e * 4 * 2 * inner; w.qkv = h->qkv + e * 4 * 3 * inner; w.act = h->act + e * 4 * inner;
-  w.gate_part = h->gate_part + e * 4 * 16 * 2 * c.num_heads; w.gated = h->gated + e * 4 * inner;
+  w.gate_part = h->gate_part + e * 4 * h->gp_chunks * 2 * c.num_heads; w.gated = h->gated + e * 4 * inner;
   w.partial = h->partial + e * c.num_heads * 32 * 4 * h->DH;
   w.s_emb = h->s_emb + e * d; w.states_pad = h->states_pad + e * h->Kpad; w.logits = h->logits + e * h->head_out;
   w.a_hi = h->a_hi + e * h->a_env; w.a_lo = h->a_lo + e * h->a_env;
@@ -257,6 +270,7 @@ int smallm_chunks(const xl_handle* h, const Slice& sl, int T, unsigned flags) {
 
 struct BlockPlan {
   bool tc_up, tc_down;
+  bool up_fused;                          // proj_up runs with the pre-cell epilogue (no conv/qkv kernel, NCH = inner/64)
   int impl;
   int up_bn, up_sp, down_bn, down_sp;     // tile width / split-K planes of proj_up and proj_down (sp = 1: none)
 };
@@ -284,6 +298,10 @@ BlockPlan block_plan(const xl_handle* h, const Slice& sl, int T, unsigned flags)
         h->gemm_up_splits <= kSplitMax)
       p.up_sp = h->gemm_up_splits;
   }
+  p.up_fused = h->up_fuse && p.tc_up && !sl.ws.low_smem && !h->debug_skip && !smallm_chunks(h, sl, T, flags) &&
+               xl::gemm_up_conv_chunks(c.inner_dim) <= h->gp_chunks &&
+               xl::gemm_up_conv_supported(T, c.conv_kernel, c.num_heads, c.inner_dim, c.embedding_dim);
+  if (p.up_fused) { p.up_bn = 64; p.up_sp = 1; }
   if (p.tc_down) {
     xl::gemm_tc_plan(M, c.embedding_dim, c.inner_dim, h->num_sms, max_sp, &p.down_bn, &p.down_sp);
     if (h->gemm_down_bn) p.down_bn = h->gemm_down_bn;
@@ -295,7 +313,7 @@ BlockPlan block_plan(const xl_handle* h, const Slice& sl, int T, unsigned flags)
 }
 
 xl::StateStepParams state_params(const xl_handle* h, void* state, const Slice& sl, int i, int T, bool tc_down,
-                                 int up_sp = 1, int small_nch = 0) {
+                                 int up_sp = 1, int small_nch = 0, bool up_fused = false) {
   const xl_config& c = h->cfg;
   const int inner = c.inner_dim, NH = c.num_heads, DH = h->DH;
   const StateLayout L = state_layout(h, sl.B);
@@ -324,9 +342,11 @@ xl::StateStepParams state_params(const xl_handle* h, void* state, const Slice& s
   sp.partial = sl.ws.partial;
   sp.B = sl.Bk; sp.T = T; sp.NH = NH; sp.DH = DH; sp.inner = inner; sp.NCH = h->NCH;
   if (small_nch) sp.NCH = small_nch;   // chunks of the small-batch front kernel (one per CTA cluster, <= 16)
+  if (up_fused) sp.NCH = xl::gemm_up_conv_chunks(inner);   // one chunk per x_m tile of the proj_up epilogue
   sp.ln_eps = c.ln_eps; sp.cell_eps = c.cell_eps;
   sp.impl = h->state_impl; sp.num_layers = c.num_blocks;
   sp.stages = h->state_stages; sp.ctas_per_sm = h->state_ctas_per_sm; sp.rows_split = h->state_rows_split;
+  sp.fuse_finalize = (h->debug_skip & (8 | 16)) ? 0 : h->state_fuse;
   if (sl.ws.low_smem) {          // leave shared memory for the co-resident kernels of the other micro-batches
     if (sp.stages <= 0) sp.stages = 4;
     sp.meta_slots = 2;
@@ -374,6 +394,19 @@ int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned
                        c.ln_eps, M, d, bp.tc_up ? ws.a_hi : nullptr, bp.tc_up ? ws.a_lo : nullptr, sl.s);
   }
   h->launches += 1;
+  if (bp.up_fused) {
+    // proj_up with the pre-cell epilogue: conv + SiLU + q/k/v + gate partials on the x_m tiles while they are on chip
+    xl::UpEpiParams ep;
+    ep.conv_state = (float*)(base + L.conv_off) + (size_t)sl.b0 * c.conv_kernel * inner;
+    ep.conv_w = (const float*)w.w[XL_W_CONV_W]; ep.conv_b = (const float*)w.w[XL_W_CONV_B];
+    ep.wq = (const float*)w.w[XL_W_Q_PROJ]; ep.wk = (const float*)w.w[XL_W_K_PROJ]; ep.wv = (const float*)w.w[XL_W_V_PROJ];
+    ep.wi = (const float*)w.w[XL_W_IGATE_W]; ep.wf = (const float*)w.w[XL_W_FGATE_W];
+    ep.qk = ws.qkv; ep.v = ws.qkv + (size_t)2 * M * inner; ep.act = ws.act; ep.gate_part = ws.gate_part;
+    ep.B = sl.Bk; ep.T = T; ep.inner = inner; ep.NCH = xl::gemm_up_conv_chunks(inner);
+    XL_CUDA(xl::launch_gemm_up_conv(ws.a_hi, ws.a_lo, (const __nv_bfloat16*)w.w[XL_W_PROJ_UP], ws.u, M, d, ep, sl.s));
+    h->launches += 1;
+    return XL_OK;
+  }
   int rc = (h->debug_skip & 2) ? 0 : linear(h, ws, ws.xn, w.w[XL_W_PROJ_UP], nullptr, nullptr,
                   bp.up_sp > 1 ? h->part_up : ws.u, M, 2 * inner,
                   d, bp.impl, sl.s, bp.tc_up, bp.up_bn, bp.up_sp, (long long)M * 2 * inner);
@@ -406,7 +439,8 @@ int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned
 // block i, part 2: the HBM-bound state stream (C update + partial numerators)
 int block_state(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned flags) {
   const BlockPlan bp = block_plan(h, sl, T, flags);
-  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp, smallm_chunks(h, sl, T, flags));
+  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp, smallm_chunks(h, sl, T, flags),
+                                              bp.up_fused);
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (h->profiling) {
     XL_CUDA(cudaEventCreate(&pe0));
@@ -432,8 +466,8 @@ int block_post(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigne
   const int M = sl.Bk * T;
   if (small_nch) {
     // M <= 16 rows: finalize emits fp32 g, then x += g W_down^T as warp GEMVs (xl_smallm.cu)
-    const xl::StateStepParams sp = state_params(h, state, sl, i, T, /*tc_down=*/false, 1, small_nch);
-    XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, sl.s));
+    xl::StateStepParams sp = state_params(h, state, sl, i, T, /*tc_down=*/false, 1, small_nch);
+    if (!xl::state_step_fuses_finalize(sp, h->num_sms)) XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, sl.s));
     xl::SmallDownParams dp;
     dp.g = ws.gated; dp.w_down = (const __nv_bfloat16*)h->blocks[i].w[XL_W_PROJ_DOWN]; dp.x = ws.x;
     dp.M = M; dp.d = c.embedding_dim; dp.inner = c.inner_dim;
@@ -441,9 +475,11 @@ int block_post(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigne
     h->launches += 2;
     return XL_OK;
   }
-  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp, small_nch);
-  if (!(h->debug_skip & 16)) XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, sl.s));
-  h->launches += 1;
+  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp, small_nch, bp.up_fused);
+  if (!xl::state_step_fuses_finalize(sp, h->num_sms)) {      // else block_state's kernel has finalized already
+    if (!(h->debug_skip & 16)) XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, sl.s));
+    h->launches += 1;
+  }
   if (h->debug_skip & 32) return XL_OK;
   if (bp.down_sp > 1)   // planes; folded into x by the next LayerNorm (block_pre of block i+1 / final_norm)
     return linear(h, ws, ws.gated, h->blocks[i].w[XL_W_PROJ_DOWN], nullptr, nullptr, h->part_down, M,
@@ -1057,7 +1093,8 @@ int xl_create(const xl_config* cfg, xl_handle** out) {
   const size_t o_x = carve(4 * M * d), o_xn = carve(4 * M * d), o_xtok = carve(4 * M * d);
   const size_t o_hid = carve(4 * M * d);
   const size_t o_u = carve(4 * M * 2 * inner), o_qkv = carve(4 * M * 3 * inner), o_act = carve(4 * M * inner);
-  const size_t o_gp = carve(4 * M * 16 * 2 * c.num_heads), o_gated = carve(4 * M * inner);
+  h->gp_chunks = std::max(16, xl::gemm_up_conv_chunks((int)inner));
+  const size_t o_gp = carve(4 * M * h->gp_chunks * 2 * c.num_heads), o_gated = carve(4 * M * inner);
   const size_t o_part = carve(4 * B * c.num_heads * 32 * 4 * DH);  // RS <= 32, T <= 4
   const size_t o_semb = carve(4 * B * d), o_sp = carve(4 * B * h->Kpad), o_lg = carve(4 * B * h->head_out);
   const size_t o_ds = carve(4 * B * c.state_dim), o_dr = carve(4 * B), o_dw = carve(4 * B);
@@ -1315,6 +1352,7 @@ int xl_mlstm_cell_step(xl_handle* h, float* C, float* n, float* m, const float* 
   sp.ln_eps = c.ln_eps; sp.cell_eps = c.cell_eps;
   sp.impl = h->state_impl; sp.num_layers = c.num_blocks;
   sp.stages = h->state_stages; sp.ctas_per_sm = h->state_ctas_per_sm;
+  sp.fuse_finalize = h->state_fuse;
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (h->profiling) {
     XL_CUDA(cudaEventCreate(&pe0));
@@ -1327,7 +1365,7 @@ int xl_mlstm_cell_step(xl_handle* h, float* C, float* n, float* m, const float* 
     h->prof_state.push_back(pe0);
     h->prof_state.push_back(pe1);
   }
-  XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, s));
+  if (!xl::state_step_fuses_finalize(sp, h->num_sms)) XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, s));
   h->launches += 3;
   return XL_OK;
 }
@@ -1572,6 +1610,13 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "state_rows_split")) {
     if (value < 0 || value > 32) return fail(XL_ERR_INVALID_ARG, "state_rows_split must be in [0, 32]");
     h->state_rows_split = value;
+  } else if (!strcmp(name, "up_fuse")) {
+    h->up_fuse = value ? 1 : 0;
+  } else if (!strcmp(name, "state_fuse")) {
+    if (value < 0 || value > 3)
+      return fail(XL_ERR_INVALID_ARG, "state_fuse must be 0 (separate finalize kernel), 1 (cluster, symmetric), "
+                                      "2 (cluster, rank 0 finalizes) or 3 (unfused kernel under the cluster shape)");
+    h->state_fuse = value;
   } else if (!strcmp(name, "microbatches")) {
     if (value < 0 || value > kMaxMicro) return fail(XL_ERR_INVALID_ARG, "microbatches must be in [0, %d]", kMaxMicro);
     h->microbatches = value;

@@ -276,6 +276,350 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Up-projection with the pre-cell epilogue (fused 3-token step): u = LN(x) W_up^T as above, but the x_m half of u
+// never reaches global memory — CausalConv1d.step + SiLU + headwise q/k/v + gate partials ([ext-xlstm]
+// mLSTMLayer.step; what conv_qkv_gates_kernel does, same arithmetic in the same order) run on the accumulator tile
+// while it is on chip. One dependent launch and one round trip of x_m less per block.
+//   * row tiles hold whole envs: 42 envs x 3 tokens = 126 of the 128 MMA rows (the TMA box still loads 128 rows);
+//   * x_m tiles are 32 channels wide (8 four-channel blocks), z tiles 64: inner/32 + inner/64 column tiles, e.g.
+//     72 x 2 = 144 CTAs at 48M x 64 envs -> one wave, and the pre-cell work is spread over 2/3 of them;
+//   * 12 epilogue warps: TMEM -> shared (x_m) or TMEM -> global (z); then thread = (env, 4-channel block): the conv
+//     window lives in registers across the 3 tokens, weights come from shared memory (fetched before the dependency
+//     wait together with the envs' conv windows), gate partials of the tile's 8 blocks meet through a shuffle
+//     reduce-scatter in a fixed order (deterministic) and leave as chunk blockIdx.x of gate_part [M, inner/32, 2*NH].
+// ------------------------------------------------------------------------------------------------------------------
+namespace upc {
+
+constexpr int kT = 3;                       // tokens per env step
+constexpr int kEnvs = BLOCK_M / kT;         // 42 envs per row tile
+constexpr int kRows = kEnvs * kT;           // 126 rows owned by a tile
+constexpr int kXW = 32;                     // x_m tile width (channels)
+constexpr int kZW = 64;                     // z tile width
+constexpr int kStages = 4;
+constexpr int kEpiWarps = 12;            // 384 threads >= 42 envs x 8 blocks: one (env, block) item per thread
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreadsUp = 64 + kEpiThreads;
+constexpr int kXS = kXW + 1;                // padded row stride of the staged x_m tile
+constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+constexpr int kWBoxBytes = kXW * BLOCK_K * 2;          // one 32-row box of W
+constexpr int kStageBytes = 2 * kABytes + 2 * kWBoxBytes;
+constexpr int kXsFloats = BLOCK_M * kXS;
+constexpr int kWinFloats = kEnvs * 3 * kXW;            // rows 1..3 of each env's conv window
+// per-tile weights in shared memory (floats): conv_w [32][4], conv_b [32], wq/wk/wv [8][16] each,
+// gate weights [gate 2][head 4][part 3][32]
+constexpr int kWConv = 0, kWBias = 128, kWQ = 160, kWK = 288, kWV = 416, kWG = 544, kWFloats = 544 + 768;
+constexpr int kEpiOff = kStages * kStageBytes + 256;
+constexpr int kSmemTotal = kEpiOff + (kXsFloats + kWinFloats + kWFloats) * 4 + 1024;
+
+__global__ void __launch_bounds__(kThreadsUp, 1)
+gemm_up_conv_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                    const __grid_constant__ CUtensorMap map_w, float* __restrict__ u, int M, int K, UpEpiParams ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + kStages * kStageBytes;        // full[kStages], empty[kStages], tmem_full, slot, win
+  const uint32_t tmem_slot = bar_base + 8 * (2 * kStages + 1);
+  const uint32_t win_bar = bar_base + 8 * (2 * kStages + 2);
+  auto full_bar = [&](int s) { return bar_base + 8 * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8 * (kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8 * (2 * kStages);
+  float* epi = reinterpret_cast<float*>(smem_raw + (base + kEpiOff - smem_u32(smem_raw)));
+  float* xs = epi;                          // [128][33]  staged x_m tile
+  float* cwin = xs + kXsFloats;             // [42][3][32] conv windows (rows 1..3)
+  float* wsm = cwin + kWinFloats;           // per-tile weights
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int inner = ep.inner, N = 2 * inner;
+  const int NX = inner / kXW;                                    // x_m column tiles come first
+  const bool xm_tile = (int)blockIdx.x < NX;
+  const int n0 = xm_tile ? blockIdx.x * kXW : inner + ((int)blockIdx.x - NX) * kZW;
+  const int nboxes = xm_tile ? 1 : 2;
+  const int m0 = blockIdx.y * kRows;
+  const int env0 = blockIdx.y * kEnvs;
+  const int envs_here = min(kEnvs, ep.B - env0);
+  const int num_kb = K / BLOCK_K;
+  const uint32_t stage_tx = (uint32_t)(2 * kABytes + nboxes * kWBoxBytes);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(win_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kZW) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  // ---- before the dependency wait: weight tiles of the first ring round (never written by a kernel), and for x_m
+  // tiles the conv windows of the tile's envs (only this kernel writes them, one env step ago) and the tile's
+  // pre-cell weights
+  const int pre_kb = num_kb < kStages ? num_kb : kStages;
+  if (warp == 0 && lane == 0) {
+    for (int kb = 0; kb < pre_kb; ++kb) {
+      mbar_expect_tx(full_bar(kb), stage_tx);
+      for (int bx = 0; bx < nboxes; ++bx)
+        tma_load_2d(base + kb * kStageBytes + 2 * kABytes + bx * kWBoxBytes, &map_w, full_bar(kb), kb * BLOCK_K,
+                    n0 + bx * kXW);
+    }
+  }
+  const int et = (int)threadIdx.x - 64;                          // epilogue thread 0..511
+  if (xm_tile && et >= 0) {
+    if (et == 0) mbar_expect_tx(win_bar, (uint32_t)(envs_here * 3 * kXW * 4));
+    asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+    if (et < envs_here * 3) {
+      const int e = et / 3, r = et - e * 3;
+      const float* src = ep.conv_state + ((int64_t)(env0 + e) * 4 + 1 + r) * inner + n0;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(cwin + et * kXW)), "l"(src), "r"((uint32_t)(kXW * 4)), "r"(win_bar)
+                   : "memory");
+    }
+    for (int i = et; i < kWFloats; i += kEpiThreads) {
+      float w;
+      if (i < kWBias) w = ep.conv_w[(int64_t)n0 * 4 + i];                       // [ch][4], contiguous for the tile
+      else if (i < kWQ) w = ep.conv_b[n0 + (i - kWBias)];
+      else if (i < kWK) w = ep.wq[(int64_t)(n0 >> 2) * 16 + (i - kWQ)];          // [block][4][4]
+      else if (i < kWV) w = ep.wk[(int64_t)(n0 >> 2) * 16 + (i - kWK)];
+      else if (i < kWG) w = ep.wv[(int64_t)(n0 >> 2) * 16 + (i - kWV)];
+      else {
+        const int g = i - kWG, gate = g / 384, rem = g - gate * 384, h = rem / 96, rem2 = rem - h * 96;
+        const int part = rem2 >> 5, ch = rem2 & 31;
+        w = (gate ? ep.wf : ep.wi)[((int64_t)h * 3 + part) * inner + n0 + ch];
+      }
+      wsm[i] = w;
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < pre_kb; ++kb) {
+        const uint32_t st = base + kb * kStageBytes;
+        tma_load_2d(st, &map_a_hi, full_bar(kb), kb * BLOCK_K, m0);
+        tma_load_2d(st + kABytes, &map_a_lo, full_bar(kb), kb * BLOCK_K, m0);
+      }
+      for (int kb = pre_kb; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t st = base + s * kStageBytes;
+        mbar_expect_tx(full_bar(s), stage_tx);
+        tma_load_2d(st, &map_a_hi, full_bar(s), kb * BLOCK_K, m0);
+        tma_load_2d(st + kABytes, &map_a_lo, full_bar(s), kb * BLOCK_K, m0);
+        for (int bx = 0; bx < nboxes; ++bx)
+          tma_load_2d(st + 2 * kABytes + bx * kWBoxBytes, &map_w, full_bar(s), kb * BLOCK_K, n0 + bx * kXW);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread): N = 32 (x_m tile) or 64 (z tile; the two 32-row W boxes are contiguous) =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(xm_tile ? kXW : kZW);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(full_bar(s), ph);
+        tcgen05_fence_after();
+        const uint32_t st = base + s * kStageBytes;
+        const uint64_t a_hi = make_smem_desc(st);
+        const uint64_t a_lo = make_smem_desc(st + kABytes);
+        const uint64_t bw = make_smem_desc(st + 2 * kABytes);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint64_t kofs = (uint64_t)((k * UMMA_K * 2) >> 4);
+          umma_bf16(tmem_base, a_hi + kofs, bw + kofs, idesc, (kb | k) != 0);
+          umma_bf16(tmem_base, a_lo + kofs, bw + kofs, idesc, 1u);
+        }
+        tcgen05_commit(empty_bar(s));
+      }
+      tcgen05_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue: 12 warps. TMEM lane quarter = warp % 4; two of the three warps of a quarter read the columns =====
+    const int q = warp & 3, cg = (warp - 2) >> 2;                  // cg 0..2
+    const int lrow = q * 32 + lane;                                // row inside the tile
+    const int row = m0 + lrow;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    auto tmem_ld16 = [&](float (&v)[16], int c0) {
+      uint32_t r[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+    };
+    if (!xm_tile) {
+      // z tile: 32 columns per reading warp (two x16 loads), straight to u[:, inner + ...]
+      if (cg < 2) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[16];
+          const int c0 = cg * 32 + half * 16;
+          tmem_ld16(v, c0);
+          if (lrow < kRows && row < M) {
+            float* orow = u + (int64_t)row * N + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+      }
+    } else {
+      // x_m tile, phase 1: 16 columns per reading warp -> shared memory
+      if (cg < 2) {
+        float v[16];
+        tmem_ld16(v, cg * 16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) xs[lrow * kXS + cg * 16 + j] = v[j];
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+      mbar_wait(win_bar, 0);
+      // phase 2: thread = (env e, 4-channel block jb); the 8 blocks of an env are 8 consecutive lanes. Threads
+      // without an env (e >= envs_here) run on env 0's data so that every lane takes part in the shuffles, and
+      // store nothing. The token loop is NOT unrolled: weights are re-read from shared memory per token instead of
+      // being hoisted into ~160 registers.
+      const int jb = et & 7, e_raw = et >> 3;
+      const bool valid = e_raw < envs_here;
+      const int e = valid ? e_raw : 0;
+      const int b = env0 + e;
+      const int c = n0 + 4 * jb;
+      float win[4][4];
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+        const float4 w4 = *reinterpret_cast<const float4*>(cwin + (e * 3 + rr) * kXW + 4 * jb);
+        win[rr + 1][0] = w4.x; win[rr + 1][1] = w4.y; win[rr + 1][2] = w4.z; win[rr + 1][3] = w4.w;
+      }
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) win[0][ch] = 0.f;
+      const float* cwp = wsm + kWConv + jb * 16;                 // [ch][4]
+      const float* wqp = wsm + kWQ + jb * 16;
+      const float* wkp = wsm + kWK + jb * 16;
+      const float* wvp = wsm + kWV + jb * 16;
+      // after the reduce-scatter (xor 4, 2, 1) lane jb holds the complete sum of gate value vi
+      const int vi = ((jb & 4) ? 4 : 0) + ((jb & 2) ? 2 : 0) + (jb & 1);
+#pragma unroll 1
+      for (int t = 0; t < kT; ++t) {
+        const int64_t grow = (int64_t)b * kT + t;
+        float xm[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) xm[ch] = xs[(e * kT + t) * kXS + 4 * jb + ch];
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) win[rr][ch] = win[rr + 1][ch];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) win[3][ch] = xm[ch];
+        float a[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float acc = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) acc = fmaf(win[rr][ch], cwp[ch * 4 + rr], acc);
+          a[ch] = silu(acc + wsm[kWBias + 4 * jb + ch]);
+        }
+        float qv[4], kv[4], vv[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          float sq = 0.f, sk = 0.f, sv = 0.f;
+#pragma unroll
+          for (int dd = 0; dd < 4; ++dd) {
+            sq = fmaf(a[dd], wqp[4 * o + dd], sq);
+            sk = fmaf(a[dd], wkp[4 * o + dd], sk);
+            sv = fmaf(xm[dd], wvp[4 * o + dd], sv);
+          }
+          qv[o] = sq; kv[o] = sk; vv[o] = sv;
+        }
+        if (valid) {
+          float* qk = ep.qk + (grow * inner + c) * 2;
+          *reinterpret_cast<float4*>(qk) = make_float4(qv[0], kv[0], qv[1], kv[1]);
+          *reinterpret_cast<float4*>(qk + 4) = make_float4(qv[2], kv[2], qv[3], kv[3]);
+          *reinterpret_cast<float4*>(ep.v + grow * inner + c) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+          *reinterpret_cast<float4*>(ep.act + grow * inner + c) = make_float4(a[0], a[1], a[2], a[3]);
+        }
+        float gp[8];                                             // [gate][head]
+#pragma unroll
+        for (int gate = 0; gate < 2; ++gate)
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float* gw = wsm + kWG + (gate * 4 + h) * 96 + 4 * jb;      // [part][32]
+            const float4 wq4 = *reinterpret_cast<const float4*>(gw);
+            const float4 wk4 = *reinterpret_cast<const float4*>(gw + 32);
+            const float4 wv4 = *reinterpret_cast<const float4*>(gw + 64);
+            float sg = qv[0] * wq4.x + qv[1] * wq4.y + qv[2] * wq4.z + qv[3] * wq4.w;
+            sg += kv[0] * wk4.x + kv[1] * wk4.y + kv[2] * wk4.z + kv[3] * wk4.w;
+            sg += vv[0] * wv4.x + vv[1] * wv4.y + vv[2] * wv4.z + vv[3] * wv4.w;
+            gp[gate * 4 + h] = sg;
+          }
+        // gate partials of the tile's 32 channels: reduce-scatter over the env's 8 lanes, always
+        // (lower lane's value) + (upper lane's value): a fixed order, so the sums are reproducible
+        float w4v[4], w2v[2], w1v;
+        {
+          const bool hi = (jb & 4) != 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float send = hi ? gp[i] : gp[i + 4];
+            const float keep = hi ? gp[i + 4] : gp[i];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+            w4v[i] = hi ? recv + keep : keep + recv;
+          }
+        }
+        {
+          const bool hi = (jb & 2) != 0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float send = hi ? w4v[i] : w4v[i + 2];
+            const float keep = hi ? w4v[i + 2] : w4v[i];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+            w2v[i] = hi ? recv + keep : keep + recv;
+          }
+        }
+        {
+          const bool hi = (jb & 1) != 0;
+          const float send = hi ? w2v[0] : w2v[1];
+          const float keep = hi ? w2v[1] : w2v[0];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+          w1v = hi ? recv + keep : keep + recv;
+        }
+        if (valid) ep.gate_part[((grow * ep.NCH) + blockIdx.x) * 8 + vi] = w1v;
+      }
+      if (valid) {
+        // the window after the step: the last 4 inputs, oldest first (reference conv_state layout)
+        float* cs = ep.conv_state + (int64_t)b * 4 * inner + c;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr)
+          *reinterpret_cast<float4*>(cs + (int64_t)rr * inner) = make_float4(win[rr][0], win[rr][1], win[rr][2], win[rr][3]);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kZW) : "memory");
+  }
+}
+
+}  // namespace upc
+
 // fp32 rows -> bf16 hi/lo planes (dense [rows, K])
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ in, int64_t in_stride,
                                                          __nv_bfloat16* __restrict__ hi,
@@ -392,6 +736,36 @@ void gemm_tc_plan(int M, int N, int K, int num_sms, int max_splits, int* bn_out,
   }
   *bn_out = best_bn;
   *splits_out = best_sp;
+}
+
+bool gemm_up_conv_supported(int T, int KS, int NH, int inner, int d) {
+  return T == tc::upc::kT && KS == 4 && NH == 4 && inner % 64 == 0 && d % tc::BLOCK_K == 0 && d >= tc::BLOCK_K;
+}
+int gemm_up_conv_chunks(int inner) { return inner / tc::upc::kXW; }
+
+// proj_up with the pre-cell epilogue: `u` [M, 2*inner] receives only its z half (columns >= inner)
+cudaError_t launch_gemm_up_conv(const void* a_hi, const void* a_lo, const __nv_bfloat16* W, float* u, int M, int d,
+                                const UpEpiParams& ep, cudaStream_t s) {
+  namespace U = tc::upc;
+  if (!gemm_up_conv_supported(ep.T, 4, 4, ep.inner, d) || M != ep.B * ep.T || ep.NCH != ep.inner / U::kXW)
+    return cudaErrorInvalidValue;
+  const int N = 2 * ep.inner;
+  CUtensorMap ma, ml, mw;
+  if (!tc::make_map(&ma, a_hi, M, d, tc::BLOCK_M) || !tc::make_map(&ml, a_lo, M, d, tc::BLOCK_M) ||
+      !tc::make_map(&mw, W, N, d, U::kXW))
+    return cudaErrorUnknown;
+  if (cudaError_t e = ensure_dyn_smem<&U::gemm_up_conv_kernel>(U::kSmemTotal); e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ep.inner / U::kXW + ep.inner / U::kZW, (ep.B + U::kEnvs - 1) / U::kEnvs, 1);
+  cfg.blockDim = dim3(U::kThreadsUp);
+  cfg.dynamicSmemBytes = U::kSmemTotal;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, U::gemm_up_conv_kernel, ma, ml, mw, u, M, d, ep);
 }
 
 // bn: 128 / 64 / 32 (0 = plan it, without split-K). splits > 1: raw partial tiles go to out + z * split_stride

@@ -104,11 +104,14 @@ struct StateStepParams {
   // partial slots per item. sk_grid == 0 -> rows_split layout of impl 0/1.
   int sk_grid, sk_q, sk_r, sk_smax;
   int num_layers;           // blocks sharing the L2 with this one (cache-policy choice); 0 = 1
+  int fuse_finalize;        // 1: let the stream kernel finalize inside a cluster per (env, head) when the tiling allows
+                            // (state_step_fuses_finalize); launch_state_finalize must then NOT be called
   float ln_eps, cell_eps;
 };
 // Kernel 1 (stream C, emit partial numerators) and kernel 2 (n/m update, normalise, gate). Both pick the
 // same tiling when rows_split / cols_per_cta are 0. Return cudaError.
 cudaError_t launch_state_step(StateStepParams p, int num_sms, cudaStream_t s);
+bool state_step_fuses_finalize(StateStepParams p, int num_sms);
 cudaError_t launch_state_finalize(StateStepParams p, int num_sms, cudaStream_t s);
 void state_step_auto_tiling(int B, int NH, int DH, int num_sms, int* rows_split, int* cols_per_cta);
 void launch_repack_qkv(const float* qkv, float* qk, float* v, int M, int inner, cudaStream_t s);
@@ -225,6 +228,20 @@ void launch_gemm_simple(const float* A, const __nv_bfloat16* W, const float* bia
                         float* out, int M, int N, int K, cudaStream_t s);
 
 // ---- xl_gemm_tc.cu -------------------------------------------------------------------------------
+// Pre-cell epilogue of the up-projection (fused 3-token step): what conv_qkv_gates_kernel computes, done on the x_m
+// tile while it is still on chip. Row tiles hold whole envs (42 envs x 3 tokens = 126 rows); gate partials come out
+// per 32-channel tile: gate_part [M, NCH = gemm_up_conv_chunks(inner) = inner/32, 2*NH].
+struct UpEpiParams {
+  float* conv_state;           // [B, 4, inner] in/out
+  const float *conv_w, *conv_b, *wq, *wk, *wv, *wi, *wf;
+  float *qk, *v, *act, *gate_part;
+  int B, T, inner, NCH;
+};
+bool gemm_up_conv_supported(int T, int KS, int NH, int inner, int d);
+int gemm_up_conv_chunks(int inner);
+cudaError_t launch_gemm_up_conv(const void* a_hi, const void* a_lo, const __nv_bfloat16* W, float* u, int M, int d,
+                                const UpEpiParams& ep, cudaStream_t s);
+
 // tcgen05 path: A given as bf16 hi/lo planes (A = hi + lo), W bf16, fp32 accumulate in TMEM.
 bool gemm_tc_supported(int M, int N, int K);
 void launch_split_bf16(const float* in, int64_t in_stride, void* hi, void* lo, int rows, int K, cudaStream_t s);

@@ -35,7 +35,7 @@ namespace xl {
 
 constexpr int kThreads = 256;        // consumer threads
 constexpr int kUnroll = 8;
-constexpr int kMaxNCH = 16;
+constexpr int kMaxNCH = 128;
 
 // stream-K partition of N stage tiles over G CTAs (impl 2): CTA c owns [sk_start(c), sk_start(c+1))
 __host__ __device__ __forceinline__ int sk_start(const StateStepParams& p, int c) {
@@ -46,6 +46,31 @@ __host__ __device__ __forceinline__ int sk_cta_of(const StateStepParams& p, int 
   return tile < big ? tile / (p.sk_q + 1) : p.sk_r + (tile - big) / p.sk_q;
 }
 
+// Gate pre-activation (token t, gate g in {i, f}) of head hd = sum of the NCH chunk partials + bias, for the warp's
+// lanes 4*(2t+g). Four lanes per sum: lane `sub` adds chunks sub, sub+4, ... (independent loads: one round trip
+// whatever NCH is), then the four sub-sums are added in a fixed order -> the same bits wherever this is evaluated
+// (stream, finalize, fused and persistent variants). Must be called by a full warp.
+template <int T>
+__device__ __forceinline__ float gate_preact(const StateStepParams& p, int b, int hd, int lane) {
+  const int NH = p.NH;
+  const int pair = lane >> 2, sub = lane & 3;
+  const int t = pair >> 1, is_f = pair & 1;
+  float s = 0.f;
+  if (pair < 2 * T) {
+    const float* gp = p.gate_part + ((int64_t)b * T + t) * p.NCH * 2 * NH + (is_f ? NH : 0) + hd;
+    for (int c = sub; c < p.NCH; c += 4) s += gp[c * 2 * NH];
+  }
+  const float s1 = __shfl_down_sync(0xffffffffu, s, 1);
+  const float s01 = s + s1;                                   // valid in sub 0 and sub 2
+  const float s23 = __shfl_down_sync(0xffffffffu, s01, 2);
+  float tot = s01 + s23;
+  if (pair < 2 * T && sub == 0) {
+    const float* bias = is_f ? p.fgate_b : p.igate_b;
+    if (bias) tot += bias[hd];
+  }
+  return tot;
+}
+
 // Gate recurrence of one (env, head) for the T tokens of the step. Called by one full warp; results in shared
 // memory. Streaming CTAs and the finalize CTA run this same code on the same inputs -> identical f, i, m.
 template <int T>
@@ -53,14 +78,9 @@ __device__ __forceinline__ void compute_gates(const StateStepParams& p, int b, i
                                               float* s_i, float* s_m, float* s_pre) {
   const int lane = threadIdx.x & 31;
   const int NH = p.NH;
-  if (lane < 2 * T) {
-    const int t = lane >> 1, is_f = lane & 1;
-    const float* gp = p.gate_part + ((int64_t)b * T + t) * p.NCH * 2 * NH + (is_f ? NH : 0) + hd;
-    float s = 0.f;
-    for (int c = 0; c < p.NCH; ++c) s += gp[c * 2 * NH];       // fixed order
-    const float* bias = is_f ? p.fgate_b : p.igate_b;
-    if (bias) s += bias[hd];
-    s_pre[lane] = s;
+  {
+    const float pre = gate_preact<T>(p, b, hd, lane);
+    if ((lane & 3) == 0 && (lane >> 2) < 2 * T) s_pre[lane >> 2] = pre;
   }
   __syncwarp();
   if (lane == 0) {
@@ -254,12 +274,277 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                : "memory");
 }
 
-template <int T, bool kStream>
+// ---- fused finalize (kFused): the CS = DH/128 column-slab CTAs of one (env, head) form a thread-block CLUSTER.
+// Each CTA ends the stream holding the complete numerators q^T C of its 128 columns (rows are not split), computes
+// q.n for the whole head redundantly (DH FMAs per token), normalises its columns, and the GroupNorm statistics of
+// the head meet over distributed shared memory: every CTA posts (sum, M2) of its 128 columns into every peer's
+// shared memory with st.async, which completes the peer's mbarrier by byte count -- no global ticket, no memory
+// fence on the streaming stores, no cluster barrier on the critical path (Chan's parallel-variance combination of
+// the CS partial statistics, in rank order, identical in every CTA). Rank 0 writes n and m back after it has
+// received every peer's statistics (which depend on the old n, m: all reads of them are done by then).
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_f32(uint32_t raddr, float v, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+               ::"r"(raddr), "r"(__float_as_uint(v)), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+
+constexpr int kNRowsMax = 4;          // n rows per consumer thread: DH <= 4 * 256
+constexpr int kMaxCluster = 8;
+
+// sum of T values over the first `nwarps` consumer warps (fixed order); every consumer thread calls it
+template <int T>
+__device__ __forceinline__ void consumer_sum(float (&v)[T], float* red /* [T][8] */, int warp, int lane, int nwarps) {
+#pragma unroll
+  for (int t = 0; t < T; ++t) v[t] = warp_sum(v[t]);
+  asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");      // protect `red` from its previous use
+  if (lane == 0 && warp < nwarps) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) red[t * 8 + warp] = v[t];
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; ++w) s += red[t * 8 + w];
+    v[t] = s;
+  }
+}
+
+template <int T>
+__device__ __forceinline__ void fused_finalize(const StateStepParams& p, const TileCoord& tc, const float* sacc,
+                                               const float* sqk, const float* sn, int tstride, const float* s_f,
+                                               const float* s_i, const float* s_m, float* s_red, float* s_x,
+                                               uint32_t xbar, int tid) {
+  constexpr int W = 128;
+  const int DH = p.DH, inner = p.inner, CS = DH / W;
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool col = tid < W;                               // threads 0..127 own one output column each
+  const int ch = tc.hd * DH + tc.c0 + (col ? tid : 0);
+  // tail operands: issued first, consumed last (a and z were written two kernels back, weights never)
+  float wn = 0.f, wskip = 0.f, act[T], zz[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int64_t row = (int64_t)tc.b * T + t;
+    act[t] = (col && p.skip) ? p.act[row * inner + ch] : 0.f;
+    zz[t] = (col && p.skip) ? p.u[row * 2 * inner + inner + ch] : 0.f;
+    if (col && p.skip)
+      for (int z = 1; z < p.u_splits; ++z) zz[t] += p.u[z * p.u_stride + row * 2 * inner + inner + ch];
+  }
+  if (col) {
+    wn = p.outnorm_w[ch];
+    wskip = p.skip ? p.skip[ch] : 0.f;
+  }
+  // numerators of this CTA's columns: sum over the 8 row lanes, fixed order
+  float num[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    float s = 0.f;
+    if (col)
+      for (int y = 0; y < 8; ++y) s += sacc[(y * T + t) * W + tid];
+    num[t] = s;
+  }
+  // n recurrence and q.n over the whole head (every CTA of the cluster computes the same numbers)
+  const float kscale = rsqrtf((float)DH);
+  float qn[T], nreg[kNRowsMax];
+#pragma unroll
+  for (int t = 0; t < T; ++t) qn[t] = 0.f;
+#pragma unroll
+  for (int j = 0; j < kNRowsMax; ++j) {
+    const int r = tid + j * kThreads;
+    nreg[j] = 0.f;
+    if (r < DH) {
+      float nv = sn[r];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const float2 q2 = *reinterpret_cast<const float2*>(sqk + t * tstride + 2 * r);
+        nv = fmaf(s_f[t], nv, s_i[t] * kscale * q2.y);
+        qn[t] = fmaf(q2.x, nv, qn[t]);
+      }
+      nreg[j] = nv;
+    }
+  }
+  consumer_sum<T>(qn, s_red, warp, lane, 8);
+  // h and the statistics of this CTA's 128 columns: sum, then M2 about the local mean
+  float hs[T], m2[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const float den = fmaxf(fabsf(qn[t]), expf(-s_m[t + 1])) + p.cell_eps;
+    num[t] = num[t] / den;
+    hs[t] = col ? num[t] : 0.f;
+  }
+  consumer_sum<T>(hs, s_red, warp, lane, 4);
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const float dlt = col ? num[t] - hs[t] * (1.f / W) : 0.f;
+    m2[t] = dlt * dlt;
+  }
+  consumer_sum<T>(m2, s_red, warp, lane, 4);
+  // post (sum, M2) into slot [rank] of every CTA of the cluster (own included)
+  if (tid < 2 * T) {
+    const float val = tid < T ? hs[tid] : m2[tid - T];
+    const uint32_t slot = smem_u32(s_x + tc.cs * 8 + tid);
+    for (int r = 0; r < CS; ++r) st_async_f32(mapa_u32(slot, (uint32_t)r), val, mapa_u32(xbar, (uint32_t)r));
+  }
+  mbar_wait(xbar, 0);
+  float mean[T], rstd[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    float tot = 0.f;
+    for (int k = 0; k < CS; ++k) tot += s_x[k * 8 + t];
+    const float mu = tot / (float)DH;
+    float M2 = 0.f;
+    for (int k = 0; k < CS; ++k) {
+      const float dk = s_x[k * 8 + t] * (1.f / W) - mu;
+      M2 += s_x[k * 8 + T + t] + (float)W * dk * dk;
+    }
+    mean[t] = mu;
+    rstd[t] = rsqrtf(M2 / (float)DH + p.ln_eps);
+  }
+  if (col) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int64_t row = (int64_t)tc.b * T + t;
+      float o = (num[t] - mean[t]) * rstd[t] * (1.f + wn);
+      if (p.h_raw) p.h_raw[row * inner + ch] = num[t];
+      if (p.skip) o = (o + wskip * act[t]) * silu_fast(zz[t]);
+      if (p.out) p.out[row * inner + ch] = o;
+      if (p.out_hi) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+        reinterpret_cast<__nv_bfloat16*>(p.out_hi)[row * inner + ch] = hi;
+        reinterpret_cast<__nv_bfloat16*>(p.out_lo)[row * inner + ch] = __float2bfloat16_rn(o - __bfloat162float(hi));
+      }
+    }
+  }
+  if (tc.cs == 0) {        // every peer's statistics are in: nobody still needs the old n, m
+#pragma unroll
+    for (int j = 0; j < kNRowsMax; ++j) {
+      const int r = tid + j * kThreads;
+      if (r < DH) p.n[(int64_t)tc.bh * DH + r] = nreg[j];
+    }
+    if (tid == 0) p.m[tc.bh] = s_m[T];
+  }
+}
+
+// Leader variant (fuse_finalize == 2): every CTA of the cluster pushes the numerators of its 128 columns into rank 0's
+// shared memory (st.async, counted by rank 0's mbarrier) and retires at once -- a fire-and-forget store from registers;
+// only rank 0 stays, waits for the CS contributions and finalizes the whole head (two-pass GroupNorm inside the CTA).
+// One tail per (env, head) instead of CS tails: the slots of the other CTAs go back to streaming immediately.
+template <int T>
+__device__ __forceinline__ void leader_finalize(const StateStepParams& p, const TileCoord& tc, const float* sacc,
+                                                const float* sqk, const float* sn, float* snum, int tstride,
+                                                const float* s_f, const float* s_i, const float* s_m, float* s_red,
+                                                uint32_t xbar, int tid) {
+  constexpr int W = 128;
+  const int DH = p.DH, inner = p.inner;
+  const int warp = tid >> 5, lane = tid & 31;
+  if (tid < W) {
+    const uint32_t rbase = mapa_u32(smem_u32(snum + (tc.cs * T) * W + tid), 0u);
+    const uint32_t rbar = mapa_u32(xbar, 0u);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      float s = 0.f;
+      for (int y = 0; y < 8; ++y) s += sacc[(y * T + t) * W + tid];      // fixed order over the 8 row lanes
+      st_async_f32(rbase + (uint32_t)(t * W * sizeof(float)), s, rbar);
+    }
+  }
+  if (tc.cs != 0) return;
+  // ---- rank 0: the whole head. Thread tid owns channels tid + j*256 (output) and rows tid + j*256 (n recurrence)
+  const float kscale = rsqrtf((float)DH);
+  float qn[T], nreg[kNRowsMax];
+#pragma unroll
+  for (int t = 0; t < T; ++t) qn[t] = 0.f;
+#pragma unroll
+  for (int j = 0; j < kNRowsMax; ++j) {
+    const int r = tid + j * kThreads;
+    nreg[j] = 0.f;
+    if (r < DH) {
+      float nv = sn[r];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const float2 q2 = *reinterpret_cast<const float2*>(sqk + t * tstride + 2 * r);
+        nv = fmaf(s_f[t], nv, s_i[t] * kscale * q2.y);
+        qn[t] = fmaf(q2.x, nv, qn[t]);
+      }
+      nreg[j] = nv;
+    }
+  }
+  consumer_sum<T>(qn, s_red, warp, lane, 8);
+  float rden[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) rden[t] = fmaxf(fabsf(qn[t]), expf(-s_m[t + 1])) + p.cell_eps;
+  mbar_wait(xbar, 0);                                  // every CTA's numerators have landed
+  auto h_of = [&](int c, int t) { return snum[((c >> 7) * T + t) * W + (c & 127)] / rden[t]; };
+  float mean[T], var[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    float s = 0.f;
+    for (int j = 0; j < kNRowsMax; ++j) {
+      const int c = tid + j * kThreads;
+      if (c < DH) s += h_of(c, t);
+    }
+    mean[t] = s;
+  }
+  consumer_sum<T>(mean, s_red, warp, lane, 8);
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    mean[t] /= (float)DH;
+    float s = 0.f;
+    for (int j = 0; j < kNRowsMax; ++j) {
+      const int c = tid + j * kThreads;
+      if (c < DH) {
+        const float dlt = h_of(c, t) - mean[t];
+        s = fmaf(dlt, dlt, s);
+      }
+    }
+    var[t] = s;
+  }
+  consumer_sum<T>(var, s_red, warp, lane, 8);
+  for (int j = 0; j < kNRowsMax; ++j) {
+    const int c = tid + j * kThreads;
+    if (c >= DH) break;
+    const int ch = tc.hd * DH + c;
+    const float wn = p.outnorm_w[ch];
+    const float wskip = p.skip ? p.skip[ch] : 0.f;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int64_t row = (int64_t)tc.b * T + t;
+      const float h = h_of(c, t);
+      float o = (h - mean[t]) * rsqrtf(var[t] / (float)DH + p.ln_eps) * (1.f + wn);
+      if (p.h_raw) p.h_raw[row * inner + ch] = h;
+      if (p.skip) {
+        float z = p.u[row * 2 * inner + inner + ch];
+        for (int zz = 1; zz < p.u_splits; ++zz) z += p.u[zz * p.u_stride + row * 2 * inner + inner + ch];
+        o = (o + wskip * p.act[row * inner + ch]) * silu_fast(z);
+      }
+      if (p.out) p.out[row * inner + ch] = o;
+      if (p.out_hi) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+        reinterpret_cast<__nv_bfloat16*>(p.out_hi)[row * inner + ch] = hi;
+        reinterpret_cast<__nv_bfloat16*>(p.out_lo)[row * inner + ch] = __float2bfloat16_rn(o - __bfloat162float(hi));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kNRowsMax; ++j) {
+    const int r = tid + j * kThreads;
+    if (r < DH) p.n[(int64_t)tc.bh * DH + r] = nreg[j];
+  }
+  if (tid == 0) p.m[tc.bh] = s_m[T];
+}
+
+template <int T, bool kStream, bool kFused>
 __global__ void __launch_bounds__(kBlock, 3)
 mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateStepParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ float s_f[T], s_i[T], s_m[T + 1], s_pre[2 * T];
-  __shared__ __align__(8) uint64_t s_bar[2 * kStages + 1];
+  __shared__ __align__(8) uint64_t s_bar[2 * kStages + 2];
+  __shared__ float s_red[4 * 8], s_x[kMaxCluster * 8];
 
   const TileCoord tc = tile_coord(p);
   const int DH = p.DH;
@@ -275,11 +560,14 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   float* stage0 = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)));
   float* sqk = stage0 + (size_t)kStages * kStageRows * W;
+  float* sn = sqk + (size_t)T * tstride;      // kFused: n of the whole head [DH]
+  float* snum = sn + DH;                      // kFused, leader variant: numerators of the head [CS][T][128] (rank 0)
   float* sacc = stage0;
   const uint32_t bar0 = smem_u32(s_bar);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
   const uint32_t qk_bar = bar0 + 8u * (2 * kStages);
+  const uint32_t xbar = bar0 + 8u * (2 * kStages + 1);
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -287,9 +575,21 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
       mbar_init(empty_bar(s), kConsumerWarps);
     }
     mbar_init(qk_bar, 1);
+    if (kFused) {
+      // the exchange barrier completes when the 2T statistics of each of the CS CTAs have landed (bytes)
+      mbar_init(xbar, 1);
+      if (p.fuse_finalize == 2) {
+        if (tc.cs == 0) mbar_expect_tx(xbar, (uint32_t)(DH * T * sizeof(float)));   // the head's numerators
+      } else {
+        mbar_expect_tx(xbar, (uint32_t)((DH / 128) * 2 * T * sizeof(float)));
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  // peers may only target this CTA's exchange barrier once it is initialised: arrive now, wait after the
+  // dependency wait (by then every CTA of the cluster has long arrived)
+  if (kFused) cluster_arrive();
 
   if (warp == kConsumerWarps) {
     // ===== producer warp =====
@@ -321,8 +621,10 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
       for (int i = 0; i < pre; ++i) issue(i);
       pdl_wait();
       pdl_trigger();
-      // the step's (q, k) pairs of this row chunk: T contiguous runs of nrows*8 bytes
-      mbar_expect_tx(qk_bar, (uint32_t)(T * tc.nrows * 8));
+      if (kFused) cluster_wait();
+      // the step's (q, k) pairs of this row chunk: T contiguous runs of nrows*8 bytes (+ n of the head when fused)
+      mbar_expect_tx(qk_bar, (uint32_t)(T * tc.nrows * 8 + (kFused ? DH * 4 : 0)));
+      if (kFused) bulk_copy_g2s(smem_u32(sn), p.n + (int64_t)tc.bh * DH, (uint32_t)(DH * 4), qk_bar);
 #pragma unroll
       for (int t = 0; t < T; ++t)
         bulk_copy_g2s(smem_u32(sqk + t * tstride),
@@ -332,6 +634,7 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
     } else {
       pdl_wait();
       pdl_trigger();
+      if (kFused) cluster_wait();
     }
     return;   // consumers only use the named barrier 1 from here on
   }
@@ -340,6 +643,7 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
   const int tx = tid % TX, ty = tid / TX;
   pdl_wait();
   pdl_trigger();
+  if (kFused) cluster_wait();
   if (warp == 0) compute_gates<T>(p, tc.b, tc.hd, tc.bh, s_f, s_i, s_m, s_pre);
   float vi[T][4];
 #pragma unroll
@@ -402,6 +706,19 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
     }
   }
   asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");   // every warp is done with the ring
+  if (kFused) {
+    // stage the per-row-lane numerators (TX == 32, TY == 8) and finish the (env, head) inside the cluster
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      *reinterpret_cast<float4*>(sacc + ((ty * T + t) * TX + tx) * 4) =
+          make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+    if (p.fuse_finalize == 2)
+      leader_finalize<T>(p, tc, sacc, sqk, sn, snum, tstride, s_f, s_i, s_m, s_red, xbar, tid);
+    else
+      fused_finalize<T>(p, tc, sacc, sqk, sn, tstride, s_f, s_i, s_m, s_red, s_x, xbar, tid);
+    return;
+  }
   write_partials<T>(p, tc, sacc, acc, tx, ty, TX, TY, tid);
 }
 
@@ -421,7 +738,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <int T, bool kStream>
+template <int T, bool kStream, bool kFused>
 static cudaError_t launch(const StateStepParams& p, cudaStream_t s) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return cudaErrorUnknown;
@@ -439,11 +756,32 @@ static cudaError_t launch(const StateStepParams& p, cudaStream_t s) {
   const size_t ring = sizeof(float) * (size_t)kStages * kStageRows * p.cols_per_cta;
   const int TY = kThreads / (p.cols_per_cta / 4);
   const size_t red = sizeof(float) * (size_t)TY * T * p.cols_per_cta;       // aliases the ring
-  const size_t smem = 128 + (ring > red ? ring : red) + sizeof(float) * (size_t)2 * T * rows_per;
-  if (cudaError_t e = ensure_dyn_smem<&mlstm_state_stream_tma_kernel<T, kStream>>(smem); e != cudaSuccess) return e;
+  const size_t smem = 128 + (ring > red ? ring : red) +
+                      sizeof(float) * ((size_t)2 * T * rows_per + (kFused ? (size_t)p.DH * (1 + T) : 0));
+  if (cudaError_t e = ensure_dyn_smem<&mlstm_state_stream_tma_kernel<T, kStream, kFused>>(smem); e != cudaSuccess)
+    return e;
   const int CS = p.DH / p.cols_per_cta;
   const int64_t grid = (int64_t)p.B * p.NH * CS * p.rows_split;
-  return launch_k(mlstm_state_stream_tma_kernel<T, kStream>, dim3((unsigned)grid), dim3(kBlock), smem, s, map, p);
+  if (!kFused && p.fuse_finalize != 3)
+    return launch_k(mlstm_state_stream_tma_kernel<T, kStream, false>, dim3((unsigned)grid), dim3(kBlock), smem, s, map,
+                    p);
+  // one cluster per (env, head): its CS column-slab CTAs
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
+  // (fuse_finalize == 3 is a measurement aid: the UNFUSED kernel under the same cluster shape)
+  return cudaLaunchKernelEx(&cfg, mlstm_state_stream_tma_kernel<T, kStream, kFused>, map, p);
 }
 
 }  // namespace tma
@@ -592,16 +930,7 @@ mlstm_state_stream_persistent_kernel(const __grid_constant__ CUtensorMap mapC, S
       float* ms = meta + (size_t)slot * mfl;
       float* s_gate = ms + T * DH * 2 + T * kW;                 // f[0..T) at +0, i[0..T) at +4
       // gate pre-activations: loads issued before anything waits
-      float pre = 0.f;
-      if (lane < 2 * T) {
-        const int t = lane >> 1, is_f = lane & 1;
-        const float* gp = p.gate_part + ((int64_t)b * T + t) * p.NCH * 2 * NH + (is_f ? NH : 0) + hd;
-        float sum = 0.f;
-        for (int c = 0; c < p.NCH; ++c) sum += gp[c * 2 * NH];   // fixed order, as compute_gates()
-        const float* bias = is_f ? p.fgate_b : p.igate_b;
-        if (bias) sum += bias[hd];
-        pre = sum;
-      }
+      const float pre = gate_preact<T>(p, b, hd, lane);          // the same sums, in the same order, as compute_gates()
       float mprev = p.m[bh];
       if (lane == 0) {
         mbar_wait(meta_empty(slot), ph ^ 1);                     // consumers released this slot
@@ -620,8 +949,8 @@ mlstm_state_stream_persistent_kernel(const __grid_constant__ CUtensorMap mapC, S
       float fv[T], iv[T];
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        const float ig = __shfl_sync(0xffffffffu, pre, 2 * t);
-        const float fg = __shfl_sync(0xffffffffu, pre, 2 * t + 1);
+        const float ig = __shfl_sync(0xffffffffu, pre, 8 * t);
+        const float fg = __shfl_sync(0xffffffffu, pre, 8 * t + 4);
         const float lf = log_sigmoid(fg);
         const float mnew = fmaxf(lf + mprev, ig);
         fv[t] = expf(lf + mprev - mnew);
@@ -901,7 +1230,10 @@ static cudaError_t launch_T(const StateStepParams& p, cudaStream_t s) {
   const int rows_per = (p.DH + p.rows_split - 1) / p.rows_split;
   cudaError_t e;
   if (p.impl >= 1 && rows_per % 4 == 0) {
-    e = stream ? tma::launch<T, true>(p, s) : tma::launch<T, false>(p, s);
+    if (p.fuse_finalize == 1 || p.fuse_finalize == 2)
+      e = stream ? tma::launch<T, true, true>(p, s) : tma::launch<T, false, true>(p, s);
+    else
+      e = stream ? tma::launch<T, true, false>(p, s) : tma::launch<T, false, false>(p, s);
   } else {
     const int TX = p.cols_per_cta / 4, TY = kThreads / TX;
     const size_t smem = sizeof(float) * ((size_t)2 * T * rows_per + (size_t)TY * T * p.cols_per_cta);
@@ -940,6 +1272,16 @@ static void resolve_tiling(StateStepParams& p, int num_sms) {
   }
 }
 
+// True when launch_state_step(p) will also finalize (n/m update, normalise, gate) inside the stream kernel: the
+// one-shot TMA kernel, rows not split, 128-column slabs, <= 8 slabs per head (the cluster), DH <= 1024.
+bool state_step_fuses_finalize(StateStepParams p, int num_sms) {
+  if (p.fuse_finalize != 1 && p.fuse_finalize != 2) return false;
+  if (p.impl != 1) return false;
+  resolve_tiling(p, num_sms);
+  return p.sk_grid == 0 && p.rows_split == 1 && p.cols_per_cta == 128 && p.DH % 128 == 0 &&
+         p.DH / 128 <= tma::kMaxCluster && p.DH <= tma::kNRowsMax * kThreads && p.T <= 4;
+}
+
 // kernel 2; p must carry the same rows_split the stream kernel ran with (resolved here the same way)
 cudaError_t launch_state_finalize(StateStepParams p, int num_sms, cudaStream_t s) {
   resolve_tiling(p, num_sms);
@@ -956,6 +1298,12 @@ cudaError_t launch_state_finalize(StateStepParams p, int num_sms, cudaStream_t s
 
 // kernel 1
 cudaError_t launch_state_step(StateStepParams p, int num_sms, cudaStream_t s) {
+  if (!state_step_fuses_finalize(p, num_sms)) {
+    // the cluster probe (3) keeps its value only where the fused kernel would have run
+    StateStepParams q = p;
+    q.fuse_finalize = 1;
+    p.fuse_finalize = (p.fuse_finalize == 3 && state_step_fuses_finalize(q, num_sms)) ? 3 : 0;
+  }
   resolve_tiling(p, num_sms);
   if (p.cols_per_cta % 4 || p.DH % p.cols_per_cta || slab_width(p.DH) % p.cols_per_cta ||
       kThreads % (p.cols_per_cta / 4) || p.DH > 1024 || p.NCH > kMaxNCH || p.rows_split > p.DH)

@@ -123,7 +123,7 @@ def test_lowlat_falls_back_when_not_eligible():
     x = torch.randn(3, 3, cfg.d).cuda()
     eng.launch_count()
     eng.encoder_step(cache, x)
-    assert eng.launch_count() >= 6 * cfg.num_blocks
+    assert eng.launch_count() >= 4 * cfg.num_blocks      # LN, proj_up (+ pre-cell epilogue), state, finalize, proj_down
     eng.close()
 
 

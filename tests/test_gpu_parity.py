@@ -751,3 +751,40 @@ def test_fp32_checkpoint_weights_error_bound(capsys):
     assert agree / total > 0.97
     assert all(m < 2e-2 for m in flipped_margin)        # only near-ties may flip
     eng.close()
+
+
+@pytest.mark.parametrize("name,B", [("16M", 64), ("48M", 40)])
+@pytest.mark.parametrize("opts", [{"up_fuse": 1}, {"state_fuse": 1}, {"state_fuse": 2}, {"up_fuse": 1, "state_fuse": 2}])
+def test_chain_fusion_options_equal_default(name, B, opts):
+    """The measured-and-not-default fusions of the per-block chain (pre-cell work in the proj_up epilogue; finalize
+    inside the state stream kernel through a thread-block cluster per (env, head), symmetric or leader variant) compute
+    the same step as the default kernels: identical action tokens, hidden states and recurrent state to rounding of
+    the differently ordered partial sums."""
+    cfg, sd, eng = _engine(name, B, seed=4)
+    states, rtg, _ = make_stream(cfg, range(B), 4, domains="mixed", seed=31)
+    res = {}
+    for tag, o in (("default", {}), ("fused", opts)):
+        for k in ("up_fuse", "state_fuse"):
+            eng.set_option(k, o.get(k, 0))
+        cache, out = eng.new_state(B), None
+        s_dev = torch.empty(B, cfg.state_dim, device="cuda")
+        r_dev = torch.empty(B, device="cuda")
+        toks, hids = [], []
+        eng.launch_count()
+        for t in range(4):
+            s_dev.copy_(torch.from_numpy(states[t]))
+            r_dev.copy_(torch.from_numpy(rtg[t]))
+            out = eng.policy_step(cache, s_dev, r_dev, flags=L.XL_FLAG_GRAPH if t else 0, want_hidden=True, out=out)
+            torch.cuda.synchronize()
+            toks.append(out["action_tokens"].cpu().clone())
+            hids.append(out["last_hidden_state"].cpu().clone())
+        last = cfg.num_blocks - 1
+        res[tag] = (torch.stack(toks), torch.stack(hids), cache.view(last, L.XL_STATE_C).cpu().clone(),
+                    cache.view(last, L.XL_STATE_N).cpu().clone(), cache.view(last, L.XL_STATE_CONV).cpu().clone(),
+                    eng.launch_count())
+    a, b = res["default"], res["fused"]
+    assert torch.equal(a[0], b[0])
+    assert _rel(b[1], a[1]) < 1e-4
+    assert _rel(b[2], a[2]) < 1e-4 and _rel(b[3], a[3]) < 1e-4 and _rel(b[4], a[4]) < 1e-5
+    assert b[5] < a[5]                                   # fewer launches: a kernel per block really disappeared
+    eng.close()
