@@ -13,10 +13,16 @@ per step. A "step" is one env step of all envs: embed + 3 tokens x 12 blocks + h
                states/rtg and D2H of tokens+actions inside the timed region, one stream sync per step
   roofline     the mLSTM state-step kernel: algorithmic C/n/m bytes per launch / average launch duration, timed
                with CUDA events around each of its launches in a profiled replay of the same steps
+  whole_step   the un-gameable figure: algorithmic bytes of the WHOLE env step (state of every block once + weights)
+               / the graph-timed step, against the same measured peak
   cpu_baseline the oracle (restated xlstm native PyTorch path, fp32) on the box's host cores, bounded sample
+  gpu_eager_baseline  the same oracle op sequence run eagerly on the GPU (fp32, ~10^3 launches per env step): the
+               like-for-like "reference on this GPU" comparator (what `inf_dummy_batch_size` measures in the
+               reference, online_decision_transformer_model.py:748-758)
 
 --impl reference: times the reference's CPU implementation of the path (the oracle port; the xlstm package is
-absent, see oracle/xlstm_oracle.py header) on the host cores for the same config/metric.
+absent, see oracle/xlstm_oracle.py header) on the host cores for the same config/metric. Both CPU legs use ONE
+sample definition (cpu_sample): the first min(envs, 8) envs of the workload, all host threads.
 """
 from __future__ import annotations
 
@@ -112,19 +118,36 @@ def workload_config(args, world):
             "domains": args.domains, "head": "discrete" if args.discrete else "continuous-tokenized"}
 
 
-def time_oracle(cfg, sd, B, n_steps, warmup, threads, budget_s=None, domains="metaworld", discrete=False):
-    """Oracle env steps on the host cores. Returns (env_steps_per_s, ms list, steps actually timed)."""
+CPU_SAMPLE_ENVS = 8
+
+
+def cpu_sample(envs: int) -> int:
+    """The ONE bounded sample both CPU legs (cpu_baseline and --impl reference) time: the first min(envs, 8) envs of
+    the workload (batch rows are independent; per-env cost on the CPU is, if anything, lower at 8 envs than at 64,
+    whose 1.75 GB of state no longer fits the host caches — so the sample flatters the CPU, not the GPU)."""
+    return min(envs, CPU_SAMPLE_ENVS)
+
+
+def time_oracle(cfg, sd, B, n_steps, warmup, threads, budget_s=None, domains="metaworld", discrete=False,
+                device="cpu"):
+    """Oracle env steps on the host cores (or, device="cuda", the same eager op sequence on the GPU).
+    Returns (env_steps_per_s, ms list, steps actually timed)."""
     from lram_b200.synth import make_stream
     from oracle.xlstm_oracle import OraclePolicy
     torch.set_num_threads(threads)
-    pol = OraclePolicy(cfg, sd)
-    states, rtg, _ = make_stream(cfg, range(B), n_steps + warmup, domains=domains)
+    pol = OraclePolicy(cfg, sd, device=device)
+    states, rtg, _ = make_stream(cfg, range(B), min(n_steps + warmup, 64), domains=domains)
+    d_states, d_rtg = torch.from_numpy(states).to(device), torch.from_numpy(rtg).to(device)
     pkv = None
     ms = []
     t_begin = time.perf_counter()
     for t in range(n_steps + warmup):
+        if device != "cpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        o = pol.step(torch.from_numpy(states[t]), torch.from_numpy(rtg[t]), past_key_values=pkv, discrete=discrete)
+        o = pol.step(d_states[t % len(states)], d_rtg[t % len(states)], past_key_values=pkv, discrete=discrete)
+        if device != "cpu":
+            o["action_tokens"].cpu()                      # the rollout reads the action on the host (evaluation.py:141)
         pkv = o["past_key_values"]
         dt = time.perf_counter() - t0
         if t >= warmup:
@@ -143,24 +166,24 @@ def run_reference(args):
         return
     from lram_b200.config import preset
     from lram_b200.synth import make_state_dict
+    if args.scaling == "strong":                      # --envs is the job's env count: per-GPU share, as the b200 arm
+        args.envs = args.envs // max(args.gpus, 1)
     cfg = preset(args.model)
     sd = make_state_dict(cfg, seed=0)
     cores = os.cpu_count() or 1
-    # bounded sample: B_ref envs of the workload's args.envs, chosen from one calibration step so that
-    # K steps end within ~2 minutes
-    b_ref = min(args.envs, 8)
+    # bounded sample (the same definition as the b200 arm's cpu_baseline): cpu_sample(envs) envs, every step one env
+    # step of those envs; K steps unless the time budget (~4 min) ends the run earlier
+    b_ref = cpu_sample(args.envs)
     kw = dict(domains=args.domains, discrete=args.discrete)
-    v, ms, _ = time_oracle(cfg, sd, b_ref, 1, 1, cores, **kw)
-    per_env_ms = ms[0] / b_ref
-    budget_ms = 120e3
-    b_ref = int(max(1, min(args.envs, budget_ms / max(per_env_ms * (args.steps + args.warmup), 1e-9))))
     value, ms, timed = time_oracle(cfg, sd, b_ref, args.steps, args.warmup, cores, budget_s=240, **kw)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": timed, "warmup": args.warmup, "ms_per_step": statistics.mean(ms), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args, max(args.gpus, 1)), backend="oracle port of the xlstm native PyTorch "
-                       "ops, CPU fp32, rank 0 only", sampled_envs=b_ref),
+        # global_envs is what THIS arm ran (the bounded sample on rank 0), not the N-GPU job's env count
+        "config": dict(workload_config(args, max(args.gpus, 1)), global_envs=b_ref, backend="oracle port of the "
+                       "xlstm native PyTorch ops, CPU fp32, rank 0 only", sampled_envs=b_ref,
+                       job_envs=args.envs * max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{b_ref} of {args.envs} envs x {timed} env steps, oracle port of the xlstm "
                                    f"native PyTorch backend (xlstm package absent), fp32, {cores} threads"},
@@ -206,6 +229,9 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=5)
     ap.add_argument("--discrete", action="store_true", help="discrete-action head (argmax over the first 18 logits)")
     ap.add_argument("--domains", default="metaworld", help="metaworld | dmcontrol | composuite | mimicgen | mixed")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --envs per GPU (default); strong: --envs is the JOB's env count, split env i -> rank i %% N "
+                         "(BASELINE.json configs[4]: 256 Atari envs on 1/2/4/8 GPUs)")
     ap.add_argument("--gather-every", type=int, default=16,
                     help="N > 1: all-gather the action tokens of this many env steps in one collective (1 = per step)")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
@@ -239,6 +265,10 @@ def main():
 
     cfg = preset(args.model)
     sd = make_state_dict(cfg, seed=0)
+    if args.scaling == "strong":
+        assert args.envs % world == 0, "--scaling strong needs --envs divisible by the GPU count"
+        args.job_envs = args.envs
+        args.envs = args.envs // world
     B = args.envs
     n_envs = B * world
     env_ids = shard_env_ids(n_envs, rank, world)
@@ -253,6 +283,7 @@ def main():
         eng.set_option(name, int(val))
         opts[name] = int(val)
     cache = eng.new_state(B)
+    cache_nbytes = cache.nbytes()
     total = K + W
     n_stream = min(total, 64)                    # the synthetic stream is cycled; values don't affect timing
     states_np, rtg_np, _ = make_stream(cfg, env_ids, n_stream, domains=args.domains)
@@ -263,7 +294,8 @@ def main():
     out = {"action_tokens": torch.zeros(B, cfg.act_dim, dtype=torch.int32, device=dev),
            "action_preds": torch.zeros(B, cfg.act_dim, dtype=torch.float32, device=dev)}
     stream = torch.cuda.current_stream(dev)
-    gatherer = OverlappedTokenGather(B, cfg.act_dim, world, dev, every=args.gather_every) if world > 1 else None
+    gatherer = OverlappedTokenGather(B, cfg.act_dim, world, dev, every=args.gather_every, engine=eng) \
+        if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -330,8 +362,7 @@ def main():
         eng.policy_step_host(cache_e, h_states[t % n_stream], h_rtg[t % n_stream], h_tok, h_act, mode=mode,
                              flags=flags)
         if world > 1:
-            g_tok.copy_(h_tok, non_blocking=True)
-            gatherer.submit(g_tok)
+            gatherer.submit(g_tok)                # tokens are already in the ring (written by the step itself)
 
     for t in range(W):
         host_step(t)
@@ -379,45 +410,81 @@ def main():
             # one launch covers the envs of one micro-batch (B envs when the step is not split)
             alg_bytes = alg_bytes * cfg.num_blocks * args.profile_steps // cnt.value
             ach = alg_bytes / (avg_ms / 1e3) / 1e9
-            traffic = None
-            tpath = os.path.join(ROOT, "profiles", "r01_state_traffic.json")
-            if os.path.exists(tpath):
-                with open(tpath) as fh:
-                    rec = json.load(fh).get(f"{args.model}:{B}:impl{opts.get('state_impl', 1)}")
-                if rec and opts.get("microbatches", 1) == 1:
-                    traffic = rec["traffic"]      # one ncu --set full capture of this kernel at this shape
+            traffic, traffic_src = None, None
+            for tname in ("r02_state_traffic.json", "r01_state_traffic.json"):
+                tpath = os.path.join(ROOT, "profiles", tname)
+                if traffic is None and os.path.exists(tpath):
+                    with open(tpath) as fh:
+                        rec = json.load(fh).get(f"{args.model}:{B}:impl{opts.get('state_impl', 1)}")
+                    if rec and opts.get("microbatches", 1) == 1 and not opts.get("state_fuse"):
+                        traffic = rec["traffic"]      # one ncu --set full capture of this kernel at this shape
+                        traffic_src = f"static: ncu --set full capture recorded in profiles/{tname} (not measured in this run)"
             roof = {"bound": "hbm", "kernel": "mlstm_state_stream_tma_kernel", "achieved": ach,
                     "peak": peaks["hbm_gbs"], "peak_kind": peak_kind, "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "avg_launch_us": avg_ms * 1e3,
+                    "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                    "avg_launch_us": avg_ms * 1e3,
                     "launches_timed": cnt.value, "algorithmic_bytes_per_launch": alg_bytes,
-                    "share_of_step": ms_sum.value / max(step_ms.value, 1e-9)}
+                    # launches per env step x their average duration / the GRAPH-timed step of the headline number
+                    "share_of_step": (cnt.value / args.profile_steps) * avg_ms / max(ms_total / K, 1e-9),
+                    "share_of_step_basis": "per-launch CUDA-event time (eager replay) x launches per step / graph-timed "
+                                           "ms_per_step"}
     if world > 1:
         dist.barrier()
+
+    # ---------------- whole-step roofline: every block's state once + the weights, over the graph-timed step ----
+    state_bytes_step = B * sum(cfg.algorithmic_bytes_per_env_layer_tokenstep() for i in range(cfg.num_blocks)
+                               if not cfg.is_slstm(i))
+    weight_bytes = 2 * cfg.encoder_params()
+    step_s = ms_total / K / 1e3
+    whole = {"algorithmic_bytes_per_step": state_bytes_step + weight_bytes,
+             "achieved": (state_bytes_step + weight_bytes) / step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+             "frac": (state_bytes_step + weight_bytes) / step_s / 1e9 / peaks["hbm_gbs"],
+             "note": "fused 3-token step: C/n/m/conv of every block read + written once per env step (SURVEY.md §8d "
+                     "per-unit bytes x B x L) + bf16 encoder weights once; divided by ms_per_step of `value`"}
+
+    # ---------------- reference on this GPU, eager (rank 0, N == 1 only) ---------------------------------------
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        eng.close()
+        del cache, cache_e
+        torch.cuda.empty_cache()
+        try:
+            v, ms, timed = time_oracle(cfg, sd, B, 30, 3, os.cpu_count() or 1, budget_s=30, domains=args.domains,
+                                       discrete=args.discrete, device="cuda")
+            gpu_eager = {"value": v, "unit": UNIT, "ms_per_step": statistics.mean(ms), "steps": timed, "envs": B,
+                         "what": "the oracle's op sequence (restated xlstm native PyTorch backend + LRAM embed/head), "
+                                 "fp32, run eagerly on this GPU through PyTorch/cuBLAS: token-by-token block stack, "
+                                 "one D2H read of the action per step"}
+        except RuntimeError as ex:          # e.g. out of memory at the largest shards: report, do not fail the bench
+            gpu_eager = {"unavailable": str(ex).splitlines()[0][:200]}
+        torch.cuda.empty_cache()
 
     # ---------------- CPU baseline (rank 0, N == 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        b_cpu = min(B, 8)
+        b_cpu = cpu_sample(B)
         v, ms, timed = time_oracle(cfg, sd, b_cpu, 1000, 2, cores, budget_s=20, domains=args.domains,
                                    discrete=args.discrete)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{b_cpu} of {B} envs x {timed} env steps (~20 s), oracle port of the xlstm native "
-                         f"PyTorch backend, fp32, {cores} threads", "p50_ms_per_step": statistics.median(ms)}
+                         f"PyTorch backend, fp32, {cores} threads (same sample definition as --impl reference)",
+               "p50_ms_per_step": statistics.median(ms)}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args, world),
                            step_mode=args.mode, cuda_graph=not args.no_graph, options=opts,
                            weights="bf16 GEMM matrices", state="fp32", parallelism=f"env-sharded x{world}",
-                           gather=(f"one NCCL all_gather of int32 action tokens per {args.gather_every} env steps, "
-                                   "side stream") if world > 1 else "none (1 GPU)",
-                           l2=(f"state stream {cache.nbytes() / 2**20:.0f} MiB per step exceeds the 126 MB L2"
-                               if cache.nbytes() > 126e6 else
-                               f"state {cache.nbytes() / 2**20:.0f} MiB fits in the 126 MB L2 and is NOT flushed between "
+                           gather=(f"one NCCL all_gather of int32 action tokens per {args.gather_every} env steps, side "
+                                   "stream, straight from the token ring the argmax kernel fills inside the graph")
+                           if world > 1 else "none (1 GPU)",
+                           l2=(f"state stream {cache_nbytes / 2**20:.0f} MiB per step exceeds the 126 MB L2"
+                               if cache_nbytes > 126e6 else
+                               f"state {cache_nbytes / 2**20:.0f} MiB fits in the 126 MB L2 and is NOT flushed between "
                                "steps (a resident state cache is this workload's steady state; latency-bound case)"),
                            l2_prefetch=("library default: 48 MiB of the next block's C warmed into L2 on a side stream "
                                         "while the current block's chain runs, when a block's C is 100-300 MB")
@@ -428,7 +495,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
+            "whole_step": whole,
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": gpu_eager,
         }
         _emit(line)
     eng.close()

@@ -25,7 +25,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define XL_ABI_VERSION 2
+#define XL_ABI_VERSION 3
 
 typedef enum {
   XL_OK = 0,
@@ -168,6 +168,14 @@ int xl_state_layout(const xl_handle* h, int B, int layer, int part, size_t* offs
  * Equivalent to `model.past_key_values = None` (src/callbacks/evaluation.py:124,251,261) per env:
  * zero C, n, m (m starts at 0, not -inf) and the conv window. */
 int xl_state_reset(xl_handle* h, void* state, const uint8_t* env_mask, int B, void* stream);
+
+/* Multi-GPU result gather without a copy between steps. The reference gathers evaluation results across ranks with
+ * gather_object (src/utils/misc.py:159-191); here every xl_policy_step* additionally stores its int32 action tokens in
+ * slot (n % slots) of the caller-owned device ring [slots, B, act_dim], n = steps since the ring was (re)armed +
+ * next_slot; the caller all-gathers ranges of slots whenever it likes. The slot index advances ON THE DEVICE (inside a
+ * captured graph too). ring == NULL disarms. Calling it again with the same ring only re-seeks to next_slot (enqueued on
+ * `stream`); a different ring drops the cached graphs. B must stay the same between arming and gathering. */
+int xl_set_token_ring(xl_handle* h, int32_t* ring, int slots, int next_slot, void* stream);
 
 /* xLSTMEncoder.forward(inputs_embeds=x_in, past_key_values=state, use_cache=True)
  * (src/algos/models/decision_xlstm.py:138-169) == T x xLSTMBlockStack.step + post_blocks_norm.

@@ -23,7 +23,7 @@ XL_FLAG_DISCRETE, XL_FLAG_GRAPH, XL_FLAG_SIMPLE_GEMM, XL_FLAG_STATE_EMBEDS = 1, 
 
 # state parts
 XL_STATE_C, XL_STATE_N, XL_STATE_M, XL_STATE_CONV, XL_STATE_SLSTM = 0, 1, 2, 3, 4
-XL_ABI_VERSION = 2
+XL_ABI_VERSION = 3
 
 # weight ids (xl_weight_id)
 W = dict(
@@ -113,6 +113,8 @@ def load():
     lib.xl_policy_prefill.restype = i32
     lib.xl_linear.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.xl_linear.restype = i32
+    lib.xl_set_token_ring.argtypes = [vp, vp, i32, i32, vp]
+    lib.xl_set_token_ring.restype = i32
     lib.xl_set_option.argtypes = [vp, C.c_char_p, i32]
     lib.xl_set_option.restype = i32
     lib.xl_profile_begin.argtypes = [vp]

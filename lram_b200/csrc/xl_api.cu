@@ -142,6 +142,10 @@ struct xl_handle {
   long long* ll_dbg = nullptr;
   int lowlat_debug = 0;                         // stamp per-phase clocks of CTA 0 ("lowlat_debug"), print with "lowlat_dump"
   size_t ll_smem_limit = 0;
+  // token ring (xl_set_token_ring): every policy step also stores its tokens in slot (step % slots) of this caller-owned
+  // device buffer [slots, B, act_dim]; the step counter lives in counters[0] and is advanced on the device
+  int32_t* tok_ring = nullptr;
+  int tok_slots = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_state;  // start/stop pairs around state-step launches
   std::vector<cudaEvent_t> prof_step;   // start/stop pairs around policy steps
@@ -723,6 +727,8 @@ int run_encoder(xl_handle* h, void* state, const Slice& sl, const float* x_in, f
   return XL_OK;
 }
 
+constexpr unsigned kFlagNoRing = 1u << 30;      // internal: steps run on behalf of xl_policy_prefill leave the token ring alone
+
 // Arguments of one policy step (device pointers for the WHOLE batch of B envs).
 struct StepArgs {
   void* state;
@@ -756,7 +762,7 @@ int policy_front(xl_handle* h, const StepArgs& a, const Slice& sl, float* xt) {
                           (const float*)PW(XL_W_EMBED_RETURN_W), (const float*)PW(XL_W_EMBED_RETURN_B),
                           (const float*)PW(XL_W_EMBED_REWARD_W), (const float*)PW(XL_W_EMBED_REWARD_B),
                           (const float*)PW(XL_W_EMBED_LN_W), (const float*)PW(XL_W_EMBED_LN_B), c.embed_ln_eps, xt,
-                          sl.Bk, d, sl.s);
+                          sl.Bk, d, (h->tok_ring && sl.b0 == 0 && !(a.flags & kFlagNoRing)) ? h->counters : nullptr, sl.s);
   h->launches += 1;
   return XL_OK;
 }
@@ -781,6 +787,8 @@ int policy_back(xl_handle* h, const StepArgs& a, const Slice& sl, const float* h
   float* actions = a.actions + (size_t)sl.b0 * c.act_dim;
   float* logits = a.logits ? a.logits + (size_t)sl.b0 * n_out : nullptr;
   int rc;
+  int32_t* ring = (h->tok_ring && !(a.flags & kFlagNoRing)) ? h->tok_ring + (size_t)sl.b0 * c.act_dim : nullptr;
+  const int64_t ring_stride = (int64_t)a.B * c.act_dim;
   if (discrete) {
     rc = linear(h, ws, xa, PW(XL_W_HEAD_W), (const float*)PW(XL_W_HEAD_B), nullptr, ws.logits, Bk, n_out, d, impl, s);
     if (rc) return rc;
@@ -788,14 +796,14 @@ int policy_back(xl_handle* h, const StepArgs& a, const Slice& sl, const float* h
       XL_CUDA(cudaMemcpyAsync(logits, ws.logits, sizeof(float) * (size_t)Bk * n_out, cudaMemcpyDeviceToDevice, s));
     }
     xl::launch_argmax_tokens(ws.logits, n_out, Bk, c.act_dim, n_out, c.discrete_actions, 1, 0.f, 0.f, tokens,
-                             actions, s);
+                             actions, ring, h->counters, h->tok_slots, ring_stride, s);
   } else {
     float* lg = logits ? logits : ws.logits;
     rc = linear(h, ws, xa, PW(XL_W_HEAD_W), (const float*)PW(XL_W_HEAD_B), nullptr, lg, Bk, n_out, d, impl, s);
     if (rc) return rc;
     const float bw = (c.tok_max_val - c.tok_min_val) / (float)c.action_channels;
     xl::launch_argmax_tokens(lg, h->head_out, Bk, c.act_dim, h->num_actions, c.discrete_actions, 0, bw,
-                             c.tok_min_val, tokens, actions, s);
+                             c.tok_min_val, tokens, actions, ring, h->counters, h->tok_slots, ring_stride, s);
   }
   h->launches += 1;
   return XL_OK;
@@ -1561,7 +1569,7 @@ int xl_policy_prefill(xl_handle* h, void* state, const float* states, const floa
       xl::launch_embed_tokens(ws.s_emb, h->pf_rtg, rewards ? h->pf_rew : nullptr, (const float*)PW(XL_W_EMBED_RETURN_W),
                               (const float*)PW(XL_W_EMBED_RETURN_B), (const float*)PW(XL_W_EMBED_REWARD_W),
                               (const float*)PW(XL_W_EMBED_REWARD_B), (const float*)PW(XL_W_EMBED_LN_W),
-                              (const float*)PW(XL_W_EMBED_LN_B), c.embed_ln_eps, ws.x, rows, d, s);
+                              (const float*)PW(XL_W_EMBED_LN_B), c.embed_ln_eps, ws.x, rows, d, nullptr, s);
       h->launches += 1;
       rc = prefill_blocks(h, state, B, Tc * T, flags, s);
       if (rc) return rc;
@@ -1580,7 +1588,7 @@ int xl_policy_prefill(xl_handle* h, void* state, const float* states, const floa
     StepArgs a;
     a.state = state; a.states = h->d_states; a.rtg = h->d_rtg; a.rewards = rewards ? h->d_rew : nullptr;
     a.tokens = h->d_tokens; a.actions = h->d_actions; a.logits = nullptr; a.hidden = nullptr;
-    a.B = B; a.mode = XL_MODE_FUSED; a.flags = flags & ~(unsigned)XL_FLAG_GRAPH;
+    a.B = B; a.mode = XL_MODE_FUSED; a.flags = (flags & ~(unsigned)XL_FLAG_GRAPH) | kFlagNoRing;
     rc = run_policy(h, a, s);
     if (rc) return rc;
   }
@@ -1594,6 +1602,25 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
   Ws w = ws_slice(h, 0, h->cfg.max_batch);
   w.a_cap = h->a_cap;                  // a stand-alone Linear may use the whole operand planes
   return linear(h, w, A, W_bf16, bias, residual, out, M, N, K, impl, (cudaStream_t)stream);
+}
+
+int xl_set_token_ring(xl_handle* h, int32_t* ring, int slots, int next_slot, void* stream) {
+  if (!h) return fail(XL_ERR_INVALID_ARG, "null handle");
+  if (ring && (slots <= 0 || next_slot < 0 || next_slot >= slots))
+    return fail(XL_ERR_INVALID_ARG, "token ring: slots=%d next_slot=%d", slots, next_slot);
+  if (ring != h->tok_ring || (ring && slots != h->tok_slots)) {
+    // the ring pointer is baked into captured graphs
+    for (auto& g : h->graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+    h->tok_ring = ring;
+    h->tok_slots = ring ? slots : 0;
+  }
+  if (ring) {
+    xl::launch_set_u32(h->counters, (unsigned)next_slot, (cudaStream_t)stream);
+    XL_CUDA(cudaGetLastError());
+  }
+  return XL_OK;
 }
 
 int xl_set_option(xl_handle* h, const char* name, int value) {

@@ -174,10 +174,13 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(
     const float* __restrict__ s_emb, const float* __restrict__ rtg, const float* __restrict__ rew,
     const float* __restrict__ w_ret, const float* __restrict__ b_ret, const float* __restrict__ w_rew,
     const float* __restrict__ b_rew, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-    float eps, float* __restrict__ x, int B, int d) {
+    float eps, float* __restrict__ x, int B, int d, unsigned* __restrict__ step_counter) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   pdl_wait();
+  // token ring (xl_set_token_ring): this is the first kernel of an env step that every step runs -> it advances the
+  // step counter the argmax kernel at the end of the step derives its ring slot from
+  if (step_counter && blockIdx.x == 0 && threadIdx.x == 0) *step_counter = *step_counter + 1;
   pdl_trigger();
   if (row >= 3 * B) return;
   const int b = row / 3, tok = row - 3 * b;
@@ -203,11 +206,12 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(
 
 void launch_embed_tokens(const float* s_emb, const float* rtg, const float* rew, const float* w_ret,
                          const float* b_ret, const float* w_rew, const float* b_rew, const float* ln_w,
-                         const float* ln_b, float eps, float* x, int B, int d, cudaStream_t s) {
+                         const float* ln_b, float eps, float* x, int B, int d, unsigned* step_counter,
+                         cudaStream_t s) {
   const int rows = 3 * B;
   dim3 grid((rows + 7) / 8);
   launch_k(embed_tokens_kernel, grid, dim3(256), 0, s, s_emb, rtg, rew, w_ret, b_ret, w_rew, b_rew, ln_w, ln_b, eps,
-           x, B, d);
+           x, B, d, step_counter);
 }
 
 __global__ void pad_rows_kernel(const float* __restrict__ in, int K, float* __restrict__ out, int Kpad,
@@ -606,7 +610,10 @@ __global__ void __launch_bounds__(256) argmax_tokens_kernel(const float* __restr
                                                             int num_actions, int discrete_actions,
                                                             int discrete, float bin_width, float min_val,
                                                             int32_t* __restrict__ tokens,
-                                                            float* __restrict__ actions) {
+                                                            float* __restrict__ actions,
+                                                            int32_t* __restrict__ ring,
+                                                            const unsigned* __restrict__ step_counter,
+                                                            int ring_slots, int64_t ring_slot_stride) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int nrows = discrete ? B : B * act_dim;
@@ -644,6 +651,9 @@ __global__ void __launch_bounds__(256) argmax_tokens_kernel(const float* __restr
     if (take) { best = ov; bi = oi; best_nan = (on != 0); }
   }
   if (lane == 0) {
+    // token ring: the step's tokens also land in slot (step - 1) % slots of the caller's ring, from where the
+    // multi-GPU result gather picks them up without a copy between graph replays
+    if (ring) ring[(int64_t)((*step_counter - 1u) % (unsigned)ring_slots) * ring_slot_stride + (int64_t)b * act_dim + j] = bi;
     if (discrete) {
       tokens[(int64_t)b * act_dim] = bi;
       actions[(int64_t)b * act_dim] = (float)bi;
@@ -658,12 +668,17 @@ __global__ void __launch_bounds__(256) argmax_tokens_kernel(const float* __restr
 
 void launch_argmax_tokens(const float* logits, int64_t row_pitch, int B, int act_dim, int num_actions,
                           int discrete_actions, int discrete, float bin_width, float min_val,
-                          int32_t* tokens, float* actions, cudaStream_t s) {
+                          int32_t* tokens, float* actions, int32_t* ring, const unsigned* step_counter,
+                          int ring_slots, int64_t ring_slot_stride, cudaStream_t s) {
   const int rows = discrete ? B : B * act_dim;
   dim3 grid((rows + 7) / 8);
   launch_k(argmax_tokens_kernel, grid, dim3(256), 0, s, logits, row_pitch, B, act_dim, num_actions,
-           discrete_actions, discrete, bin_width, min_val, tokens, actions);
+           discrete_actions, discrete, bin_width, min_val, tokens, actions, ring, step_counter, ring_slots,
+           ring_slot_stride);
 }
+
+__global__ void set_u32_kernel(unsigned* p, unsigned v) { *p = v; }
+void launch_set_u32(unsigned* p, unsigned v, cudaStream_t s) { set_u32_kernel<<<1, 1, 0, s>>>(p, v); }
 
 // ------------------------------------------------------------------------------------------------
 // per-env state reset (past_key_values = None for the masked envs; evaluation.py:124,251,261)

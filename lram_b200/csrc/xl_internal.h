@@ -26,7 +26,8 @@ void launch_ln_rows_reduce(float* x, const float* part, int splits, int64_t part
 //   tok 2 = rew[b]*w_rew + b_rew (rew == nullptr -> 0), then embed_ln (weight, bias).
 void launch_embed_tokens(const float* s_emb, const float* rtg, const float* rew, const float* w_ret,
                          const float* b_ret, const float* w_rew, const float* b_rew, const float* ln_w,
-                         const float* ln_b, float eps, float* x, int B, int d, cudaStream_t s);
+                         const float* ln_b, float eps, float* x, int B, int d, unsigned* step_counter,
+                         cudaStream_t s);
 
 // zero-pad states [B, K] -> [B, Kpad]
 void launch_pad_rows(const float* in, int K, float* out, int Kpad, int rows, cudaStream_t s);
@@ -63,7 +64,9 @@ bool launch_conv_qkv_gates(const ConvQkvParams& p, cudaStream_t s);
 // logits row b starts at logits + b*row_pitch.
 void launch_argmax_tokens(const float* logits, int64_t row_pitch, int B, int act_dim, int num_actions,
                           int discrete_actions, int discrete, float bin_width, float min_val,
-                          int32_t* tokens, float* actions, cudaStream_t s);
+                          int32_t* tokens, float* actions, int32_t* ring, const unsigned* step_counter,
+                          int ring_slots, int64_t ring_slot_stride, cudaStream_t s);
+void launch_set_u32(unsigned* p, unsigned v, cudaStream_t s);
 
 void launch_state_reset(float* C, float* n, float* m, float* conv, const uint8_t* mask, int B,
                         int64_t c_per_env, int64_t n_per_env, int64_t m_per_env, int64_t conv_per_env,

@@ -369,6 +369,17 @@ class XLSTMEngine:
         return out
 
     @_on_device
+    def set_token_ring(self, ring: Optional[torch.Tensor], next_slot: int = 0):
+        """Arm (or, `ring=None`, disarm) the token ring: int32 cuda tensor [slots, B, act_dim]; every policy step then
+        also stores its action tokens in slot (steps since arming + next_slot) % slots. Same ring again = re-seek."""
+        if ring is not None:
+            assert ring.is_cuda and ring.dtype == torch.int32 and ring.is_contiguous() and ring.dim() == 3
+            assert ring.shape[2] == self.cfg.act_dim
+        self._token_ring = ring                       # keep it alive
+        L.check(self.lib.xl_set_token_ring(self.handle, _ptr(ring), 0 if ring is None else ring.shape[0],
+                                           int(next_slot), self._stream()))
+
+    @_on_device
     def set_option(self, name: str, value: int):
         L.check(self.lib.xl_set_option(self.handle, name.encode(), int(value)))
 

@@ -60,17 +60,29 @@ class OverlappedTokenGather:
     Requires equal shards (B_local * world == n_envs). `results` collects, per flush, a [world, n_steps, B_local, A]
     tensor when `keep=True` (tests / callers that consume the gathered tokens); `global_view()` puts one step back
     in env order (env i lives on rank i % world). On CPU tensors (gloo) the same logic runs without streams.
+
+    With `engine=` the two staging rings ARE the library's token ring (`xl_set_token_ring`): the argmax kernel at the
+    end of every policy step writes the step's tokens into the ring slot itself (slot index advanced on the device,
+    inside the captured graph), so `submit()` enqueues nothing between two graph replays — it only counts steps and
+    launches the all-gather when a ring is full. Every policy step on that engine must then be followed by exactly
+    one `submit()`.
     """
 
     def __init__(self, B_local: int, act_dim: int, world_size: int, device, group=None, every: int = 1,
-                 keep: bool = False):
+                 keep: bool = False, engine=None):
         assert every >= 1
         self.world, self.group, self.every, self.keep = world_size, group, int(every), keep
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
         self.side = torch.cuda.Stream(device=self.device) if self.cuda else None
         mk = lambda *shape: torch.zeros(*shape, dtype=torch.int32, device=self.device)  # noqa: E731
-        self.stage = [mk(self.every, B_local, act_dim) for _ in range(2)]
+        self.engine = engine
+        if engine is not None:
+            self.ring = mk(2 * self.every, B_local, act_dim)
+            self.stage = [self.ring[: self.every], self.ring[self.every:]]
+            engine.set_token_ring(self.ring, 0)
+        else:
+            self.stage = [mk(self.every, B_local, act_dim) for _ in range(2)]
         self.out = [mk(world_size, self.every, B_local, act_dim) for _ in range(2)]
         self.done = [None, None]
         self.k = 0            # ring being filled
@@ -82,11 +94,12 @@ class OverlappedTokenGather:
         """Queue one step's local tokens [B_local, A]. Returns the gathered [world, n, B_local, A] tensor of the
         flush this call triggered (valid on the compute stream after `finish()` or an event wait), else None."""
         k = self.k
-        if self.cuda:
-            cur = torch.cuda.current_stream(self.device)
-            if self.j == 0 and self.done[k] is not None:
-                cur.wait_event(self.done[k])             # the previous gather of ring k still reads it
-        self.stage[k][self.j].copy_(tokens, non_blocking=True)
+        if self.engine is None:
+            if self.cuda:
+                cur = torch.cuda.current_stream(self.device)
+                if self.j == 0 and self.done[k] is not None:
+                    cur.wait_event(self.done[k])             # the previous gather of ring k still reads it
+            self.stage[k][self.j].copy_(tokens, non_blocking=True)
         self.j += 1
         if self.j == self.every:
             return self._flush()
@@ -120,6 +133,12 @@ class OverlappedTokenGather:
         self.flushes += 1
         self.k ^= 1
         self.j = 0
+        if self.engine is not None:
+            if self.cuda and self.done[self.k] is not None:
+                # the next step writes into ring self.k: its previous gather must have finished reading it
+                torch.cuda.current_stream(self.device).wait_event(self.done[self.k])
+            if n != self.every:
+                self.engine.set_token_ring(self.ring, self.k * self.every)   # partial flush: re-seek the device slot
         return dst
 
     def finish(self):

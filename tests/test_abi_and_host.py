@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 14 and "xl_policy_step" in syms and "xl_mlstm_cell_step" in syms
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/xlstm_b200.h but not exported"
-    assert lib.xl_abi_version() == L.XL_ABI_VERSION == 2
+    assert lib.xl_abi_version() == L.XL_ABI_VERSION == 3
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
