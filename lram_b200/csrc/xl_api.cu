@@ -86,6 +86,9 @@ struct xl_handle {
   int state_stages = 0;                // impl 2 ring depth (0 = default)        (xl_set_option "state_stages")
   int state_ctas_per_sm = 0;           // impl 2 persistent CTAs per SM (0 = 1)  (xl_set_option "state_ctas_per_sm")
   int state_rows_split = 0;            // 0 = automatic                          (xl_set_option "state_rows_split")
+  int fuse_ends = 1;                   // 1: pad+split of the states in one kernel, block 0's pre-norm inside the embed
+                                       // kernel, post-norm of the action rows only + head operand split in one kernel
+                                       // (4 launches fewer per env step); 0: the separate kernels ("fuse_ends")
   int up_fuse = 0;                     // 1: conv / q k v / gate partials run in the proj_up epilogue (fused 3-token step,
                                        // tcgen05 path, no split-K); 0: separate pre-cell kernel ("up_fuse"). Measured on
                                        // B200 (profiles/r02_chain_fusion.md): one launch fewer per block but 3 % SLOWER at
@@ -272,6 +275,9 @@ int smallm_chunks(const xl_handle* h, const Slice& sl, int T, unsigned flags) {
   return xl::smallm_pre_chunks(sl.Bk, T, c.embedding_dim, c.inner_dim, c.num_heads, c.conv_kernel);
 }
 
+constexpr unsigned kFlagLn0DoneEarly = 1u << 29;   // == kFlagLn0Done (defined with the policy-level flags below)
+constexpr unsigned kFlagHeadOnlyEarly = 1u << 28;  // == kFlagHeadOnly
+
 struct BlockPlan {
   bool tc_up, tc_down;
   bool up_fused;                          // proj_up runs with the pre-cell epilogue (no conv/qkv kernel, NCH = inner/64)
@@ -388,6 +394,8 @@ int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned
     return XL_OK;
   }
   if (h->debug_skip & 1) {
+  } else if (i == 0 && (flags & kFlagLn0DoneEarly)) {
+    h->launches -= 1;    // block 0's pre-norm ran inside the embed kernel (policy_front): nothing to launch
   } else if (i > 0 && bp.down_sp > 1 && !is_slstm(h, i - 1)) {
     // the previous (mLSTM) block's proj_down left split-K planes: x += planes, then normalise
     xl::launch_ln_rows_reduce(ws.x, h->part_down, bp.down_sp, (int64_t)M * d, bp.tc_up ? nullptr : ws.xn, d,
@@ -697,7 +705,7 @@ int run_encoder(xl_handle* h, void* state, const Slice& sl, const float* x_in, f
     } else {
       int rc = run_blocks(h, state, sl, T, flags);
       if (rc) return rc;
-      final_norm(h, sl, T, flags, x_out, d);
+      if (!(flags & kFlagHeadOnlyEarly)) final_norm(h, sl, T, flags, x_out, d);
     }
   } else if (mode == XL_MODE_PER_TOKEN) {
     // reference order: for token: for block  (decision_xlstm.py:161-165). x_in may alias x_out: token t's
@@ -727,6 +735,9 @@ int run_encoder(xl_handle* h, void* state, const Slice& sl, const float* x_in, f
   return XL_OK;
 }
 
+constexpr unsigned kFlagLn0Done = 1u << 29;     // internal: the embed kernel already ran block 0's pre-norm (operands in place)
+constexpr unsigned kFlagHeadOnly = 1u << 28;    // internal: nobody reads the hidden states: post_blocks_norm only on the
+                                                // action-token rows, fused with the head's operand split (policy_back)
 constexpr unsigned kFlagNoRing = 1u << 30;      // internal: steps run on behalf of xl_policy_prefill leave the token ring alone
 
 // Arguments of one policy step (device pointers for the WHOLE batch of B envs).
@@ -752,17 +763,32 @@ int policy_front(xl_handle* h, const StepArgs& a, const Slice& sl, float* xt) {
     // discrete_decision_transformer_model.py:187-203, runs in PyTorch/cuDNN before this call)
     s_emb = a.states + (size_t)sl.b0 * d;
   } else {
-    xl::launch_pad_rows(a.states + (size_t)sl.b0 * c.state_dim, c.state_dim, ws.states_pad, h->Kpad, sl.Bk, sl.s);
+    const bool tc = impl != 1 && xl::gemm_tc_supported(sl.Bk, d, h->Kpad) && (size_t)sl.Bk * h->Kpad <= ws.a_cap;
+    if (tc) {       // zero-pad + bf16 hi/lo split in one kernel, straight into the GEMM's operand planes
+      xl::launch_pad_split(a.states + (size_t)sl.b0 * c.state_dim, c.state_dim, ws.a_hi, ws.a_lo, h->Kpad, sl.Bk, sl.s);
+    } else {
+      xl::launch_pad_rows(a.states + (size_t)sl.b0 * c.state_dim, c.state_dim, ws.states_pad, h->Kpad, sl.Bk, sl.s);
+    }
     h->launches += 1;
     int rc = linear(h, ws, ws.states_pad, PW(XL_W_EMBED_STATE_W), (const float*)PW(XL_W_EMBED_STATE_B), nullptr,
-                    ws.s_emb, sl.Bk, d, h->Kpad, impl, sl.s);
+                    ws.s_emb, sl.Bk, d, h->Kpad, impl, sl.s, /*presplit=*/tc);
     if (rc) return rc;
+  }
+  // block 0's pre-norm rides on the embed kernel when the stack will consume it as is (kFlagLn0Done set by run_policy)
+  const float* ln0_w = nullptr;
+  float* xn0 = nullptr;
+  void *hi0 = nullptr, *lo0 = nullptr;
+  if (a.flags & kFlagLn0Done) {
+    const BlockPlan bp = block_plan(h, sl, c.tokens_per_step, a.flags);
+    ln0_w = (const float*)h->blocks[0].w[XL_W_XLSTM_NORM];
+    if (bp.tc_up) { hi0 = ws.a_hi; lo0 = ws.a_lo; } else { xn0 = ws.xn; }
   }
   xl::launch_embed_tokens(s_emb, a.rtg + sl.b0, a.rewards ? a.rewards + sl.b0 : nullptr,
                           (const float*)PW(XL_W_EMBED_RETURN_W), (const float*)PW(XL_W_EMBED_RETURN_B),
                           (const float*)PW(XL_W_EMBED_REWARD_W), (const float*)PW(XL_W_EMBED_REWARD_B),
                           (const float*)PW(XL_W_EMBED_LN_W), (const float*)PW(XL_W_EMBED_LN_B), c.embed_ln_eps, xt,
-                          sl.Bk, d, (h->tok_ring && sl.b0 == 0 && !(a.flags & kFlagNoRing)) ? h->counters : nullptr, sl.s);
+                          sl.Bk, d, (h->tok_ring && sl.b0 == 0 && !(a.flags & kFlagNoRing)) ? h->counters : nullptr,
+                          ln0_w, c.ln_eps, xn0, hi0, lo0, sl.s);
   h->launches += 1;
   return XL_OK;
 }
@@ -778,7 +804,17 @@ int policy_back(xl_handle* h, const StepArgs& a, const Slice& sl, const float* h
   const int Bk = sl.Bk;
   // gather row b*T + pos to a dense [Bk,d], then Linear(d -> 2192 / 274)
   float* xa = ws.s_emb;  // reuse [Bk,d]
-  xl::launch_copy_rows(hid + (size_t)c.action_token_pos * d, (int64_t)T * d, xa, d, Bk, d, s);
+  const bool head_only = (a.flags & kFlagHeadOnly) != 0;
+  if (head_only) {
+    // post_blocks_norm of the action-token rows only (+ the last proj_down's pending planes), emitted as the head
+    // GEMM's bf16 hi/lo operand planes: one launch instead of norm-all-rows + gather + split
+    const BlockPlan bp = block_plan(h, sl, T, a.flags);
+    const int pend = is_slstm(h, c.num_blocks - 1) ? 1 : bp.down_sp;
+    xl::launch_ln_rows_gather(ws.x, h->part_down, pend, (int64_t)Bk * T * d, (const float*)PW(XL_W_POST_NORM), c.ln_eps,
+                              Bk, d, T, c.action_token_pos, ws.a_hi, ws.a_lo, s);
+  } else {
+    xl::launch_copy_rows(hid + (size_t)c.action_token_pos * d, (int64_t)T * d, xa, d, Bk, d, s);
+  }
   h->launches += 1;
   const bool discrete = (a.flags & XL_FLAG_DISCRETE) != 0;
   // discrete branch only needs the first num_actions logits (multi_domain_discrete_dt_model.py:99-101)
@@ -790,7 +826,8 @@ int policy_back(xl_handle* h, const StepArgs& a, const Slice& sl, const float* h
   int32_t* ring = (h->tok_ring && !(a.flags & kFlagNoRing)) ? h->tok_ring + (size_t)sl.b0 * c.act_dim : nullptr;
   const int64_t ring_stride = (int64_t)a.B * c.act_dim;
   if (discrete) {
-    rc = linear(h, ws, xa, PW(XL_W_HEAD_W), (const float*)PW(XL_W_HEAD_B), nullptr, ws.logits, Bk, n_out, d, impl, s);
+    rc = linear(h, ws, xa, PW(XL_W_HEAD_W), (const float*)PW(XL_W_HEAD_B), nullptr, ws.logits, Bk, n_out, d, impl, s,
+                head_only);
     if (rc) return rc;
     if (logits) {
       XL_CUDA(cudaMemcpyAsync(logits, ws.logits, sizeof(float) * (size_t)Bk * n_out, cudaMemcpyDeviceToDevice, s));
@@ -799,7 +836,7 @@ int policy_back(xl_handle* h, const StepArgs& a, const Slice& sl, const float* h
                              actions, ring, h->counters, h->tok_slots, ring_stride, s);
   } else {
     float* lg = logits ? logits : ws.logits;
-    rc = linear(h, ws, xa, PW(XL_W_HEAD_W), (const float*)PW(XL_W_HEAD_B), nullptr, lg, Bk, n_out, d, impl, s);
+    rc = linear(h, ws, xa, PW(XL_W_HEAD_W), (const float*)PW(XL_W_HEAD_B), nullptr, lg, Bk, n_out, d, impl, s, head_only);
     if (rc) return rc;
     const float bw = (c.tok_max_val - c.tok_min_val) / (float)c.action_channels;
     xl::launch_argmax_tokens(lg, h->head_out, Bk, c.act_dim, h->num_actions, c.discrete_actions, 0, bw,
@@ -829,6 +866,18 @@ int run_policy(xl_handle* h, const StepArgs& a, cudaStream_t s) {
   if (MB == 1) {
     const Slice sl = make_slice(h, a.B, 0, a.B, s);
     float* xt = (a.mode == XL_MODE_FUSED) ? sl.ws.x : sl.ws.xtok;
+    // launch-saving fusions of the step's head and tail (fused mode, multi-kernel stack)
+    StepArgs af = a;
+    size_t ll_smem = 0;
+    if (h->fuse_ends && a.mode == XL_MODE_FUSED && !h->debug_skip && !lowlat_eligible(h, sl, T, a.flags, &ll_smem)) {
+      if (!is_slstm(h, 0) && !smallm_chunks(h, sl, T, a.flags)) af.flags |= kFlagLn0Done;
+      const int impl = (a.flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
+      const int n_out = (a.flags & XL_FLAG_DISCRETE) ? h->num_actions : h->head_out;
+      if (!a.hidden && impl != 1 && xl::gemm_tc_supported(a.B, n_out, d) && (size_t)a.B * d <= sl.ws.a_cap &&
+          d <= 4096)
+        af.flags |= kFlagHeadOnly;
+    }
+    const StepArgs& a = af;        // (shadows the parameter for the rest of this branch)
     int rc = policy_front(h, a, sl, xt);
     if (rc) return rc;
     float* hid = a.hidden ? a.hidden : sl.ws.hid;
@@ -1569,7 +1618,8 @@ int xl_policy_prefill(xl_handle* h, void* state, const float* states, const floa
       xl::launch_embed_tokens(ws.s_emb, h->pf_rtg, rewards ? h->pf_rew : nullptr, (const float*)PW(XL_W_EMBED_RETURN_W),
                               (const float*)PW(XL_W_EMBED_RETURN_B), (const float*)PW(XL_W_EMBED_REWARD_W),
                               (const float*)PW(XL_W_EMBED_REWARD_B), (const float*)PW(XL_W_EMBED_LN_W),
-                              (const float*)PW(XL_W_EMBED_LN_B), c.embed_ln_eps, ws.x, rows, d, nullptr, s);
+                              (const float*)PW(XL_W_EMBED_LN_B), c.embed_ln_eps, ws.x, rows, d, nullptr, nullptr, 0.f,
+                              nullptr, nullptr, nullptr, s);
       h->launches += 1;
       rc = prefill_blocks(h, state, B, Tc * T, flags, s);
       if (rc) return rc;
@@ -1637,6 +1687,8 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "state_rows_split")) {
     if (value < 0 || value > 32) return fail(XL_ERR_INVALID_ARG, "state_rows_split must be in [0, 32]");
     h->state_rows_split = value;
+  } else if (!strcmp(name, "fuse_ends")) {
+    h->fuse_ends = value ? 1 : 0;
   } else if (!strcmp(name, "up_fuse")) {
     h->up_fuse = value ? 1 : 0;
   } else if (!strcmp(name, "state_fuse")) {

@@ -87,9 +87,11 @@ __global__ void __launch_bounds__(1024) ln_rows_cta_kernel(const float* __restri
                                                            float eps, int d, __nv_bfloat16* __restrict__ a_hi,
                                                            __nv_bfloat16* __restrict__ a_lo,
                                                            const float* __restrict__ part, int splits,
-                                                           int64_t part_stride, float* __restrict__ x_out) {
+                                                           int64_t part_stride, float* __restrict__ x_out,
+                                                           int src_row_mul, int src_row_off) {
   __shared__ float red[32];
-  const int row = blockIdx.x;
+  const int row = blockIdx.x;                             // output row
+  const int srow = row * src_row_mul + src_row_off;       // input row (gather: e.g. the action-token row of each env)
   const int i = threadIdx.x;
   const bool ok = i < (d >> 2);
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -101,15 +103,15 @@ __global__ void __launch_bounds__(1024) ln_rows_cta_kernel(const float* __restri
   pdl_wait();
   pdl_trigger();
   if (ok) {
-    v = reinterpret_cast<const float4*>(in + (int64_t)row * in_stride)[i];
+    v = reinterpret_cast<const float4*>(in + (int64_t)srow * in_stride)[i];
     if (part) {
       // residual stream += split-K planes of proj_down, in plane order (deterministic); written back in place
-      const float4* pp = reinterpret_cast<const float4*>(part + (int64_t)row * d) + i;
+      const float4* pp = reinterpret_cast<const float4*>(part + (int64_t)srow * d) + i;
       for (int z = 0; z < splits; ++z) {
         const float4 a4 = pp[(z * part_stride) >> 2];
         v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
       }
-      reinterpret_cast<float4*>(x_out + (int64_t)row * in_stride)[i] = v;
+      if (x_out) reinterpret_cast<float4*>(x_out + (int64_t)srow * in_stride)[i] = v;
     }
   }
   const float mean = block_sum((v.x + v.y) + (v.z + v.w), red) / (float)d;
@@ -146,7 +148,7 @@ void launch_ln_rows(const float* in, int64_t in_stride, float* out, int64_t out_
     const int threads = (((d >> 2) + 31) / 32) * 32;
     launch_k(ln_rows_cta_kernel, dim3(rows), dim3(threads), 0, s, in, in_stride, out, out_stride, w, bias,
              residual_weight, eps, d, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, (const float*)nullptr, 0,
-             (int64_t)0, (float*)nullptr);
+             (int64_t)0, (float*)nullptr, 1, 0);
     return;
   }
   const int warps_per_block = 8;
@@ -162,7 +164,20 @@ void launch_ln_rows_reduce(float* x, const float* part, int splits, int64_t part
   const int threads = (((d >> 2) + 31) / 32) * 32;     // d <= 4096 (checked where the split is planned)
   launch_k(ln_rows_cta_kernel, dim3(rows), dim3(threads), 0, s, (const float*)x, (int64_t)d, out, out_stride, w,
            (const float*)nullptr, 1, eps, d, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, part, splits, part_stride,
-           x);
+           x, 1, 0);
+}
+
+// post_blocks_norm of ONE token row per env (the action-token row: x row b*row_mul + row_off, plus the pending
+// split-K planes of the last proj_down) -> dense [rows, d] bf16 hi/lo operand planes of the action head. Replaces
+// norm-all-rows + row gather + split when the caller does not ask for the hidden states.
+void launch_ln_rows_gather(const float* x, const float* part, int splits, int64_t part_stride, const float* w,
+                           float eps, int rows, int d, int row_mul, int row_off, void* a_hi, void* a_lo,
+                           cudaStream_t s) {
+  if (rows <= 0) return;
+  const int threads = (((d >> 2) + 31) / 32) * 32;
+  launch_k(ln_rows_cta_kernel, dim3(rows), dim3(threads), 0, s, x, (int64_t)d, (float*)nullptr, (int64_t)0, w,
+           (const float*)nullptr, 1, eps, d, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, splits > 1 ? part : nullptr,
+           splits, part_stride, (float*)nullptr, row_mul, row_off);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -174,7 +189,9 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(
     const float* __restrict__ s_emb, const float* __restrict__ rtg, const float* __restrict__ rew,
     const float* __restrict__ w_ret, const float* __restrict__ b_ret, const float* __restrict__ w_rew,
     const float* __restrict__ b_rew, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-    float eps, float* __restrict__ x, int B, int d, unsigned* __restrict__ step_counter) {
+    float eps, float* __restrict__ x, int B, int d, unsigned* __restrict__ step_counter,
+    const float* __restrict__ ln0_w, float ln0_eps, float* __restrict__ xn0, __nv_bfloat16* __restrict__ a_hi,
+    __nv_bfloat16* __restrict__ a_lo) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   pdl_wait();
@@ -202,16 +219,126 @@ __global__ void __launch_bounds__(256) embed_tokens_kernel(
   const float rstd = rsqrtf(q / (float)d + eps);
   float* o = x + (int64_t)row * d;
   for (int i = lane; i < d; i += 32) o[i] = (val(i) - mean) * rstd * ln_w[i] + ln_b[i];
+  if (!ln0_w) return;
+  // the first block's pre-norm (xlstm LayerNorm, gamma = 1 + w) on the row this warp just produced: the block stack's
+  // first LayerNorm launch disappears. Each lane re-reads only what it wrote itself.
+  float s2 = 0.f;
+  for (int i = lane; i < d; i += 32) s2 += o[i];
+  s2 = warp_sum(s2);
+  const float mean2 = s2 / (float)d;
+  float q2 = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float a = o[i] - mean2;
+    q2 += a * a;
+  }
+  q2 = warp_sum(q2);
+  const float rstd2 = rsqrtf(q2 / (float)d + ln0_eps);
+  for (int i = lane; i < d; i += 32) {
+    const float r = (o[i] - mean2) * rstd2 * (1.f + ln0_w[i]);
+    if (xn0) xn0[(int64_t)row * d + i] = r;
+    if (a_hi) {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(r);
+      a_hi[(int64_t)row * d + i] = hi;
+      a_lo[(int64_t)row * d + i] = __float2bfloat16_rn(r - __bfloat162float(hi));
+    }
+  }
+}
+
+// CTA-per-row version (d <= 4096): one float4 per thread held in registers, block reductions; the token row is read
+// once and both LayerNorms (embed_ln, then optionally block 0's pre-norm) run on registers.
+__global__ void __launch_bounds__(1024) embed_tokens_cta_kernel(
+    const float* __restrict__ s_emb, const float* __restrict__ rtg, const float* __restrict__ rew,
+    const float* __restrict__ w_ret, const float* __restrict__ b_ret, const float* __restrict__ w_rew,
+    const float* __restrict__ b_rew, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+    float eps, float* __restrict__ x, int B, int d, unsigned* __restrict__ step_counter,
+    const float* __restrict__ ln0_w, float ln0_eps, float* __restrict__ xn0, __nv_bfloat16* __restrict__ a_hi,
+    __nv_bfloat16* __restrict__ a_lo) {
+  __shared__ float red[32];
+  const int row = blockIdx.x, i = threadIdx.x;
+  const bool ok = i < (d >> 2);
+  const int b = row / 3, tok = row - 3 * b;
+  // weights before the dependency wait
+  float4 g = make_float4(0.f, 0.f, 0.f, 0.f), bb = g, wv = g, bv = g, g0 = g;
+  if (ok) {
+    g = reinterpret_cast<const float4*>(ln_w)[i];
+    bb = reinterpret_cast<const float4*>(ln_b)[i];
+    if (tok != 0) {
+      wv = reinterpret_cast<const float4*>(tok == 1 ? w_ret : w_rew)[i];
+      bv = reinterpret_cast<const float4*>(tok == 1 ? b_ret : b_rew)[i];
+    }
+    if (ln0_w) g0 = reinterpret_cast<const float4*>(ln0_w)[i];
+  }
+  pdl_wait();
+  if (step_counter && blockIdx.x == 0 && threadIdx.x == 0) *step_counter = *step_counter + 1;   // token ring slot
+  pdl_trigger();
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok) {
+    if (tok == 0) {
+      v = reinterpret_cast<const float4*>(s_emb + (int64_t)b * d)[i];
+    } else {
+      const float scal = (tok == 1) ? rtg[b] : (rew ? rew[b] : 0.f);
+      v = make_float4(fmaf(scal, wv.x, bv.x), fmaf(scal, wv.y, bv.y), fmaf(scal, wv.z, bv.z), fmaf(scal, wv.w, bv.w));
+    }
+  }
+  float mean = block_sum((v.x + v.y) + (v.z + v.w), red) / (float)d;
+  float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+  float rstd = rsqrtf(block_sum(ok ? (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3) : 0.f, red) / (float)d + eps);
+  float4 o = make_float4(a0 * rstd * g.x + bb.x, a1 * rstd * g.y + bb.y, a2 * rstd * g.z + bb.z, a3 * rstd * g.w + bb.w);
+  if (ok) reinterpret_cast<float4*>(x + (int64_t)row * d)[i] = o;
+  if (!ln0_w) return;
+  if (!ok) o = make_float4(0.f, 0.f, 0.f, 0.f);
+  mean = block_sum((o.x + o.y) + (o.z + o.w), red) / (float)d;
+  a0 = o.x - mean; a1 = o.y - mean; a2 = o.z - mean; a3 = o.w - mean;
+  rstd = rsqrtf(block_sum(ok ? (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3) : 0.f, red) / (float)d + ln0_eps);
+  if (!ok) return;
+  const float r[4] = {a0 * rstd * (1.f + g0.x), a1 * rstd * (1.f + g0.y), a2 * rstd * (1.f + g0.z), a3 * rstd * (1.f + g0.w)};
+  if (xn0) reinterpret_cast<float4*>(xn0 + (int64_t)row * d)[i] = make_float4(r[0], r[1], r[2], r[3]);
+  if (a_hi) {
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = __float2bfloat16_rn(r[j]);
+      lo[j] = __float2bfloat16_rn(r[j] - __bfloat162float(hi[j]));
+    }
+    const int64_t base = (int64_t)row * d + 4 * i;
+    *reinterpret_cast<uint2*>(a_hi + base) = *reinterpret_cast<uint2*>(hi);
+    *reinterpret_cast<uint2*>(a_lo + base) = *reinterpret_cast<uint2*>(lo);
+  }
 }
 
 void launch_embed_tokens(const float* s_emb, const float* rtg, const float* rew, const float* w_ret,
                          const float* b_ret, const float* w_rew, const float* b_rew, const float* ln_w,
                          const float* ln_b, float eps, float* x, int B, int d, unsigned* step_counter,
-                         cudaStream_t s) {
+                         const float* ln0_w, float ln0_eps, float* xn0, void* a_hi, void* a_lo, cudaStream_t s) {
   const int rows = 3 * B;
+  if (d <= 4096 && (d & 3) == 0) {
+    const int threads = (((d >> 2) + 31) / 32) * 32;
+    launch_k(embed_tokens_cta_kernel, dim3(rows), dim3(threads), 0, s, s_emb, rtg, rew, w_ret, b_ret, w_rew, b_rew, ln_w,
+             ln_b, eps, x, B, d, step_counter, ln0_w, ln0_eps, xn0, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo);
+    return;
+  }
   dim3 grid((rows + 7) / 8);
   launch_k(embed_tokens_kernel, grid, dim3(256), 0, s, s_emb, rtg, rew, w_ret, b_ret, w_rew, b_rew, ln_w, ln_b, eps,
-           x, B, d, step_counter);
+           x, B, d, step_counter, ln0_w, ln0_eps, xn0, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo);
+}
+
+// zero-pad states [rows, K] -> bf16 hi/lo operand planes [rows, Kpad] of the embed_state GEMM (pad + split in one)
+__global__ void pad_split_kernel(const float* __restrict__ in, int K, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, int Kpad, int rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
+  if (i >= (int64_t)rows * Kpad) return;
+  const int r = (int)(i / Kpad), c = (int)(i - (int64_t)r * Kpad);
+  const float v = c < K ? in[(int64_t)r * K + c] : 0.f;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+void launch_pad_split(const float* in, int K, void* hi, void* lo, int Kpad, int rows, cudaStream_t s) {
+  const int64_t n = (int64_t)rows * Kpad;
+  launch_k(pad_split_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, s, in, K, (__nv_bfloat16*)hi,
+           (__nv_bfloat16*)lo, Kpad, rows);
 }
 
 __global__ void pad_rows_kernel(const float* __restrict__ in, int K, float* __restrict__ out, int Kpad,

@@ -27,7 +27,12 @@ void launch_ln_rows_reduce(float* x, const float* part, int splits, int64_t part
 void launch_embed_tokens(const float* s_emb, const float* rtg, const float* rew, const float* w_ret,
                          const float* b_ret, const float* w_rew, const float* b_rew, const float* ln_w,
                          const float* ln_b, float eps, float* x, int B, int d, unsigned* step_counter,
-                         cudaStream_t s);
+                         const float* ln0_w, float ln0_eps, float* xn0, void* a_hi, void* a_lo, cudaStream_t s);
+// ln0_w != nullptr: also the first block's pre-norm of the produced rows -> xn0 (fp32) and/or bf16 hi/lo planes
+void launch_pad_split(const float* in, int K, void* hi, void* lo, int Kpad, int rows, cudaStream_t s);
+void launch_ln_rows_gather(const float* x, const float* part, int splits, int64_t part_stride, const float* w,
+                           float eps, int rows, int d, int row_mul, int row_off, void* a_hi, void* a_lo,
+                           cudaStream_t s);
 
 // zero-pad states [B, K] -> [B, Kpad]
 void launch_pad_rows(const float* in, int K, float* out, int Kpad, int rows, cudaStream_t s);

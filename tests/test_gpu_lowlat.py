@@ -159,5 +159,6 @@ def test_smallm_front_kernel_equals_three_kernel_path(name, B, mode):
         assert _rel(res[1][2][f"block_{i}"]["conv_state"][0].cpu(), res[0][2][f"block_{i}"]["conv_state"][0].cpu()) < 1e-5
     # two launches fewer per block and token pass (LN and conv/qkv folded into the GEMV kernel)
     passes = 1 if mode == L.XL_MODE_FUSED else cfg.tokens_per_step
-    assert launches[0] - launches[1] >= 2 * cfg.num_blocks * passes, launches
+    # (the multi-kernel path itself saves block 0's LayerNorm launch in fused mode: it rides on the embed kernel)
+    assert launches[0] - launches[1] >= 2 * cfg.num_blocks * passes - 1, launches
     eng.close()

@@ -788,3 +788,41 @@ def test_chain_fusion_options_equal_default(name, B, opts):
     assert _rel(b[2], a[2]) < 1e-4 and _rel(b[3], a[3]) < 1e-4 and _rel(b[4], a[4]) < 1e-5
     assert b[5] < a[5]                                   # fewer launches: a kernel per block really disappeared
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# chunkwise context prefill vs SEQUENTIAL oracle stepping on an S = 3000-token prefix
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["16M", "48M"])
+def test_prefill_3000_token_prefix_vs_sequential_oracle(name):
+    """`xl_policy_prefill` over 1000 timesteps = 3000 tokens (s, rtg, r) of one env — chunk after chunk through the
+    tensor-core sequence cell — must leave the recurrent state where 3000 sequential oracle token steps leave it
+    (`xLSTMBlockStack.step` in a loop, decision_xlstm.py:161-165: the only way the reference reaches such a context),
+    and the rollout that follows must produce the oracle's action tokens bit-exactly. 206M: tools/bench_prefill.py --check."""
+    from oracle import xlstm_oracle as O
+    Tn, Tr = 1000, 3
+    cfg, sd, eng = _engine(name, 1, seed=6)
+    ora = O.OraclePolicy(cfg, sd)
+    states, rtg, _ = make_stream(cfg, range(1), Tn + Tr, domains="dmcontrol", seed=2024)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    cache = eng.new_state(1)
+    eng.policy_prefill(cache, dev(states[:Tn].transpose(1, 0, 2)), dev(rtg[:Tn].T))
+    pkv = None
+    for t in range(Tn):                                   # 3000 sequential token steps on the CPU, fp32
+        x = ora.embed(torch.from_numpy(states[t]), torch.from_numpy(rtg[t]), torch.zeros(1))
+        _, pkv = ora.encoder.forward_cached(x, pkv)
+    exp = cache.to_past_key_values()
+    for i in range(cfg.num_blocks):
+        c, n, m = pkv[f"block_{i}"]["mlstm_state"]
+        ce, ne, me = exp[f"block_{i}"]["mlstm_state"]
+        assert _rel(ce.cpu(), c) < REL_TOL and _rel(ne.cpu(), n) < REL_TOL, f"block {i}"
+        assert (me.cpu() - m).abs().max() < 1e-3 * max(1.0, m.abs().max().item()), f"block {i}"
+        assert _rel(exp[f"block_{i}"]["conv_state"][0].cpu(), pkv[f"block_{i}"]["conv_state"][0]) < 1e-4
+    for t in range(Tn, Tn + Tr):
+        out = eng.policy_step(cache, dev(states[t]), dev(rtg[t]), want_hidden=True, want_logits=True)
+        ref = ora.step(torch.from_numpy(states[t]), torch.from_numpy(rtg[t]), past_key_values=pkv)
+        pkv = ref["past_key_values"]
+        margins = _margin_ok(ref["action_logits"], out["action_tokens"].cpu().long(), ref["action_tokens"])
+        assert not margins, f"token mismatches after the prefill at t={t}: oracle top-2 margins {margins}"
+        assert _rel(out["last_hidden_state"].cpu(), ref["last_hidden_state"]) < REL_TOL
+    eng.close()
