@@ -1687,6 +1687,11 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "state_rows_split")) {
     if (value < 0 || value > 32) return fail(XL_ERR_INVALID_ARG, "state_rows_split must be in [0, 32]");
     h->state_rows_split = value;
+  } else if (!strcmp(name, "gemm_bm")) {
+    if (value != 0 && value != 64 && value != 128) return fail(XL_ERR_INVALID_ARG, "gemm_bm must be 0, 64 or 128");
+    xl::g_gemm_bm = value;               // process-wide
+  } else if (!strcmp(name, "gemm_m64_layout")) {
+    xl::gemm_tc_set_m64_layout(value);   // process-wide probe
   } else if (!strcmp(name, "fuse_ends")) {
     h->fuse_ends = value ? 1 : 0;
   } else if (!strcmp(name, "up_fuse")) {

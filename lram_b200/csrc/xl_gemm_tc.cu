@@ -72,8 +72,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 
 // kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = BLOCK_N.
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m = BLOCK_M) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -86,21 +86,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
-template <int BLOCK_N, int kStages>
+// kBM = rows of the MMA tile: 128, or 64 for skinny batches (M <= 192 rows leave a quarter of a second 128-row tile
+// empty, and — what matters at these sizes — a 64-row tile halves the A bytes per k-block, so the ring holds twice as
+// many k-blocks in flight: the K loop of these GEMMs is bound by (k-blocks / ring depth) L2 round trips).
+template <int BLOCK_N, int kStages, int kBM = BLOCK_M>
 struct Smem {
-  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kABytes = kBM * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = 2 * kABytes + kBBytes;
   static constexpr int kTotal = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, int kStages>
+template <int BLOCK_N, int kStages, int kBM>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
                const float* __restrict__ residual, float* __restrict__ out, int M, int N, int K,
-               long long split_stride) {
-  using S = Smem<BLOCK_N, kStages>;
+               long long split_stride, int m64_rows_contiguous) {
+  using S = Smem<BLOCK_N, kStages, kBM>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = base + kStages * S::kStageBytes;     // full[kStages], empty[kStages], tmem_full
@@ -110,7 +113,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const uint32_t tmem_full_bar = bar_base + 8 * (2 * kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * BLOCK_M;
+  const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * kBM;
   // split-K: blockIdx.z owns k-blocks [kb0, kb0 + num_kb) and writes its raw partial tile to the plane
   // out + blockIdx.z * split_stride; the CONSUMER kernels (LayerNorm, conv/qkv, finalize) add the planes in
   // plane order, so there is no reduction step, no atomics and no inter-CTA synchronisation here.
@@ -177,7 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+      constexpr uint32_t idesc = make_idesc(BLOCK_N, kBM);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
@@ -203,11 +206,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   // TMEM -> registers -> (bias, residual: only when splits == 1, host-enforced) -> global, 32 columns at a time.
   const bool is_epi = warp >= 2;
   const int q = warp & 3;
-  const int row = m0 + q * 32 + lane;
+  // M = 128: accumulator row r lives in TMEM lane r. M = 64 (cta_group::1): the 64 rows occupy lanes 0-15 of each
+  // 32-lane quarter (row r -> lane 32*(r/16) + r%16), so each epilogue warp owns 16 rows in its lanes 0..15.
+  // (m64_rows_contiguous = 1 selects the alternative reading, rows = lanes 0..63; kept as a probe, see the unit test.)
+  int lrow = q * 32 + lane;
+  bool row_ok = true;
+  if (kBM == 64) {
+    if (m64_rows_contiguous) { row_ok = q < 2; }
+    else { lrow = q * 16 + lane; row_ok = lane < 16; }
+  }
+  const int row = m0 + lrow;
   out += (long long)blockIdx.z * split_stride;
 
   auto store_chunk = [&](const float (&v)[32], int c) {       // bias + residual + store of 32 columns
-    if (row >= M) return;
+    if (row >= M || !row_ok) return;
     const int col0 = n0 + c;
     float* orow = out + (int64_t)row * N + col0;
     const float* rrow = residual ? residual + (int64_t)row * N + col0 : nullptr;
@@ -671,14 +683,16 @@ static bool make_map(CUtensorMap* m, const void* ptr, int rows, int K, int box_r
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N, int kStages>
+int g_m64_rows_contiguous = 0;     // xl_set_option("gemm_m64_layout"): probe of the M = 64 accumulator layout
+
+template <int BLOCK_N, int kStages, int kBM = BLOCK_M>
 static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& ml, const CUtensorMap& mw, const float* bias,
                           const float* residual, float* out, int M, int N, int K, int splits, long long split_stride,
                           cudaStream_t s) {
-  using S = Smem<BLOCK_N, kStages>;
-  if (cudaError_t e = ensure_dyn_smem<&gemm_tc_kernel<BLOCK_N, kStages>>(S::kTotal); e != cudaSuccess) return e;
+  using S = Smem<BLOCK_N, kStages, kBM>;
+  if (cudaError_t e = ensure_dyn_smem<&gemm_tc_kernel<BLOCK_N, kStages, kBM>>(S::kTotal); e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((N + BLOCK_N - 1) / BLOCK_N, (M + BLOCK_M - 1) / BLOCK_M, splits);
+  cfg.gridDim = dim3((N + BLOCK_N - 1) / BLOCK_N, (M + kBM - 1) / kBM, splits);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = s;
@@ -691,11 +705,14 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& ml, const CU
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kStages>, ma, ml, mw, bias, residual, out, M, N, K,
-                            split_stride);
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kStages, kBM>, ma, ml, mw, bias, residual, out, M, N, K,
+                            split_stride, g_m64_rows_contiguous);
 }
 
 }  // namespace tc
+
+int g_gemm_bm = 0;     // xl_set_option("gemm_bm"): 64 = 64-row MMA tiles where the shape allows, 0 / 128 = 128-row tiles
+void gemm_tc_set_m64_layout(int contiguous) { tc::g_m64_rows_contiguous = contiguous ? 1 : 0; }
 
 bool gemm_tc_supported(int M, int N, int K) { return K % tc::BLOCK_K == 0 && K >= tc::BLOCK_K && M >= 1 && N >= 8; }
 
@@ -780,10 +797,17 @@ cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat
     int sp;
     gemm_tc_plan(M, N, K, num_sms, 1, &bn, &sp);
   }
+  // 64-row MMA tiles (option "gemm_bm" = 64): half the A bytes per k-block and a ring twice as deep (9 stages), no
+  // empty quarter tile at M = 192. Bit-identical results; measured 1.2 % SLOWER on the 48M x 64 step (3 row tiles read
+  // W three times: 42 MB instead of 38 MB of L2 -> SM traffic for proj_up, and these GEMMs sit at the aggregate L2
+  // read rate), equal elsewhere (profiles/r02_chain_fusion.md) -> not the default.
+  const bool bm64 = g_gemm_bm == 64 && !low_smem && bn == 64 && M > 16;
   CUtensorMap ma, ml, mw;
-  if (!tc::make_map(&ma, a_hi, M, K, tc::BLOCK_M) || !tc::make_map(&ml, a_lo, M, K, tc::BLOCK_M) ||
+  const int box_m = bm64 ? 64 : tc::BLOCK_M;
+  if (!tc::make_map(&ma, a_hi, M, K, box_m) || !tc::make_map(&ml, a_lo, M, K, box_m) ||
       !tc::make_map(&mw, W, N, K, bn))
     return cudaErrorUnknown;
+  if (bm64) return tc::launch<64, 9, 64>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
   if (low_smem) {
     // shallow rings (<= 110 KB): the CTA must fit beside a resident state-stream CTA of another micro-batch
     switch (bn) {
