@@ -249,8 +249,15 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
  *   "pdl": [1] programmatic dependent launch of every kernel (process-wide)
  *   "l2_prefetch_mb": [-1 = automatic] MiB of the next block's C warmed into L2 on a side stream while the current
  *                   block's latency-bound chain runs (0 = off; automatic = 48 when a block's C is 100..300 MB)
- *   "lowlat": [0] small-batch path: whole block stack as one persistent cooperative kernel for B*T <= 16 rows
- *                   (parity-tested; measured slower than the default on B200, see profiles/r01_lowlat_persistent.md)
+ *   "state_fuse": [0] finalize (n/m update, GroupNorm, output gate) inside the state stream kernel through one
+ *                   thread-block cluster per (env, head): 1 = every CTA finishes its 128 columns, statistics over DSMEM;
+ *                   2 = numerators pushed to rank 0, which finalizes the head. One launch fewer per block; measured
+ *                   +1-2 % at 206M x 128 / 48M x 256 envs, -5 % at 48M x 64 (profiles/r02_chain_fusion.md)
+ *   "up_fuse": [0] conv + SiLU + q/k/v + gate partials in the proj_up epilogue (gemm_up_conv_kernel); one launch fewer
+ *                   per block, x_m never leaves the chip; measured 3-9 % slower (more CTAs re-read the A planes from L2)
+ *   "gemm_bm": [0] 64 = 64-row tcgen05 tiles for proj_up / proj_down (bit-identical; measured 1 % slower at 48M x 64)
+ *   "fuse_ends": [1] pad+split of the states in one kernel, block 0's pre-norm inside the embed kernel, post-norm of the
+ *                   action-token rows only fused with the head's operand split (3-4 launches fewer per env step)
  *   "conv_impl": [0] pre-cell kernel (conv + SiLU + q/k/v + gate partials): 0 = one thread per 4-channel block walking
  *                   the step's tokens in sequence, 1 = one thread per (4-channel block, token); bit-identical outputs, measured 5 %
  *                   slower on the 48M x 64 step (3x the per-thread weight loads), kept for A/B

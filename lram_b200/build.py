@@ -18,7 +18,11 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libxlstm_b200.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
 
-NVCC_FLAGS = [
+# XL_DEBUG_OPTIONS=1 compiles the measurement-only options in (xl_set_option "debug_skip": skip kernel classes to read
+# their marginal cost; results are garbage while set). The product library is built without them.
+_DEBUG = ["-DXL_DEBUG_OPTIONS"] if os.environ.get("XL_DEBUG_OPTIONS") == "1" else []
+
+NVCC_FLAGS = _DEBUG + [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",

@@ -132,19 +132,6 @@ struct xl_handle {
                                                 // rows and d <= 1024, where they are measured faster (16M x 1 env: 168 vs 196 us,
                                                 // 48M: 312 vs 359, 110M: 481 vs 506; 206M equal; slower from 2 envs on —
                                                 // profiles/r01_lowlat_persistent.md)
-  // small-batch latency path (xl_lowlat.cu): device table of per-block weight pointers + private workspace,
-  // built lazily (outside any capture) by lowlat_prepare
-  int lowlat = 0;                               // 1: use the persistent-kernel stack when B*T <= 16 ("lowlat")
-  int lowlat_coop = 1;                          // launch it with the cooperative attribute ("lowlat_coop")
-  bool ll_ready = false;
-  char* ll_buf = nullptr;
-  xl::LowLatLayer* ll_layers = nullptr;
-  float *ll_z = nullptr, *ll_q = nullptr, *ll_k = nullptr, *ll_v = nullptr, *ll_act = nullptr, *ll_g = nullptr,
-        *ll_gate_part = nullptr, *ll_gates = nullptr, *ll_partial = nullptr;
-  unsigned* ll_bar = nullptr;
-  long long* ll_dbg = nullptr;
-  int lowlat_debug = 0;                         // stamp per-phase clocks of CTA 0 ("lowlat_debug"), print with "lowlat_dump"
-  size_t ll_smem_limit = 0;
   // token ring (xl_set_token_ring): every policy step also stores its tokens in slot (step % slots) of this caller-owned
   // device buffer [slots, B, act_dim]; the step counter lives in counters[0] and is advanced on the device
   int32_t* tok_ring = nullptr;
@@ -564,88 +551,6 @@ void final_norm(xl_handle* h, const Slice& sl, int T, unsigned flags, float* out
   h->launches += 1;
 }
 
-// ---- small-batch latency path (xl_lowlat.cu) -----------------------------------------------------------
-// Eligible: option on, whole-batch slice of an mLSTM-only stack, B*T <= 16 rows, shapes the kernel supports.
-bool lowlat_eligible(const xl_handle* h, const Slice& sl, int T, unsigned flags, size_t* smem) {
-  const xl_config& c = h->cfg;
-  if (!h->lowlat || h->slstm_mask || (flags & XL_FLAG_SIMPLE_GEMM) || h->debug_skip) return false;
-  if (sl.b0 != 0 || sl.Bk != sl.B || sl.ws.low_smem) return false;
-  return xl::lowlat_supported(sl.Bk, T, c.embedding_dim, c.inner_dim, c.num_heads, h->DH, c.conv_kernel,
-                              h->ll_smem_limit, smem);
-}
-
-// Builds the device table of per-block weight pointers and the private workspace. Synchronous copies: must run
-// outside stream capture (xl_policy_step / xl_encoder_step call it before anything is enqueued).
-int lowlat_prepare(xl_handle* h) {
-  if (h->ll_ready || !h->lowlat || h->slstm_mask) return XL_OK;
-  const xl_config& c = h->cfg;
-  if (!h->ll_smem_limit) {
-    int lim = 0;
-    XL_CUDA(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    h->ll_smem_limit = (size_t)lim;
-  }
-  const size_t inner = c.inner_dim, DH = h->DH, L = c.num_blocks;
-  if (!h->ll_buf) {
-    size_t off = 0;
-    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    const size_t o_lay = carve(sizeof(xl::LowLatLayer) * L);
-    const size_t o_z = carve(4 * 16 * inner), o_q = carve(4 * 16 * inner), o_k = carve(4 * 16 * inner);
-    const size_t o_v = carve(4 * 16 * inner), o_a = carve(4 * 16 * inner), o_g = carve(4 * 16 * inner);
-    const size_t o_gp = carve(4 * (size_t)256 * 16 * 16), o_gt = carve(4 * (size_t)16 * 8 * 16);
-    const size_t o_pt = carve(4 * 16 * inner * (DH / 16 + 1)), o_bar = carve(64);
-    const size_t o_dbg = carve(8 * 9 * L);
-    XL_CUDA(cudaMalloc((void**)&h->ll_buf, off));
-    XL_CUDA(cudaMemset(h->ll_buf, 0, off));
-    h->ll_layers = (xl::LowLatLayer*)(h->ll_buf + o_lay);
-    h->ll_z = (float*)(h->ll_buf + o_z); h->ll_q = (float*)(h->ll_buf + o_q); h->ll_k = (float*)(h->ll_buf + o_k);
-    h->ll_v = (float*)(h->ll_buf + o_v); h->ll_act = (float*)(h->ll_buf + o_a); h->ll_g = (float*)(h->ll_buf + o_g);
-    h->ll_gate_part = (float*)(h->ll_buf + o_gp); h->ll_gates = (float*)(h->ll_buf + o_gt);
-    h->ll_partial = (float*)(h->ll_buf + o_pt); h->ll_bar = (unsigned*)(h->ll_buf + o_bar);
-    h->ll_dbg = (long long*)(h->ll_buf + o_dbg);
-  }
-  std::vector<xl::LowLatLayer> tab(L);
-  for (size_t i = 0; i < L; ++i) {
-    const BlockWeights& w = h->blocks[i];
-    xl::LowLatLayer& t = tab[i];
-    t.norm_w = (const float*)w.w[XL_W_XLSTM_NORM];
-    t.w_up = (const __nv_bfloat16*)w.w[XL_W_PROJ_UP];
-    t.wq = (const float*)w.w[XL_W_Q_PROJ]; t.wk = (const float*)w.w[XL_W_K_PROJ]; t.wv = (const float*)w.w[XL_W_V_PROJ];
-    t.conv_w = (const float*)w.w[XL_W_CONV_W]; t.conv_b = (const float*)w.w[XL_W_CONV_B];
-    t.wi = (const float*)w.w[XL_W_IGATE_W]; t.wf = (const float*)w.w[XL_W_FGATE_W];
-    t.bi = (const float*)w.w[XL_W_IGATE_B]; t.bf = (const float*)w.w[XL_W_FGATE_B];
-    t.outnorm = (const float*)w.w[XL_W_OUTNORM]; t.skip = (const float*)w.w[XL_W_SKIP];
-    t.w_down = (const __nv_bfloat16*)w.w[XL_W_PROJ_DOWN];
-  }
-  XL_CUDA(cudaMemcpy(h->ll_layers, tab.data(), sizeof(xl::LowLatLayer) * L, cudaMemcpyHostToDevice));
-  h->ll_ready = true;
-  return XL_OK;
-}
-
-// The whole stack + post_blocks_norm over the M = Bk*T rows of ws.x -> out (rows out_stride apart): one launch.
-int lowlat_stack(xl_handle* h, void* state, const Slice& sl, int T, size_t smem, float* out, int64_t out_stride) {
-  const xl_config& c = h->cfg;
-  if (!h->ll_ready) return fail(XL_ERR_NOT_READY, "lowlat tables not built (internal)");
-  const StateLayout lay = state_layout(h, sl.B);
-  xl::LowLatParams p;
-  memset(&p, 0, sizeof(p));
-  p.layers = h->ll_layers;
-  p.state = (char*)state;
-  p.layer_bytes = lay.layer_bytes; p.c_off = lay.c_off; p.n_off = lay.n_off; p.m_off = lay.m_off;
-  p.conv_off = lay.conv_off;
-  p.x = sl.ws.x; p.out = out; p.out_stride = out_stride;
-  p.post_w = (const float*)h->pw[XL_W_POST_NORM - XL_W_POST_NORM];
-  p.z = h->ll_z; p.q = h->ll_q; p.k = h->ll_k; p.v = h->ll_v; p.act = h->ll_act; p.g = h->ll_g;
-  p.gate_part = h->ll_gate_part; p.gates = h->ll_gates; p.partial = h->ll_partial; p.bar = h->ll_bar;
-  p.dbg = h->lowlat_debug ? h->ll_dbg : nullptr;
-  p.L = c.num_blocks; p.B = sl.Bk; p.T = T; p.M = sl.Bk * T; p.d = c.embedding_dim; p.inner = c.inner_dim;
-  p.NH = c.num_heads; p.DH = h->DH; p.G = h->num_sms < 256 ? h->num_sms : 256;
-  xl::lowlat_plan_state(p.B, p.NH, p.DH, p.G, &p.rpu, &p.RS);
-  p.ln_eps = c.ln_eps; p.cell_eps = c.cell_eps;
-  XL_CUDA(xl::launch_lowlat_stack(p, smem, h->lowlat_coop, sl.s));
-  h->launches += 1;
-  return XL_OK;
-}
-
 // One pass of the block stack over M = Bk*T rows held in ws.x (rows ordered [b][t]).
 int run_blocks(xl_handle* h, void* state, const Slice& sl, int T, unsigned flags) {
   const int L = h->cfg.num_blocks;
@@ -698,15 +603,9 @@ int run_encoder(xl_handle* h, void* state, const Slice& sl, const float* x_in, f
     if (x_in != ws.x) {
       XL_CUDA(cudaMemcpyAsync(ws.x, x_in, sizeof(float) * (size_t)B * T * d, cudaMemcpyDeviceToDevice, s));
     }
-    size_t ll_smem = 0;
-    if (lowlat_eligible(h, sl, T, flags, &ll_smem)) {
-      int rc = lowlat_stack(h, state, sl, T, ll_smem, x_out, d);
-      if (rc) return rc;
-    } else {
-      int rc = run_blocks(h, state, sl, T, flags);
-      if (rc) return rc;
-      if (!(flags & kFlagHeadOnlyEarly)) final_norm(h, sl, T, flags, x_out, d);
-    }
+    int rc = run_blocks(h, state, sl, T, flags);
+    if (rc) return rc;
+    if (!(flags & kFlagHeadOnlyEarly)) final_norm(h, sl, T, flags, x_out, d);
   } else if (mode == XL_MODE_PER_TOKEN) {
     // reference order: for token: for block  (decision_xlstm.py:161-165). x_in may alias x_out: token t's
     // input row is consumed (gathered) before its output row is written.
@@ -718,12 +617,6 @@ int run_encoder(xl_handle* h, void* state, const Slice& sl, const float* x_in, f
     for (int t = 0; t < T; ++t) {
       xl::launch_copy_rows(src + (size_t)t * d, (int64_t)T * d, ws.x, d, B, d, s);
       h->launches += 1;
-      size_t ll_smem = 0;
-      if (lowlat_eligible(h, sl, 1, flags, &ll_smem)) {
-        int rc = lowlat_stack(h, state, sl, 1, ll_smem, x_out + (size_t)t * d, (int64_t)T * d);
-        if (rc) return rc;
-        continue;
-      }
       int rc = run_blocks(h, state, sl, 1, flags);
       if (rc) return rc;
       final_norm(h, sl, 1, flags, x_out + (size_t)t * d, (int64_t)T * d);
@@ -868,8 +761,7 @@ int run_policy(xl_handle* h, const StepArgs& a, cudaStream_t s) {
     float* xt = (a.mode == XL_MODE_FUSED) ? sl.ws.x : sl.ws.xtok;
     // launch-saving fusions of the step's head and tail (fused mode, multi-kernel stack)
     StepArgs af = a;
-    size_t ll_smem = 0;
-    if (h->fuse_ends && a.mode == XL_MODE_FUSED && !h->debug_skip && !lowlat_eligible(h, sl, T, a.flags, &ll_smem)) {
+    if (h->fuse_ends && a.mode == XL_MODE_FUSED && !h->debug_skip) {
       if (!is_slstm(h, 0) && !smallm_chunks(h, sl, T, a.flags)) af.flags |= kFlagLn0Done;
       const int impl = (a.flags & XL_FLAG_SIMPLE_GEMM) ? 1 : h->gemm_impl;
       const int n_out = (a.flags & XL_FLAG_DISCRETE) ? h->num_actions : h->head_out;
@@ -958,7 +850,6 @@ int ensure_prefill_ws(xl_handle* h, int rows) {
   const size_t o_pc = carve(pc_bytes), o_pv = carve(pv_bytes);
   XL_CUDA(cudaDeviceSynchronize());            // nothing may still be using the old workspace
   if (h->pf_buf) cudaFree(h->pf_buf);
-  if (h->ll_buf) cudaFree(h->ll_buf);
   h->pf_buf = nullptr;
   h->pf_rows = 0;
   cudaError_t e = cudaMalloc((void**)&h->pf_buf, off);
@@ -1268,7 +1159,6 @@ int xl_bind_weight(xl_handle* h, int layer, int which, const void* dev_ptr, int 
   if (((uintptr_t)dev_ptr) % 16) return fail(XL_ERR_INVALID_ARG, "weight pointer must be 16-byte aligned");
   if (layer >= 0) h->blocks[layer].w[which] = dev_ptr;
   else h->pw[which - XL_W_POST_NORM] = dev_ptr;
-  h->ll_ready = false;       // the latency path's device table of weight pointers is rebuilt on next use
   // bound pointers are baked into cached graphs
   for (auto& g : h->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -1374,8 +1264,6 @@ int xl_encoder_step(xl_handle* h, void* state, const float* x_in, float* x_out, 
   if (T < 1 || T > 4) return fail(XL_ERR_UNSUPPORTED, "T=%d outside [1,4]", T);
   rc = weights_ready(h, true);
   if (rc) return rc;
-  rc = lowlat_prepare(h);
-  if (rc) return rc;
   const Slice sl = make_slice(h, B, 0, B, (cudaStream_t)stream);
   return run_encoder(h, state, sl, x_in, x_out, T, mode, flags);
 }
@@ -1441,8 +1329,6 @@ int xl_policy_step(xl_handle* h, void* state, const float* states, const float* 
   if (!(flags & XL_FLAG_GRAPH)) {
     rc = xl_weights_ready(h);
     if (rc) return rc;
-    rc = lowlat_prepare(h);
-    if (rc) return rc;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (h->profiling) {
       XL_CUDA(cudaEventCreate(&pe0));
@@ -1468,8 +1354,6 @@ int xl_policy_step(xl_handle* h, void* state, const float* states, const float* 
     }
   }
   rc = xl_weights_ready(h);
-  if (rc) return rc;
-  rc = lowlat_prepare(h);
   if (rc) return rc;
   // make sure every lazy attribute (dynamic smem opt-in) is set before capture: one eager warm-up is NOT
   // done here because it would advance the state; attributes are set inside launch paths, which is legal
@@ -1732,41 +1616,12 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "smallm")) {
     if (value < -1 || value > 1) return fail(XL_ERR_INVALID_ARG, "smallm must be -1 (automatic), 0 or 1");
     h->smallm = value;
-  } else if (!strcmp(name, "lowlat")) {
-    h->lowlat = value ? 1 : 0;
-  } else if (!strcmp(name, "lowlat_coop")) {
-    h->lowlat_coop = value ? 1 : 0;
-  } else if (!strcmp(name, "lowlat_debug")) {
-    h->lowlat_debug = value ? 1 : 0;
-  } else if (!strcmp(name, "lowlat_dump")) {
-    // prints the per-phase SM-clock breakdown of the LAST latency-kernel launch (CTA 0's view) to stderr
-    if (h->ll_dbg) {
-      const int L = h->cfg.num_blocks;
-      std::vector<long long> st((size_t)9 * L);
-      XL_CUDA(cudaDeviceSynchronize());
-      XL_CUDA(cudaMemcpy(st.data(), h->ll_dbg, sizeof(long long) * st.size(), cudaMemcpyDeviceToHost));
-      double acc[8] = {0};
-      for (int l = 0; l < L; ++l)
-        for (int k = 0; k < 8; ++k) acc[k] += (double)(st[l * 9 + k + 1] - st[l * 9 + k]);
-      static const char* nm[8] = {"A work", "A barrier", "C work", "C barrier", "D1 work", "D1 barrier", "D2 work", "D2 barrier"};
-      fprintf(stderr, "lowlat phases (avg SM clocks per block over %d blocks; whole stack %lld clocks):\n", L,
-              st[(size_t)9 * L - 1] - st[0]);
-      for (int k = 0; k < 8; ++k) fprintf(stderr, "  %-10s %9.0f\n", nm[k], acc[k] / L);
-    }
-    return XL_OK;
-  } else if (!strcmp(name, "lowlat_check")) {
-    // synchronises the device, reads and clears the latency kernel's barrier words; error if a grid barrier
-    // ever timed out (the kernel then fell through with garbage instead of hanging)
-    if (h->ll_bar) {
-      unsigned w[3] = {0, 0, 0};
-      XL_CUDA(cudaDeviceSynchronize());
-      XL_CUDA(cudaMemcpy(w, h->ll_bar, sizeof(w), cudaMemcpyDeviceToHost));
-      XL_CUDA(cudaMemset(h->ll_bar, 0, sizeof(w)));
-      if (w[2]) return fail(XL_ERR_CUDA, "lowlat: a grid barrier timed out (arrivals %u, generation %u)", w[0], w[1]);
-    }
-    return XL_OK;
+#ifdef XL_DEBUG_OPTIONS
   } else if (!strcmp(name, "debug_skip")) {
+    // measurement aid (marginal cost of a kernel class): results are garbage while set. Compiled in only with
+    // -DXL_DEBUG_OPTIONS (XL_DEBUG_OPTIONS=1 python -m lram_b200.build --force); absent from the product library.
     h->debug_skip = value;
+#endif
   } else if (!strcmp(name, "gemm_impl")) {
     if (value < 0 || value > 2) return fail(XL_ERR_INVALID_ARG, "gemm_impl must be 0, 1 or 2");
     h->gemm_impl = value;

@@ -169,38 +169,6 @@ cudaError_t launch_finalize_seq(const float* num, const float* qn, const float* 
                                 void* out_lo, int B, int S, int NH, int DH, int inner, float ln_eps, float cell_eps,
                                 cudaStream_t s);
 
-// ---- xl_lowlat.cu --------------------------------------------------------------------------------
-// Small-batch latency path: the whole mLSTM block stack + post_blocks_norm as one persistent kernel (one CTA per SM,
-// grid barriers between the phases of a block). M = B*T <= 16 rows.
-struct LowLatLayer {            // one entry per block, device resident
-  const float* norm_w;
-  const __nv_bfloat16* w_up;
-  const float *wq, *wk, *wv, *conv_w, *conv_b, *wi, *wf, *bi, *bf, *outnorm, *skip;
-  const __nv_bfloat16* w_down;
-};
-struct LowLatParams {
-  const LowLatLayer* layers;
-  char* state;                  // block i's slot at state + i*layer_bytes (mLSTM-only stacks)
-  size_t layer_bytes, c_off, n_off, m_off, conv_off;
-  float* x;                     // [M, d] residual stream, in/out
-  float* out;                   // [M rows, out_stride apart] post_blocks_norm output
-  int64_t out_stride;
-  const float* post_w;
-  float *z, *q, *k, *v, *act, *g;   // [16, inner] each
-  float* gate_part;             // [G, MR, 16]
-  float* gates;                 // [B*NH, 3T+1]
-  float* partial;               // [strips, RS, T, 128]
-  unsigned* bar;                // arrivals, generation, abort flag
-  long long* dbg;               // nullable: clock64 stamps of CTA 0, [L][9] (measurement aid)
-  int L, B, T, M, d, inner, NH, DH, G;
-  int rpu, RS;                  // phase C: rows per unit, row chunks per strip
-  float ln_eps, cell_eps;
-};
-int lowlat_row_bucket(int M);
-bool lowlat_supported(int B, int T, int d, int inner, int NH, int DH, int KS, size_t smem_limit, size_t* smem_bytes);
-void lowlat_plan_state(int B, int NH, int DH, int G, int* rpu_out, int* rs_out);
-cudaError_t launch_lowlat_stack(const LowLatParams& p, size_t smem, int coop, cudaStream_t s);
-
 // ---- xl_smallm.cu --------------------------------------------------------------------------------
 // Front half of an mLSTM block for M = B*T <= 16 rows as one GEMV-style kernel: LN + proj_up + conv/SiLU +
 // headwise q/k/v + gate partials (one chunk per CTA that owns x_m columns). Outputs in the layouts the state-stream
