@@ -1326,9 +1326,10 @@ int xl_policy_step(xl_handle* h, void* state, const float* states, const float* 
   StepArgs args;
   args.state = state; args.states = states; args.rtg = rtg; args.rewards = rewards; args.tokens = tokens;
   args.actions = actions; args.logits = logits; args.hidden = hidden; args.B = B; args.mode = mode; args.flags = flags;
-  if (!(flags & XL_FLAG_GRAPH)) {
+  if (!(flags & XL_FLAG_GRAPH) || h->profiling) {     // profiling brackets eager launches with events: no replay
     rc = xl_weights_ready(h);
     if (rc) return rc;
+    args.flags &= ~(unsigned)XL_FLAG_GRAPH;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (h->profiling) {
       XL_CUDA(cudaEventCreate(&pe0));
@@ -1345,9 +1346,9 @@ int xl_policy_step(xl_handle* h, void* state, const float* states, const float* 
   }
   // ---- CUDA-graph replay: capture once per distinct argument tuple --------------------------------
   for (auto& g : h->graphs) {
-    if (g.state == state && g.states == states && g.rtg == rtg && g.rewards == rewards && g.tokens == tokens &&
-        g.actions == actions && g.logits == logits && g.hidden == hidden && g.B == B && g.mode == mode &&
-        g.flags == flags) {
+    if (g.state == state && g.states == states && g.rtg == rtg && g.rewards == rewards &&
+        g.tokens == tokens && g.actions == actions && g.logits == logits && g.hidden == hidden && g.B == B &&
+        g.mode == mode && g.flags == flags) {
       XL_CUDA(cudaGraphLaunch(g.exec, s));
       h->launches += g.launches;
       return XL_OK;
@@ -1397,6 +1398,10 @@ int xl_policy_step_host(xl_handle* h, void* state, const float* h_states, const 
                                     "(use xl_policy_step with XL_FLAG_STATE_EMBEDS)");
   cudaStream_t s = (cudaStream_t)stream;
   const xl_config& c = h->cfg;
+  // (Measured and dropped in round 2: capturing these copies as nodes of the step's graph — one launch per env step —
+  // made the end-to-end step 1.5x SLOWER on B200, 1.48 ms vs 0.99 ms at 48M x 64 envs; memcpy nodes to / from pinned
+  // host memory serialise badly against the programmatic-dependent-launch kernel nodes. Plain async copies around the
+  // graph launch it is.)
   XL_CUDA(cudaMemcpyAsync(h->d_states, h_states, sizeof(float) * (size_t)B * c.state_dim, cudaMemcpyHostToDevice, s));
   XL_CUDA(cudaMemcpyAsync(h->d_rtg, h_rtg, sizeof(float) * (size_t)B, cudaMemcpyHostToDevice, s));
   if (h_rewards) XL_CUDA(cudaMemcpyAsync(h->d_rew, h_rewards, sizeof(float) * (size_t)B, cudaMemcpyHostToDevice, s));

@@ -175,11 +175,23 @@ class BatchedRollout:
         self.rtg0 = np.asarray(envs.rtg0, dtype=np.float32)
         self.scale = np.asarray(envs.reward_scale, dtype=np.float32)
 
-    def run(self, n_steps: int, record: bool = False) -> Dict[str, object]:
+    def prefill_context(self, states, rtg, rewards=None) -> None:
+        """Warm the recurrent state of every env with a context of Tn earlier timesteps before the rollout starts —
+        the batched counterpart of `persist_context` (src/callbacks/evaluation.py:213-237), where the reference keeps
+        the previous episodes' tokens in front of the new episode: states [B, Tn, state_dim], rtg [B, Tn], rewards
+        [B, Tn] or None (the 0 placeholder the rollout feeds). One chunkwise-parallel pass (`xl_policy_prefill`) leaves
+        the state exactly where Tn recurrent env steps would. Follow with `run(..., keep_state=True)`."""
+        dev = self.engine.device
+        to = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(dev)  # noqa: E731
+        self.engine.reset(self.state)
+        self.engine.policy_prefill(self.state, to(states), to(rtg), to(rewards))
+
+    def run(self, n_steps: int, record: bool = False, keep_state: bool = False) -> Dict[str, object]:
         envs, B = self.envs, self.B
         obs = envs.reset()
         rtg = self.rtg0.copy()
-        self.engine.reset(self.state)
+        if not keep_state:
+            self.engine.reset(self.state)
         ep_ret = np.zeros(B, dtype=np.float64)
         returns: List[List[float]] = [[] for _ in range(B)]
         toks = [] if record else None

@@ -826,3 +826,83 @@ def test_prefill_3000_token_prefix_vs_sequential_oracle(name):
         assert not margins, f"token mismatches after the prefill at t={t}: oracle top-2 margins {margins}"
         assert _rel(out["last_hidden_state"].cpu(), ref["last_hidden_state"]) < REL_TOL
     eng.close()
+
+
+def test_batched_rollout_with_context_prefill():
+    """BatchedRollout.prefill_context (the batched `persist_context`: a context of earlier timesteps warms the state in
+    one chunkwise pass) + run(keep_state=True) == stepping through the context first and then rolling out."""
+    from lram_b200.rollout import BatchedRollout
+    from lram_b200.synth import SyntheticEnvBatch
+    cfg, sd, eng = _engine("16M", 4, seed=8)
+    Tn, Tr = 19, 5
+    ctx_states, ctx_rtg, _ = make_stream(cfg, range(4), Tn, domains="mixed", seed=55)
+    res = {}
+    for tag in ("prefill", "stepped"):
+        envs = SyntheticEnvBatch(cfg, range(4), domains="mixed", ep_len=3, seed=77)
+        ro = BatchedRollout(eng, envs, use_graph=True)
+        if tag == "prefill":
+            ro.prefill_context(ctx_states.transpose(1, 0, 2), ctx_rtg.T)
+        else:
+            eng.reset(ro.state)
+            for t in range(Tn):
+                eng.policy_step(ro.state, torch.from_numpy(ctx_states[t]).cuda(), torch.from_numpy(ctx_rtg[t]).cuda())
+        res[tag] = ro.run(Tr, record=True, keep_state=True)
+    assert np.array_equal(res["prefill"]["tokens"], res["stepped"]["tokens"])
+    assert np.array_equal(res["prefill"]["actions"], res["stepped"]["actions"])
+    eng.close()
+
+
+def test_host_step_equals_device_step():
+    """`xl_policy_step_host` (host buffers in, host buffers out, graph-replayed step in between) gives the tokens /
+    actions of the device-pointer entry point, step after step, with alternating pinned buffers and with pageable ones."""
+    cfg, sd, eng = _engine("16M", 6, seed=2)
+    states, rtg, _ = make_stream(cfg, range(6), 5, domains="mixed")
+    ca, cb = eng.new_state(6), eng.new_state(6)
+    bufs = [(torch.zeros(6, cfg.state_dim).pin_memory(), torch.zeros(6).pin_memory(),
+             torch.zeros(6, cfg.act_dim, dtype=torch.int32).pin_memory(), torch.zeros(6, cfg.act_dim).pin_memory())
+            for _ in range(2)]
+    for t in range(5):
+        hs, hr, ht, ha = bufs[t % 2]
+        hs.copy_(torch.from_numpy(states[t]))
+        hr.copy_(torch.from_numpy(rtg[t]))
+        eng.policy_step_host(ca, hs, hr, ht, ha, flags=L.XL_FLAG_GRAPH)
+        o = eng.policy_step(cb, torch.from_numpy(states[t]).cuda(), torch.from_numpy(rtg[t]).cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(ht, o["action_tokens"].cpu()) and torch.equal(ha, o["action_preds"].cpu()), t
+    # pageable host memory works too (synchronous staging by the driver)
+    hs, hr = torch.from_numpy(states[0]).clone(), torch.from_numpy(rtg[0]).clone()
+    ht, ha = torch.zeros(6, cfg.act_dim, dtype=torch.int32), torch.zeros(6, cfg.act_dim)
+    cc, cd = eng.new_state(6), eng.new_state(6)
+    eng.policy_step_host(cc, hs, hr, ht, ha, flags=L.XL_FLAG_GRAPH)
+    o = eng.policy_step(cd, hs.cuda(), hr.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(ht, o["action_tokens"].cpu())
+    eng.close()
+
+
+def test_token_ring_single_gpu():
+    """`xl_set_token_ring`: every policy step (eager or graph-replayed) also stores its tokens in the next ring slot;
+    re-seeking and disarming work."""
+    cfg, sd, eng = _engine("toy128", 5)
+    states, rtg, _ = make_stream(cfg, range(5), 7, domains="mixed")
+    ring = torch.full((4, 5, cfg.act_dim), -1, dtype=torch.int32, device="cuda")
+    eng.set_token_ring(ring, 0)
+    cache, out, toks = eng.new_state(5), None, []
+    s_dev, r_dev = torch.empty(5, cfg.state_dim, device="cuda"), torch.empty(5, device="cuda")
+    for t in range(7):
+        s_dev.copy_(torch.from_numpy(states[t]))
+        r_dev.copy_(torch.from_numpy(rtg[t]))
+        out = eng.policy_step(cache, s_dev, r_dev, flags=L.XL_FLAG_GRAPH if t % 2 else 0, out=out)
+        torch.cuda.synchronize()
+        toks.append(out["action_tokens"].clone())
+        assert torch.equal(ring[t % 4], toks[-1]), t
+    eng.set_token_ring(ring, 2)                       # re-seek: the next step lands in slot 2
+    out = eng.policy_step(cache, s_dev, r_dev, flags=L.XL_FLAG_GRAPH, out=out)
+    torch.cuda.synchronize()
+    assert torch.equal(ring[2], out["action_tokens"])
+    eng.set_token_ring(None)
+    before = ring.clone()
+    eng.policy_step(cache, s_dev, r_dev, flags=L.XL_FLAG_GRAPH, out=out)
+    torch.cuda.synchronize()
+    assert torch.equal(ring, before)
+    eng.close()
