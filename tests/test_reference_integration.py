@@ -166,3 +166,20 @@ def test_whole_policy_mirror_loads_a_reference_checkpoint(ref):
     bad.pop("module._orig_mod.embed_ln.bias")
     with pytest.raises(KeyError, match="embed_ln.bias"):
         ours.load_state_dict(bad)
+
+
+def test_action_sampling_equals_reference_sample_from_logits(ref):
+    """`a_sample_kwargs` (discrete_decision_transformer_sb3.py:62-63): our restatement draws the reference's samples
+    under the same torch seed, for the shapes the reference can sample ([1, 274] discrete head, [274] per-dimension)."""
+    from src.algos.models.model_utils import sample_from_logits as ref_sample
+    g = torch.Generator().manual_seed(3)
+    for shape in ((1, 274), (274,)):
+        logits = torch.randn(*shape, generator=g) * 3
+        for kw in (dict(temperature=1.0, top_k=0, top_p=0.5), dict(temperature=0.7, top_k=5, top_p=0.0),
+                   dict(temperature=1.3, top_k=0, top_p=0.9)):
+            for seed in range(5):
+                torch.manual_seed(seed)
+                a = ref_sample(logits.clone(), **kw)
+                torch.manual_seed(seed)
+                b = DX.sample_from_logits(logits.clone(), **kw)
+                assert torch.equal(a, b), (shape, kw, seed)
