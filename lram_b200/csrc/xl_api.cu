@@ -1576,6 +1576,9 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "state_rows_split")) {
     if (value < 0 || value > 32) return fail(XL_ERR_INVALID_ARG, "state_rows_split must be in [0, 32]");
     h->state_rows_split = value;
+  } else if (!strcmp(name, "gemm_cluster")) {
+    if (value != 1 && value != 2 && value != 4) return fail(XL_ERR_INVALID_ARG, "gemm_cluster must be 1, 2 or 4");
+    xl::g_gemm_cluster = value;          // process-wide
   } else if (!strcmp(name, "gemm_bm")) {
     if (value != 0 && value != 64 && value != 128) return fail(XL_ERR_INVALID_ARG, "gemm_bm must be 0, 64 or 128");
     xl::g_gemm_bm = value;               // process-wide

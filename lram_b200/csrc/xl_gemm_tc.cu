@@ -53,6 +53,28 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast forms (thread-block cluster of column-tile CTAs sharing one A tile)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -97,13 +119,21 @@ struct Smem {
   static constexpr int kTotal = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, int kStages, int kBM>
+// kCX > 1: the kCX column-tile CTAs of a thread-block cluster (consecutive blockIdx.x) share their A tile. CTA r
+// loads rows [r, r+1) * kBM/kCX of the hi and lo planes and MULTICASTS them into every CTA of the cluster (one L2 read
+// instead of kCX); each CTA's full barrier counts the bytes of all slices + its own W tile, and a stage is released to
+// every producer of the cluster (tcgen05.commit multicast on the empty barriers, which expect kCX arrivals).
+template <int BLOCK_N, int kStages, int kBM, int kCX>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
                const float* __restrict__ residual, float* __restrict__ out, int M, int N, int K,
                long long split_stride, int m64_rows_contiguous) {
   using S = Smem<BLOCK_N, kStages, kBM>;
+  constexpr uint16_t kMask = (uint16_t)((1u << kCX) - 1u);
+  constexpr int kSliceRows = kBM / kCX;
+  constexpr int kSliceBytes = kSliceRows * BLOCK_K * 2;
+  const uint32_t crank = kCX > 1 ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = base + kStages * S::kStageBytes;     // full[kStages], empty[kStages], tmem_full
@@ -129,7 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), kCX);
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -157,23 +187,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   pdl_wait();
   pdl_trigger();
+  // peers multicast into this CTA's ring and arrive on its barriers: those must be initialised cluster-wide first
+  if (kCX > 1) cluster_sync_all();
 
+  // A tile of one stage: the whole tile (kCX == 1) or this CTA's row slice, multicast to the cluster
+  auto load_a = [&](uint32_t st, uint32_t bar, int kcol) {
+    if (kCX == 1) {
+      tma_load_2d(st, &map_a_hi, bar, kcol, m0);
+      tma_load_2d(st + S::kABytes, &map_a_lo, bar, kcol, m0);
+    } else {
+      const int r0 = m0 + (int)crank * kSliceRows;
+      tma_load_2d_mc(st + crank * kSliceBytes, &map_a_hi, bar, kcol, r0, kMask);
+      tma_load_2d_mc(st + S::kABytes + crank * kSliceBytes, &map_a_lo, bar, kcol, r0, kMask);
+    }
+  };
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int kb = 0; kb < pre_kb; ++kb) {
-        const uint32_t st = base + kb * S::kStageBytes;
-        tma_load_2d(st, &map_a_hi, full_bar(kb), (kb0 + kb) * BLOCK_K, m0);
-        tma_load_2d(st + S::kABytes, &map_a_lo, full_bar(kb), (kb0 + kb) * BLOCK_K, m0);
-      }
+      for (int kb = 0; kb < pre_kb; ++kb) load_a(base + kb * S::kStageBytes, full_bar(kb), (kb0 + kb) * BLOCK_K);
       for (int kb = pre_kb; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_wait(empty_bar(s), ph ^ 1);              // every CTA of the cluster has consumed this stage
         const uint32_t st = base + s * S::kStageBytes;
         mbar_expect_tx(full_bar(s), S::kStageBytes);
-        tma_load_2d(st, &map_a_hi, full_bar(s), (kb0 + kb) * BLOCK_K, m0);
-        tma_load_2d(st + S::kABytes, &map_a_lo, full_bar(s), (kb0 + kb) * BLOCK_K, m0);
+        load_a(st, full_bar(s), (kb0 + kb) * BLOCK_K);
         tma_load_2d(st + 2 * S::kABytes, &map_w, full_bar(s), (kb0 + kb) * BLOCK_K, n0);
       }
     }
@@ -196,7 +234,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           umma_bf16(tmem_base, a_hi + kofs, bw + kofs, idesc, (kb | k) != 0);
           umma_bf16(tmem_base, a_lo + kofs, bw + kofs, idesc, 1u);
         }
-        tcgen05_commit(empty_bar(s));            // frees the smem stage when these MMAs retire
+        // frees the smem stage when these MMAs retire — in every CTA of the cluster that multicasts into it
+        if (kCX == 1) tcgen05_commit(empty_bar(s));
+        else tcgen05_commit_mc(empty_bar(s), kMask);
       }
       tcgen05_commit(tmem_full_bar);             // accumulator complete
     }
@@ -286,6 +326,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BLOCK_N) : "memory");
   }
+  // peers' stage releases still arrive on this CTA's empty barriers: nobody leaves before everybody is done
+  if (kCX > 1) cluster_sync_all();
 }
 
 
@@ -685,32 +727,41 @@ static bool make_map(CUtensorMap* m, const void* ptr, int rows, int K, int box_r
 
 int g_m64_rows_contiguous = 0;     // xl_set_option("gemm_m64_layout"): probe of the M = 64 accumulator layout
 
-template <int BLOCK_N, int kStages, int kBM = BLOCK_M>
+template <int BLOCK_N, int kStages, int kBM = BLOCK_M, int kCX = 1>
 static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& ml, const CUtensorMap& mw, const float* bias,
                           const float* residual, float* out, int M, int N, int K, int splits, long long split_stride,
                           cudaStream_t s) {
   using S = Smem<BLOCK_N, kStages, kBM>;
-  if (cudaError_t e = ensure_dyn_smem<&gemm_tc_kernel<BLOCK_N, kStages, kBM>>(S::kTotal); e != cudaSuccess) return e;
+  if (cudaError_t e = ensure_dyn_smem<&gemm_tc_kernel<BLOCK_N, kStages, kBM, kCX>>(S::kTotal); e != cudaSuccess)
+    return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((N + BLOCK_N - 1) / BLOCK_N, (M + kBM - 1) / kBM, splits);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   int na = 0;
   if (g_use_pdl) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
+  if (kCX > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = kCX;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kStages, kBM>, ma, ml, mw, bias, residual, out, M, N, K,
+  return cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BLOCK_N, kStages, kBM, kCX>, ma, ml, mw, bias, residual, out, M, N, K,
                             split_stride, g_m64_rows_contiguous);
 }
 
 }  // namespace tc
 
+int g_gemm_cluster = 1;   // xl_set_option("gemm_cluster"): 1 = off, 2 / 4 = A-tile TMA multicast across that many column tiles
 int g_gemm_bm = 0;     // xl_set_option("gemm_bm"): 64 = 64-row MMA tiles where the shape allows, 0 / 128 = 128-row tiles
 void gemm_tc_set_m64_layout(int contiguous) { tc::g_m64_rows_contiguous = contiguous ? 1 : 0; }
 
@@ -802,12 +853,18 @@ cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat
   // W three times: 42 MB instead of 38 MB of L2 -> SM traffic for proj_up, and these GEMMs sit at the aggregate L2
   // read rate), equal elsewhere (profiles/r02_chain_fusion.md) -> not the default.
   const bool bm64 = g_gemm_bm == 64 && !low_smem && bn == 64 && M > 16;
+  // A-tile multicast across a cluster of 2 or 4 column-tile CTAs (option "gemm_cluster"; 128-row, 64-wide tiles only)
+  const int n_tiles = (N + bn - 1) / bn;
+  int cx = (!bm64 && !low_smem && bn == 64 && N % 64 == 0) ? g_gemm_cluster : 1;
+  while (cx > 1 && n_tiles % cx) cx >>= 1;
   CUtensorMap ma, ml, mw;
-  const int box_m = bm64 ? 64 : tc::BLOCK_M;
+  const int box_m = bm64 ? 64 : tc::BLOCK_M / (cx > 1 ? cx : 1);
   if (!tc::make_map(&ma, a_hi, M, K, box_m) || !tc::make_map(&ml, a_lo, M, K, box_m) ||
       !tc::make_map(&mw, W, N, K, bn))
     return cudaErrorUnknown;
   if (bm64) return tc::launch<64, 9, 64>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
+  if (cx == 2) return tc::launch<64, 4, tc::BLOCK_M, 2>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
+  if (cx == 4) return tc::launch<64, 4, tc::BLOCK_M, 4>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
   if (low_smem) {
     // shallow rings (<= 110 KB): the CTA must fit beside a resident state-stream CTA of another micro-batch
     switch (bn) {

@@ -220,6 +220,7 @@ cudaError_t launch_gemm_up_conv(const void* a_hi, const void* a_lo, const __nv_b
 
 // tcgen05 path: A given as bf16 hi/lo planes (A = hi + lo), W bf16, fp32 accumulate in TMEM.
 bool gemm_tc_supported(int M, int N, int K);
+extern int g_gemm_cluster;                     // 1 off, 2 / 4: A-tile multicast across column-tile CTAs ("gemm_cluster")
 extern int g_gemm_bm;                          // 0 automatic, 64 / 128 forced ("gemm_bm")
 void gemm_tc_set_m64_layout(int contiguous);   // probe of the M = 64 TMEM accumulator layout ("gemm_m64_layout")
 void launch_split_bf16(const float* in, int64_t in_stride, void* hi, void* lo, int rows, int K, cudaStream_t s);
