@@ -358,9 +358,13 @@ def main():
     h_act = torch.zeros(B, cfg.act_dim, dtype=torch.float32).pin_memory()
     g_tok = torch.zeros(B, cfg.act_dim, dtype=torch.int32, device=dev)
 
+    h_s_in = torch.zeros(B, cfg.state_dim).pin_memory()     # the env-side buffers of the step: written by the host
+    h_r_in = torch.zeros(B).pin_memory()                     # every step, read by the library every step
+
     def host_step(t):
-        eng.policy_step_host(cache_e, h_states[t % n_stream], h_rtg[t % n_stream], h_tok, h_act, mode=mode,
-                             flags=flags)
+        h_s_in.copy_(h_states[t % n_stream])                 # what an env does: put the new observation in place
+        h_r_in.copy_(h_rtg[t % n_stream])
+        eng.policy_step_host(cache_e, h_s_in, h_r_in, h_tok, h_act, mode=mode, flags=flags)
         if world > 1:
             gatherer.submit(g_tok)                # tokens are already in the ring (written by the step itself)
 

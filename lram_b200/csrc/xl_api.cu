@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/xlstm_b200.h"
@@ -134,6 +135,10 @@ struct xl_handle {
                                                 // profiles/r01_lowlat_persistent.md)
   // token ring (xl_set_token_ring): every policy step also stores its tokens in slot (step % slots) of this caller-owned
   // device buffer [slots, B, act_dim]; the step counter lives in counters[0] and is advanced on the device
+  int host_zero_copy = 1;        // xl_policy_step_host: kernels read the step's inputs from / write its results to the
+                                 // caller's PINNED (mapped) host buffers directly instead of 4 staged DMA copies
+                                 // ("host_zero_copy"); pageable buffers fall back to staging copies
+  std::vector<std::pair<const void*, void*>> host_map;   // host pointer -> device alias (nullptr: not mapped)
   int32_t* tok_ring = nullptr;
   int tok_slots = 0;
   bool profiling = false;
@@ -1398,6 +1403,35 @@ int xl_policy_step_host(xl_handle* h, void* state, const float* h_states, const 
                                     "(use xl_policy_step with XL_FLAG_STATE_EMBEDS)");
   cudaStream_t s = (cudaStream_t)stream;
   const xl_config& c = h->cfg;
+  if (h->host_zero_copy) {
+    // Pinned host memory is mapped into the device address space (UVA): the first kernel of the step reads the 52 KB
+    // of states / rtg over PCIe itself and the argmax kernel stores the 4 KB of tokens / actions straight into the
+    // caller's buffers — no DMA copy launches (each ~8-10 us of latency) around the graph launch, one stream
+    // synchronisation at the end. The graph is keyed on the device aliases, so callers should reuse their buffers.
+    auto alias = [&](const void* p) -> void* {
+      for (auto& kv : h->host_map)
+        if (kv.first == p) return kv.second;
+      cudaPointerAttributes at;
+      void* d = nullptr;
+      if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost) d = at.devicePointer;
+      cudaGetLastError();
+      if (h->host_map.size() >= 64) h->host_map.erase(h->host_map.begin());
+      h->host_map.emplace_back(p, d);
+      return d;
+    };
+    void* ds = alias(h_states);
+    void* dr = alias(h_rtg);
+    void* dw = h_rewards ? alias(h_rewards) : nullptr;
+    void* dt = alias(h_tokens);
+    void* da = alias(h_actions);
+    if (ds && dr && dt && da && (!h_rewards || dw)) {
+      rc = xl_policy_step(h, state, (const float*)ds, (const float*)dr, (const float*)dw, (int32_t*)dt, (float*)da,
+                          nullptr, nullptr, B, mode, flags, s);
+      if (rc) return rc;
+      XL_CUDA(cudaStreamSynchronize(s));
+      return XL_OK;
+    }
+  }
   // (Measured and dropped in round 2: capturing these copies as nodes of the step's graph — one launch per env step —
   // made the end-to-end step 1.5x SLOWER on B200, 1.48 ms vs 0.99 ms at 48M x 64 envs; memcpy nodes to / from pinned
   // host memory serialise badly against the programmatic-dependent-launch kernel nodes. Plain async copies around the
@@ -1576,6 +1610,8 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "state_rows_split")) {
     if (value < 0 || value > 32) return fail(XL_ERR_INVALID_ARG, "state_rows_split must be in [0, 32]");
     h->state_rows_split = value;
+  } else if (!strcmp(name, "host_zero_copy")) {
+    h->host_zero_copy = value ? 1 : 0;
   } else if (!strcmp(name, "gemm_cluster")) {
     if (value != 1 && value != 2 && value != 4) return fail(XL_ERR_INVALID_ARG, "gemm_cluster must be 1, 2 or 4");
     xl::g_gemm_cluster = value;          // process-wide

@@ -906,3 +906,27 @@ def test_token_ring_single_gpu():
     torch.cuda.synchronize()
     assert torch.equal(ring, before)
     eng.close()
+
+
+@pytest.mark.parametrize("opt,val", [("gemm_bm", 64), ("gemm_cluster", 2), ("gemm_cluster", 4)])
+def test_gemm_tile_variants_bit_identical(opt, val):
+    """64-row UMMA tiles (cta_group::1, M = 64: accumulator rows in lanes 0-15 of each TMEM quarter) and the A-tile TMA
+    multicast across a cluster of column-tile CTAs compute exactly the plain tcgen05 Linear: same products, same order."""
+    cfg, sd, eng = _engine("toy", 1)
+    g = torch.Generator().manual_seed(5)
+    try:
+        for (M, N, K) in [(192, 3072, 768), (192, 768, 1536), (100, 640, 256), (33, 128, 64)]:
+            A = torch.randn(M, K, generator=g).cuda()
+            W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
+            bias = torch.randn(N, generator=g).cuda()
+            eng.set_option(opt, 0 if opt == "gemm_bm" else 1)
+            ref = eng.linear(A, W, bias, None, impl=2)
+            eng.set_option(opt, val)
+            out = eng.linear(A, W, bias, None, impl=2)
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref), (opt, val, M, N, K)
+            ref64 = (A.double() @ W.double().t() + bias.double()).float()
+            assert _rel(out, ref64) < 2e-5
+    finally:
+        eng.set_option(opt, 0 if opt == "gemm_bm" else 1)      # process-wide switches: restore
+        eng.close()
