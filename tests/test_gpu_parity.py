@@ -310,11 +310,27 @@ def test_fused_equals_per_token_and_graph_replay():
     eng.close()
 
 
+def _microbatches_enabled(eng):
+    """The env micro-batch pipeline is experimental (known mismatch at >= 128 envs, see xl_set_option): the product build
+    refuses it loudly; only XL_DEBUG_OPTIONS builds run the tests below."""
+    from lram_b200._lib import XLError
+    try:
+        eng.set_option("microbatches", 2)
+    except XLError as ex:
+        assert "experimental" in str(ex)
+        return False
+    eng.set_option("microbatches", 0)
+    return True
+
+
 @pytest.mark.parametrize("name,B", [("16M", 40), ("toy128", 7)])
 def test_microbatch_pipeline_equals_single_stream(name, B):
     """The env micro-batch pipeline (side streams, state-stream kernels taking turns) computes the same step as
     the single-stream path: same tokens, hidden states within rounding of the partial-sum order; graph == eager."""
     cfg, sd, eng = _engine(name, B)
+    if not _microbatches_enabled(eng):
+        eng.close()
+        pytest.skip("microbatches > 1 refused by the product build (experimental option)")
     states, rtg, _ = make_stream(cfg, range(B), 5, domains="mixed")
     res = {}
     for tag, mb, order, flags in (("mb1", 1, 1, 0), ("mb4", 4, 1, 0), ("mb3_free", 3, 0, 0),
@@ -596,9 +612,9 @@ def test_slstm_prefill_reset_and_microbatches():
     of = eng.policy_step(eng.new_state(B), dev(states[2]), dev(rtg[2]), want_hidden=True)
     torch.cuda.synchronize()
     assert torch.equal(o1["last_hidden_state"].cpu()[[0, 3]], of["last_hidden_state"].cpu()[[0, 3]])
-    # micro-batches
+    # micro-batches (experimental option: only debug builds accept it)
     ca, cb = eng.new_state(B), eng.new_state(B)
-    for t in range(3):
+    for t in range(3 if _microbatches_enabled(eng) else 0):
         eng.set_option("microbatches", 1)
         a = eng.policy_step(ca, dev(states[t]), dev(rtg[t]), want_hidden=True)
         eng.set_option("microbatches", 2)
