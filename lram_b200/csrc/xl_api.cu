@@ -1269,8 +1269,51 @@ int xl_encoder_step(xl_handle* h, void* state, const float* x_in, float* x_out, 
   if (T < 1 || T > 4) return fail(XL_ERR_UNSUPPORTED, "T=%d outside [1,4]", T);
   rc = weights_ready(h, true);
   if (rc) return rc;
-  const Slice sl = make_slice(h, B, 0, B, (cudaStream_t)stream);
-  return run_encoder(h, state, sl, x_in, x_out, T, mode, flags);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!(flags & XL_FLAG_GRAPH) || h->profiling) {
+    const Slice sl = make_slice(h, B, 0, B, s);
+    return run_encoder(h, state, sl, x_in, x_out, T, mode, flags & ~(unsigned)XL_FLAG_GRAPH);
+  }
+  // CUDA-graph replay of the encoder step (the encoder-only swap of decision_xlstm.py:188-189 at small batch is
+  // launch-bound when its ~6 kernels per block are enqueued eagerly): one graph per distinct argument tuple, in the
+  // same cache as the policy step's (keys: x_in in `states`, x_out in `hidden`, T in the upper bits of `mode`).
+  const int key_mode = mode | (T << 8) | (1 << 16);
+  for (auto& g : h->graphs) {
+    if (g.state == state && g.states == x_in && g.hidden == x_out && !g.rtg && !g.tokens && g.B == B &&
+        g.mode == key_mode && g.flags == flags) {
+      XL_CUDA(cudaGraphLaunch(g.exec, s));
+      h->launches += g.launches;
+      return XL_OK;
+    }
+  }
+  GraphCacheEntry g;
+  g.state = state; g.states = x_in; g.hidden = x_out; g.B = B; g.mode = key_mode; g.flags = flags;
+  cudaGraph_t graph = nullptr;
+  const int64_t before = h->launches;
+  XL_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+  {
+    const Slice sl = make_slice(h, B, 0, B, h->cap_stream);
+    rc = run_encoder(h, state, sl, x_in, x_out, T, mode, flags & ~(unsigned)XL_FLAG_GRAPH);
+  }
+  cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
+  g.launches = h->launches - before;
+  h->launches = before;
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(XL_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(XL_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  if (h->graphs.size() >= 8) {
+    cudaGraphExecDestroy(h->graphs.front().exec);
+    h->graphs.erase(h->graphs.begin());
+  }
+  h->graphs.push_back(g);
+  XL_CUDA(cudaGraphLaunch(g.exec, s));
+  h->launches += g.launches;
+  return XL_OK;
 }
 
 int xl_mlstm_cell_step(xl_handle* h, float* C, float* n, float* m, const float* qkv, const float* igate,

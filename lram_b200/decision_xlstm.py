@@ -139,8 +139,11 @@ class FusedXLSTMEncoder(nn.Module):
     A reference-format dict ({"block_i": {...}}) is accepted too and imported into a fresh cache.
     """
 
-    def __init__(self, config=None, mode: int = L.XL_MODE_PER_TOKEN, max_batch: int = 64, device=None, **_unused):
+    def __init__(self, config=None, mode: int = L.XL_MODE_PER_TOKEN, max_batch: int = 64, device=None,
+                 use_graph: bool = True, **_unused):
         super().__init__()
+        self.use_graph = use_graph        # replay the step from a CUDA graph (persistent input / output staging buffers)
+        self._io: Dict[tuple, tuple] = {}
         self._engine: Optional[XLSTMEngine] = None
         self._owns_engine = True
         self._engine_provider = None      # set by a policy that shares its (full) engine with this encoder
@@ -196,6 +199,7 @@ class FusedXLSTMEncoder(nn.Module):
         return None
 
     def invalidate_engine(self):
+        self._io.clear()
         if self._owns_engine and self._engine is not None:
             self._engine.close()
             self._engine = None
@@ -249,6 +253,16 @@ class FusedXLSTMEncoder(nn.Module):
         if x.shape[1] > 4:
             # a whole context at once: what `chunkwise_step` (decision_xlstm.py:158-159) asks of layers.step
             hs = engine.prefill(cache, x)
+        elif self.use_graph:
+            # a graph is keyed on its pointers: stage the step's input / output in persistent buffers
+            key = (id(engine), B, x.shape[1])
+            io = self._io.get(key)
+            if io is None:
+                io = (torch.empty_like(x, memory_format=torch.contiguous_format), torch.empty_like(x))
+                self._io[key] = io
+            io[0].copy_(x, non_blocking=True)
+            engine.encoder_step(cache, io[0], mode=self.mode, flags=L.XL_FLAG_GRAPH, out=io[1])
+            hs = io[1].clone()
         else:
             hs = engine.encoder_step(cache, x, mode=self.mode)
         return _Output(last_hidden_state=hs, past_key_values=cache, hidden_states=None, attentions=None)
@@ -277,7 +291,7 @@ class MultiDomainDiscreteDecisionXLSTMModel(nn.Module):
     """
 
     def __init__(self, config, state_dict: Optional[Dict[str, torch.Tensor]] = None, max_batch: int = 1,
-                 device=None, mode: int = L.XL_MODE_FUSED, use_graph: bool = False, image_shape=(3, 64, 64),
+                 device=None, mode: int = L.XL_MODE_FUSED, use_graph: bool = True, image_shape=(3, 64, 64),
                  img_is_encoded: bool = False, with_image: Optional[bool] = None):
         super().__init__()
         cfg = config_from_reference(config)

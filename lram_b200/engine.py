@@ -263,11 +263,15 @@ class XLSTMEngine:
 
     # ---- compute ----------------------------------------------------------------------------------
     @_on_device
-    def encoder_step(self, state: StateCache, x: torch.Tensor, mode: int = L.XL_MODE_FUSED, flags: int = 0):
-        """x [B,T,d] fp32 cuda -> last_hidden_state [B,T,d]; state advanced in place."""
+    def encoder_step(self, state: StateCache, x: torch.Tensor, mode: int = L.XL_MODE_FUSED, flags: int = 0,
+                     out: Optional[torch.Tensor] = None):
+        """x [B,T,d] fp32 cuda -> last_hidden_state [B,T,d]; state advanced in place. With XL_FLAG_GRAPH the step is
+        replayed from a CUDA graph keyed on (state, x, out): pass the same tensors every step."""
         assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[0] == state.B
         x = x.contiguous()
-        out = torch.empty_like(x)
+        if out is None:
+            out = torch.empty_like(x)
+        assert out.is_contiguous() and out.shape == x.shape and out.dtype == torch.float32
         L.check(self.lib.xl_encoder_step(self.handle, _ptr(state.buf), _ptr(x), _ptr(out), x.shape[0], x.shape[1],
                                          mode, flags, self._stream()))
         return out

@@ -203,15 +203,16 @@ def test_cuda_policy_equals_reference_forward(fwd, tag, use_graph):
 
 
 @gpu
+@pytest.mark.parametrize("use_graph", [True, False])
 @pytest.mark.parametrize("tag", ["toy128_cont", "16M_cont", "toy128ms_cont"])
-def test_cuda_encoder_swap_equals_reference_hidden(fwd, tag):
+def test_cuda_encoder_swap_equals_reference_hidden(fwd, tag, use_graph):
     """Encoder-only integration (the swap at decision_xlstm.py:188-189): an `nn.Module` `FusedXLSTMEncoder(config=...)`
     whose `layers.*` parameters are filled by `load_state_dict` AFTER construction, engine built lazily; embeddings by
     the checker (oracle). last_hidden_state must equal what the reference's encoder produced inside its policy."""
     from lram_b200.decision_xlstm import FusedXLSTMEncoder
     from oracle.xlstm_oracle import OraclePolicy
     cfg, sd, B, n_steps, discrete, states_np, rtg_np, _ = _case(fwd, tag)
-    enc = FusedXLSTMEncoder(config=cfg, max_batch=B)
+    enc = FusedXLSTMEncoder(config=cfg, max_batch=B, use_graph=use_graph)
     enc_sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
     res = enc.load_state_dict(enc_sd)
     assert not res.missing_keys and not res.unexpected_keys
