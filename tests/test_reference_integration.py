@@ -56,8 +56,11 @@ class _OracleEngine:
     def new_state(self, B):
         return _OracleCache(self, B)
 
-    def encoder_step(self, cache, x, mode=0, flags=0):
+    def encoder_step(self, cache, x, mode=0, flags=0, out=None):
         hs, cache.pkv = self.enc.forward_cached(x, cache.pkv)
+        if out is not None:
+            out.copy_(hs)
+            return out
         return hs
 
     def close(self):
