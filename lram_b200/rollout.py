@@ -251,6 +251,8 @@ def custom_evaluate_policy(model, env, n_eval_episodes: int = 10, deterministic:
       * rtg_{t+1} = rtg_t - r_t / reward_scale in fp32 (:152-168),
       * on done: rtg <- target return; the recurrent state is reset (`past_key_values = None`, :238-251) UNLESS
         `model.persist_context` (:213-237), where the context — here the recurrent state — carries over episodes,
+      * `model.reset_inf_cache_freq` (decision_transformer_sb3.py:663-666): an env's state is also dropped after the
+        prediction at every timestep t > 0 with t % freq == 0,
       * episodes are divided among the envs as SB3 does (:87-89); episode reward / length bookkeeping follows
         :199-211 (Monitor `info["episode"]` when present; otherwise the reference appends the LAST step's reward).
     """
@@ -271,6 +273,8 @@ def custom_evaluate_policy(model, env, n_eval_episodes: int = 10, deterministic:
     reward_scale = np.float32(model.get_reward_scale_for_env(envid=env_name))
     model.past_key_values = None                                   # :120-124
     persist = bool(getattr(model, "persist_context", False))
+    reset_freq = getattr(model, "reset_inf_cache_freq", None)
+    timestep = np.zeros(n_envs, dtype="int")                         # per-env `timesteps[0, -1]` of the reference loop
     start_time = [time.time()] * n_envs
     while (episode_counts < episode_count_targets).any():
         obs_t = torch.from_numpy(observations)
@@ -301,9 +305,13 @@ def custom_evaluate_policy(model, env, n_eval_episodes: int = 10, deterministic:
                         episode_rewards.append(reward[i:i + 1] if n_envs > 1 else reward)   # :208 (sic)
                         episode_lengths.append(current_lengths[i] if n_envs > 1 else current_lengths[0])
                     episode_counts[i] += 1
-        if done.any() and not persist and model.past_key_values is not None:
+        drop = done & (not persist)
+        if reset_freq is not None:
+            drop = drop | ((timestep > 0) & (timestep % int(reset_freq) == 0))
+        timestep = np.where(done, 0, timestep + 1)
+        if drop.any() and model.past_key_values is not None:
             cache = model.past_key_values
-            cache.engine.reset(cache, torch.from_numpy(done.astype(np.uint8)))
+            cache.engine.reset(cache, torch.from_numpy(drop.astype(np.uint8)))
         if render:
             env.render()
     model.past_key_values = None                                   # :259-262

@@ -164,7 +164,7 @@ def policy_forward_case(out, tag, cfg_name, seed, B, n_steps, discrete, image=Fa
 
 
 @torch.no_grad()
-def rollout_case(out, tag, cfg_name, seed, kind, n_episodes, ep_len):
+def rollout_case(out, tag, cfg_name, seed, kind, n_episodes, ep_len, persist_context=False, reset_inf_cache_freq=None):
     """`custom_evaluate_policy` + `DiscreteDecisionXLSTM.predict`, one env, scripted observations."""
     ref_stubs.install()
     import gym
@@ -187,6 +187,8 @@ def rollout_case(out, tag, cfg_name, seed, kind, n_episodes, ep_len):
         raise ValueError(kind)
     env = ref_stubs.ScriptedVecEnv(obs, act_space, obs_space, ep_len=ep_len)
     agent = build_reference_agent(policy, cfg, target_return / reward_scale, reward_scale)
+    agent.persist_context = persist_context                  # evaluation.py:213-237: context carried over episode ends
+    agent.reset_inf_cache_freq = reset_inf_cache_freq        # decision_transformer_sb3.py:663-666
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         ep_rewards, ep_lengths, _ = custom_evaluate_policy(agent, env, n_eval_episodes=n_episodes,
@@ -195,6 +197,8 @@ def rollout_case(out, tag, cfg_name, seed, kind, n_episodes, ep_len):
     out[f"{tag}.actions"] = np.stack([np.asarray(a).reshape(-1) for a in env.actions_seen])
     out[f"{tag}.ep_lengths"] = np.array(ep_lengths, dtype=np.int64)
     out[f"{tag}.meta"] = np.array([seed, n_episodes, ep_len], dtype=np.int64)
+    out[f"{tag}.flags"] = np.array([int(persist_context), -1 if reset_inf_cache_freq is None else reset_inf_cache_freq],
+                                   dtype=np.int64)
     out[f"{tag}.scalars"] = np.array([target_return, reward_scale], dtype=np.float64)
     out[f"{tag}.cfg"] = np.array(cfg_name)
     out[f"{tag}.kind"] = np.array(kind)
@@ -212,11 +216,15 @@ def main():
     policy_forward_case(fwd, "16M_cont", "16M", seed=15, B=2, n_steps=4, discrete=False, domains="dmcontrol")
     policy_forward_case(fwd, "48M_cont", "48M", seed=16, B=2, n_steps=3, discrete=False, domains="metaworld")
     policy_forward_case(fwd, "110M_disc", "110M", seed=17, B=2, n_steps=3, discrete=True, domains="mixed")
+    policy_forward_case(fwd, "206M_cont", "206M", seed=18, B=1, n_steps=2, discrete=False, domains="mimicgen")
     np.savez_compressed(os.path.join(HERE, "ref_policy_forward.npz"), **fwd)
     ro = {}
     rollout_case(ro, "toy128_metaworld", "toy128", seed=21, kind="metaworld", n_episodes=3, ep_len=7)
     rollout_case(ro, "toy128_atari", "toy128", seed=22, kind="atari", n_episodes=2, ep_len=5)
     rollout_case(ro, "16M_metaworld", "16M", seed=23, kind="metaworld", n_episodes=2, ep_len=6)
+    rollout_case(ro, "toy128_persist", "toy128", seed=24, kind="metaworld", n_episodes=3, ep_len=5, persist_context=True)
+    rollout_case(ro, "toy128_resetfreq", "toy128", seed=25, kind="metaworld", n_episodes=2, ep_len=9,
+                 reset_inf_cache_freq=4)
     np.savez_compressed(os.path.join(HERE, "ref_rollout.npz"), **ro)
     for f in ("ref_policy_forward.npz", "ref_rollout.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

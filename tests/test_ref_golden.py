@@ -23,8 +23,11 @@ from lram_b200.synth import make_state_dict, make_stream
 REL_TOL = 1e-3
 IMAGE_SHAPE = (3, 64, 64)
 C_STRIDE = (37, 41)
-FWD_TAGS = ["toy128_cont", "toy128_disc", "toy128_img_disc", "toy128ms_cont", "16M_cont", "48M_cont", "110M_disc"]
-ROLLOUT_TAGS = ["toy128_metaworld", "toy128_atari", "16M_metaworld"]
+FWD_TAGS = ["toy128_cont", "toy128_disc", "toy128_img_disc", "toy128ms_cont", "16M_cont", "48M_cont", "110M_disc",
+            "206M_cont"]
+# persist: `persist_context` (evaluation.py:213-237) — the recurrent state survives episode ends;
+# resetfreq: `reset_inf_cache_freq` (decision_transformer_sb3.py:663-666) — the cache is dropped every 4 timesteps
+ROLLOUT_TAGS = ["toy128_metaworld", "toy128_atari", "16M_metaworld", "toy128_persist", "toy128_resetfreq"]
 gpu = pytest.mark.gpu
 
 
@@ -97,6 +100,7 @@ def _oracle_rollout(z, tag):
     sd.update(make_impala_state_dict(cfg.d, IMAGE_SHAPE, seed=seed + 100))
     ora = OraclePolicy(cfg, sd)
     obs = z[f"{tag}.obs"]
+    persist, freq = (int(v) for v in z[f"{tag}.flags"]) if f"{tag}.flags" in z.files else (0, -1)
     target = np.float32(target_return / reward_scale)
     rtg, pkv, acts = target, None, []
     for k in range(n_episodes * ep_len):
@@ -111,8 +115,13 @@ def _oracle_rollout(z, tag):
             out = ora.step(s, torch.tensor([rtg]), past_key_values=pkv, discrete=False)
             acts.append(out["action_preds"].numpy().reshape(-1)[:4])
         pkv = out["past_key_values"]
+        ts = k % ep_len                                  # timestep of the prediction just made
+        if freq > 0 and ts > 0 and ts % freq == 0:
+            pkv = None                                   # reset_inf_cache_freq
         if (k + 1) % ep_len == 0:
-            rtg, pkv = target, None
+            rtg = target
+            if not persist:
+                pkv = None
         else:
             rtg = np.float32(rtg - np.float32(1.0) / np.float32(reward_scale))
     return np.stack(acts)
@@ -242,8 +251,10 @@ def test_cuda_rollout_equals_reference_rollout(rollouts, tag):
     kind = str(z[f"{tag}.kind"])
     sd = make_state_dict(cfg, seed=seed)
     sd.update(make_impala_state_dict(cfg.d, IMAGE_SHAPE, seed=seed + 100))
+    persist, freq = (int(v) for v in z[f"{tag}.flags"]) if f"{tag}.flags" in z.files else (0, -1)
     policy = MultiDomainDiscreteDecisionXLSTMModel(cfg, sd, max_batch=1)
-    agent = DiscreteDecisionXLSTM(policy, target_return=target_return / reward_scale, reward_scale=reward_scale)
+    agent = DiscreteDecisionXLSTM(policy, target_return=target_return / reward_scale, reward_scale=reward_scale,
+                                  persist_context=bool(persist), reset_inf_cache_freq=freq if freq > 0 else None)
     if kind == "atari":
         spaces = (Discrete(18), Box(0, 255, IMAGE_SHAPE, np.uint8))
     else:
