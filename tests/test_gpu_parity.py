@@ -946,3 +946,50 @@ def test_gemm_tile_variants_bit_identical(opt, val):
     finally:
         eng.set_option(opt, 0 if opt == "gemm_bm" else 1)      # process-wide switches: restore
         eng.close()
+
+
+def test_argmax_head_edge_cases_match_torch_semantics():
+    """The fused argmax / inv_tokenize kernel on crafted logits (head weight 0, so logits == bias exactly): ties take the
+    FIRST index and NaN counts as the maximum (torch.argmax, multi_domain_discrete_dt_model.py:83-94); ids below the
+    tokenizer shift decode to min_val (minmax_tokenizer.py:34-37); the discrete branch only looks at the first 18 logits."""
+    from lram_b200.engine import XLSTMEngine
+    from oracle.xlstm_oracle import OracleMinMaxTokenizer
+    cfg = preset("toy")
+    sd = make_state_dict(cfg, seed=1)
+    sd["action_net.0.weight"] = torch.zeros_like(sd["action_net.0.weight"])
+    g = torch.Generator().manual_seed(0)
+    bias = torch.randn(cfg.act_dim, cfg.num_actions, generator=g)
+    bias[0, :] = 0.25                                   # all equal -> token 0
+    bias[1, 17] = 9.0                                   # id below the shift -> decodes to -1.0
+    bias[2, 18] = 9.0                                   # first continuous bin
+    bias[3, 273] = 9.0                                  # last bin
+    bias[4, 100] = float("nan")                         # NaN is the maximum
+    bias[5, 200] = float("nan"); bias[5, 50] = float("nan")     # first NaN wins
+    bias[6, 40] = 7.0; bias[6, 30] = 7.0                # tie -> first
+    bias[7, :] = -float("inf"); bias[7, 60] = -1e30     # -inf everywhere else
+    sd["action_net.0.bias"] = bias.reshape(-1).clone()
+    eng = XLSTMEngine(cfg, sd, max_batch=3)
+    states, rtg, _ = make_stream(cfg, range(3), 1, domains="mixed")
+    out = eng.policy_step(eng.new_state(3), torch.from_numpy(states[0]).cuda(), torch.from_numpy(rtg[0]).cuda(),
+                          want_logits=True)
+    torch.cuda.synchronize()
+    lg = out["action_logits"].cpu().view(3, cfg.act_dim, cfg.num_actions)
+    assert torch.equal(torch.nan_to_num(lg[0], nan=123.0), torch.nan_to_num(bias, nan=123.0))     # logits == bias, bit for bit
+    ref_tok = torch.argmax(lg, dim=-1)
+    assert ref_tok[0].tolist() == [0, 17, 18, 273, 100, 50, 30, 60]
+    assert torch.equal(out["action_tokens"].cpu().long(), ref_tok)
+    ref_act = OracleMinMaxTokenizer(cfg.action_channels, cfg.discrete_actions).inv_tokenize(ref_tok)
+    assert torch.equal(out["action_preds"].cpu(), ref_act)
+    assert ref_act[0, :3].tolist() == [-1.0, -1.0, -1.0] and ref_act[0, 3].item() == 255 * (2.0 / 256) - 1.0
+    # discrete branch: argmax over logits[:18] of the first action dimension only
+    bias_d = bias.clone()
+    bias_d[0, :] = torch.randn(cfg.num_actions, generator=g)
+    bias_d[0, 20] = 50.0                                # the global maximum sits outside the 18 discrete actions
+    bias_d[0, 5] = 10.0
+    sd["action_net.0.bias"] = bias_d.reshape(-1).clone()
+    eng2 = XLSTMEngine(cfg, sd, max_batch=3)
+    out = eng2.policy_step(eng2.new_state(3), torch.from_numpy(states[0]).cuda(), torch.from_numpy(rtg[0]).cuda(),
+                           flags=L.XL_FLAG_DISCRETE)
+    torch.cuda.synchronize()
+    assert out["action_tokens"].cpu()[:, 0].tolist() == [5, 5, 5]
+    eng.close(); eng2.close()
