@@ -20,7 +20,14 @@ run() { # tool, per-case timeout, cases...
   done
   echo "--- $tool"; grep -E "=== exit|ERROR SUMMARY|RACECHECK SUMMARY|sanitize_step" "$log"
 }
-run memcheck 600 fused_eager fused_graph per_token one_env discrete real_16M slstm prefill
-run synccheck 600 fused_eager per_token one_env real_16M slstm prefill
+R2="state_fuse1 state_fuse2 up_fuse gemm_bm64 gemm_cluster token_ring"
+if [ "${1:-all}" = "r2" ]; then   # only the kernels / options added in round 2
+  run memcheck 600 $R2
+  run synccheck 600 $R2
+  run racecheck 900 state_fuse1 state_fuse2 up_fuse gemm_cluster
+  exit 0
+fi
+run memcheck 600 fused_eager fused_graph per_token one_env discrete real_16M slstm prefill $R2
+run synccheck 600 fused_eager per_token one_env real_16M slstm prefill $R2
 run initcheck 600 fused_eager one_env real_16M prefill
-run racecheck 900 fused_eager one_env real_16M prefill
+run racecheck 900 fused_eager one_env real_16M prefill state_fuse1 state_fuse2 up_fuse gemm_cluster

@@ -25,10 +25,16 @@ def rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
-def steps_case(name, B, mode, flags, n=3, discrete=False):
+def steps_case(name, B, mode, flags, n=3, discrete=False, opts=None, ring=False):
     cfg = preset(name)
     sd = make_state_dict(cfg, seed=1)
     eng = XLSTMEngine(cfg, sd, max_batch=B)
+    for k, v in (opts or {}).items():
+        eng.set_option(k, v)
+    tok_ring = None
+    if ring:
+        tok_ring = torch.zeros(4, B, cfg.act_dim, dtype=torch.int32, device="cuda")
+        eng.set_token_ring(tok_ring, 0)
     ora = O.OraclePolicy(cfg, sd)
     states, rtg, _ = make_stream(cfg, range(B), n, domains="mixed")
     cache, pkv, out = eng.new_state(B), None, None
@@ -46,6 +52,8 @@ def steps_case(name, B, mode, flags, n=3, discrete=False):
         tok = tok[:, :1] if discrete else tok
         assert torch.equal(tok, ref["action_tokens"]), (name, t)
         assert rel(out["last_hidden_state"].cpu(), ref["last_hidden_state"]) < 1e-3
+        if tok_ring is not None:
+            assert torch.equal(tok_ring[t % 4], out["action_tokens"])
         if t == 1:
             mask = torch.zeros(B, dtype=torch.uint8)
             mask[0] = 1
@@ -82,6 +90,13 @@ CASES = {
     "real_16M": lambda: steps_case("16M", 8, L.XL_MODE_FUSED, L.XL_FLAG_GRAPH, n=2),  # DH=256: TMA ring, split-K planes
     "slstm": lambda: steps_case("toy128-ms", 4, L.XL_MODE_FUSED, 0),
     "prefill": lambda: prefill_case("toy128", 2, 32),                            # 96 tokens: tensor-core cell + tail
+    # round-2 kernels and options (process-wide GEMM switches are restored by the option's own case ending the process)
+    "state_fuse1": lambda: steps_case("16M", 64, L.XL_MODE_FUSED, L.XL_FLAG_GRAPH, n=2, opts={"state_fuse": 1}),
+    "state_fuse2": lambda: steps_case("16M", 64, L.XL_MODE_FUSED, L.XL_FLAG_GRAPH, n=2, opts={"state_fuse": 2}),
+    "up_fuse": lambda: steps_case("16M", 50, L.XL_MODE_FUSED, L.XL_FLAG_GRAPH, n=2, opts={"up_fuse": 1}),
+    "gemm_bm64": lambda: steps_case("16M", 40, L.XL_MODE_FUSED, 0, n=2, opts={"gemm_bm": 64}),
+    "gemm_cluster": lambda: steps_case("16M", 40, L.XL_MODE_FUSED, 0, n=2, opts={"gemm_cluster": 2}),
+    "token_ring": lambda: steps_case("toy128", 6, L.XL_MODE_FUSED, L.XL_FLAG_GRAPH, n=4, ring=True),
 }
 
 if __name__ == "__main__":
