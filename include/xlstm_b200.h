@@ -253,6 +253,9 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
  *                   thread-block cluster per (env, head): 1 = every CTA finishes its 128 columns, statistics over DSMEM;
  *                   2 = numerators pushed to rank 0, which finalizes the head. One launch fewer per block; measured
  *                   +1-2 % at 206M x 128 / 48M x 256 envs, -5 % at 48M x 64 (profiles/r02_chain_fusion.md)
+ *   "small_state_fuse": [0] few-env path (B*T <= 16 rows, see "smallm"): variant 2 of "state_fuse" over the head's
+ *                   slab x row-chunk tiles (one cluster of <= 16 CTAs; 2..16 = cluster cap). One launch fewer per block;
+ *                   measured slower at 16M / 48M x 1 env (+3 us per block), 3 % faster at 206M x 1 and 48M x 4
  *   "up_fuse": [0] conv + SiLU + q/k/v + gate partials in the proj_up epilogue (gemm_up_conv_kernel); one launch fewer
  *                   per block, x_m never leaves the chip; measured 3-9 % slower (more CTAs re-read the A planes from L2)
  *   "gemm_bm": [0] 64 = 64-row tcgen05 tiles for proj_up / proj_down (bit-identical; measured 1 % slower at 48M x 64)

@@ -103,6 +103,11 @@ struct xl_handle {
                                        // Measured (profiles/r02_chain_fusion.md): variant 2 wins 1-2 % at 206M x 128 and
                                        // 48M x 256, loses 5 % at 48M x 64 and 2 % at 110M x 256: cluster co-scheduling alone
                                        // costs 1.4 us per launch there, and the tails no longer overlap ("state_fuse")
+  int small_state_fuse = 0;            // few-env path (M <= 16 rows): variant 2 over the head's slab x row-chunk tiles (one
+                                       // cluster of <= 16 CTAs; 2..16 = cap). One launch fewer per block, yet measured
+                                       // SLOWER where the launch chain is the step: 16M x 1 env 153 -> 189 us, 48M x 1
+                                       // 285 -> 364 us; 206M x 1 and 48M x 4 gain 3 % (profiles/r02_chain_fusion.md s7).
+                                       // 0 = separate finalize kernel (default)            ("small_state_fuse")
   int gemm_impl = 0;                   // 0 auto, 1 CUDA-core, 2 tcgen05      (xl_set_option "gemm_impl")
   int gemm_splitk = 8;                 // max split-K planes of proj_up / proj_down, 0/1 = off ("gemm_splitk")
   int gemm_up_bn = 0, gemm_up_splits = 0, gemm_down_bn = 0, gemm_down_splits = 0;   // 0 = cost model; A/B overrides
@@ -349,6 +354,11 @@ xl::StateStepParams state_params(const xl_handle* h, void* state, const Slice& s
   sp.impl = h->state_impl; sp.num_layers = c.num_blocks;
   sp.stages = h->state_stages; sp.ctas_per_sm = h->state_ctas_per_sm; sp.rows_split = h->state_rows_split;
   sp.fuse_finalize = (h->debug_skip & (8 | 16)) ? 0 : h->state_fuse;
+  // few-env path: the launch chain IS the step time, so the head's tiles form one cluster whose rank 0 finalizes
+  if (small_nch && h->state_fuse == 0 && h->small_state_fuse) {
+    sp.fuse_finalize = 2;
+    sp.max_cluster = h->small_state_fuse > 1 ? h->small_state_fuse : 0;
+  }
   if (sl.ws.low_smem) {          // leave shared memory for the co-resident kernels of the other micro-batches
     if (sp.stages <= 0) sp.stages = 4;
     sp.meta_slots = 2;
@@ -443,8 +453,11 @@ int block_pre(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned
 // block i, part 2: the HBM-bound state stream (C update + partial numerators)
 int block_state(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigned flags) {
   const BlockPlan bp = block_plan(h, sl, T, flags);
-  const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp, smallm_chunks(h, sl, T, flags),
-                                              bp.up_fused);
+  const int small_nch = smallm_chunks(h, sl, T, flags);
+  // (few-env path: fp32 g for the GEMV proj_down and no split-K planes -- the same parameters block_post() builds,
+  // because the stream kernel may finalize the head itself)
+  const xl::StateStepParams sp = small_nch ? state_params(h, state, sl, i, T, /*tc_down=*/false, 1, small_nch)
+                                           : state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp, 0, bp.up_fused);
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   if (h->profiling) {
     XL_CUDA(cudaEventCreate(&pe0));
@@ -471,12 +484,13 @@ int block_post(xl_handle* h, void* state, const Slice& sl, int i, int T, unsigne
   if (small_nch) {
     // M <= 16 rows: finalize emits fp32 g, then x += g W_down^T as warp GEMVs (xl_smallm.cu)
     xl::StateStepParams sp = state_params(h, state, sl, i, T, /*tc_down=*/false, 1, small_nch);
-    if (!xl::state_step_fuses_finalize(sp, h->num_sms)) XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, sl.s));
+    const bool fused = xl::state_step_fuses_finalize(sp, h->num_sms);
+    if (!fused) XL_CUDA(xl::launch_state_finalize(sp, h->num_sms, sl.s));
     xl::SmallDownParams dp;
     dp.g = ws.gated; dp.w_down = (const __nv_bfloat16*)h->blocks[i].w[XL_W_PROJ_DOWN]; dp.x = ws.x;
     dp.M = M; dp.d = c.embedding_dim; dp.inner = c.inner_dim;
     XL_CUDA(xl::launch_smallm_down(dp, sl.s));
-    h->launches += 2;
+    h->launches += fused ? 1 : 2;
     return XL_OK;
   }
   const xl::StateStepParams sp = state_params(h, state, sl, i, T, bp.tc_down, bp.up_sp, small_nch, bp.up_fused);
@@ -1667,6 +1681,9 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
     h->fuse_ends = value ? 1 : 0;
   } else if (!strcmp(name, "up_fuse")) {
     h->up_fuse = value ? 1 : 0;
+  } else if (!strcmp(name, "small_state_fuse")) {
+    if (value < 0 || value > 16) return fail(XL_ERR_INVALID_ARG, "small_state_fuse must be in [0, 16]");
+    h->small_state_fuse = value;     // 0 off, 1 on (clusters of <= 16 CTAs), 2..16 = on with that cluster cap
   } else if (!strcmp(name, "state_fuse")) {
     if (value < 0 || value > 3)
       return fail(XL_ERR_INVALID_ARG, "state_fuse must be 0 (separate finalize kernel), 1 (cluster, symmetric), "

@@ -112,6 +112,7 @@ struct StateStepParams {
   // partial slots per item. sk_grid == 0 -> rows_split layout of impl 0/1.
   int sk_grid, sk_q, sk_r, sk_smax;
   int num_layers;           // blocks sharing the L2 with this one (cache-policy choice); 0 = 1
+  int max_cluster;          // leader variant: most CTAs (slabs x row chunks) per cluster, 0 = 16 (the opt-in maximum)
   int fuse_finalize;        // 1: let the stream kernel finalize inside a cluster per (env, head) when the tiling allows
                             // (state_step_fuses_finalize); launch_state_finalize must then NOT be called
   float ln_eps, cell_eps;

@@ -296,6 +296,7 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 
 constexpr int kNRowsMax = 4;          // n rows per consumer thread: DH <= 4 * 256
 constexpr int kMaxCluster = 8;
+constexpr int kMaxClusterOptIn = 16;   // non-portable cluster size (per-kernel opt-in)
 
 // sum of T values over the first `nwarps` consumer warps (fixed order); every consumer thread calls it
 template <int T>
@@ -431,20 +432,47 @@ __device__ __forceinline__ void fused_finalize(const StateStepParams& p, const T
   }
 }
 
-// Leader variant (fuse_finalize == 2): every CTA of the cluster pushes the numerators of its 128 columns into rank 0's
-// shared memory (st.async, counted by rank 0's mbarrier) and retires at once -- a fire-and-forget store from registers;
-// only rank 0 stays, waits for the CS contributions and finalizes the whole head (two-pass GroupNorm inside the CTA).
-// One tail per (env, head) instead of CS tails: the slots of the other CTAs go back to streaming immediately.
+// Leader variant (fuse_finalize == 2): every CTA of the cluster pushes the numerators of its [rows chunk x 128 columns]
+// tile into rank 0's shared memory (st.async, counted by rank 0's mbarrier) and retires at once -- a fire-and-forget
+// store from registers; only rank 0 stays, waits for the CS*RS contributions and finalizes the whole head.
+// One tail per (env, head) instead of one per CTA. Rows may be split (RS > 1, the few-env tilings): the cluster is
+// then the CS*RS tiles of the head and rank 0 adds the RS row-chunk numerators in chunk order.
+// The sums are the finalize kernel's, in its order: value j of thread tid stands for that kernel's thread tid + 256*j,
+// and leader_sum() reproduces its block_sum_n() tree (warp sums, then one warp sum over the warp totals). n, m and the
+// numerators come out bit-identical to the two-kernel step; h differs in the last ulp (the compiler folds the
+// division by the per-token denominator differently in the two kernels), 1e-7 relative on the hidden states.
+template <int T>
+__device__ __forceinline__ void leader_sum(float (&v)[kNRowsMax][T], float (&out)[T], float* red /* [T][32] */,
+                                           int warp, int lane, int nw) {
+#pragma unroll
+  for (int j = 0; j < kNRowsMax; ++j)
+#pragma unroll
+    for (int t = 0; t < T; ++t) v[j][t] = warp_sum(v[j][t]);
+  asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");      // protect `red` from its previous use
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kNRowsMax; ++j)
+      if (warp + 8 * j < nw) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) red[t * 32 + warp + 8 * j] = v[j][t];
+      }
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+#pragma unroll
+  for (int t = 0; t < T; ++t) out[t] = warp_sum(lane < nw ? red[t * 32 + lane] : 0.f);
+}
+
 template <int T>
 __device__ __forceinline__ void leader_finalize(const StateStepParams& p, const TileCoord& tc, const float* sacc,
-                                                const float* sqk, const float* sn, float* snum, int tstride,
-                                                const float* s_f, const float* s_i, const float* s_m, float* s_red,
-                                                uint32_t xbar, int tid) {
+                                                const float* sqk, const float* sqkh, const float* sn, float* snum,
+                                                int tstride, const float* s_f, const float* s_i, const float* s_m,
+                                                float* s_red, uint32_t xbar, int tid) {
   constexpr int W = 128;
-  const int DH = p.DH, inner = p.inner;
+  const int DH = p.DH, inner = p.inner, CS = DH / W, RS = p.rows_split;
   const int warp = tid >> 5, lane = tid & 31;
+  const int tile = tc.rs * CS + tc.cs;                   // == rank of this CTA in the cluster
   if (tid < W) {
-    const uint32_t rbase = mapa_u32(smem_u32(snum + (tc.cs * T) * W + tid), 0u);
+    const uint32_t rbase = mapa_u32(smem_u32(snum + (tile * T) * W + tid), 0u);
     const uint32_t rbar = mapa_u32(xbar, 0u);
 #pragma unroll
     for (int t = 0; t < T; ++t) {
@@ -453,87 +481,83 @@ __device__ __forceinline__ void leader_finalize(const StateStepParams& p, const 
       st_async_f32(rbase + (uint32_t)(t * W * sizeof(float)), s, rbar);
     }
   }
-  if (tc.cs != 0) return;
-  // ---- rank 0: the whole head. Thread tid owns channels tid + j*256 (output) and rows tid + j*256 (n recurrence)
+  if (tile != 0) return;
+  // ---- rank 0: the whole head. Thread tid owns channels (and n rows) tid + j*256
+  const float* qkh = RS > 1 ? sqkh : sqk;                // (q,k) of every row of the head
+  const int hstride = RS > 1 ? 2 * DH : tstride;
+  const int nw = (DH + 31) >> 5;
   const float kscale = rsqrtf((float)DH);
-  float qn[T], nreg[kNRowsMax];
-#pragma unroll
-  for (int t = 0; t < T; ++t) qn[t] = 0.f;
+  float nreg[kNRowsMax], v[kNRowsMax][T], qn[T];
 #pragma unroll
   for (int j = 0; j < kNRowsMax; ++j) {
     const int r = tid + j * kThreads;
-    nreg[j] = 0.f;
-    if (r < DH) {
-      float nv = sn[r];
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const float2 q2 = *reinterpret_cast<const float2*>(sqk + t * tstride + 2 * r);
-        nv = fmaf(s_f[t], nv, s_i[t] * kscale * q2.y);
-        qn[t] = fmaf(q2.x, nv, qn[t]);
-      }
-      nreg[j] = nv;
-    }
-  }
-  consumer_sum<T>(qn, s_red, warp, lane, 8);
-  float rden[T];
-#pragma unroll
-  for (int t = 0; t < T; ++t) rden[t] = fmaxf(fabsf(qn[t]), expf(-s_m[t + 1])) + p.cell_eps;
-  mbar_wait(xbar, 0);                                  // every CTA's numerators have landed
-  auto h_of = [&](int c, int t) { return snum[((c >> 7) * T + t) * W + (c & 127)] / rden[t]; };
-  float mean[T], var[T];
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    float s = 0.f;
-    for (int j = 0; j < kNRowsMax; ++j) {
-      const int c = tid + j * kThreads;
-      if (c < DH) s += h_of(c, t);
-    }
-    mean[t] = s;
-  }
-  consumer_sum<T>(mean, s_red, warp, lane, 8);
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    mean[t] /= (float)DH;
-    float s = 0.f;
-    for (int j = 0; j < kNRowsMax; ++j) {
-      const int c = tid + j * kThreads;
-      if (c < DH) {
-        const float dlt = h_of(c, t) - mean[t];
-        s = fmaf(dlt, dlt, s);
-      }
-    }
-    var[t] = s;
-  }
-  consumer_sum<T>(var, s_red, warp, lane, 8);
-  for (int j = 0; j < kNRowsMax; ++j) {
-    const int c = tid + j * kThreads;
-    if (c >= DH) break;
-    const int ch = tc.hd * DH + c;
-    const float wn = p.outnorm_w[ch];
-    const float wskip = p.skip ? p.skip[ch] : 0.f;
+    float nv = r < DH ? sn[r] : 0.f;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-      const int64_t row = (int64_t)tc.b * T + t;
-      const float h = h_of(c, t);
-      float o = (h - mean[t]) * rsqrtf(var[t] / (float)DH + p.ln_eps) * (1.f + wn);
-      if (p.h_raw) p.h_raw[row * inner + ch] = h;
-      if (p.skip) {
-        float z = p.u[row * 2 * inner + inner + ch];
-        for (int zz = 1; zz < p.u_splits; ++zz) z += p.u[zz * p.u_stride + row * 2 * inner + inner + ch];
-        o = (o + wskip * p.act[row * inner + ch]) * silu_fast(z);
-      }
-      if (p.out) p.out[row * inner + ch] = o;
-      if (p.out_hi) {
-        const __nv_bfloat16 hi = __float2bfloat16_rn(o);
-        reinterpret_cast<__nv_bfloat16*>(p.out_hi)[row * inner + ch] = hi;
-        reinterpret_cast<__nv_bfloat16*>(p.out_lo)[row * inner + ch] = __float2bfloat16_rn(o - __bfloat162float(hi));
-      }
+      const float2 q2 = r < DH ? *reinterpret_cast<const float2*>(qkh + t * hstride + 2 * r) : make_float2(0.f, 0.f);
+      nv = fmaf(s_f[t], nv, s_i[t] * kscale * q2.y);
+      v[j][t] = q2.x * nv;
     }
+    nreg[j] = nv;
   }
+  leader_sum<T>(v, qn, s_red, warp, lane, nw);
+  float den[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) den[t] = fmaxf(fabsf(qn[t]), expf(-s_m[t + 1])) + p.cell_eps;
+  mbar_wait(xbar, 0);                                    // every tile's numerators have landed
+  float hh[kNRowsMax][T], mean[T], var[T];
 #pragma unroll
   for (int j = 0; j < kNRowsMax; ++j) {
-    const int r = tid + j * kThreads;
-    if (r < DH) p.n[(int64_t)tc.bh * DH + r] = nreg[j];
+    const int c = tid + j * kThreads;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      float s = 0.f;
+      if (c < DH)
+        for (int r = 0; r < RS; ++r) s += snum[((r * CS + (c >> 7)) * T + t) * W + (c & 127)];   // chunk order
+      hh[j][t] = s / den[t];
+      v[j][t] = hh[j][t];
+    }
+  }
+  leader_sum<T>(v, mean, s_red, warp, lane, nw);
+#pragma unroll
+  for (int t = 0; t < T; ++t) mean[t] /= (float)DH;
+#pragma unroll
+  for (int j = 0; j < kNRowsMax; ++j) {
+    const int c = tid + j * kThreads;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float dlt = c < DH ? hh[j][t] - mean[t] : 0.f;
+      v[j][t] = dlt * dlt;
+    }
+  }
+  leader_sum<T>(v, var, s_red, warp, lane, nw);
+#pragma unroll
+  for (int j = 0; j < kNRowsMax; ++j) {
+    const int c = tid + j * kThreads;
+    if (c < DH) {
+      const int ch = tc.hd * DH + c;
+      const float wn = p.outnorm_w[ch];
+      const float wskip = p.skip ? p.skip[ch] : 0.f;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int64_t row = (int64_t)tc.b * T + t;
+        const float rstd = rsqrtf(var[t] / (float)DH + p.ln_eps);
+        float o = (hh[j][t] - mean[t]) * rstd * (1.f + wn);
+        if (p.h_raw) p.h_raw[row * inner + ch] = hh[j][t];
+        if (p.skip) {
+          float z = p.u[row * 2 * inner + inner + ch];
+          for (int zz = 1; zz < p.u_splits; ++zz) z += p.u[zz * p.u_stride + row * 2 * inner + inner + ch];
+          o = (o + wskip * p.act[row * inner + ch]) * silu_fast(z);
+        }
+        if (p.out) p.out[row * inner + ch] = o;
+        if (p.out_hi) {
+          const __nv_bfloat16 hi = __float2bfloat16_rn(o);
+          reinterpret_cast<__nv_bfloat16*>(p.out_hi)[row * inner + ch] = hi;
+          reinterpret_cast<__nv_bfloat16*>(p.out_lo)[row * inner + ch] = __float2bfloat16_rn(o - __bfloat162float(hi));
+        }
+      }
+      p.n[(int64_t)tc.bh * DH + c] = nreg[j];
+    }
   }
   if (tid == 0) p.m[tc.bh] = s_m[T];
 }
@@ -544,11 +568,13 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
   extern __shared__ uint8_t smem_raw[];
   __shared__ float s_f[T], s_i[T], s_m[T + 1], s_pre[2 * T];
   __shared__ __align__(8) uint64_t s_bar[2 * kStages + 2];
-  __shared__ float s_red[4 * 8], s_x[kMaxCluster * 8];
+  __shared__ float s_red[4 * 32], s_x[kMaxCluster * 8];
 
   const TileCoord tc = tile_coord(p);
   const int DH = p.DH;
   const int W = p.cols_per_cta;
+  const bool leader = kFused && p.fuse_finalize == 2 && tc.rs == 0 && tc.cs == 0;
+  const bool head_qk = leader && p.rows_split > 1;       // rank 0 of a row-split cluster needs every (q,k) of the head
   const int TX = W >> 2, TY = kThreads / TX;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tstride = 2 * tc.rows_per;
@@ -561,7 +587,8 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
   float* stage0 = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)));
   float* sqk = stage0 + (size_t)kStages * kStageRows * W;
   float* sn = sqk + (size_t)T * tstride;      // kFused: n of the whole head [DH]
-  float* snum = sn + DH;                      // kFused, leader variant: numerators of the head [CS][T][128] (rank 0)
+  float* snum = sn + DH;                      // kFused, leader variant: numerators of the head [RS*CS][T][128] (rank 0)
+  float* sqkh = snum + (size_t)p.rows_split * T * DH;   // leader of a row-split cluster: (q,k) of the head [T][DH][2]
   float* sacc = stage0;
   const uint32_t bar0 = smem_u32(s_bar);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -579,7 +606,7 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
       // the exchange barrier completes when the 2T statistics of each of the CS CTAs have landed (bytes)
       mbar_init(xbar, 1);
       if (p.fuse_finalize == 2) {
-        if (tc.cs == 0) mbar_expect_tx(xbar, (uint32_t)(DH * T * sizeof(float)));   // the head's numerators
+        if (leader) mbar_expect_tx(xbar, (uint32_t)(p.rows_split * DH * T * sizeof(float)));   // the head's numerators
       } else {
         mbar_expect_tx(xbar, (uint32_t)((DH / 128) * 2 * T * sizeof(float)));
       }
@@ -623,8 +650,14 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
       pdl_trigger();
       if (kFused) cluster_wait();
       // the step's (q, k) pairs of this row chunk: T contiguous runs of nrows*8 bytes (+ n of the head when fused)
-      mbar_expect_tx(qk_bar, (uint32_t)(T * tc.nrows * 8 + (kFused ? DH * 4 : 0)));
+      mbar_expect_tx(qk_bar, (uint32_t)(T * tc.nrows * 8 + (kFused ? DH * 4 : 0) + (head_qk ? T * DH * 8 : 0)));
       if (kFused) bulk_copy_g2s(smem_u32(sn), p.n + (int64_t)tc.bh * DH, (uint32_t)(DH * 4), qk_bar);
+      if (head_qk) {
+#pragma unroll
+        for (int t = 0; t < T; ++t)
+          bulk_copy_g2s(smem_u32(sqkh + t * 2 * DH), p.qk + ((((int64_t)tc.b * T + t) * p.NH + tc.hd) * DH) * 2,
+                        (uint32_t)(DH * 8), qk_bar);
+      }
 #pragma unroll
       for (int t = 0; t < T; ++t)
         bulk_copy_g2s(smem_u32(sqk + t * tstride),
@@ -714,7 +747,7 @@ mlstm_state_stream_tma_kernel(const __grid_constant__ CUtensorMap mapC, StateSte
           make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
     asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
     if (p.fuse_finalize == 2)
-      leader_finalize<T>(p, tc, sacc, sqk, sn, snum, tstride, s_f, s_i, s_m, s_red, xbar, tid);
+      leader_finalize<T>(p, tc, sacc, sqk, sqkh, sn, snum, tstride, s_f, s_i, s_m, s_red, xbar, tid);
     else
       fused_finalize<T>(p, tc, sacc, sqk, sn, tstride, s_f, s_i, s_m, s_red, s_x, xbar, tid);
     return;
@@ -757,7 +790,8 @@ static cudaError_t launch(const StateStepParams& p, cudaStream_t s) {
   const int TY = kThreads / (p.cols_per_cta / 4);
   const size_t red = sizeof(float) * (size_t)TY * T * p.cols_per_cta;       // aliases the ring
   const size_t smem = 128 + (ring > red ? ring : red) +
-                      sizeof(float) * ((size_t)2 * T * rows_per + (kFused ? (size_t)p.DH * (1 + T) : 0));
+                      sizeof(float) * ((size_t)2 * T * rows_per +
+                                       (kFused ? (size_t)p.DH * (1 + T * p.rows_split + (p.rows_split > 1 ? 2 * T : 0)) : 0));
   if (cudaError_t e = ensure_dyn_smem<&mlstm_state_stream_tma_kernel<T, kStream, kFused>>(smem); e != cudaSuccess)
     return e;
   const int CS = p.DH / p.cols_per_cta;
@@ -765,7 +799,21 @@ static cudaError_t launch(const StateStepParams& p, cudaStream_t s) {
   if (!kFused && p.fuse_finalize != 3)
     return launch_k(mlstm_state_stream_tma_kernel<T, kStream, false>, dim3((unsigned)grid), dim3(kBlock), smem, s, map,
                     p);
-  // one cluster per (env, head): its CS column-slab CTAs
+  // one cluster per (env, head): its CS column-slab (x RS row-chunk) CTAs
+  const int csize = CS * p.rows_split;
+  if (csize > 8) {      // > 8 CTAs per cluster is a per-kernel opt-in
+    static std::atomic<bool> allowed[kMaxDevices];
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess) return e;
+    const bool tracked = dev >= 0 && dev < kMaxDevices;
+    if (!tracked || !allowed[dev].load(std::memory_order_acquire)) {
+      if (cudaError_t e = cudaFuncSetAttribute(mlstm_state_stream_tma_kernel<T, kStream, kFused>,
+                                               cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+          e != cudaSuccess)
+        return e;
+      if (tracked) allowed[dev].store(true, std::memory_order_release);
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kBlock);
@@ -773,7 +821,7 @@ static cudaError_t launch(const StateStepParams& p, cudaStream_t s) {
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)CS;
+  attr[0].val.clusterDim.x = (unsigned)csize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1267,23 +1315,45 @@ static void resolve_tiling(StateStepParams& p, int num_sms) {
   if (p.rows_split <= 0 || p.cols_per_cta <= 0) {
     int rs, cols;
     state_step_auto_tiling(p.B, p.NH, p.DH, num_sms, &rs, &cols);
+    // leader-fused finalize: the CS*RS tiles of a head are one thread-block cluster (<= 16 CTAs)
+    if (p.fuse_finalize == 2 && cols == 128) {
+      const int cap = (p.max_cluster > 0 && p.max_cluster < tma::kMaxClusterOptIn) ? p.max_cluster : tma::kMaxClusterOptIn;
+      while (rs > 1 && (p.DH / 128) * rs > cap) rs >>= 1;
+    }
     if (p.rows_split <= 0) p.rows_split = rs;
     if (p.cols_per_cta <= 0) p.cols_per_cta = cols;
   }
 }
 
 // True when launch_state_step(p) will also finalize (n/m update, normalise, gate) inside the stream kernel: the
-// one-shot TMA kernel, rows not split, 128-column slabs, <= 8 slabs per head (the cluster), DH <= 1024.
+// one-shot TMA kernel, 128-column slabs, DH <= 1024, and the tiles of a head fit one cluster -- rows not split and
+// <= 8 slabs for the symmetric variant (1); <= 16 tiles (slabs x row chunks) for the leader variant (2).
 bool state_step_fuses_finalize(StateStepParams p, int num_sms) {
   if (p.fuse_finalize != 1 && p.fuse_finalize != 2) return false;
   if (p.impl != 1) return false;
   resolve_tiling(p, num_sms);
-  return p.sk_grid == 0 && p.rows_split == 1 && p.cols_per_cta == 128 && p.DH % 128 == 0 &&
-         p.DH / 128 <= tma::kMaxCluster && p.DH <= tma::kNRowsMax * kThreads && p.T <= 4;
+  if (p.sk_grid != 0 || p.cols_per_cta != 128 || p.DH % 128 != 0 || p.DH > tma::kNRowsMax * kThreads || p.T > 4)
+    return false;
+  const int CS = p.DH / 128;
+  if (p.fuse_finalize == 1) return p.rows_split == 1 && CS <= tma::kMaxCluster;
+  return p.DH % (p.rows_split * 4) == 0 && CS * p.rows_split <= tma::kMaxClusterOptIn &&
+         (p.rows_split == 1 ? CS <= tma::kMaxCluster : true);
+}
+
+// The separate finalize kernel and the stream kernel must resolve the same tiling: a fuse request the stream kernel
+// cannot honour is dropped before the tiling is resolved (the leader variant caps the row split).
+static void drop_unfusable(StateStepParams& p, int num_sms) {
+  if (!state_step_fuses_finalize(p, num_sms)) {
+    // the cluster probe (3) keeps its value only where the fused kernel would have run
+    StateStepParams q = p;
+    q.fuse_finalize = 1;
+    p.fuse_finalize = (p.fuse_finalize == 3 && state_step_fuses_finalize(q, num_sms)) ? 3 : 0;
+  }
 }
 
 // kernel 2; p must carry the same rows_split the stream kernel ran with (resolved here the same way)
 cudaError_t launch_state_finalize(StateStepParams p, int num_sms, cudaStream_t s) {
+  drop_unfusable(p, num_sms);
   resolve_tiling(p, num_sms);
   const int thr = ((p.DH + 31) / 32) * 32;
   switch (p.T) {
@@ -1298,12 +1368,7 @@ cudaError_t launch_state_finalize(StateStepParams p, int num_sms, cudaStream_t s
 
 // kernel 1
 cudaError_t launch_state_step(StateStepParams p, int num_sms, cudaStream_t s) {
-  if (!state_step_fuses_finalize(p, num_sms)) {
-    // the cluster probe (3) keeps its value only where the fused kernel would have run
-    StateStepParams q = p;
-    q.fuse_finalize = 1;
-    p.fuse_finalize = (p.fuse_finalize == 3 && state_step_fuses_finalize(q, num_sms)) ? 3 : 0;
-  }
+  drop_unfusable(p, num_sms);
   resolve_tiling(p, num_sms);
   if (p.cols_per_cta % 4 || p.DH % p.cols_per_cta || slab_width(p.DH) % p.cols_per_cta ||
       kThreads % (p.cols_per_cta / 4) || p.DH > 1024 || p.NCH > kMaxNCH || p.rows_split > p.DH)

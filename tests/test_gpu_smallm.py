@@ -96,3 +96,38 @@ def test_smallm_front_kernel_equals_three_kernel_path(name, B, mode):
     # (the multi-kernel path itself saves block 0's LayerNorm launch in fused mode: it rides on the embed kernel)
     assert launches[0] - launches[1] >= 2 * cfg.num_blocks * passes - 1, launches
     eng.close()
+
+
+@pytest.mark.parametrize("name,B,mode", [("16M", 1, L.XL_MODE_FUSED), ("48M", 1, L.XL_MODE_FUSED), ("48M", 2, L.XL_MODE_FUSED),
+                                         ("110M", 5, L.XL_MODE_FUSED), ("206M", 1, L.XL_MODE_FUSED),
+                                         ("16M", 7, L.XL_MODE_PER_TOKEN)])
+def test_small_batch_cluster_finalize_equals_two_kernel_step(name, B, mode):
+    """Few-env path, option "small_state_fuse": the state kernel's cluster (column slabs x row chunks of a head, <= 16
+    CTAs) pushes its numerators to rank 0, which finalizes the head -- one launch fewer per block than with the separate
+    finalize kernel, same sums in the same order. Tokens are compared with ==; hidden states and the carried state agree
+    to 1e-6 (the division by the per-token denominator is folded differently by the compiler in the two kernels)."""
+    cfg, sd, eng = _engine(name, B)
+    steps = 3
+    states, rtg, _ = make_stream(cfg, range(B), steps, domains="mixed")
+    res, launches = {}, {}
+    for on in (0, 1):
+        eng.set_option("smallm", 1)
+        eng.set_option("small_state_fuse", on)
+        cache = eng.new_state(B)
+        toks, hids = [], []
+        eng.launch_count()
+        for t in range(steps):
+            out = eng.policy_step(cache, torch.from_numpy(states[t]).cuda(), torch.from_numpy(rtg[t]).cuda(), mode=mode,
+                                  want_hidden=True)
+            toks.append(out["action_tokens"].cpu().clone())
+            hids.append(out["last_hidden_state"].cpu().clone())
+        launches[on] = eng.launch_count() / steps
+        res[on] = (torch.stack(toks), torch.stack(hids), cache.to_past_key_values())
+    assert torch.equal(res[1][0], res[0][0])
+    assert _rel(res[1][1], res[0][1]) < 1e-6
+    for i in range(cfg.num_blocks):
+        for a, b in zip(res[1][2][f"block_{i}"]["mlstm_state"], res[0][2][f"block_{i}"]["mlstm_state"]):
+            assert _rel(a.cpu(), b.cpu()) < 1e-6 or (a - b).abs().max().item() < 1e-6
+    passes = 1 if mode == L.XL_MODE_FUSED else cfg.tokens_per_step
+    assert launches[0] - launches[1] == cfg.num_blocks * passes, launches
+    eng.close()
