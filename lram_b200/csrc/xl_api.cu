@@ -132,7 +132,10 @@ struct xl_handle {
         *pf_semb = nullptr, *pf_spad = nullptr, *pf_sin = nullptr, *pf_rtg = nullptr, *pf_rew = nullptr;
   __nv_bfloat16 *pf_hi = nullptr, *pf_lo = nullptr;
   uint8_t *pf_pc = nullptr, *pf_pv = nullptr;   // prepared operands of the chunkwise tensor-core cell
-  int prefill_cell = 1;                         // 1: chunkwise mma.sync cell (xl_prefill_mma.cu), 0: fp32 sequence cell
+  char* pf_tc = nullptr;                        // workspace of the tcgen05 chunkwise cell (grow-only)
+  size_t pf_tc_bytes = 0;
+  int prefill_cell = 2;                         // 2: chunkwise tcgen05 cell (xl_prefill_tc.cu), 1: chunkwise mma.sync cell
+                                                // (xl_prefill_mma.cu), 0: fp32 sequence cell            ("prefill_cell")
   int smallm = -1;                              // GEMV-style front (LN + proj_up + conv/qkv) and back (proj_down) kernels
                                                 // ("smallm"): 1 = whenever B*T <= 16 rows, 0 = never, -1 = automatic: B*T <= 4
                                                 // rows and d <= 1024, where they are measured faster (16M x 1 env: 168 vs 196 us,
@@ -886,6 +889,19 @@ int ensure_prefill_ws(xl_handle* h, int rows) {
   return XL_OK;
 }
 
+int ensure_prefill_tc_ws(xl_handle* h, int B, int Sc) {
+  const size_t need = xl::prefill_cell_tc_ws_bytes(B, Sc, h->cfg.num_heads, h->DH);
+  if (need <= h->pf_tc_bytes) return XL_OK;
+  XL_CUDA(cudaDeviceSynchronize());            // nothing may still be using the old workspace
+  if (h->pf_tc) cudaFree(h->pf_tc);
+  h->pf_tc = nullptr;
+  h->pf_tc_bytes = 0;
+  cudaError_t e = cudaMalloc((void**)&h->pf_tc, need);
+  if (e != cudaSuccess) return fail(XL_ERR_CUDA, "cudaMalloc(prefill cell workspace %zu B) failed: %s", need, cudaGetErrorString(e));
+  h->pf_tc_bytes = need;
+  return XL_OK;
+}
+
 Ws prefill_ws(const xl_handle* h) {
   Ws w;
   memset(&w, 0, sizeof(w));
@@ -929,7 +945,9 @@ int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cud
     xl::launch_ln_rows(ws.x, d, tc_up ? nullptr : ws.xn, d, (const float*)w.w[XL_W_XLSTM_NORM], nullptr, 1, c.ln_eps,
                        M, d, tc_up ? ws.a_hi : nullptr, tc_up ? ws.a_lo : nullptr, s);
     h->launches += 1;
-    int rc = linear(h, ws, ws.xn, w.w[XL_W_PROJ_UP], nullptr, nullptr, ws.u, M, 2 * inner, d, impl, s, tc_up);
+    XL_CUDA(cudaGetLastError());
+    int rc = linear(h, ws, ws.xn, w.w[XL_W_PROJ_UP], nullptr, nullptr, ws.u, M, 2 * inner, d, impl, s, tc_up,
+                    h->gemm_up_bn);
     if (rc) return rc;
     xl::ConvQkvParams cp;
     cp.u = ws.u;
@@ -951,9 +969,17 @@ int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cud
     cp.impl = 0;
     if (!xl::launch_conv_qkv_gates_seq(cp, Sc, s))
       return fail(XL_ERR_UNSUPPORTED, "sequence conv/qkv kernel not instantiated for KS=%d NH=%d", cp.KS, cp.NH);
+    XL_CUDA(cudaGetLastError());
     xl::launch_gate_scan_seq(ws.gate_part, (const float*)w.w[XL_W_IGATE_B], (const float*)w.w[XL_W_FGATE_B],
                              (float*)(base + L.m_off), h->pf_f, h->pf_i, h->pf_m, B, Sc, NH, h->NCH, s);
-    if (h->prefill_cell == 1 && xl::prefill_cell_mma_supported(DH) && Sc % xl::prefill_cell_mma_chunk() == 0) {
+    XL_CUDA(cudaGetLastError());
+    if (h->prefill_cell == 2 && xl::prefill_cell_tc_supported(DH)) {
+      if (int rcw = ensure_prefill_tc_ws(h, B, Sc)) return rcw;
+      XL_CUDA(xl::launch_cell_tc((float*)(base + L.c_off), (float*)(base + L.n_off), cp.qk, cp.qk + (size_t)M * inner,
+                                 cp.v, h->pf_f, h->pf_i, h->pf_num, h->pf_qn, h->pf_tc, B, Sc, NH, DH, inner, s));
+      h->launches += 6;
+      XL_CUDA(cudaGetLastError());
+    } else if (h->prefill_cell >= 1 && xl::prefill_cell_mma_supported(DH) && Sc % xl::prefill_cell_mma_chunk() == 0) {
       XL_CUDA(xl::launch_cell_mma((float*)(base + L.c_off), (float*)(base + L.n_off), cp.qk,
                                   cp.qk + (size_t)M * inner, cp.v, h->pf_f, h->pf_i, h->pf_num, h->pf_qn, h->pf_pc,
                                   h->pf_pv, B, Sc, NH, DH, inner, s));
@@ -968,7 +994,8 @@ int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cud
                                     tc_down ? ws.a_hi : nullptr, tc_down ? ws.a_lo : nullptr, B, Sc, NH, DH, inner,
                                     c.ln_eps, c.cell_eps, s));
     h->launches += 5;
-    rc = linear(h, ws, ws.gated, w.w[XL_W_PROJ_DOWN], nullptr, ws.x, ws.x, M, d, inner, impl, s, tc_down);
+    rc = linear(h, ws, ws.gated, w.w[XL_W_PROJ_DOWN], nullptr, ws.x, ws.x, M, d, inner, impl, s, tc_down,
+                h->gemm_down_bn);
     if (rc) return rc;
   }
   XL_CUDA(cudaGetLastError());
@@ -1113,6 +1140,7 @@ void xl_destroy(xl_handle* h) {
   for (auto& g : h->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->ws) cudaFree(h->ws);
+  if (h->pf_tc) cudaFree(h->pf_tc);
   if (h->pf_buf) cudaFree(h->pf_buf);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (int k = 0; k < kMaxMicro - 1; ++k) {
@@ -1522,7 +1550,7 @@ int xl_prefill(xl_handle* h, void* state, const float* x_in, float* y_out, int B
     while (S - pos >= 8) {
       int Sc = std::min(sc_max, (S - pos) / 8 * 8);
       // whole 16-token chunks go to the tensor-core cell; an 8-token remainder takes the fp32 cell next round
-      if (h->prefill_cell == 1 && xl::prefill_cell_mma_supported(h->DH) && Sc >= 16) Sc = Sc / 16 * 16;
+      if (h->prefill_cell >= 1 && xl::prefill_cell_mma_supported(h->DH) && Sc >= 16) Sc = Sc / 16 * 16;
       rc = ensure_prefill_ws(h, B * Sc);
       if (rc) return rc;
       XL_CUDA(cudaMemcpy2DAsync(h->pf_x, sizeof(float) * (size_t)Sc * d, x_in + (size_t)pos * d,
@@ -1575,7 +1603,7 @@ int xl_policy_prefill(xl_handle* h, void* state, const float* states, const floa
     while (Tn - pos >= 8) {
       int Tc = std::min(tc_max, (Tn - pos) / 8 * 8);             // 8 timesteps = 24 tokens = 3 cell stages
       // 16 timesteps = 48 tokens = 3 chunks of the tensor-core cell; an 8-timestep remainder takes the fp32 cell
-      if (h->prefill_cell == 1 && xl::prefill_cell_mma_supported(h->DH) && Tc >= 16) Tc = Tc / 16 * 16;
+      if (h->prefill_cell >= 1 && xl::prefill_cell_mma_supported(h->DH) && Tc >= 16) Tc = Tc / 16 * 16;
       const int rows = B * Tc;
       rc = ensure_prefill_ws(h, rows * T);
       if (rc) return rc;
@@ -1703,8 +1731,14 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
 #endif
     h->microbatches = value;
   } else if (!strcmp(name, "prefill_cell")) {
-    if (value < 0 || value > 1) return fail(XL_ERR_INVALID_ARG, "prefill_cell must be 0 (fp32 sequence cell) or 1 (chunkwise mma)");
+    if (value < 0 || value > 2)
+      return fail(XL_ERR_INVALID_ARG, "prefill_cell must be 0 (fp32 sequence cell), 1 (chunkwise mma.sync) or 2 (chunkwise tcgen05)");
     h->prefill_cell = (int)value;
+  } else if (!strcmp(name, "prefill_conv_run")) {
+    if (value < 4 || value > 64 || value % 4) return fail(XL_ERR_INVALID_ARG, "prefill_conv_run must be a multiple of 4 in [4, 64]");
+    xl::g_prefill_conv_run = value;           // process-wide: tokens per CTA of the sequence conv/qkv kernel
+  } else if (!strcmp(name, "prefill_tc_fused")) {
+    xl::g_prefill_tc_fused = value ? 1 : 0;   // process-wide A/B: chunk update + scan in one kernel (1) or through HBM (0)
   } else if (!strcmp(name, "pdl")) {
     xl::g_use_pdl = value ? 1 : 0;       // process-wide: programmatic dependent launch of every kernel
   } else if (!strcmp(name, "l2_prefetch_mb")) {

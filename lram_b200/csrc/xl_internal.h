@@ -165,6 +165,16 @@ void prefill_cell_mma_ws(int rows, int NH, int DH, size_t* common_bytes, size_t*
 cudaError_t launch_cell_mma(float* C, float* n, const float* q, const float* k, const float* v, const float* fseq,
                             const float* iseq, float* num, float* qn, void* common, void* vblk, int B, int S, int NH,
                             int DH, int inner, cudaStream_t s);
+// chunkwise sequence cell on tcgen05 (xl_prefill_tc.cu): 128-token chunks, every contraction a batched tcgen05 GEMM over
+// the (env, head, chunk) triples of the run; any S >= 1 (a ragged last chunk is padded with neutral gates)
+extern int g_prefill_tc_fused;
+extern int g_prefill_conv_run;
+bool prefill_cell_tc_supported(int DH);
+int prefill_cell_tc_chunk();
+size_t prefill_cell_tc_ws_bytes(int B, int S, int NH, int DH);
+cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, const float* v, const float* fseq,
+                           const float* iseq, float* num, float* qn, void* ws, int B, int S, int NH, int DH, int inner,
+                           cudaStream_t s);
 cudaError_t launch_finalize_seq(const float* num, const float* qn, const float* mseq, const float* outnorm_w,
                                 const float* skip, const float* act, const float* u, float* out, void* out_hi,
                                 void* out_lo, int B, int S, int NH, int DH, int inner, float ln_eps, float cell_eps,

@@ -224,16 +224,18 @@ __global__ void __launch_bounds__(256) conv_state_seq_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------
 // Gate scan: per (env, head) the stabiliser recurrence over the chunk's tokens,
 //   lf = logsigmoid(f~);  m' = max(lf + m, i~);  f = exp(lf + m - m');  i = exp(i~ - m')
-// with exactly the arithmetic of compute_gates() (xl_state_step.cu). One CTA per (env, head): the
-// pre-activations of 512 tokens are summed / log-sigmoided in parallel, one warp runs the max-plus chain over
-// shared memory, f and i are again computed in parallel. Outputs are [B*NH][S]: a head's tokens are contiguous.
+// with exactly the arithmetic of compute_gates() (xl_state_step.cu). One CTA of 1024 threads per (env, head): the
+// pre-activations of up to 2048 tokens are summed / log-sigmoided in parallel (two tokens per thread: the loads of the
+// whole run are in flight at once), one warp runs the max-plus chain over shared memory, f and i are again computed in
+// parallel. Outputs are [B*NH][S]: a head's tokens are contiguous.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) gate_scan_seq_kernel(const float* __restrict__ gate_part,
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) gate_scan_seq_kernel(const float* __restrict__ gate_part,
                                                             const float* __restrict__ igate_b,
                                                             const float* __restrict__ fgate_b, float* __restrict__ m_state,
                                                             float* __restrict__ fseq, float* __restrict__ iseq,
                                                             float* __restrict__ mseq, int B, int S, int NH, int NCH) {
-  constexpr int kSuper = 512;                    // tokens per super-chunk (4 per thread)
+  constexpr int kSuper = 2048;                   // tokens per super-chunk (2 per thread)
   __shared__ float s_ig[kSuper + 32], s_lf[kSuper + 32], s_mp[kSuper], s_mn[kSuper];
   pdl_wait();
   pdl_trigger();
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(128) gate_scan_seq_kernel(const float* __restr
   for (int s0 = 0; s0 < S; s0 += kSuper) {
     const int cnt = min(kSuper, S - s0);
     // (A) pre-activations of all tokens of the super-chunk, in parallel
-    for (int u = tid; u < cnt; u += 128) {
+    for (int u = tid; u < cnt; u += kScanThreads) {
       const float* gp = gate_part + ((int64_t)b * S + s0 + u) * NCH * 2 * NH + hd;
       float si = 0.f, sf = 0.f;
       for (int c = 0; c < NCH; ++c) {            // fixed order, as compute_gates()
@@ -256,31 +258,42 @@ __global__ void __launch_bounds__(128) gate_scan_seq_kernel(const float* __restr
       s_lf[u] = log_sigmoid(sf + bf);
     }
     __syncthreads();
-    // (B) the max-plus chain m' = max(lf + m, i~): warp 0, every lane runs it on broadcast values (the loads do
-    //     not depend on the chain, so add + max are the critical path)
+    // (B) the max-plus chain m' = max(lf + m, i~) as a segmented scan in warp 0: a token is the map m -> max(m + lf, i~);
+    //     maps compose as (A1, B1) then (A2, B2) = (A1 + A2, max(B1 + A2, B2)). Each lane folds its contiguous segment,
+    //     the 32 segment maps are scanned with shuffles, and each lane replays its segment from its true start value
+    //     (2 x cnt/32 dependent steps instead of cnt). m differs from token-by-token stepping only by the association of
+    //     the lf sums between resets (~1 ulp of m; the stabiliser cancels in h).
     if (tid < 32) {
-      for (int g0 = 0; g0 < cnt; g0 += 32) {
-        float lfv[32], igv[32];
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {        // broadcast loads, all issued before the chain starts
-          lfv[jj] = s_lf[g0 + jj];
-          igv[jj] = s_ig[g0 + jj];
-        }
-        float mp_mine = 0.f, mn_mine = 0.f;
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          if (g0 + jj < cnt) {                   // warp-uniform
-            const float mn = fmaxf(lfv[jj] + m, igv[jj]);
-            if (jj == lane) { mp_mine = m; mn_mine = mn; }
-            m = mn;
-          }
-        }
-        if (g0 + lane < cnt) { s_mp[g0 + lane] = mp_mine; s_mn[g0 + lane] = mn_mine; }
+      const int seg = ((cnt + 31) / 32) | 1;             // odd stride: conflict-free shared-memory walks
+      const int lo = min(cnt, lane * seg), hi = min(cnt, lo + seg);
+      float A = 0.f, Bv = -INFINITY;
+      for (int u = lo; u < hi; ++u) {
+        A += s_lf[u];
+        Bv = fmaxf(Bv + s_lf[u], s_ig[u]);
       }
+      float Ai = A, Bi = Bv;                             // inclusive scan of the segment maps
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float Ap = __shfl_up_sync(0xffffffffu, Ai, o);
+        const float Bp = __shfl_up_sync(0xffffffffu, Bi, o);
+        if (lane >= o) {
+          Bi = fmaxf(Bp + Ai, Bi);
+          Ai = Ap + Ai;
+        }
+      }
+      float Aex = __shfl_up_sync(0xffffffffu, Ai, 1), Bex = __shfl_up_sync(0xffffffffu, Bi, 1);
+      float mm = lane == 0 ? m : fmaxf(m + Aex, Bex);    // m at the start of this lane's segment
+      for (int u = lo; u < hi; ++u) {
+        const float mn = fmaxf(s_lf[u] + mm, s_ig[u]);
+        s_mp[u] = mm;
+        s_mn[u] = mn;
+        mm = mn;
+      }
+      m = __shfl_sync(0xffffffffu, mm, (cnt - 1) / seg);  // the m the last token left (what mseq holds for it)
     }
     __syncthreads();
     // (C) f, i of all tokens, in parallel
-    for (int u = tid; u < cnt; u += 128) {
+    for (int u = tid; u < cnt; u += kScanThreads) {
       const float mp = s_mp[u], mn = s_mn[u];
       const int64_t o = (int64_t)bh * S + s0 + u;
       fseq[o] = expf(s_lf[u] + mp - mn);
@@ -543,7 +556,8 @@ struct FinalizeSeqParams {
   float ln_eps, cell_eps;
 };
 
-// one warp per (row, head): shuffle reductions only, no block barriers
+// one warp per (row, head): shuffle reductions only, no block barriers. A lane owns groups of 4 consecutive channels
+// (128-bit loads of num / a / z, 64-bit stores of the bf16 planes); DH % 4 == 0, DH <= 1024.
 __global__ void __launch_bounds__(256) mlstm_finalize_seq_kernel(FinalizeSeqParams p) {
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -557,49 +571,63 @@ __global__ void __launch_bounds__(256) mlstm_finalize_seq_kernel(FinalizeSeqPara
   const float qn = p.qn[row * p.NH + hd];
   const float m = p.mseq[((int64_t)b * p.NH + hd) * p.S + s];
   const float den = fmaxf(fabsf(qn), expf(-m)) + p.cell_eps;
-  const float* num = p.num + row * inner + hd * DH;
-  // up to 32 channels per lane (DH <= 1024) held in registers: every global load is issued up front
-  float hv[32], av[32], zv[32];
-  float sum = 0.f;
+  const float4* num = reinterpret_cast<const float4*>(p.num + row * inner + hd * DH);
+  const float4* act = reinterpret_cast<const float4*>(p.act + row * inner + hd * DH);
+  const float4* zz = reinterpret_cast<const float4*>(p.u + row * 2 * inner + inner + hd * DH);
+  const int ng = DH >> 2;
+  constexpr int E = 8;
+  float4 hv[E], av[E], zv[E];
+  // every global load is issued up front
 #pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    const int a = lane + 32 * e;
-    hv[e] = 0.f; av[e] = 0.f; zv[e] = 0.f;
-    if (a < DH) {
-      hv[e] = num[a];
-      av[e] = p.act[row * inner + hd * DH + a];
-      zv[e] = p.u[row * 2 * inner + inner + hd * DH + a];
+  for (int e = 0; e < E; ++e) {
+    const int g = lane + 32 * e;
+    hv[e] = av[e] = zv[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < ng) {
+      hv[e] = num[g];
+      av[e] = act[g];
+      zv[e] = zz[g];
     }
   }
+  float sum = 0.f;
 #pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    if (lane + 32 * e < DH) {
-      hv[e] = hv[e] / den;
-      sum += hv[e];
+  for (int e = 0; e < E; ++e) {
+    if (lane + 32 * e < ng) {
+      hv[e].x /= den; hv[e].y /= den; hv[e].z /= den; hv[e].w /= den;
+      sum += (hv[e].x + hv[e].y) + (hv[e].z + hv[e].w);
     }
   }
   const float mean = warp_sum(sum) / (float)DH;
   float sq = 0.f;
 #pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    if (lane + 32 * e < DH) {
-      const float dlt = hv[e] - mean;
-      sq += dlt * dlt;
+  for (int e = 0; e < E; ++e) {
+    if (lane + 32 * e < ng) {
+      const float d0 = hv[e].x - mean, d1 = hv[e].y - mean, d2 = hv[e].z - mean, d3 = hv[e].w - mean;
+      sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
     }
   }
   const float rstd = rsqrtf(warp_sum(sq) / (float)DH + p.ln_eps);
 #pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    const int a = lane + 32 * e;
-    if (a < DH) {
-      const int ch = hd * DH + a;
-      float o = (hv[e] - mean) * rstd * (1.f + p.outnorm_w[ch]);
-      o = (o + p.skip[ch] * av[e]) * silu_fast(zv[e]);
-      if (p.out) p.out[row * inner + ch] = o;
+  for (int e = 0; e < E; ++e) {
+    const int g = lane + 32 * e;
+    if (g < ng) {
+      const int ch = hd * DH + 4 * g;
+      const float4 wn = *reinterpret_cast<const float4*>(p.outnorm_w + ch);
+      const float4 sk = *reinterpret_cast<const float4*>(p.skip + ch);
+      float o[4];
+      o[0] = ((hv[e].x - mean) * rstd * (1.f + wn.x) + sk.x * av[e].x) * silu_fast(zv[e].x);
+      o[1] = ((hv[e].y - mean) * rstd * (1.f + wn.y) + sk.y * av[e].y) * silu_fast(zv[e].y);
+      o[2] = ((hv[e].z - mean) * rstd * (1.f + wn.z) + sk.z * av[e].z) * silu_fast(zv[e].z);
+      o[3] = ((hv[e].w - mean) * rstd * (1.f + wn.w) + sk.w * av[e].w) * silu_fast(zv[e].w);
+      if (p.out) *reinterpret_cast<float4*>(p.out + row * inner + ch) = make_float4(o[0], o[1], o[2], o[3]);
       if (p.out_hi) {
-        const __nv_bfloat16 hi = __float2bfloat16_rn(o);
-        p.out_hi[row * inner + ch] = hi;
-        p.out_lo[row * inner + ch] = __float2bfloat16_rn(o - __bfloat162float(hi));
+        __nv_bfloat16 h4[4], l4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          h4[j] = __float2bfloat16_rn(o[j]);
+          l4[j] = __float2bfloat16_rn(o[j] - __bfloat162float(h4[j]));
+        }
+        *reinterpret_cast<uint2*>(p.out_hi + row * inner + ch) = *reinterpret_cast<uint2*>(h4);
+        *reinterpret_cast<uint2*>(p.out_lo + row * inner + ch) = *reinterpret_cast<uint2*>(l4);
       }
     }
   }
@@ -627,11 +655,13 @@ bool prefill_cell_supported(int DH) {
   return cell_plan(DH, &R, &CPT, &NW);
 }
 
+int g_prefill_conv_run = 8;    // xl_set_option("prefill_conv_run")
+
 bool launch_conv_qkv_gates_seq(const ConvQkvParams& p, int S, cudaStream_t s) {
   const int nblk = p.inner / 4;
   const int per_chunk = (nblk + p.NCH - 1) / p.NCH;
   const int threads = ((per_chunk + 31) / 32) * 32;
-  const int run = 8;                                    // tokens per CTA
+  const int run = g_prefill_conv_run;                   // tokens per CTA (multiple of 4)
   dim3 grid(p.NCH, p.B, (S + run - 1) / run);
   if (p.KS == 4 && p.NH == 4) {
     launch_k(pf::conv_qkv_gates_seq_kernel<4, 4>, grid, dim3(threads), 0, s, p, S, run);
@@ -652,7 +682,7 @@ bool launch_conv_qkv_gates_seq(const ConvQkvParams& p, int S, cudaStream_t s) {
 
 void launch_gate_scan_seq(const float* gate_part, const float* igate_b, const float* fgate_b, float* m_state,
                           float* fseq, float* iseq, float* mseq, int B, int S, int NH, int NCH, cudaStream_t s) {
-  launch_k(pf::gate_scan_seq_kernel, dim3(B * NH), dim3(128), 0, s, gate_part, igate_b, fgate_b, m_state, fseq, iseq,
+  launch_k(pf::gate_scan_seq_kernel, dim3(B * NH), dim3(pf::kScanThreads), 0, s, gate_part, igate_b, fgate_b, m_state, fseq, iseq,
            mseq, B, S, NH, NCH);
 }
 
