@@ -132,6 +132,7 @@ struct xl_handle {
         *pf_semb = nullptr, *pf_spad = nullptr, *pf_sin = nullptr, *pf_rtg = nullptr, *pf_rew = nullptr;
   __nv_bfloat16 *pf_hi = nullptr, *pf_lo = nullptr;
   uint8_t *pf_pc = nullptr, *pf_pv = nullptr;   // prepared operands of the chunkwise tensor-core cell
+  int prefill_rows = 16384;                     // rows (envs x tokens) per prefill chunk                  ("prefill_rows")
   char* pf_tc = nullptr;                        // workspace of the tcgen05 chunkwise cell (grow-only)
   size_t pf_tc_bytes = 0;
   int prefill_cell = 2;                         // 2: chunkwise tcgen05 cell (xl_prefill_tc.cu), 1: chunkwise mma.sync cell
@@ -916,8 +917,8 @@ Ws prefill_ws(const xl_handle* h) {
 
 // tokens per env in one prefill chunk: ~2048 rows per chunk over all envs, a multiple of 48 (whole (s, rtg, r)
 // timesteps, whole 8-token stages of the fp32 cell and whole 16-token chunks of the tensor-core cell)
-int prefill_chunk_tokens(int B) {
-  int sc = 2048 / B;
+int prefill_chunk_tokens(const xl_handle* h, int B) {
+  int sc = h->prefill_rows / B;
   if (sc < 48) sc = 48;
   return sc / 48 * 48;
 }
@@ -1546,7 +1547,7 @@ int xl_prefill(xl_handle* h, void* state, const float* x_in, float* y_out, int B
   const float* post_w = (const float*)h->pw[XL_W_POST_NORM - XL_W_POST_NORM];
   int pos = 0;
   if (prefill_fast_path(h)) {
-    const int sc_max = prefill_chunk_tokens(B);
+    const int sc_max = prefill_chunk_tokens(h, B);
     while (S - pos >= 8) {
       int Sc = std::min(sc_max, (S - pos) / 8 * 8);
       // whole 16-token chunks go to the tensor-core cell; an 8-token remainder takes the fp32 cell next round
@@ -1599,7 +1600,7 @@ int xl_policy_prefill(xl_handle* h, void* state, const float* states, const floa
   auto PW = [&](int id) { return h->pw[id - XL_W_POST_NORM]; };
   int pos = 0;   // timesteps done
   if (prefill_fast_path(h)) {
-    const int tc_max = prefill_chunk_tokens(B) / T;
+    const int tc_max = prefill_chunk_tokens(h, B) / T;
     while (Tn - pos >= 8) {
       int Tc = std::min(tc_max, (Tn - pos) / 8 * 8);             // 8 timesteps = 24 tokens = 3 cell stages
       // 16 timesteps = 48 tokens = 3 chunks of the tensor-core cell; an 8-timestep remainder takes the fp32 cell
@@ -1734,6 +1735,9 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
     if (value < 0 || value > 2)
       return fail(XL_ERR_INVALID_ARG, "prefill_cell must be 0 (fp32 sequence cell), 1 (chunkwise mma.sync) or 2 (chunkwise tcgen05)");
     h->prefill_cell = (int)value;
+  } else if (!strcmp(name, "prefill_rows")) {
+    if (value < 48 || value > 32768) return fail(XL_ERR_INVALID_ARG, "prefill_rows must be in [48, 32768]");
+    h->prefill_rows = value;
   } else if (!strcmp(name, "prefill_conv_run")) {
     if (value < 4 || value > 64 || value % 4) return fail(XL_ERR_INVALID_ARG, "prefill_conv_run must be a multiple of 4 in [4, 64]");
     xl::g_prefill_conv_run = value;           // process-wide: tokens per CTA of the sequence conv/qkv kernel

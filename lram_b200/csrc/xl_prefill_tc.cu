@@ -47,6 +47,8 @@ constexpr int kGemmThreads = 192;
 constexpr int kABytes = BM * BK * 2, kWBytes = BN * BK * 2;
 constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
 constexpr int kSmemTotal = kStages * kStageBytes + 1024 + 256;
+constexpr int kScanStage = 4 * 32 * 256;                       // update_scan_kernel: per-warp [32 rows][256 B] store staging
+constexpr int kSmemScan = kSmemTotal + kScanStage;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -188,10 +190,14 @@ bgemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__
     const int q = warp & 3;
     const int c = z % o.nchunk, bh = z / o.nchunk, b = bh / o.NH, hd = bh - b * o.NH;
     const int mvalid = o.rows_valid > 0 ? min(M, o.rows_valid - c * BM) : M;
-    const int row = m0 + q * 32 + lane;
-    float* orow = o.out + (long long)b * o.s_b + (long long)hd * o.s_h + (long long)c * o.s_c + (long long)row * o.ldo + n0;
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait(tmem_full_bar, 0);       // every MMA has retired: the ring is free, its first 64 KB stage the tile out
     tcgen05_fence_after();
+    // A lane holds one accumulator row; written as is, a warp store would touch 32 different lines. Each 32-column
+    // piece goes through a per-warp [32 rows][128 B] buffer (16-byte chunks XOR-swizzled by row) and leaves as 4 rows
+    // x 128 contiguous bytes per warp store.
+    const uint32_t wst = base + (uint32_t)q * 4096u;
+    const int rbase = m0 + q * 32;
+    float* otile = o.out + (long long)b * o.s_b + (long long)hd * o.s_h + (long long)c * o.s_c + (long long)rbase * o.ldo + n0;
 #pragma unroll
     for (int cc = 0; cc < BN; cc += 32) {
       uint32_t r[32];
@@ -208,12 +214,23 @@ bgemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__
           : "r"(taddr)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < mvalid && n0 + cc < N) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(orow + cc + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      for (int k = 0; k < 8; ++k)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)lane * 128u + (uint32_t)((k ^ (lane & 7)) << 4)),
+                     "r"(r[4 * k]), "r"(r[4 * k + 1]), "r"(r[4 * k + 2]), "r"(r[4 * k + 3]) : "memory");
+      __syncwarp();
+      if (n0 + cc < N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3), kk = lane & 7;
+          uint32_t v0, v1, v2, v3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                       : "r"(wst + (uint32_t)rr * 128u + (uint32_t)((kk ^ (rr & 7)) << 4)) : "memory");
+          if (rbase + rr < mvalid)
+            *reinterpret_cast<uint4*>(otile + (long long)rr * o.ldo + cc + kk * 4) = make_uint4(v0, v1, v2, v3);
+        }
       }
+      __syncwarp();
     }
   }
   tcgen05_fence_before();
@@ -386,7 +403,7 @@ update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_cons
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;                               // dv row of the tile == TMEM lane
-    const int dv = m0 + r;
+    const uint32_t wst = base + kStages * kStageBytes + 256 + (uint32_t)q * 8192u;
     // state tile: C[dk = n0 + j][dv] at slab (dv / 128) = blockIdx.y, column r
     float* cs = p.C + (((int64_t)bh * (DH >> 7) + blockIdx.y) * DH + n0) * 128 + r;
     float cv[BN];
@@ -396,15 +413,34 @@ update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_cons
       const int b = c & 1, use = c >> 1;
       const int64_t z = (int64_t)bh * nchunk + c;
       const float F = p.w.FL[z];
-      __nv_bfloat16* wh = p.w.w3_hi + (z * DH + dv) * K3 + n0;
-      __nv_bfloat16* wl = p.w.w3_lo + (z * DH + dv) * K3 + n0;
+      // chunk-start tile -> W3 planes. A lane holds one row (256 B per plane): staged through a per-warp
+      // [32 rows][256 B] buffer (16-byte chunks XOR-swizzled by row), so a warp store writes 2 rows x 256 contiguous bytes
+      // instead of 32 different lines
 #pragma unroll
-      for (int j = 0; j < BN; j += 8) {
-        uint32_t h[4], l[4];
+      for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split2(cv[j + 2 * e], cv[j + 2 * e + 1], h[e], l[e]);
-        *reinterpret_cast<uint4*>(wh + j) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(wl + j) = make_uint4(l[0], l[1], l[2], l[3]);
+        for (int k = 0; k < 16; ++k) {
+          uint32_t wv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t hh, ll;
+            split2(cv[8 * k + 2 * e], cv[8 * k + 2 * e + 1], hh, ll);
+            wv[e] = pl ? ll : hh;
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)lane * 256u + (uint32_t)((k ^ (lane & 15)) << 4)),
+                       "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
+        }
+        __syncwarp();
+        __nv_bfloat16* gt = (pl ? p.w.w3_lo : p.w.w3_hi) + (z * DH + m0 + q * 32) * K3 + n0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int rr = 2 * i + (lane >> 4), kk = lane & 15;
+          uint32_t v0, v1, v2, v3;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                       : "r"(wst + (uint32_t)rr * 256u + (uint32_t)((kk ^ (rr & 15)) << 4)) : "memory");
+          *reinterpret_cast<uint4*>(gt + (int64_t)rr * K3 + kk * 8) = make_uint4(v0, v1, v2, v3);
+        }
+        __syncwarp();
       }
       mbar_wait(tfull_bar(b), use & 1);
       tcgen05_fence_after();
@@ -795,8 +831,8 @@ cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, c
         !make_map3(&mkh, p.w.kt_hi, L, DH, nb, L, (int64_t)DH * L) ||
         !make_map3(&mkl, p.w.kt_lo, L, DH, nb, L, (int64_t)DH * L))
       return cudaErrorUnknown;
-    if ((e = ensure_dyn_smem<&update_scan_kernel>(kSmemTotal)) != cudaSuccess) return e;
-    if ((e = launch_k(update_scan_kernel, dim3(DH / BN, DH / BM, BH), dim3(kGemmThreads), kSmemTotal, s, mvh, mvl, mkh,
+    if ((e = ensure_dyn_smem<&update_scan_kernel>(kSmemScan)) != cudaSuccess) return e;
+    if ((e = launch_k(update_scan_kernel, dim3(DH / BN, DH / BM, BH), dim3(kGemmThreads), kSmemScan, s, mvh, mvl, mkh,
                       mkl, p)) != cudaSuccess)
       return e;
     if ((e = launch_k(nscan_kernel, dim3(BH, (DH + 127) / 128), dim3(128), 0, s, p)) != cudaSuccess) return e;
