@@ -129,7 +129,7 @@ struct xl_handle {
   int pf_rows = 0;
   float *pf_x = nullptr, *pf_xn = nullptr, *pf_u = nullptr, *pf_qkv = nullptr, *pf_act = nullptr, *pf_gp = nullptr,
         *pf_gated = nullptr, *pf_num = nullptr, *pf_qn = nullptr, *pf_f = nullptr, *pf_i = nullptr, *pf_m = nullptr,
-        *pf_semb = nullptr, *pf_spad = nullptr, *pf_sin = nullptr, *pf_rtg = nullptr, *pf_rew = nullptr;
+        *pf_semb = nullptr, *pf_spad = nullptr, *pf_sin = nullptr, *pf_rtg = nullptr, *pf_rew = nullptr, *pf_gsc = nullptr;
   __nv_bfloat16 *pf_hi = nullptr, *pf_lo = nullptr;
   uint8_t *pf_pc = nullptr, *pf_pv = nullptr;   // prepared operands of the chunkwise tensor-core cell
   int prefill_rows = 16384;                     // rows (envs x tokens) per prefill chunk                  ("prefill_rows")
@@ -867,6 +867,8 @@ int ensure_prefill_ws(xl_handle* h, int rows) {
   const size_t o_f = carve(4 * R * NH), o_i = carve(4 * R * NH), o_m = carve(4 * R * NH);
   const size_t o_semb = carve(4 * R * d), o_spad = carve(4 * R * h->Kpad), o_sin = carve(4 * R * c.state_dim);
   const size_t o_rtg = carve(4 * R), o_rew = carve(4 * R);
+  // gate-scan maps: B*NH*(1 + 2*ceil(S/2048)) floats with B <= R/48 + 1 envs of S = R/B tokens
+  const size_t o_gsc = carve(4 * NH * (3 * (R / 48 + 16) + R / 1024 + 16));
   const size_t o_hi = carve(2 * R * kmax), o_lo = carve(2 * R * kmax);
   size_t pc_bytes = 0, pv_bytes = 0;
   if (xl::prefill_cell_mma_supported(h->DH)) xl::prefill_cell_mma_ws(rows, (int)NH, h->DH, &pc_bytes, &pv_bytes);
@@ -884,6 +886,7 @@ int ensure_prefill_ws(xl_handle* h, int rows) {
   h->pf_f = (float*)(b + o_f); h->pf_i = (float*)(b + o_i); h->pf_m = (float*)(b + o_m);
   h->pf_semb = (float*)(b + o_semb); h->pf_spad = (float*)(b + o_spad); h->pf_sin = (float*)(b + o_sin);
   h->pf_rtg = (float*)(b + o_rtg); h->pf_rew = (float*)(b + o_rew);
+  h->pf_gsc = (float*)(b + o_gsc);
   h->pf_hi = (__nv_bfloat16*)(b + o_hi); h->pf_lo = (__nv_bfloat16*)(b + o_lo);
   h->pf_pc = (uint8_t*)(b + o_pc); h->pf_pv = (uint8_t*)(b + o_pv);
   h->pf_rows = rows;
@@ -947,8 +950,9 @@ int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cud
                        M, d, tc_up ? ws.a_hi : nullptr, tc_up ? ws.a_lo : nullptr, s);
     h->launches += 1;
     XL_CUDA(cudaGetLastError());
-    int rc = linear(h, ws, ws.xn, w.w[XL_W_PROJ_UP], nullptr, nullptr, ws.u, M, 2 * inner, d, impl, s, tc_up,
-                    h->gemm_up_bn);
+    // GEMM-sized M: 128 x 256 tiles for proj_up (2/3 of the operand bytes per flop; measured -2 % on the 206M prefill)
+    const int up_bn = h->gemm_up_bn ? h->gemm_up_bn : (M >= 1024 && (2 * inner) % 256 == 0 ? 256 : 0);
+    int rc = linear(h, ws, ws.xn, w.w[XL_W_PROJ_UP], nullptr, nullptr, ws.u, M, 2 * inner, d, impl, s, tc_up, up_bn);
     if (rc) return rc;
     xl::ConvQkvParams cp;
     cp.u = ws.u;
@@ -972,7 +976,7 @@ int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cud
       return fail(XL_ERR_UNSUPPORTED, "sequence conv/qkv kernel not instantiated for KS=%d NH=%d", cp.KS, cp.NH);
     XL_CUDA(cudaGetLastError());
     xl::launch_gate_scan_seq(ws.gate_part, (const float*)w.w[XL_W_IGATE_B], (const float*)w.w[XL_W_FGATE_B],
-                             (float*)(base + L.m_off), h->pf_f, h->pf_i, h->pf_m, B, Sc, NH, h->NCH, s);
+                             (float*)(base + L.m_off), h->pf_f, h->pf_i, h->pf_m, h->pf_gsc, B, Sc, NH, h->NCH, s);
     XL_CUDA(cudaGetLastError());
     if (h->prefill_cell == 2 && xl::prefill_cell_tc_supported(DH)) {
       if (int rcw = ensure_prefill_tc_ws(h, B, Sc)) return rcw;
@@ -1756,8 +1760,8 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
     if (value < 0 || value > kSplitMax) return fail(XL_ERR_INVALID_ARG, "gemm_splitk must be in [0, %d]", kSplitMax);
     h->gemm_splitk = value;
   } else if (!strcmp(name, "gemm_up_bn") || !strcmp(name, "gemm_down_bn")) {
-    if (value != 0 && value != 32 && value != 64 && value != 128)
-      return fail(XL_ERR_INVALID_ARG, "%s must be 0, 32, 64 or 128", name);
+    if (value != 0 && value != 32 && value != 64 && value != 128 && value != 256)
+      return fail(XL_ERR_INVALID_ARG, "%s must be 0, 32, 64, 128 or 256", name);
     (name[5] == 'u' ? h->gemm_up_bn : h->gemm_down_bn) = value;
   } else if (!strcmp(name, "gemm_up_splits") || !strcmp(name, "gemm_down_splits")) {
     if (value < 0 || value > kSplitMax) return fail(XL_ERR_INVALID_ARG, "%s must be in [0, %d]", name, kSplitMax);

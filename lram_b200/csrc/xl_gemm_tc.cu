@@ -844,10 +844,11 @@ cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat
   if (!gemm_tc_supported(M, N, K)) return cudaErrorInvalidValue;
   if (splits < 1) splits = 1;
   if (splits > 1 && (bias || residual || (K / tc::BLOCK_K) % splits)) return cudaErrorInvalidValue;
-  if (bn != 128 && bn != 64 && bn != 32) {
+  if (bn != 256 && bn != 128 && bn != 64 && bn != 32) {
     int sp;
     gemm_tc_plan(M, N, K, num_sms, 1, &bn, &sp);
   }
+  if (bn == 256 && (low_smem || N % 256 != 0)) bn = 128;
   // 64-row MMA tiles (option "gemm_bm" = 64): half the A bytes per k-block and a ring twice as deep (9 stages), no
   // empty quarter tile at M = 192. Bit-identical results; measured 1.2 % SLOWER on the 48M x 64 step (3 row tiles read
   // W three times: 42 MB instead of 38 MB of L2 -> SM traffic for proj_up, and these GEMMs sit at the aggregate L2
@@ -874,6 +875,8 @@ cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat
     }
   }
   switch (bn) {
+    // 128 x 256 tiles (GEMM-sized M, e.g. the context prefill): 2/3 of the operand bytes per flop of a 128 x 128 tile
+    case 256: return tc::launch<256, 3>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
     case 128: return tc::launch<128, 4>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
     case 64: return tc::launch<64, 4>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
     default: return tc::launch<32, 6>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);

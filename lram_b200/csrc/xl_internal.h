@@ -151,9 +151,11 @@ bool prefill_cell_supported(int DH);
 // conv + SiLU + q/k/v + gate partials over the chunk, then conv_state <- last KS inputs. p.qk receives the q
 // plane [M, inner] followed by the k plane [M, inner] (M = B*S). false: no instantiation
 bool launch_conv_qkv_gates_seq(const ConvQkvParams& p, int S, cudaStream_t s);
-// m/f/i per token ([B*NH][S] each) from the gate partials; m_state [B*NH] in/out
+// m/f/i per token ([B*NH][S] each) from the gate partials; m_state [B*NH] in/out; scratch: gate_scan_seq_scratch_floats()
+size_t gate_scan_seq_scratch_floats(int B, int S, int NH);
 void launch_gate_scan_seq(const float* gate_part, const float* igate_b, const float* fgate_b, float* m_state,
-                          float* fseq, float* iseq, float* mseq, int B, int S, int NH, int NCH, cudaStream_t s);
+                          float* fseq, float* iseq, float* mseq, float* scratch, int B, int S, int NH, int NCH,
+                          cudaStream_t s);
 // C / n advanced over the S tokens on chip; num [B*S, inner] = q^T C, qn [B*S, NH] = q.n per token
 cudaError_t launch_cell_seq(float* C, float* n, const float* q, const float* k, const float* v, const float* fseq,
                             const float* iseq, float* num, float* qn, int B, int S, int NH, int DH, int inner,

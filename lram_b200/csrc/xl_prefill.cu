@@ -57,13 +57,20 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
 // token. grid = (NCH channel chunks, B envs, token runs); a thread owns one 4-channel block for a run of
 // tokens and keeps the conv window in registers; gate partials are reduced 4 tokens at a time.
 // ------------------------------------------------------------------------------------------------
+constexpr int kConvRuns = 4;       // token runs per CTA (threadIdx.y): they share the gate weights in shared memory
 template <int KS, int NH>
-__global__ void __launch_bounds__(128, 2) conv_qkv_gates_seq_kernel(ConvQkvParams p, int S, int run) {
+__global__ void __launch_bounds__(64 * kConvRuns, 2) conv_qkv_gates_seq_kernel(ConvQkvParams p, int S, int run) {
   constexpr int TG = 4;                                  // tokens per gate-reduction group
-  __shared__ float red[2 * NH * TG * 4];
+  __shared__ float red[kConvRuns][2 * NH * TG * 4];
+  // gate weights of the chunk's channels, [gate][head][q|k|v][channel]: kept out of the registers (hoisted there, the 96
+  // loop-invariant values per thread cut the occupancy to 8 warps per SM)
+  extern __shared__ __align__(16) float s_gw[];
   const int b = blockIdx.y, chunk = blockIdx.x;
-  const int s_begin = blockIdx.z * run;
+  const int sub = threadIdx.y;
+  const int nruns = blockDim.y;
+  const int s_begin = min(S, ((int)blockIdx.z * nruns + sub) * run);
   const int s_end = min(S, s_begin + run);
+  const int s_cta_end = min(S, (int)blockIdx.z * nruns * run + run);   // longest run of the CTA (sub 0): loop bound
   const int inner = p.inner;
   const int nblk = inner >> 2;
   const int blk_per_chunk = (nblk + p.NCH - 1) / p.NCH;
@@ -72,16 +79,27 @@ __global__ void __launch_bounds__(128, 2) conv_qkv_gates_seq_kernel(ConvQkvParam
   const int c = 4 * (active ? j : 0);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nw = (blockDim.x + 31) >> 5;
+  const int cw = 4 * blockDim.x;                          // channels covered by the CTA's threads
+  {
+    const int c_base = 4 * chunk * blk_per_chunk;
+    const int flat = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    for (int i = flat; i < 2 * NH * 3 * cw; i += nthr) {
+      const int ch = i % cw, row = i / cw;                // row = (gate * NH + head) * 3 + part
+      const int gate = row / (NH * 3), hp = row - gate * NH * 3;
+      const int gc = c_base + ch;
+      s_gw[i] = gc < inner ? (gate ? p.wf : p.wi)[(int64_t)hp * inner + gc] : 0.f;
+    }
+  }
 
   float win[KS][4];
-  float cw[4][KS];
+  float cw4[4][KS];
   float cbv[4] = {0.f, 0.f, 0.f, 0.f};
   float wq[16], wk[16], wv[16];
   if (active) {
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-      for (int r = 0; r < KS; ++r) cw[ch][r] = p.conv_w[(int64_t)(c + ch) * KS + r];
+      for (int r = 0; r < KS; ++r) cw4[ch][r] = p.conv_w[(int64_t)(c + ch) * KS + r];
     const float4 cb = *reinterpret_cast<const float4*>(p.conv_b + c);
     cbv[0] = cb.x; cbv[1] = cb.y; cbv[2] = cb.z; cbv[3] = cb.w;
 #pragma unroll
@@ -96,7 +114,8 @@ __global__ void __launch_bounds__(128, 2) conv_qkv_gates_seq_kernel(ConvQkvParam
   }
   pdl_wait();
   pdl_trigger();
-  if (active) {
+  __syncthreads();                                        // s_gw
+  if (active && s_begin < s_end) {
     // window rows 1..KS-1 = the KS-1 inputs before token s_begin: earlier rows of this chunk, or the carried
     // conv_state (rows = last KS inputs, oldest first) for tokens before the chunk
 #pragma unroll
@@ -110,19 +129,27 @@ __global__ void __launch_bounds__(128, 2) conv_qkv_gates_seq_kernel(ConvQkvParam
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) win[0][ch] = 0.f;
   }
-  for (int s0 = s_begin; s0 < s_end; s0 += TG) {
+  const int nsteps = (s_cta_end - (int)blockIdx.z * nruns * run + TG - 1) / TG;   // same for every thread of the CTA
+  for (int st = 0; st < nsteps; ++st) {
+    const int s0 = s_begin + st * TG;
     float gi[NH][TG], gf[NH][TG];
 #pragma unroll
     for (int h = 0; h < NH; ++h)
 #pragma unroll
       for (int t = 0; t < TG; ++t) gi[h][t] = gf[h][t] = 0.f;
     if (active) {
+      // the group's inputs are requested together (the stores below would otherwise order the loads token by token)
+      float4 xg[TG];
+#pragma unroll
+      for (int t = 0; t < TG; ++t)
+        xg[t] = s0 + t < s_end ? *reinterpret_cast<const float4*>(p.u + ((int64_t)b * S + s0 + t) * 2 * inner + c)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int t = 0; t < TG; ++t) {
         const int s = s0 + t;
         if (s < s_end) {
           const int64_t row = (int64_t)b * S + s;
-          const float4 x4 = *reinterpret_cast<const float4*>(p.u + row * 2 * inner + c);
+          const float4 x4 = xg[t];
           const float xm[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
           for (int r = 0; r < KS - 1; ++r)
@@ -135,7 +162,7 @@ __global__ void __launch_bounds__(128, 2) conv_qkv_gates_seq_kernel(ConvQkvParam
           for (int ch = 0; ch < 4; ++ch) {
             float acc = 0.f;
 #pragma unroll
-            for (int r = 0; r < KS; ++r) acc = fmaf(win[r][ch], cw[ch][r], acc);
+            for (int r = 0; r < KS; ++r) acc = fmaf(win[r][ch], cw4[ch][r], acc);
             a[ch] = silu(acc + cbv[ch]);
           }
           float q[4], k[4], v[4];
@@ -157,15 +184,14 @@ __global__ void __launch_bounds__(128, 2) conv_qkv_gates_seq_kernel(ConvQkvParam
           *reinterpret_cast<float4*>(p.act + row * inner + c) = make_float4(a[0], a[1], a[2], a[3]);
 #pragma unroll
           for (int h = 0; h < NH; ++h) {
-            // gate weights of this 4-channel block: L1-resident after the first token of the run
-            const float* wi = p.wi + (int64_t)h * 3 * inner + c;
-            const float* wf = p.wf + (int64_t)h * 3 * inner + c;
+            const float* wi = s_gw + (h * 3) * cw + 4 * threadIdx.x;
+            const float* wf = s_gw + ((NH + h) * 3) * cw + 4 * threadIdx.x;
             const float4 iq = *reinterpret_cast<const float4*>(wi);
-            const float4 ik = *reinterpret_cast<const float4*>(wi + inner);
-            const float4 iv = *reinterpret_cast<const float4*>(wi + 2 * inner);
+            const float4 ik = *reinterpret_cast<const float4*>(wi + cw);
+            const float4 iv = *reinterpret_cast<const float4*>(wi + 2 * cw);
             const float4 fq = *reinterpret_cast<const float4*>(wf);
-            const float4 fk = *reinterpret_cast<const float4*>(wf + inner);
-            const float4 fv = *reinterpret_cast<const float4*>(wf + 2 * inner);
+            const float4 fk = *reinterpret_cast<const float4*>(wf + cw);
+            const float4 fv = *reinterpret_cast<const float4*>(wf + 2 * cw);
             float si = q[0] * iq.x + q[1] * iq.y + q[2] * iq.z + q[3] * iq.w;
             si += k[0] * ik.x + k[1] * ik.y + k[2] * ik.z + k[3] * ik.w;
             si += v[0] * iv.x + v[1] * iv.y + v[2] * iv.z + v[3] * iv.w;
@@ -178,7 +204,7 @@ __global__ void __launch_bounds__(128, 2) conv_qkv_gates_seq_kernel(ConvQkvParam
         }
       }
     }
-    // chunk-level partial sums of the 4 tokens: warp tree, then fixed-order sum over the (<= 4) warps
+    // chunk-level partial sums of the 4 tokens: warp tree, then fixed-order sum over the (<= 4) warps of the run
 #pragma unroll
     for (int h = 0; h < NH; ++h)
 #pragma unroll
@@ -186,8 +212,8 @@ __global__ void __launch_bounds__(128, 2) conv_qkv_gates_seq_kernel(ConvQkvParam
         const float si = warp_sum(gi[h][t]);
         const float sf = warp_sum(gf[h][t]);
         if (lane == 0) {
-          red[((h * 2 + 0) * TG + t) * 4 + wid] = si;
-          red[((h * 2 + 1) * TG + t) * 4 + wid] = sf;
+          red[sub][((h * 2 + 0) * TG + t) * 4 + wid] = si;
+          red[sub][((h * 2 + 1) * TG + t) * 4 + wid] = sf;
         }
       }
     __syncthreads();
@@ -197,7 +223,7 @@ __global__ void __launch_bounds__(128, 2) conv_qkv_gates_seq_kernel(ConvQkvParam
       const int g = rem / TG, t = rem - g * TG;
       if (s0 + t < s_end) {
         float s = 0.f;
-        for (int w = 0; w < nw; ++w) s += red[((h * 2 + g) * TG + t) * 4 + w];
+        for (int w = 0; w < nw; ++w) s += red[sub][((h * 2 + g) * TG + t) * 4 + w];
         p.gate_part[(((int64_t)b * S + s0 + t) * p.NCH + chunk) * 2 * NH + g * NH + h] = s;
       }
     }
@@ -224,85 +250,135 @@ __global__ void __launch_bounds__(256) conv_state_seq_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------
 // Gate scan: per (env, head) the stabiliser recurrence over the chunk's tokens,
 //   lf = logsigmoid(f~);  m' = max(lf + m, i~);  f = exp(lf + m - m');  i = exp(i~ - m')
-// with exactly the arithmetic of compute_gates() (xl_state_step.cu). One CTA of 1024 threads per (env, head): the
-// pre-activations of up to 2048 tokens are summed / log-sigmoided in parallel (two tokens per thread: the loads of the
-// whole run are in flight at once), one warp runs the max-plus chain over shared memory, f and i are again computed in
-// parallel. Outputs are [B*NH][S]: a head's tokens are contiguous.
+// A token is the map m -> max(m + lf, i~); maps compose as (A1, B1) then (A2, B2) = (A1 + A2, max(B1 + A2, B2)), so the
+// chain is a scan. Two kernels over a grid of (env*head, super-chunks of 2048 tokens), 1024 threads:
+//   gate_pre_seq_kernel : pre-activations of the super-chunk's tokens summed (fixed order, as compute_gates() of
+//                         xl_state_step.cu) and log-sigmoided in parallel -> lf, i~ (parked in fseq / iseq) and the
+//                         composed map of the whole super-chunk;
+//   gate_scan_seq_kernel: m at the start of the super-chunk from the carried m and the maps of the super-chunks before it,
+//                         then warp 0 scans the 32 segment maps of its super-chunk with shuffles and every lane replays
+//                         its segment from its true start value; f, i, m of all tokens again in parallel.
+// m differs from token-by-token stepping only by the association of the lf sums between resets (~1 ulp of m; the
+// stabiliser cancels in h). Outputs are [B*NH][S]: a head's tokens are contiguous. scratch: [B*NH] carried m, then
+// [B*NH][nsuper][2] maps.
 // ------------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 1024;
-__global__ void __launch_bounds__(kScanThreads) gate_scan_seq_kernel(const float* __restrict__ gate_part,
-                                                            const float* __restrict__ igate_b,
-                                                            const float* __restrict__ fgate_b, float* __restrict__ m_state,
-                                                            float* __restrict__ fseq, float* __restrict__ iseq,
-                                                            float* __restrict__ mseq, int B, int S, int NH, int NCH) {
-  constexpr int kSuper = 2048;                   // tokens per super-chunk (2 per thread)
+constexpr int kSuper = 2048;                     // tokens per super-chunk (2 per thread)
+
+// fold of this lane's segment [lo, hi) and the inclusive scan of the 32 segment maps (full warp)
+__device__ __forceinline__ void segment_scan(const float* s_lf, const float* s_ig, int lo, int hi, int lane, float& Ai,
+                                             float& Bi) {
+  float A = 0.f, Bv = -INFINITY;
+  for (int u = lo; u < hi; ++u) {
+    A += s_lf[u];
+    Bv = fmaxf(Bv + s_lf[u], s_ig[u]);
+  }
+  Ai = A;
+  Bi = Bv;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float Ap = __shfl_up_sync(0xffffffffu, Ai, o);
+    const float Bp = __shfl_up_sync(0xffffffffu, Bi, o);
+    if (lane >= o) {
+      Bi = fmaxf(Bp + Ai, Bi);
+      Ai = Ap + Ai;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) gate_pre_seq_kernel(const float* __restrict__ gate_part,
+                                                                    const float* __restrict__ igate_b,
+                                                                    const float* __restrict__ fgate_b,
+                                                                    const float* __restrict__ m_state,
+                                                                    float* __restrict__ fseq, float* __restrict__ iseq,
+                                                                    float* __restrict__ scratch, int B, int S, int NH,
+                                                                    int NCH) {
+  __shared__ float s_ig[kSuper + 32], s_lf[kSuper + 32];
+  pdl_wait();
+  pdl_trigger();
+  const int bh = blockIdx.x, sp = blockIdx.y, nsuper = gridDim.y;
+  const int b = bh / NH, hd = bh - b * NH;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const float bi = igate_b ? igate_b[hd] : 0.f, bf = fgate_b ? fgate_b[hd] : 0.f;
+  const int s0 = sp * kSuper;
+  const int cnt = min(kSuper, S - s0);
+  for (int u = tid; u < cnt; u += kScanThreads) {
+    const float* gp = gate_part + ((int64_t)b * S + s0 + u) * NCH * 2 * NH + hd;
+    float si = 0.f, sf = 0.f;
+    for (int c = 0; c < NCH; ++c) {            // fixed order, as compute_gates()
+      si += gp[c * 2 * NH];
+      sf += gp[c * 2 * NH + NH];
+    }
+    const float ig = si + bi, lf = log_sigmoid(sf + bf);
+    s_ig[u] = ig;
+    s_lf[u] = lf;
+    const int64_t o = (int64_t)bh * S + s0 + u;
+    iseq[o] = ig;
+    fseq[o] = lf;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int seg = ((cnt + 31) / 32) | 1;               // odd stride: conflict-free shared-memory walks
+    const int lo = min(cnt, lane * seg), hi = min(cnt, lo + seg);
+    float Ai, Bi;
+    segment_scan(s_lf, s_ig, lo, hi, lane, Ai, Bi);
+    if (lane == 31) {
+      float* comp = scratch + (int64_t)B * NH + ((int64_t)bh * nsuper + sp) * 2;
+      comp[0] = Ai;
+      comp[1] = Bi;
+    }
+    if (sp == 0 && lane == 0) scratch[bh] = m_state[bh];
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) gate_scan_seq_kernel(float* __restrict__ m_state, float* __restrict__ fseq,
+                                                                     float* __restrict__ iseq, float* __restrict__ mseq,
+                                                                     const float* __restrict__ scratch, int B, int S,
+                                                                     int NH) {
   __shared__ float s_ig[kSuper + 32], s_lf[kSuper + 32], s_mp[kSuper], s_mn[kSuper];
   pdl_wait();
   pdl_trigger();
-  const int bh = blockIdx.x;
-  const int b = bh / NH, hd = bh - b * NH;
+  const int bh = blockIdx.x, sp = blockIdx.y, nsuper = gridDim.y;
   const int tid = threadIdx.x, lane = tid & 31;
-  float m = m_state[bh];                         // carried by warp 0
-  const float bi = igate_b ? igate_b[hd] : 0.f, bf = fgate_b ? fgate_b[hd] : 0.f;
-  for (int s0 = 0; s0 < S; s0 += kSuper) {
-    const int cnt = min(kSuper, S - s0);
-    // (A) pre-activations of all tokens of the super-chunk, in parallel
-    for (int u = tid; u < cnt; u += kScanThreads) {
-      const float* gp = gate_part + ((int64_t)b * S + s0 + u) * NCH * 2 * NH + hd;
-      float si = 0.f, sf = 0.f;
-      for (int c = 0; c < NCH; ++c) {            // fixed order, as compute_gates()
-        si += gp[c * 2 * NH];
-        sf += gp[c * 2 * NH + NH];
-      }
-      s_ig[u] = si + bi;
-      s_lf[u] = log_sigmoid(sf + bf);
-    }
-    __syncthreads();
-    // (B) the max-plus chain m' = max(lf + m, i~) as a segmented scan in warp 0: a token is the map m -> max(m + lf, i~);
-    //     maps compose as (A1, B1) then (A2, B2) = (A1 + A2, max(B1 + A2, B2)). Each lane folds its contiguous segment,
-    //     the 32 segment maps are scanned with shuffles, and each lane replays its segment from its true start value
-    //     (2 x cnt/32 dependent steps instead of cnt). m differs from token-by-token stepping only by the association of
-    //     the lf sums between resets (~1 ulp of m; the stabiliser cancels in h).
-    if (tid < 32) {
-      const int seg = ((cnt + 31) / 32) | 1;             // odd stride: conflict-free shared-memory walks
-      const int lo = min(cnt, lane * seg), hi = min(cnt, lo + seg);
-      float A = 0.f, Bv = -INFINITY;
-      for (int u = lo; u < hi; ++u) {
-        A += s_lf[u];
-        Bv = fmaxf(Bv + s_lf[u], s_ig[u]);
-      }
-      float Ai = A, Bi = Bv;                             // inclusive scan of the segment maps
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float Ap = __shfl_up_sync(0xffffffffu, Ai, o);
-        const float Bp = __shfl_up_sync(0xffffffffu, Bi, o);
-        if (lane >= o) {
-          Bi = fmaxf(Bp + Ai, Bi);
-          Ai = Ap + Ai;
-        }
-      }
-      float Aex = __shfl_up_sync(0xffffffffu, Ai, 1), Bex = __shfl_up_sync(0xffffffffu, Bi, 1);
-      float mm = lane == 0 ? m : fmaxf(m + Aex, Bex);    // m at the start of this lane's segment
-      for (int u = lo; u < hi; ++u) {
-        const float mn = fmaxf(s_lf[u] + mm, s_ig[u]);
-        s_mp[u] = mm;
-        s_mn[u] = mn;
-        mm = mn;
-      }
-      m = __shfl_sync(0xffffffffu, mm, (cnt - 1) / seg);  // the m the last token left (what mseq holds for it)
-    }
-    __syncthreads();
-    // (C) f, i of all tokens, in parallel
-    for (int u = tid; u < cnt; u += kScanThreads) {
-      const float mp = s_mp[u], mn = s_mn[u];
-      const int64_t o = (int64_t)bh * S + s0 + u;
-      fseq[o] = expf(s_lf[u] + mp - mn);
-      iseq[o] = expf(s_ig[u] - mn);
-      mseq[o] = mn;
-    }
-    __syncthreads();
+  const int s0 = sp * kSuper;
+  const int cnt = min(kSuper, S - s0);
+  for (int u = tid; u < cnt; u += kScanThreads) {
+    const int64_t o = (int64_t)bh * S + s0 + u;
+    s_ig[u] = iseq[o];
+    s_lf[u] = fseq[o];
   }
-  if (tid == 0) m_state[bh] = m;
+  __syncthreads();
+  if (tid < 32) {
+    // m at the start of this super-chunk: the carried m through the maps of the super-chunks before it
+    float m = scratch[bh];
+    const float* comp = scratch + (int64_t)B * NH + (int64_t)bh * nsuper * 2;
+    for (int k = 0; k < sp; ++k) m = fmaxf(m + comp[2 * k], comp[2 * k + 1]);
+    const int seg = ((cnt + 31) / 32) | 1;
+    const int lo = min(cnt, lane * seg), hi = min(cnt, lo + seg);
+    float Ai, Bi;
+    segment_scan(s_lf, s_ig, lo, hi, lane, Ai, Bi);
+    const float Aex = __shfl_up_sync(0xffffffffu, Ai, 1), Bex = __shfl_up_sync(0xffffffffu, Bi, 1);
+    float mm = lane == 0 ? m : fmaxf(m + Aex, Bex);      // m at the start of this lane's segment
+    for (int u = lo; u < hi; ++u) {
+      const float mn = fmaxf(s_lf[u] + mm, s_ig[u]);
+      s_mp[u] = mm;
+      s_mn[u] = mn;
+      mm = mn;
+    }
+    // NOTE the maps of the super-chunks (pre kernel) and this replay agree to rounding; the carried m is the replay's
+    if (sp == nsuper - 1) {
+      const float mlast = __shfl_sync(0xffffffffu, mm, (cnt - 1) / seg);
+      if (lane == 0) m_state[bh] = mlast;
+    }
+  }
+  __syncthreads();
+  for (int u = tid; u < cnt; u += kScanThreads) {
+    const float mp = s_mp[u], mn = s_mn[u];
+    const int64_t o = (int64_t)bh * S + s0 + u;
+    fseq[o] = expf(s_lf[u] + mp - mn);
+    iseq[o] = expf(s_ig[u] - mn);
+    mseq[o] = mn;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -655,22 +731,26 @@ bool prefill_cell_supported(int DH) {
   return cell_plan(DH, &R, &CPT, &NW);
 }
 
-int g_prefill_conv_run = 8;    // xl_set_option("prefill_conv_run")
+int g_prefill_conv_run = 16;   // xl_set_option("prefill_conv_run")
 
 bool launch_conv_qkv_gates_seq(const ConvQkvParams& p, int S, cudaStream_t s) {
   const int nblk = p.inner / 4;
   const int per_chunk = (nblk + p.NCH - 1) / p.NCH;
   const int threads = ((per_chunk + 31) / 32) * 32;
-  const int run = g_prefill_conv_run;                   // tokens per CTA (multiple of 4)
-  dim3 grid(p.NCH, p.B, (S + run - 1) / run);
+  const int run = g_prefill_conv_run;                   // tokens per run (multiple of 4); kConvRuns runs per CTA
+  if (threads > 128) return false;
+  const int nruns = threads > 64 ? pf::kConvRuns / 2 : pf::kConvRuns;   // <= 256 threads per CTA
+  dim3 grid(p.NCH, p.B, (S + run * nruns - 1) / (run * nruns));
+  const dim3 block(threads, nruns);
+  const size_t smem = sizeof(float) * 2 * p.NH * 3 * 4 * threads;
   if (p.KS == 4 && p.NH == 4) {
-    launch_k(pf::conv_qkv_gates_seq_kernel<4, 4>, grid, dim3(threads), 0, s, p, S, run);
+    launch_k(pf::conv_qkv_gates_seq_kernel<4, 4>, grid, block, smem, s, p, S, run);
   } else if (p.KS == 4 && p.NH == 8) {
-    launch_k(pf::conv_qkv_gates_seq_kernel<4, 8>, grid, dim3(threads), 0, s, p, S, run);
+    launch_k(pf::conv_qkv_gates_seq_kernel<4, 8>, grid, block, smem, s, p, S, run);
   } else if (p.KS == 4 && p.NH == 2) {
-    launch_k(pf::conv_qkv_gates_seq_kernel<4, 2>, grid, dim3(threads), 0, s, p, S, run);
+    launch_k(pf::conv_qkv_gates_seq_kernel<4, 2>, grid, block, smem, s, p, S, run);
   } else if (p.KS == 4 && p.NH == 1) {
-    launch_k(pf::conv_qkv_gates_seq_kernel<4, 1>, grid, dim3(threads), 0, s, p, S, run);
+    launch_k(pf::conv_qkv_gates_seq_kernel<4, 1>, grid, block, smem, s, p, S, run);
   } else {
     return false;
   }
@@ -680,10 +760,18 @@ bool launch_conv_qkv_gates_seq(const ConvQkvParams& p, int S, cudaStream_t s) {
   return true;
 }
 
+size_t gate_scan_seq_scratch_floats(int B, int S, int NH) {
+  return (size_t)B * NH * (1 + 2 * (size_t)((S + pf::kSuper - 1) / pf::kSuper));
+}
+
 void launch_gate_scan_seq(const float* gate_part, const float* igate_b, const float* fgate_b, float* m_state,
-                          float* fseq, float* iseq, float* mseq, int B, int S, int NH, int NCH, cudaStream_t s) {
-  launch_k(pf::gate_scan_seq_kernel, dim3(B * NH), dim3(pf::kScanThreads), 0, s, gate_part, igate_b, fgate_b, m_state, fseq, iseq,
-           mseq, B, S, NH, NCH);
+                          float* fseq, float* iseq, float* mseq, float* scratch, int B, int S, int NH, int NCH,
+                          cudaStream_t s) {
+  const dim3 grid(B * NH, (S + pf::kSuper - 1) / pf::kSuper);
+  launch_k(pf::gate_pre_seq_kernel, grid, dim3(pf::kScanThreads), 0, s, gate_part, igate_b, fgate_b,
+           (const float*)m_state, fseq, iseq, scratch, B, S, NH, NCH);
+  launch_k(pf::gate_scan_seq_kernel, grid, dim3(pf::kScanThreads), 0, s, m_state, fseq, iseq, mseq,
+           (const float*)scratch, B, S, NH);
 }
 
 template <int R, int CPT, int NW>
