@@ -220,8 +220,9 @@ int xl_policy_step_host(xl_handle* h, void* state, const float* h_states, const 
  * (last_hidden_state of every token). Leaves `state` exactly where S calls of xLSTMBlockStack.step would
  * (src/algos/models/decision_xlstm.py:161-165; this is what the reference's `chunkwise_step` hook :158-159
  * asks of layers.step with S > 1). Runs layer-major over chunks of tokens: the projections are tcgen05 GEMMs
- * over all rows of a chunk, the matrix memory stays on chip for the chunk (xl_prefill.cu). Allocates / grows a
- * private workspace on first use (synchronises the device then); B <= max_batch. */
+ * over all rows of a chunk; the mLSTM cell is the chunkwise form over 128-token chunks with every contraction a batched
+ * tcgen05 GEMM over the (env, head, chunk) triples (xl_prefill_tc.cu; options "prefill_cell", "prefill_rows").
+ * Allocates / grows private workspaces on first use (synchronises the device then); B <= max_batch. */
 int xl_prefill(xl_handle* h, void* state, const float* x_in, float* y_out, int B, int S, unsigned flags, void* stream);
 
 /* Same for the whole policy: Tn timesteps of context per env, states fp32 [B, Tn, state_dim], rtg fp32 [B, Tn],
@@ -267,6 +268,10 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
  *   "smallm": [-1 = automatic] LN + proj_up + conv/qkv as one GEMV-style kernel and proj_down as another (4 kernels
  *                   per block instead of 6, fp32 activations against bf16 weights on CUDA cores). 1 = whenever
  *                   B*T <= 16 rows, 0 = never, automatic = B*T <= 4 rows and d <= 1024 (one env: -14 % step latency)
+ *   "prefill_cell": [2] sequence cell of the context prefill: 2 = chunkwise on tcgen05 (128-token chunks, head dims that
+ *                   are multiples of 128), 1 = chunkwise on mma.sync (16-token chunks), 0 = fp32 token-order cell
+ *   "prefill_rows": [16384] rows (envs x tokens) per prefill chunk; "prefill_conv_run": [16] tokens per thread run of the
+ *                   sequence conv/qkv kernel; "prefill_tc_fused": [1] chunk update + scan in one kernel (0 = through HBM)
  *   "microbatches": [1] env micro-batches of a fused step, pipelined on side streams; "pipeline_order": [1]
  *                   their state-stream kernels take turns */
 int xl_set_option(xl_handle* h, const char* name, int value);

@@ -399,6 +399,44 @@ def test_prefill_vs_oracle_steps(name, B, S):
     eng.close()
 
 
+@pytest.mark.parametrize("name,B,S", [("16M", 2, 304), ("110M", 1, 176)])
+def test_prefill_cells_agree_and_match_oracle_steps(name, B, S):
+    """The three sequence cells of the context prefill -- chunkwise tcgen05 (default, xl_prefill_tc.cu: 128-token chunks,
+    S here spans a ragged last chunk), chunkwise mma.sync (16-token chunks) and the fp32 token-order cell -- must leave
+    the same hidden states and recurrent state, and that state must be what S sequential oracle steps leave."""
+    from oracle import xlstm_oracle as O
+    cfg, sd, eng = _engine(name, B)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, S, cfg.d, generator=g)
+    res = {}
+    for cell in (2, 1, 0):
+        eng.set_option("prefill_cell", cell)
+        cache = eng.new_state(B)
+        eng.launch_count()
+        hs = eng.prefill(cache, x.cuda())
+        torch.cuda.synchronize()
+        res[cell] = (hs.cpu(), cache.to_past_key_values(), eng.launch_count())
+    eng.set_option("prefill_cell", 2)
+    assert res[2][2] > res[1][2]          # the tcgen05 cell is several launches per block: proof that it ran
+    for cell in (1, 0):
+        assert _rel(res[cell][0], res[2][0]) < 1e-4, cell
+        for i in range(cfg.num_blocks):
+            for a, b in zip(res[cell][1][f"block_{i}"]["mlstm_state"], res[2][1][f"block_{i}"]["mlstm_state"]):
+                assert _rel(a.cpu(), b.cpu()) < 1e-4 or (a.cpu() - b.cpu()).abs().max() < 1e-5, (cell, i)
+    ora = O.OracleEncoder(cfg, sd)
+    pkv, refs = None, []
+    for t in range(S):
+        r, pkv = ora.forward_cached(x[:, t:t + 1], pkv)
+        refs.append(r)
+    assert _rel(res[2][0], torch.cat(refs, dim=1)) < REL_TOL
+    for i in range(cfg.num_blocks):
+        c, n, m = pkv[f"block_{i}"]["mlstm_state"]
+        ce, ne, me = res[2][1][f"block_{i}"]["mlstm_state"]
+        assert _rel(ce.cpu(), c) < REL_TOL and _rel(ne.cpu(), n) < REL_TOL, f"block {i}"
+        assert (me.cpu() - m).abs().max() < 1e-4
+    eng.close()
+
+
 def test_policy_prefill_equals_stepping():
     """xl_policy_prefill(context of Tn timesteps) then a rollout == stepping through the context: same action
     tokens afterwards (needs no oracle: both sides are this library; the step path is oracle-checked above)."""
