@@ -20,7 +20,24 @@ run() { # tool, per-case timeout, cases...
   done
   echo "--- $tool"; grep -E "=== exit|ERROR SUMMARY|RACECHECK SUMMARY|sanitize_step" "$log"
 }
-R2="state_fuse1 state_fuse2 up_fuse gemm_bm64 gemm_cluster token_ring"
+R2="state_fuse1 state_fuse2 up_fuse gemm_bm64 gemm_cluster token_ring prefill_tc small_fuse"
+if [ "${1:-all}" = "r2b" ]; then  # the prefill cell on tcgen05 and the row-split cluster finalize (late round 2)
+  run memcheck 900 prefill_tc small_fuse
+  run synccheck 900 prefill_tc small_fuse
+  run racecheck 1200 small_fuse
+  # racecheck of the whole prefill_tc case ends without a report ("process didn't terminate successfully", no hazard
+  # printed, also with the pre-existing kernels only); the kernels that hand data through shared memory are therefore
+  # instrumented one at a time (--kernel-regex): the case runs to its oracle check each time.
+  log=gpurun_out/sanitize_racecheck.log
+  for k in bgemm update_scan prep_kernel pmat_kernel gate_pre gate_scan_seq conv_qkv_gates_seq finalize_seq; do
+    echo "=== racecheck :: prefill_tc, kernels matching $k" >> "$log"
+    timeout 900 "$CS" --tool racecheck --error-exitcode 9 --print-limit 20 --kernel-regex kns=$k \
+      python tools/sanitize_step.py prefill_tc >> "$log" 2>&1
+    echo "=== exit $? (prefill_tc / $k)" >> "$log"
+  done
+  grep -E "=== exit|RACECHECK SUMMARY|sanitize_step" "$log"
+  exit 0
+fi
 if [ "${1:-all}" = "r2" ]; then   # only the kernels / options added in round 2
   run memcheck 600 $R2
   run synccheck 600 $R2

@@ -62,10 +62,12 @@ def steps_case(name, B, mode, flags, n=3, discrete=False, opts=None, ring=False)
     eng.close()
 
 
-def prefill_case(name, B, Tn):
+def prefill_case(name, B, Tn, opts=None):
     cfg = preset(name)
     sd = make_state_dict(cfg, seed=2)
     eng = XLSTMEngine(cfg, sd, max_batch=B)
+    for k, v in (opts or {}).items():
+        eng.set_option(k, v)
     states, rtg, _ = make_stream(cfg, range(B), Tn + 1, domains="mixed")
     st = torch.from_numpy(np.ascontiguousarray(states[:Tn].transpose(1, 0, 2))).cuda()
     rg = torch.from_numpy(np.ascontiguousarray(rtg[:Tn].T)).cuda()
@@ -97,6 +99,11 @@ CASES = {
     "gemm_bm64": lambda: steps_case("16M", 40, L.XL_MODE_FUSED, 0, n=2, opts={"gemm_bm": 64}),
     "gemm_cluster": lambda: steps_case("16M", 40, L.XL_MODE_FUSED, 0, n=2, opts={"gemm_cluster": 2}),
     "token_ring": lambda: steps_case("toy128", 6, L.XL_MODE_FUSED, L.XL_FLAG_GRAPH, n=4, ring=True),
+    # tcgen05 chunkwise prefill cell (DH = 256): 132 tokens per env = one full 128-token chunk + a ragged one; batched
+    # hi/lo GEMMs, fused chunk update + scan (2 TMEM accumulators, shared-memory store staging), two-level gate scan
+    "prefill_tc": lambda: prefill_case("16M", 2, 44),
+    "prefill_tc_unfused": lambda: prefill_case("16M", 2, 44, opts={"prefill_tc_fused": 0}),
+    "small_fuse": lambda: steps_case("16M", 1, L.XL_MODE_FUSED, L.XL_FLAG_GRAPH, n=2, opts={"small_state_fuse": 1}),
 }
 
 if __name__ == "__main__":
