@@ -19,6 +19,8 @@ per step. A "step" is one env step of all envs: embed + 3 tokens x 12 blocks + h
   gpu_eager_baseline  the same oracle op sequence run eagerly on the GPU (fp32, ~10^3 launches per env step): the
                like-for-like "reference on this GPU" comparator (what `inf_dummy_batch_size` measures in the
                reference, online_decision_transformer_model.py:748-758)
+  context_prefill  BASELINE.json configs[3] on the side (N = 1): 49 998-token chunkwise prefill of one 206M env, tokens/s
+               and the bf16 MMA rate of the whole prefill against the sustained cuBLAS rate (tensor-pipe utilisation)
 
 --impl reference: times the reference's CPU implementation of the path (the oracle port; the xlstm package is
 absent, see oracle/xlstm_oracle.py header) on the host cores for the same config/metric. Both CPU legs use ONE
@@ -196,6 +198,49 @@ def run_reference(args):
 _JSON_FD = None
 
 
+def prefill_leg(peaks, model="206M", tokens=49998, reps=2):
+    """BASELINE.json configs[3]: chunkwise context prefill of one env (tcgen05 cell + tcgen05 projections), timed with
+    CUDA events over whole xl_policy_prefill calls (inputs resident in HBM). `tensor` relates the bf16 MMA work the
+    prefill issues (hi/lo passes included) to the sustained cuBLAS bf16 rate of MEASURED_PEAKS.json."""
+    from lram_b200.config import preset
+    from lram_b200.engine import XLSTMEngine
+    from lram_b200.synth import make_state_dict, make_stream
+    cfg = preset(model)
+    sd = make_state_dict(cfg, seed=0)
+    eng = XLSTMEngine(cfg, sd, max_batch=1)
+    Tn = tokens // 3
+    st_np, rtg_np, _ = make_stream(cfg, range(1), 256, domains="mixed")
+    rep = (Tn + 255) // 256
+    states = torch.from_numpy(np.ascontiguousarray(np.tile(st_np, (rep, 1, 1))[:Tn].transpose(1, 0, 2))).cuda()
+    rtg = torch.from_numpy(np.ascontiguousarray(np.tile(rtg_np, (rep, 1))[:Tn].T)).cuda()
+    cache = eng.new_state(1)
+    times = []
+    for r in range(reps + 1):
+        eng.reset(cache)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.policy_prefill(cache, states, rtg)
+        e1.record()
+        torch.cuda.synchronize()
+        if r > 0:                                   # the first call allocates the prefill workspaces
+            times.append(e0.elapsed_time(e1))
+    eng.close()
+    ms = statistics.median(times)
+    S, d, inner, NH, DH, Lb = Tn * 3, cfg.d, cfg.inner, cfg.num_heads, cfg.head_dim, cfg.num_blocks
+    proj = 2 * (2.0 * S * d * 2 * inner + 2.0 * S * inner * d)                       # A = hi + lo: two MMA passes
+    chunks = (S + 127) // 128
+    cell = 3 * chunks * NH * (2.0 * DH * DH * 128 + 2.0 * 128 * 128 * DH + 2.0 * 128 * DH * (DH + 128))   # hi/lo x hi/lo
+    mma = Lb * (proj + cell)
+    peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+    return {"workload": f"xLSTM {model}, 1 env, {S}-token context (chunkwise prefill, then O(1) recurrent rollout)",
+            "tokens_per_s": S / (ms / 1e3), "ms": ms, "reps": reps,
+            "tensor": {"bound": "tensor", "achieved": mma / (ms / 1e3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                       "frac": mma / (ms / 1e3) / 1e12 / peak if peak else None,
+                       "note": "bf16 MMA flops issued by the projections (2 passes) and the chunkwise cell (3 passes) "
+                               "over the WHOLE prefill time, non-GEMM kernels included; peak = sustained cuBLAS bf16"}}
+
+
 def _quiet_stdout():
     """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner from C), so
     fd 1 is pointed at stderr for the whole run and the JSON line goes to a duplicate of the original stdout."""
@@ -226,6 +271,7 @@ def main():
     ap.add_argument("--mode", default="fused", choices=["fused", "per_token"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true", help="skip the context-prefill leg (configs[3], N = 1 only)")
     ap.add_argument("--profile-steps", type=int, default=5)
     ap.add_argument("--discrete", action="store_true", help="discrete-action head (argmax over the first 18 logits)")
     ap.add_argument("--domains", default="metaworld", help="metaworld | dmcontrol | composuite | mimicgen | mixed")
@@ -463,6 +509,15 @@ def main():
             gpu_eager = {"unavailable": str(ex).splitlines()[0][:200]}
         torch.cuda.empty_cache()
 
+    # ---------------- context prefill, BASELINE.json configs[3] (rank 0, N == 1 only) -----------------------------
+    prefill = None
+    if rank == 0 and world == 1 and not args.no_prefill and not args.no_cpu_baseline:
+        try:
+            prefill = prefill_leg(peaks)
+        except RuntimeError as ex:
+            prefill = {"unavailable": str(ex).splitlines()[0][:200]}
+        torch.cuda.empty_cache()
+
     # ---------------- CPU baseline (rank 0, N == 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -502,6 +557,7 @@ def main():
             "whole_step": whole,
             "cpu_baseline": cpu,
             "gpu_eager_baseline": gpu_eager,
+            "context_prefill": prefill,
         }
         _emit(line)
     eng.close()
