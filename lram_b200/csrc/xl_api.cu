@@ -978,7 +978,10 @@ int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cud
     xl::launch_gate_scan_seq(ws.gate_part, (const float*)w.w[XL_W_IGATE_B], (const float*)w.w[XL_W_FGATE_B],
                              (float*)(base + L.m_off), h->pf_f, h->pf_i, h->pf_m, h->pf_gsc, B, Sc, NH, h->NCH, s);
     XL_CUDA(cudaGetLastError());
-    if (h->prefill_cell == 2 && xl::prefill_cell_tc_supported(DH)) {
+    // tcgen05 cell: whole 128-token chunks per (env, head) -- short runs of many envs (Sc < 64: more than half of every
+    // chunk would be padding) or a workspace beyond 8 GiB fall through to the 16-token mma.sync cell
+    if (h->prefill_cell == 2 && xl::prefill_cell_tc_supported(DH) && Sc >= 64 &&
+        xl::prefill_cell_tc_ws_bytes(B, Sc, NH, DH) <= ((size_t)8 << 30)) {
       if (int rcw = ensure_prefill_tc_ws(h, B, Sc)) return rcw;
       XL_CUDA(xl::launch_cell_tc((float*)(base + L.c_off), (float*)(base + L.n_off), cp.qk, cp.qk + (size_t)M * inner,
                                  cp.v, h->pf_f, h->pf_i, h->pf_num, h->pf_qn, h->pf_tc, B, Sc, NH, DH, inner, s));
