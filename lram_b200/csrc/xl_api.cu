@@ -132,6 +132,7 @@ struct xl_handle {
         *pf_semb = nullptr, *pf_spad = nullptr, *pf_sin = nullptr, *pf_rtg = nullptr, *pf_rew = nullptr, *pf_gsc = nullptr;
   __nv_bfloat16 *pf_hi = nullptr, *pf_lo = nullptr;
   uint8_t *pf_pc = nullptr, *pf_pv = nullptr;   // prepared operands of the chunkwise tensor-core cell
+  int prefill_gemm_2cta = 0;                    // A/B: shallow-ring Linear tiles, two CTAs per SM        ("prefill_gemm_2cta")
   int prefill_rows = 16384;                     // rows (envs x tokens) per prefill chunk                  ("prefill_rows")
   char* pf_tc = nullptr;                        // workspace of the tcgen05 chunkwise cell (grow-only)
   size_t pf_tc_bytes = 0;
@@ -914,7 +915,7 @@ Ws prefill_ws(const xl_handle* h) {
   w.a_hi = h->pf_hi; w.a_lo = h->pf_lo;
   const size_t kmax = std::max(std::max((size_t)h->cfg.inner_dim, (size_t)h->cfg.embedding_dim), (size_t)h->Kpad);
   w.a_cap = (size_t)h->pf_rows * kmax;
-  w.low_smem = 0;
+  w.low_smem = h->prefill_gemm_2cta;
   return w;
 }
 
@@ -1742,6 +1743,8 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
     if (value < 0 || value > 2)
       return fail(XL_ERR_INVALID_ARG, "prefill_cell must be 0 (fp32 sequence cell), 1 (chunkwise mma.sync) or 2 (chunkwise tcgen05)");
     h->prefill_cell = (int)value;
+  } else if (!strcmp(name, "prefill_gemm_2cta")) {
+    h->prefill_gemm_2cta = value ? 1 : 0;
   } else if (!strcmp(name, "prefill_rows")) {
     if (value < 48 || value > 32768) return fail(XL_ERR_INVALID_ARG, "prefill_rows must be in [48, 32768]");
     h->prefill_rows = value;
