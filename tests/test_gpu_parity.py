@@ -399,7 +399,7 @@ def test_prefill_vs_oracle_steps(name, B, S):
     eng.close()
 
 
-@pytest.mark.parametrize("name,B,S", [("16M", 2, 304), ("110M", 1, 176)])
+@pytest.mark.parametrize("name,B,S", [("16M", 2, 304), ("110M", 1, 176), ("206M", 1, 144)])
 def test_prefill_cells_agree_and_match_oracle_steps(name, B, S):
     """The three sequence cells of the context prefill -- chunkwise tcgen05 (default, xl_prefill_tc.cu: 128-token chunks,
     S here spans a ragged last chunk), chunkwise mma.sync (16-token chunks) and the fp32 token-order cell -- must leave
