@@ -1709,6 +1709,8 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "gemm_cluster")) {
     if (value != 1 && value != 2 && value != 4) return fail(XL_ERR_INVALID_ARG, "gemm_cluster must be 1, 2 or 4");
     xl::g_gemm_cluster = value;          // process-wide
+  } else if (!strcmp(name, "gemm_2cta")) {
+    xl::g_gemm_2cta = value ? 1 : 0;     // process-wide
   } else if (!strcmp(name, "gemm_bm")) {
     if (value != 0 && value != 64 && value != 128) return fail(XL_ERR_INVALID_ARG, "gemm_bm must be 0, 64 or 128");
     xl::g_gemm_bm = value;               // process-wide

@@ -332,6 +332,192 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
 
 // ------------------------------------------------------------------------------------------------------------------
+// 2-SM variant for GEMM-sized M (context prefill): a CTA PAIR (cluster of 2 along M) computes one 256 x 256 tile with
+// tcgen05.mma.cta_group::2. Each CTA stages its own 128 rows of the A planes and only HALF of the W tile (128 of its
+// 256 rows): 48 KB of operands per k-block and SM for a 128 x 256 output slice instead of 64 KB -- these GEMMs are bound
+// by operand delivery (L2 -> SM), not by the tensor pipe. Protocol (CUTLASS sm100 2-SM mainloop): both CTAs' TMA loads
+// (cp.async.bulk.tensor ... .cta_group::2) complete on the LEADER's full barrier, which expects the bytes of both; the
+// leader issues the MMAs (it reads the peer's shared memory at the same offsets) and releases a stage / publishes the
+// accumulator in both CTAs with tcgen05.commit.cta_group::2 ... multicast::cluster; each CTA's epilogue reads its own 128
+// accumulator rows from its own TMEM.
+// ------------------------------------------------------------------------------------------------------------------
+namespace two {
+
+constexpr int BN2 = 256;
+constexpr int kABytes = BLOCK_M * BLOCK_K * 2;        // one A plane of this CTA's 128 rows
+constexpr int kWBytes = 128 * BLOCK_K * 2;            // this CTA's half of the W tile
+constexpr int kStageBytes = 2 * kABytes + kWBytes;    // 48 KB
+constexpr int kStages = 4;
+constexpr int kTotal = kStages * kStageBytes + 1024 + 256;
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// TMA load of this CTA's tile into its own shared memory; completion bytes go to `bar` (an address in the cluster window:
+// the leader's full barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit2_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
+                const float* __restrict__ residual, float* __restrict__ out, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + kStages * kStageBytes;     // full[kStages], empty[kStages], tmem_full, slot
+  const uint32_t tmem_slot = bar_base + 8 * (2 * kStages + 1);
+  auto full_bar = [&](int s) { return bar_base + 8 * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8 * (kStages + s); };
+  const uint32_t tmem_full_bar = bar_base + 8 * (2 * kStages);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int n0 = blockIdx.y * BN2;
+  const int m0 = ((int)blockIdx.x >> 1) * 2 * BLOCK_M + (int)crank * BLOCK_M;      // the pair = consecutive blockIdx.x
+  const int num_kb = K / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {     // the same warp of BOTH CTAs allocates the pair's accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN2) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  pdl_wait();
+  pdl_trigger();
+  cluster_sync_all();        // the peer signals this CTA's barriers: they must be initialised cluster-wide first
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        if (kb >= kStages) mbar_wait(empty_bar(s), ((kb / kStages) & 1) ^ 1);
+        const uint32_t st = base + s * kStageBytes;
+        if (leader) mbar_expect_tx(full_bar(s), 2 * kStageBytes);          // the bytes of both CTAs
+        const uint32_t lbar = mapa_u32(full_bar(s), 0u);
+        tma_load_2d_pair(st, &map_a_hi, lbar, kb * BLOCK_K, m0);
+        tma_load_2d_pair(st + kABytes, &map_a_lo, lbar, kb * BLOCK_K, m0);
+        tma_load_2d_pair(st + 2 * kABytes, &map_w, lbar, kb * BLOCK_K, n0 + (int)crank * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(BN2, 2 * BLOCK_M);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        mbar_wait(full_bar(s), (kb / kStages) & 1);
+        tcgen05_fence_after();
+        const uint32_t st = base + s * kStageBytes;
+        const uint64_t a_hi = make_smem_desc(st);
+        const uint64_t a_lo = make_smem_desc(st + kABytes);
+        const uint64_t bw = make_smem_desc(st + 2 * kABytes);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint64_t kofs = (uint64_t)((k * UMMA_K * 2) >> 4);
+          umma2_bf16(tmem_base, a_hi + kofs, bw + kofs, idesc, (kb | k) != 0);
+          umma2_bf16(tmem_base, a_lo + kofs, bw + kofs, idesc, 1u);
+        }
+        commit2_mc(empty_bar(s), (uint16_t)3);       // the stage is free in both CTAs once these MMAs retire
+      }
+      commit2_mc(tmem_full_bar, (uint16_t)3);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN2; c += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+            "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+            "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int col0 = n0 + c;
+      if (row < M && col0 < N) {
+        float* orow = out + (int64_t)row * N + col0;
+        const float* rrow = residual ? residual + (int64_t)row * N + col0 : nullptr;
+        if (col0 + 32 <= N && (N & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                   __uint_as_float(r[j + 3]));
+            if (bias) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + j);
+              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            }
+            if (rrow) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
+              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+            }
+            *reinterpret_cast<float4*>(orow + j) = o;
+          }
+        } else {
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < N) {
+              float o = __uint_as_float(r[j]);
+              if (bias) o += bias[col0 + j];
+              if (rrow) o += rrow[j];
+              orow[j] = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // nobody frees TMEM or leaves while the pair's MMAs / barrier signals may still be in flight
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN2) : "memory");
+  }
+}
+
+}  // namespace two
+
+// ------------------------------------------------------------------------------------------------------------------
 // Up-projection with the pre-cell epilogue (fused 3-token step): u = LN(x) W_up^T as above, but the x_m half of u
 // never reaches global memory — CausalConv1d.step + SiLU + headwise q/k/v + gate partials ([ext-xlstm]
 // mLSTMLayer.step; what conv_qkv_gates_kernel does, same arithmetic in the same order) run on the accumulator tile
@@ -761,6 +947,7 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& ml, const CU
 
 }  // namespace tc
 
+int g_gemm_2cta = 0;      // xl_set_option("gemm_2cta"): 1 = 2-SM (cta_group::2) 256 x 256 tiles for GEMM-sized M (>= 512 rows)
 int g_gemm_cluster = 1;   // xl_set_option("gemm_cluster"): 1 = off, 2 / 4 = A-tile TMA multicast across that many column tiles
 int g_gemm_bm = 0;     // xl_set_option("gemm_bm"): 64 = 64-row MMA tiles where the shape allows, 0 / 128 = 128-row tiles
 void gemm_tc_set_m64_layout(int contiguous) { tc::g_m64_rows_contiguous = contiguous ? 1 : 0; }
@@ -848,6 +1035,28 @@ cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat
     int sp;
     gemm_tc_plan(M, N, K, num_sms, 1, &bn, &sp);
   }
+  if (g_gemm_2cta && M >= 512 && splits == 1 && !low_smem && N >= 256 && (bn == 256 || bn == 128)) {
+    CUtensorMap ma2, ml2, mw2;
+    if (!tc::make_map(&ma2, a_hi, M, K, tc::BLOCK_M) || !tc::make_map(&ml2, a_lo, M, K, tc::BLOCK_M) ||
+        !tc::make_map(&mw2, W, N, K, 128))
+      return cudaErrorUnknown;
+    if (cudaError_t e = ensure_dyn_smem<&tc::two::gemm_tc2_kernel>(tc::two::kTotal); e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ((M + 255) / 256), (N + 255) / 256, 1);
+    cfg.blockDim = dim3(tc::kThreads);
+    cfg.dynamicSmemBytes = tc::two::kTotal;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, tc::two::gemm_tc2_kernel, ma2, ml2, mw2, bias, residual, out, M, N, K);
+  }
   if (bn == 256 && (low_smem || N % 256 != 0)) bn = 128;
   // 64-row MMA tiles (option "gemm_bm" = 64): half the A bytes per k-block and a ring twice as deep (9 stages), no
   // empty quarter tile at M = 192. Bit-identical results; measured 1.2 % SLOWER on the 48M x 64 step (3 row tiles read
@@ -856,7 +1065,7 @@ cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat
   const bool bm64 = g_gemm_bm == 64 && !low_smem && bn == 64 && M > 16;
   // A-tile multicast across a cluster of 2 or 4 column-tile CTAs (option "gemm_cluster"; 128-row, 64-wide tiles only)
   const int n_tiles = (N + bn - 1) / bn;
-  int cx = (!bm64 && !low_smem && bn == 64 && N % 64 == 0) ? g_gemm_cluster : 1;
+  int cx = (!bm64 && !low_smem && (bn == 64 || bn == 128) && N % bn == 0) ? g_gemm_cluster : 1;
   while (cx > 1 && n_tiles % cx) cx >>= 1;
   CUtensorMap ma, ml, mw;
   const int box_m = bm64 ? 64 : tc::BLOCK_M / (cx > 1 ? cx : 1);
@@ -864,8 +1073,10 @@ cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat
       !tc::make_map(&mw, W, N, K, bn))
     return cudaErrorUnknown;
   if (bm64) return tc::launch<64, 9, 64>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
-  if (cx == 2) return tc::launch<64, 4, tc::BLOCK_M, 2>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
-  if (cx == 4) return tc::launch<64, 4, tc::BLOCK_M, 4>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
+  if (cx == 2 && bn == 64) return tc::launch<64, 4, tc::BLOCK_M, 2>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
+  if (cx == 4 && bn == 64) return tc::launch<64, 4, tc::BLOCK_M, 4>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
+  if (cx == 2) return tc::launch<128, 4, tc::BLOCK_M, 2>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
+  if (cx == 4) return tc::launch<128, 4, tc::BLOCK_M, 4>(ma, ml, mw, bias, residual, out, M, N, K, splits, split_stride, s);
   if (low_smem) {
     // shallow rings (<= 110 KB): the CTA must fit beside a resident state-stream CTA of another micro-batch
     switch (bn) {

@@ -169,6 +169,7 @@ cudaError_t launch_cell_mma(float* C, float* n, const float* q, const float* k, 
                             int DH, int inner, cudaStream_t s);
 // chunkwise sequence cell on tcgen05 (xl_prefill_tc.cu): 128-token chunks, every contraction a batched tcgen05 GEMM over
 // the (env, head, chunk) triples of the run; any S >= 1 (a ragged last chunk is padded with neutral gates)
+extern int g_gemm_2cta;
 extern int g_prefill_tc_fused;
 extern int g_prefill_conv_run;
 bool prefill_cell_tc_supported(int DH);

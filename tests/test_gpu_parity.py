@@ -986,6 +986,31 @@ def test_gemm_tile_variants_bit_identical(opt, val):
         eng.close()
 
 
+def test_gemm_2sm_pair_bit_identical():
+    """2-SM Linear (option "gemm_2cta": a CTA pair computes a 256 x 256 tile with tcgen05.mma.cta_group::2, each CTA
+    staging its 128 rows of the A planes and half of the W tile) == the 1-SM tcgen05 Linear bit for bit (same products in
+    the same order), incl. ragged M / N edges, bias and residual."""
+    cfg, sd, eng = _engine("toy", 1)
+    g = torch.Generator().manual_seed(7)
+    try:
+        for (M, N, K) in [(1000, 2560, 768), (640, 1280, 1024), (600, 2192, 512), (512, 256, 64), (1300, 768, 640)]:
+            A = torch.randn(M, K, generator=g).cuda()
+            W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
+            bias = torch.randn(N, generator=g).cuda()
+            res = torch.randn(M, N, generator=g).cuda()
+            eng.set_option("gemm_2cta", 0)
+            ref = eng.linear(A, W, bias, res, impl=2)
+            eng.set_option("gemm_2cta", 1)
+            out = eng.linear(A, W, bias, res, impl=2)
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref), (M, N, K, (out - ref).abs().max().item())
+            ref64 = (A.double() @ W.double().t() + bias.double() + res.double()).float()
+            assert _rel(out, ref64) < 2e-5
+    finally:
+        eng.set_option("gemm_2cta", 0)       # process-wide switch: restore
+        eng.close()
+
+
 def test_argmax_head_edge_cases_match_torch_semantics():
     """The fused argmax / inv_tokenize kernel on crafted logits (head weight 0, so logits == bias exactly): ties take the
     FIRST index and NaN counts as the maximum (torch.argmax, multi_domain_discrete_dt_model.py:83-94); ids below the

@@ -20,7 +20,13 @@ run() { # tool, per-case timeout, cases...
   done
   echo "--- $tool"; grep -E "=== exit|ERROR SUMMARY|RACECHECK SUMMARY|sanitize_step" "$log"
 }
-R2="state_fuse1 state_fuse2 up_fuse gemm_bm64 gemm_cluster token_ring prefill_tc small_fuse"
+R2="state_fuse1 state_fuse2 up_fuse gemm_bm64 gemm_cluster token_ring prefill_tc small_fuse gemm_2sm"
+if [ "${1:-all}" = "2sm" ]; then
+  run memcheck 600 gemm_2sm
+  run synccheck 600 gemm_2sm
+  run racecheck 900 gemm_2sm
+  exit 0
+fi
 if [ "${1:-all}" = "r2b" ]; then  # the prefill cell on tcgen05 and the row-split cluster finalize (late round 2)
   run memcheck 900 prefill_tc small_fuse
   run synccheck 900 prefill_tc small_fuse

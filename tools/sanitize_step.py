@@ -83,6 +83,26 @@ def prefill_case(name, B, Tn, opts=None):
     eng.close()
 
 
+def linear_2sm_case():
+    """2-SM (cta_group::2) Linear against the 1-SM kernel (bit-identical) and fp64, ragged M and N."""
+    cfg = preset("toy")
+    eng = XLSTMEngine(cfg, make_state_dict(cfg, seed=1), max_batch=1)
+    g = torch.Generator().manual_seed(3)
+    for (M, N, K) in [(600, 720, 128), (520, 256, 64)]:
+        A = torch.randn(M, K, generator=g).cuda()
+        W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
+        bias, res = torch.randn(N, generator=g).cuda(), torch.randn(M, N, generator=g).cuda()
+        eng.set_option("gemm_2cta", 0)
+        ref = eng.linear(A, W, bias, res, impl=2)
+        eng.set_option("gemm_2cta", 1)
+        out = eng.linear(A, W, bias, res, impl=2)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+        assert rel(out, (A.double() @ W.double().t() + bias.double() + res.double()).float()) < 2e-5
+    eng.set_option("gemm_2cta", 0)
+    eng.close()
+
+
 CASES = {
     "fused_eager": lambda: steps_case("toy128", 6, L.XL_MODE_FUSED, 0),
     "fused_graph": lambda: steps_case("toy128", 6, L.XL_MODE_FUSED, L.XL_FLAG_GRAPH),
@@ -103,6 +123,7 @@ CASES = {
     # hi/lo GEMMs, fused chunk update + scan (2 TMEM accumulators, shared-memory store staging), two-level gate scan
     "prefill_tc": lambda: prefill_case("16M", 2, 44),
     "prefill_tc_unfused": lambda: prefill_case("16M", 2, 44, opts={"prefill_tc_fused": 0}),
+    "gemm_2sm": linear_2sm_case,
     "small_fuse": lambda: steps_case("16M", 1, L.XL_MODE_FUSED, L.XL_FLAG_GRAPH, n=2, opts={"small_state_fuse": 1}),
 }
 
