@@ -260,9 +260,10 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
  *   "up_fuse": [0] conv + SiLU + q/k/v + gate partials in the proj_up epilogue (gemm_up_conv_kernel); one launch fewer
  *                   per block, x_m never leaves the chip; measured 3-9 % slower (more CTAs re-read the A planes from L2)
  *   "gemm_bm": [0] 64 = 64-row tcgen05 tiles for proj_up / proj_down (bit-identical; measured 1 % slower at 48M x 64)
- *   "gemm_2cta": [0] 2-SM Linear for GEMM-sized M (>= 512 rows): a CTA pair computes a 256 x 256 tile with
- *                   tcgen05.mma.cta_group::2, each CTA staging half of the W tile (bit-identical; measured equal to the 1-SM
- *                   128 x 256 tiles in the context prefill, profiles/r02_prefill_tcgen05.md)
+ *   "gemm_2cta": [-1 = automatic] 2-SM Linear: a CTA pair computes 256 x 256 tiles with tcgen05.mma.cta_group::2, each CTA
+ *                   staging its 128 A rows and half of the W tile; 2 = persistent pairs with a double-buffered TMEM
+ *                   accumulator (the epilogue of a tile overlaps the MMAs of the next), 1 = one tile per pair, 0 = never,
+ *                   automatic = the persistent form for M >= 2048 rows (context prefill: -7 %). Bit-identical to the 1-SM kernel
  *   "fuse_ends": [1] pad+split of the states in one kernel, block 0's pre-norm inside the embed kernel, post-norm of the
  *                   action-token rows only fused with the head's operand split (3-4 launches fewer per env step)
  *   "conv_impl": [0] pre-cell kernel (conv + SiLU + q/k/v + gate partials): 0 = one thread per 4-channel block walking

@@ -1710,7 +1710,9 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
     if (value != 1 && value != 2 && value != 4) return fail(XL_ERR_INVALID_ARG, "gemm_cluster must be 1, 2 or 4");
     xl::g_gemm_cluster = value;          // process-wide
   } else if (!strcmp(name, "gemm_2cta")) {
-    xl::g_gemm_2cta = value ? 1 : 0;     // process-wide
+    if (value < -1 || value > 2)
+      return fail(XL_ERR_INVALID_ARG, "gemm_2cta must be -1 (automatic), 0, 1 (2-SM tiles) or 2 (persistent 2-SM)");
+    xl::g_gemm_2cta = value;             // process-wide
   } else if (!strcmp(name, "gemm_bm")) {
     if (value != 0 && value != 64 && value != 128) return fail(XL_ERR_INVALID_ARG, "gemm_bm must be 0, 64 or 128");
     xl::g_gemm_bm = value;               // process-wide

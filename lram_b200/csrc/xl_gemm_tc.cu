@@ -515,6 +515,185 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   }
 }
 
+// Persistent form of the same 2-SM kernel: one CTA pair per SM pair walks the 256 x 256 tiles p, p + P, ... The
+// accumulator is double-buffered in TMEM (2 x 256 columns): the MMAs of tile j+1 run while both CTAs' epilogue warps drain
+// tile j (tcgen05.ld -> bias / residual -> global) and hand the buffer back by arriving -- the peer CTA remotely -- on the
+// leader's tmem-empty barrier. The operand ring simply continues across tiles.
+constexpr int kStagesP = 4;
+constexpr int kTotalP = kStagesP * kStageBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc2p_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_w, const float* __restrict__ bias,
+                 const float* __restrict__ residual, float* __restrict__ out, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = base + kStagesP * kStageBytes;   // full[S], empty[S], tfull[2], tempty[2], slot
+  auto full_bar = [&](int s) { return bar_base + 8 * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8 * (kStagesP + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8 * (2 * kStagesP + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8 * (2 * kStagesP + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8 * (2 * kStagesP + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int num_kb = K / BLOCK_K;
+  const int ntiles_n = (N + BN2 - 1) / BN2, ntiles_m = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int ntiles = ntiles_n * ntiles_m;
+  const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < kStagesP; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 8);          // 4 epilogue warps of each CTA of the pair (used in the leader only)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN2) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  pdl_wait();
+  pdl_trigger();
+  cluster_sync_all();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        const int mt = t / ntiles_n, nt = t - mt * ntiles_n;
+        const int m0 = mt * 2 * BLOCK_M + (int)crank * BLOCK_M, n0 = nt * BN2;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStagesP;
+          if (it >= kStagesP) mbar_wait(empty_bar(s), ((it / kStagesP) & 1) ^ 1);
+          const uint32_t st = base + s * kStageBytes;
+          if (leader) mbar_expect_tx(full_bar(s), 2 * kStageBytes);
+          const uint32_t lbar = mapa_u32(full_bar(s), 0u);
+          tma_load_2d_pair(st, &map_a_hi, lbar, kb * BLOCK_K, m0);
+          tma_load_2d_pair(st + kABytes, &map_a_lo, lbar, kb * BLOCK_K, m0);
+          tma_load_2d_pair(st + 2 * kABytes, &map_w, lbar, kb * BLOCK_K, n0 + (int)crank * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(BN2, 2 * BLOCK_M);
+      int it = 0, j = 0;
+      for (int t = pair; t < ntiles; t += npairs, ++j) {
+        const int b = j & 1, use = j >> 1;
+        if (use > 0) {                      // both CTAs' epilogues have drained this accumulator
+          mbar_wait(tempty_bar(b), (use - 1) & 1);
+          tcgen05_fence_after();
+        }
+        const uint32_t tacc = tmem_base + (uint32_t)(b * BN2);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStagesP;
+          mbar_wait(full_bar(s), (it / kStagesP) & 1);
+          tcgen05_fence_after();
+          const uint32_t st = base + s * kStageBytes;
+          const uint64_t a_hi = make_smem_desc(st);
+          const uint64_t a_lo = make_smem_desc(st + kABytes);
+          const uint64_t bw = make_smem_desc(st + 2 * kABytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t kofs = (uint64_t)((k * UMMA_K * 2) >> 4);
+            umma2_bf16(tacc, a_hi + kofs, bw + kofs, idesc, (kb | k) != 0);
+            umma2_bf16(tacc, a_lo + kofs, bw + kofs, idesc, 1u);
+          }
+          commit2_mc(empty_bar(s), (uint16_t)3);
+        }
+        commit2_mc(tfull_bar(b), (uint16_t)3);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const uint32_t lead_tempty0 = mapa_u32(tempty_bar(0), 0u), lead_tempty1 = mapa_u32(tempty_bar(1), 0u);
+    int j = 0;
+    for (int t = pair; t < ntiles; t += npairs, ++j) {
+      const int b = j & 1, use = j >> 1;
+      const int mt = t / ntiles_n, nt = t - mt * ntiles_n;
+      const int m0 = mt * 2 * BLOCK_M + (int)crank * BLOCK_M, n0 = nt * BN2;
+      const int row = m0 + q * 32 + lane;
+      mbar_wait(tfull_bar(b), use & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN2; c += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN2 + c);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+              "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+              "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int col0 = n0 + c;
+        if (row < M && col0 < N) {
+          float* orow = out + (int64_t)row * N + col0;
+          const float* rrow = residual ? residual + (int64_t)row * N + col0 : nullptr;
+          if (col0 + 32 <= N && (N & 3) == 0) {
+            float4 rv[8];
+            if (rrow) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) rv[jj] = *reinterpret_cast<const float4*>(rrow + 4 * jj);   // all in flight
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              float4 o = make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]),
+                                     __uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3]));
+              if (bias) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + col0 + 4 * jj);
+                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+              }
+              if (rrow) { o.x += rv[jj].x; o.y += rv[jj].y; o.z += rv[jj].z; o.w += rv[jj].w; }
+              *reinterpret_cast<float4*>(orow + 4 * jj) = o;
+            }
+          } else {
+            for (int jj = 0; jj < 32; ++jj) {
+              if (col0 + jj < N) {
+                float o = __uint_as_float(r[jj]);
+                if (bias) o += bias[col0 + jj];
+                if (rrow) o += rrow[jj];
+                orow[jj] = o;
+              }
+            }
+          }
+        }
+      }
+      // this warp is done with accumulator b: tell the leader's MMA thread (remote arrive from the peer CTA)
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(b ? lead_tempty1 : lead_tempty0)
+                     : "memory");
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN2) : "memory");
+  }
+}
+
 }  // namespace two
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -947,7 +1126,10 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& ml, const CU
 
 }  // namespace tc
 
-int g_gemm_2cta = 0;      // xl_set_option("gemm_2cta"): 1 = 2-SM (cta_group::2) 256 x 256 tiles for GEMM-sized M (>= 512 rows)
+// xl_set_option("gemm_2cta"): the 2-SM (cta_group::2) Linear with 256 x 256 tiles per CTA pair. -1 (default) = the
+// persistent form for M >= 2048 rows (context prefill; measured -7 % on the 206M prefill), 0 = never, 1 / 2 = the
+// one-tile-per-pair / persistent form whenever M >= 512
+int g_gemm_2cta = -1;
 int g_gemm_cluster = 1;   // xl_set_option("gemm_cluster"): 1 = off, 2 / 4 = A-tile TMA multicast across that many column tiles
 int g_gemm_bm = 0;     // xl_set_option("gemm_bm"): 64 = 64-row MMA tiles where the shape allows, 0 / 128 = 128-row tiles
 void gemm_tc_set_m64_layout(int contiguous) { tc::g_m64_rows_contiguous = contiguous ? 1 : 0; }
@@ -1035,16 +1217,23 @@ cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat
     int sp;
     gemm_tc_plan(M, N, K, num_sms, 1, &bn, &sp);
   }
-  if (g_gemm_2cta && M >= 512 && splits == 1 && !low_smem && N >= 256 && (bn == 256 || bn == 128)) {
+  const int two_sm = g_gemm_2cta < 0 ? (M >= 2048 ? 2 : 0) : (M >= 512 ? g_gemm_2cta : 0);
+  if (two_sm && splits == 1 && !low_smem && N >= 256 && (bn == 256 || bn == 128)) {
     CUtensorMap ma2, ml2, mw2;
     if (!tc::make_map(&ma2, a_hi, M, K, tc::BLOCK_M) || !tc::make_map(&ml2, a_lo, M, K, tc::BLOCK_M) ||
         !tc::make_map(&mw2, W, N, K, 128))
       return cudaErrorUnknown;
-    if (cudaError_t e = ensure_dyn_smem<&tc::two::gemm_tc2_kernel>(tc::two::kTotal); e != cudaSuccess) return e;
+    const bool persistent = two_sm == 2;
+    if (cudaError_t e = persistent ? ensure_dyn_smem<&tc::two::gemm_tc2p_kernel>(tc::two::kTotalP)
+                                   : ensure_dyn_smem<&tc::two::gemm_tc2_kernel>(tc::two::kTotal);
+        e != cudaSuccess)
+      return e;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * ((M + 255) / 256), (N + 255) / 256, 1);
+    const int tiles = ((M + 255) / 256) * ((N + 255) / 256);
+    const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+    cfg.gridDim = persistent ? dim3(2 * pairs, 1, 1) : dim3(2 * ((M + 255) / 256), (N + 255) / 256, 1);
     cfg.blockDim = dim3(tc::kThreads);
-    cfg.dynamicSmemBytes = tc::two::kTotal;
+    cfg.dynamicSmemBytes = persistent ? tc::two::kTotalP : tc::two::kTotal;
     cfg.stream = s;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1055,6 +1244,7 @@ cudaError_t launch_gemm_tc(const void* a_hi, const void* a_lo, const __nv_bfloat
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 2 : 1;
+    if (persistent) return cudaLaunchKernelEx(&cfg, tc::two::gemm_tc2p_kernel, ma2, ml2, mw2, bias, residual, out, M, N, K);
     return cudaLaunchKernelEx(&cfg, tc::two::gemm_tc2_kernel, ma2, ml2, mw2, bias, residual, out, M, N, K);
   }
   if (bn == 256 && (low_smem || N % 256 != 0)) bn = 128;

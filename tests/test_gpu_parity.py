@@ -993,21 +993,24 @@ def test_gemm_2sm_pair_bit_identical():
     cfg, sd, eng = _engine("toy", 1)
     g = torch.Generator().manual_seed(7)
     try:
-        for (M, N, K) in [(1000, 2560, 768), (640, 1280, 1024), (600, 2192, 512), (512, 256, 64), (1300, 768, 640)]:
+        # (the last shape has 160 tiles: more than the 74 CTA pairs, so the persistent variant walks 2-3 tiles per pair)
+        for (M, N, K) in [(1000, 2560, 768), (640, 1280, 1024), (600, 2192, 512), (512, 256, 64), (1300, 768, 640),
+                          (4000, 2560, 256)]:
             A = torch.randn(M, K, generator=g).cuda()
             W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16).cuda()
             bias = torch.randn(N, generator=g).cuda()
             res = torch.randn(M, N, generator=g).cuda()
             eng.set_option("gemm_2cta", 0)
             ref = eng.linear(A, W, bias, res, impl=2)
-            eng.set_option("gemm_2cta", 1)
-            out = eng.linear(A, W, bias, res, impl=2)
-            torch.cuda.synchronize()
-            assert torch.equal(out, ref), (M, N, K, (out - ref).abs().max().item())
+            for variant in (1, 2):        # 1 = one tile per CTA pair, 2 = persistent pairs, double-buffered TMEM accumulator
+                eng.set_option("gemm_2cta", variant)
+                out = eng.linear(A, W, bias, res, impl=2)
+                torch.cuda.synchronize()
+                assert torch.equal(out, ref), (variant, M, N, K, (out - ref).abs().max().item())
             ref64 = (A.double() @ W.double().t() + bias.double() + res.double()).float()
             assert _rel(out, ref64) < 2e-5
     finally:
-        eng.set_option("gemm_2cta", 0)       # process-wide switch: restore
+        eng.set_option("gemm_2cta", -1)      # process-wide switch: restore the default
         eng.close()
 
 

@@ -94,12 +94,13 @@ def linear_2sm_case():
         bias, res = torch.randn(N, generator=g).cuda(), torch.randn(M, N, generator=g).cuda()
         eng.set_option("gemm_2cta", 0)
         ref = eng.linear(A, W, bias, res, impl=2)
-        eng.set_option("gemm_2cta", 1)
-        out = eng.linear(A, W, bias, res, impl=2)
-        torch.cuda.synchronize()
-        assert torch.equal(out, ref)
+        for variant in (1, 2):
+            eng.set_option("gemm_2cta", variant)
+            out = eng.linear(A, W, bias, res, impl=2)
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref)
         assert rel(out, (A.double() @ W.double().t() + bias.double() + res.double()).float()) < 2e-5
-    eng.set_option("gemm_2cta", 0)
+    eng.set_option("gemm_2cta", -1)
     eng.close()
 
 
