@@ -112,21 +112,36 @@ struct BatchOut {
   int ldo, NH, nchunk, rows_valid;
 };
 
-// out_z[M, N] = (A_hi + A_lo)_z[M, K] (W_hi + W_lo)_z[N, K]^T  without the lo*lo term; grid = (N/128, M/128, batches)
+// out_z[M, N] = (A_hi + A_lo)_z[M, K] (W_hi + W_lo)_z[N, K]^T  without the lo*lo term.
+// PERSISTENT: grid = min(tiles, SMs) CTAs walk the (batch, row tile, column tile) list; the accumulator is double-buffered
+// in TMEM (2 x 128 columns), so the epilogue of a tile (tcgen05.ld -> swizzled shared-memory transpose -> coalesced
+// stores) overlaps the MMAs of the next one, and the operand ring runs on across tiles.
+constexpr int kEpiStage = 4 * 4096;                    // per-warp [32 rows][128 B] store staging
+constexpr int kSmemGemm = kStages * kStageBytes + 1024 + 256 + kEpiStage;
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 bgemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
              const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl, BatchOut o, int M,
-             int N, int K) {
+             int N, int K, int nb) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + kStages * kStageBytes;       // full[kStages], empty[kStages], tmem_full, slot
-  const uint32_t tmem_slot = bar_base + 8 * (2 * kStages + 1);
+  const uint32_t bar_base = base + kStages * kStageBytes;       // full[S], empty[S], tfull[2], tempty[2], slot
   auto full_bar = [&](int s) { return bar_base + 8 * s; };
   auto empty_bar = [&](int s) { return bar_base + 8 * (kStages + s); };
-  const uint32_t tmem_full_bar = bar_base + 8 * (2 * kStages);
+  auto tfull_bar = [&](int b) { return bar_base + 8 * (2 * kStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8 * (2 * kStages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8 * (2 * kStages + 4);
+  const uint32_t epi_base = bar_base + 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM, z = blockIdx.z;
   const int num_kb = K / BK;
+  const int tn = N / BN, tm = M / BM;
+  const int ntiles = nb * tm * tn;
+  auto tile_of = [&](int t, int& z, int& m0, int& n0) {         // column tiles of one (batch, row tile) are neighbours
+    z = t / (tm * tn);
+    const int r = t - z * tm * tn;
+    m0 = (r / tn) * BM;
+    n0 = (r % tn) * BN;
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah) : "memory");
@@ -137,11 +152,14 @@ bgemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);                                // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -154,72 +172,90 @@ bgemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        if (kb >= kStages) mbar_wait(empty_bar(s), ((kb / kStages) & 1) ^ 1);
-        const uint32_t st = base + s * kStageBytes;
-        mbar_expect_tx(full_bar(s), kStageBytes);
-        tma_load_3d(st, &map_ah, full_bar(s), kb * BK, m0, z);
-        tma_load_3d(st + kABytes, &map_al, full_bar(s), kb * BK, m0, z);
-        tma_load_3d(st + 2 * kABytes, &map_wh, full_bar(s), kb * BK, n0, z);
-        tma_load_3d(st + 2 * kABytes + kWBytes, &map_wl, full_bar(s), kb * BK, n0, z);
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int z, m0, n0;
+        tile_of(t, z, m0, n0);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          if (it >= kStages) mbar_wait(empty_bar(s), ((it / kStages) & 1) ^ 1);
+          const uint32_t st = base + s * kStageBytes;
+          mbar_expect_tx(full_bar(s), kStageBytes);
+          tma_load_3d(st, &map_ah, full_bar(s), kb * BK, m0, z);
+          tma_load_3d(st + kABytes, &map_al, full_bar(s), kb * BK, m0, z);
+          tma_load_3d(st + 2 * kABytes, &map_wh, full_bar(s), kb * BK, n0, z);
+          tma_load_3d(st + 2 * kABytes + kWBytes, &map_wl, full_bar(s), kb * BK, n0, z);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kStages;
-        mbar_wait(full_bar(s), (kb / kStages) & 1);
-        tcgen05_fence_after();
-        const uint32_t st = base + s * kStageBytes;
-        const uint64_t ah = smem_desc(st), al = smem_desc(st + kABytes);
-        const uint64_t wh = smem_desc(st + 2 * kABytes), wl = smem_desc(st + 2 * kABytes + kWBytes);
-#pragma unroll
-        for (int k = 0; k < BK / UK; ++k) {
-          const uint64_t kofs = (uint64_t)((k * UK * 2) >> 4);       // advance inside the 128-B swizzle row
-          umma(tmem_base, al + kofs, wh + kofs, (kb | k) != 0);      // small terms first
-          umma(tmem_base, ah + kofs, wl + kofs, 1u);
-          umma(tmem_base, ah + kofs, wh + kofs, 1u);
+      int it = 0, j = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+        const int b = j & 1, use = j >> 1;
+        if (use > 0) {                                            // the epilogue has drained this accumulator
+          mbar_wait(tempty_bar(b), (use - 1) & 1);
+          tcgen05_fence_after();
         }
-        tcgen05_commit(empty_bar(s));
+        const uint32_t tacc = tmem_base + (uint32_t)(b * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(full_bar(s), (it / kStages) & 1);
+          tcgen05_fence_after();
+          const uint32_t st = base + s * kStageBytes;
+          const uint64_t ah = smem_desc(st), al = smem_desc(st + kABytes);
+          const uint64_t wh = smem_desc(st + 2 * kABytes), wl = smem_desc(st + 2 * kABytes + kWBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t kofs = (uint64_t)((k * UK * 2) >> 4);     // advance inside the 128-B swizzle row
+            umma(tacc, al + kofs, wh + kofs, (kb | k) != 0);         // small terms first
+            umma(tacc, ah + kofs, wl + kofs, 1u);
+            umma(tacc, ah + kofs, wh + kofs, 1u);
+          }
+          tcgen05_commit(empty_bar(s));
+        }
+        tcgen05_commit(tfull_bar(b));
       }
-      tcgen05_commit(tmem_full_bar);
     }
   } else {
     // ===== epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31; accumulator row r lives in lane r =====
+    // A lane holds one accumulator row; written as is, a warp store would touch 32 different lines. Each 32-column piece
+    // goes through a per-warp [32 rows][128 B] buffer (16-byte chunks XOR-swizzled by row) and leaves as 4 rows x 128
+    // contiguous bytes per warp store.
     const int q = warp & 3;
-    const int c = z % o.nchunk, bh = z / o.nchunk, b = bh / o.NH, hd = bh - b * o.NH;
-    const int mvalid = o.rows_valid > 0 ? min(M, o.rows_valid - c * BM) : M;
-    mbar_wait(tmem_full_bar, 0);       // every MMA has retired: the ring is free, its first 64 KB stage the tile out
-    tcgen05_fence_after();
-    // A lane holds one accumulator row; written as is, a warp store would touch 32 different lines. Each 32-column
-    // piece goes through a per-warp [32 rows][128 B] buffer (16-byte chunks XOR-swizzled by row) and leaves as 4 rows
-    // x 128 contiguous bytes per warp store.
-    const uint32_t wst = base + (uint32_t)q * 4096u;
-    const int rbase = m0 + q * 32;
-    float* otile = o.out + (long long)b * o.s_b + (long long)hd * o.s_h + (long long)c * o.s_c + (long long)rbase * o.ldo + n0;
+    const uint32_t wst = epi_base + (uint32_t)q * 4096u;
+    int j = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
+      const int b = j & 1, use = j >> 1;
+      int z, m0, n0;
+      tile_of(t, z, m0, n0);
+      const int c = z % o.nchunk, bh = z / o.nchunk, be = bh / o.NH, hd = bh - be * o.NH;
+      const int mvalid = o.rows_valid > 0 ? min(M, o.rows_valid - c * BM) : M;
+      const int rbase = m0 + q * 32;
+      float* otile = o.out + (long long)be * o.s_b + (long long)hd * o.s_h + (long long)c * o.s_c + (long long)rbase * o.ldo + n0;
+      mbar_wait(tfull_bar(b), use & 1);
+      tcgen05_fence_after();
 #pragma unroll
-    for (int cc = 0; cc < BN; cc += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
-            "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
-            "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int cc = 0; cc < BN; cc += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + cc);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+              "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+              "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)lane * 128u + (uint32_t)((k ^ (lane & 7)) << 4)),
-                     "r"(r[4 * k]), "r"(r[4 * k + 1]), "r"(r[4 * k + 2]), "r"(r[4 * k + 3]) : "memory");
-      __syncwarp();
-      if (n0 + cc < N) {
+        for (int k = 0; k < 8; ++k)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)lane * 128u + (uint32_t)((k ^ (lane & 7)) << 4)),
+                       "r"(r[4 * k]), "r"(r[4 * k + 1]), "r"(r[4 * k + 2]), "r"(r[4 * k + 3]) : "memory");
+        __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = 4 * i + (lane >> 3), kk = lane & 7;
@@ -229,15 +265,18 @@ bgemm_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__
           if (rbase + rr < mvalid)
             *reinterpret_cast<uint4*>(otile + (long long)rr * o.ldo + cc + kk * 4) = make_uint4(v0, v1, v2, v3);
         }
+        __syncwarp();
       }
+      tcgen05_fence_before();
       __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(b)) : "memory");
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 }
 
@@ -792,9 +831,15 @@ static cudaError_t launch_bgemm(const Operand& a, const Operand& w, const BatchO
   if (!make_map3(&mah, a.hi, K, M, nb, a.ld, a.bs) || !make_map3(&mal, a.lo, K, M, nb, a.ld, a.bs) ||
       !make_map3(&mwh, w.hi, K, N, nb, w.ld, w.bs) || !make_map3(&mwl, w.lo, K, N, nb, w.ld, w.bs))
     return cudaErrorUnknown;
-  if (cudaError_t e = ensure_dyn_smem<&bgemm_kernel>(kSmemTotal); e != cudaSuccess) return e;
-  return launch_k(bgemm_kernel, dim3(N / BN, M / BM, nb), dim3(kGemmThreads), kSmemTotal, s, mah, mal, mwh, mwl, o, M, N,
-                  K);
+  if (cudaError_t e = ensure_dyn_smem<&bgemm_kernel>(kSmemGemm); e != cudaSuccess) return e;
+  static const int sms = [] {                     // SMs of the current device (every device of a box is the same part)
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  const int tiles = nb * (M / BM) * (N / BN);
+  return launch_k(bgemm_kernel, dim3(tiles < sms ? tiles : sms), dim3(kGemmThreads), kSmemGemm, s, mah, mal, mwh, mwl, o,
+                  M, N, K, nb);
 }
 
 }  // namespace ptc
