@@ -205,17 +205,41 @@ __global__ void __launch_bounds__(64 * kConvRuns, 2) conv_qkv_gates_seq_kernel(C
       }
     }
     // chunk-level partial sums of the 4 tokens: warp tree, then fixed-order sum over the (<= 4) warps of the run
+    if constexpr (NH * 2 * TG == 32) {
+      // 32 values x 32 lanes: a transposing butterfly (each xor step halves the values a lane carries) needs 31 shuffles
+      // instead of 160 and forms exactly the pairwise sums of warp_sum(); lane l ends with the warp total of value l
+      float vals[32];
 #pragma unroll
-    for (int h = 0; h < NH; ++h)
+      for (int h = 0; h < NH; ++h)
 #pragma unroll
-      for (int t = 0; t < TG; ++t) {
-        const float si = warp_sum(gi[h][t]);
-        const float sf = warp_sum(gf[h][t]);
-        if (lane == 0) {
-          red[sub][((h * 2 + 0) * TG + t) * 4 + wid] = si;
-          red[sub][((h * 2 + 1) * TG + t) * 4 + wid] = sf;
+        for (int t = 0; t < TG; ++t) {
+          vals[(h * 2 + 0) * TG + t] = gi[h][t];
+          vals[(h * 2 + 1) * TG + t] = gf[h][t];
+        }
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < m; ++i) {
+          const float keep = up ? vals[i + m] : vals[i];
+          const float send = up ? vals[i] : vals[i + m];
+          vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
         }
       }
+      red[sub][lane * 4 + wid] = vals[0];
+    } else {
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+#pragma unroll
+        for (int t = 0; t < TG; ++t) {
+          const float si = warp_sum(gi[h][t]);
+          const float sf = warp_sum(gf[h][t]);
+          if (lane == 0) {
+            red[sub][((h * 2 + 0) * TG + t) * 4 + wid] = si;
+            red[sub][((h * 2 + 1) * TG + t) * 4 + wid] = sf;
+          }
+        }
+    }
     __syncthreads();
     if ((int)threadIdx.x < NH * 2 * TG) {
       const int h = threadIdx.x / (2 * TG);

@@ -616,43 +616,62 @@ __global__ void __launch_bounds__(256) prep_kernel(CellParams p) {
   if (ch0 >= ch1) return;
   const int w4 = (ch1 - ch0) >> 2;
 
-  // token-major planes: Q, K [L][DH]; e^{a_t} q_t into A3[:, 0:DH]
-  for (int idx = tid; idx < L * w4; idx += 256) {
-    const int t = idx / w4, c4 = idx - t * w4;
-    const int ch = ch0 + 4 * c4;
-    float4 xq = make_float4(0.f, 0.f, 0.f, 0.f), xk = xq;
-    if (t < nvalid) {
-      xq = *reinterpret_cast<const float4*>(p.q + (row0 + t) * inner + hoff + ch);
-      xk = *reinterpret_cast<const float4*>(p.k + (row0 + t) * inner + hoff + ch);
+  // token-major planes: Q, K [L][DH]; e^{a_t} q_t into A3[:, 0:DH]. The loads of 4 items are issued together (the plane
+  // stores in between would otherwise order them one item at a time: the kernel is bound by load latency)
+  const int nit = L * w4;
+  for (int i0 = tid; i0 < nit; i0 += 4 * 256) {
+    float4 xq[4], xk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = i0 + u * 256;
+      const int t = idx / w4, c4 = idx - t * w4;
+      xq[u] = xk[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < nit && t < nvalid) {
+        xq[u] = *reinterpret_cast<const float4*>(p.q + (row0 + t) * inner + hoff + ch0 + 4 * c4);
+        xk[u] = *reinterpret_cast<const float4*>(p.k + (row0 + t) * inner + hoff + ch0 + 4 * c4);
+      }
     }
-    uint32_t h0, l0, h1, l1;
-    const int64_t o = (z * L + t) * DH + ch;
-    split2(xq.x, xq.y, h0, l0);
-    split2(xq.z, xq.w, h1, l1);
-    *reinterpret_cast<uint2*>(p.w.q_hi + o) = make_uint2(h0, h1);
-    *reinterpret_cast<uint2*>(p.w.q_lo + o) = make_uint2(l0, l1);
-    split2(xk.x, xk.y, h0, l0);
-    split2(xk.z, xk.w, h1, l1);
-    *reinterpret_cast<uint2*>(p.w.k_hi + o) = make_uint2(h0, h1);
-    *reinterpret_cast<uint2*>(p.w.k_lo + o) = make_uint2(l0, l1);
-    const float F = s_F[t];
-    const int64_t o3 = (z * L + t) * K3 + ch;
-    split2(F * xq.x, F * xq.y, h0, l0);
-    split2(F * xq.z, F * xq.w, h1, l1);
-    *reinterpret_cast<uint2*>(p.w.a3_hi + o3) = make_uint2(h0, h1);
-    *reinterpret_cast<uint2*>(p.w.a3_lo + o3) = make_uint2(l0, l1);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = i0 + u * 256;
+      if (idx >= nit) break;
+      const int t = idx / w4, c4 = idx - t * w4;
+      const int ch = ch0 + 4 * c4;
+      uint32_t h0, l0, h1, l1;
+      const int64_t o = (z * L + t) * DH + ch;
+      split2(xq[u].x, xq[u].y, h0, l0);
+      split2(xq[u].z, xq[u].w, h1, l1);
+      *reinterpret_cast<uint2*>(p.w.q_hi + o) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(p.w.q_lo + o) = make_uint2(l0, l1);
+      split2(xk[u].x, xk[u].y, h0, l0);
+      split2(xk[u].z, xk[u].w, h1, l1);
+      *reinterpret_cast<uint2*>(p.w.k_hi + o) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(p.w.k_lo + o) = make_uint2(l0, l1);
+      const float F = s_F[t];
+      const int64_t o3 = (z * L + t) * K3 + ch;
+      split2(F * xq[u].x, F * xq[u].y, h0, l0);
+      split2(F * xq[u].z, F * xq[u].w, h1, l1);
+      *reinterpret_cast<uint2*>(p.w.a3_hi + o3) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(p.w.a3_lo + o3) = make_uint2(l0, l1);
+    }
   }
-  // channel-major planes: K~^T [DH][L], V^T into W3[:, DH:DH+L]; item = (token group of 16, channel)
+  // channel-major planes: K~^T [DH][L], V^T into W3[:, DH:DH+L]; item = (token group of 16, channel). k and v of the item
+  // are loaded together, before any store
   const int nchs = ch1 - ch0;
   for (int idx = tid; idx < (L / 16) * nchs; idx += 256) {
     const int g = idx / nchs, r = ch0 + (idx - g * nchs);
+    float kv[16], vv[16];
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      const int j = g * 16 + jj;
+      kv[jj] = j < nvalid ? p.k[(row0 + j) * inner + hoff + r] : 0.f;
+      vv[jj] = j < nvalid ? p.v[(row0 + j) * inner + hoff + r] : 0.f;
+    }
     uint32_t h[8], l[8];
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       const int j0 = g * 16 + 2 * jj;
-      const float x0 = j0 < nvalid ? p.k[(row0 + j0) * inner + hoff + r] * s_ks[j0] : 0.f;
-      const float x1 = j0 + 1 < nvalid ? p.k[(row0 + j0 + 1) * inner + hoff + r] * s_ks[j0 + 1] : 0.f;
-      split2(x0, x1, h[jj], l[jj]);
+      split2(kv[2 * jj] * s_ks[j0], kv[2 * jj + 1] * s_ks[j0 + 1], h[jj], l[jj]);
     }
     const int64_t ok = (z * DH + r) * L + g * 16;
     *reinterpret_cast<uint4*>(p.w.kt_hi + ok) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -660,23 +679,36 @@ __global__ void __launch_bounds__(256) prep_kernel(CellParams p) {
     *reinterpret_cast<uint4*>(p.w.kt_lo + ok) = make_uint4(l[0], l[1], l[2], l[3]);
     *reinterpret_cast<uint4*>(p.w.kt_lo + ok + 8) = make_uint4(l[4], l[5], l[6], l[7]);
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) {
-      const int j0 = g * 16 + 2 * jj;
-      const float x0 = j0 < nvalid ? p.v[(row0 + j0) * inner + hoff + r] : 0.f;
-      const float x1 = j0 + 1 < nvalid ? p.v[(row0 + j0 + 1) * inner + hoff + r] : 0.f;
-      split2(x0, x1, h[jj], l[jj]);
-    }
+    for (int jj = 0; jj < 8; ++jj) split2(vv[2 * jj], vv[2 * jj + 1], h[jj], l[jj]);
     const int64_t ov = (z * DH + r) * K3 + DH + g * 16;
     *reinterpret_cast<uint4*>(p.w.w3_hi + ov) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(p.w.w3_hi + ov + 8) = make_uint4(h[4], h[5], h[6], h[7]);
     *reinterpret_cast<uint4*>(p.w.w3_lo + ov) = make_uint4(l[0], l[1], l[2], l[3]);
     *reinterpret_cast<uint4*>(p.w.w3_lo + ov + 8) = make_uint4(l[4], l[5], l[6], l[7]);
   }
-  // dn[r] = sum_j K~_j[r] (token order)
-  for (int r = ch0 + tid; r < ch1; r += 256) {
-    float s = 0.f;
-    for (int j = 0; j < nvalid; ++j) s = fmaf(p.k[(row0 + j) * inner + hoff + r], s_ks[j], s);
-    p.w.dn[z * DH + r] = s;
+  // dn[r] = sum_j K~_j[r]: two threads per channel (token halves), 8 loads in flight each, halves added in a fixed order
+  {
+    __shared__ float s_part[256];
+    const int rr = tid & 127, half = tid >> 7;
+    for (int rb = 0; rb < nchs; rb += 128) {             // (CTA-uniform trip count)
+      const int r = ch0 + rb + rr;
+      float acc = 0.f;
+      if (r < ch1) {
+        const int j0 = half * (L / 2), j1 = min(nvalid, j0 + L / 2);
+        for (int jb = j0; jb < j1; jb += 8) {
+          float kk[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) kk[u] = jb + u < j1 ? p.k[(row0 + jb + u) * inner + hoff + r] : 0.f;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (jb + u < j1) acc = fmaf(kk[u], s_ks[jb + u], acc);
+        }
+      }
+      __syncthreads();
+      s_part[tid] = acc;
+      __syncthreads();
+      if (half == 0 && r < ch1) p.w.dn[z * DH + r] = s_part[rr] + s_part[rr + 128];
+    }
   }
 }
 
