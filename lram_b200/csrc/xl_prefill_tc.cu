@@ -345,14 +345,16 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Chunk update + scan (G2 + scan above). grid = (DH/128 dk tiles, DH/128 dv tiles, B*NH), 192 threads, 1 CTA / SM.
+// Chunk update + scan (G2 + scan above). grid = (DH/128 dk tiles, DH/128 dv tiles, B*NH), 320 threads, 1 CTA / SM.
 //   warp 0: TMA producer over the flattened (chunk, k-block) sequence of the run (3-stage ring, runs up to 1.5 chunks ahead)
 //   warp 1: tcgen05.mma issuer; chunk c accumulates into TMEM buffer c & 1 (2 x 128 columns)
-//   warps 2..5: thread = one dv row of the tile with its 128 dk values of C^T in registers. Per chunk: chunk-start values
-//               -> bf16 hi/lo, 256 contiguous bytes per plane into W3[:, 0:DH]; then tcgen05.ld of dC and
+//   warps 2..9: thread = one dv row of the tile with 64 of its 128 dk values of C^T in registers (two warps share a TMEM
+//               lane quarter and split the columns: the per-chunk epilogue is what bounds this kernel). Per chunk:
+//               chunk-start values -> bf16 hi/lo planes into W3[:, 0:DH] (coalesced through shared memory); then tcgen05.ld of dC and
 //               C <- e^{a_L} C + dC. First / last: the state tile (slab-major [dk][dv]: a warp reads 32 consecutive dv).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGemmThreads, 1)
+constexpr int kScanThreads = 64 + 8 * 32;      // TMA warp + MMA warp + 8 epilogue warps
+__global__ void __launch_bounds__(kScanThreads, 1)
 update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_vl,
                    const __grid_constant__ CUtensorMap map_kh, const __grid_constant__ CUtensorMap map_kl, CellParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -380,7 +382,7 @@ update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4);                            // one arrival per epilogue warp
+      mbar_init(tempty_bar(b), kScanThreads / 32 - 2);        // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -440,25 +442,29 @@ update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_cons
       }
     }
   } else {
-    const int q = warp & 3;
+    // 8 epilogue warps: warp w reads TMEM lanes 32*(w%4).. (the hardware rule) and owns column half (w-2)/4 of the tile,
+    // i.e. a thread carries 64 dk values of one dv row
+    constexpr int HC = BN / 2;
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;                               // dv row of the tile == TMEM lane
-    const uint32_t wst = base + kStages * kStageBytes + 256 + (uint32_t)q * 8192u;
-    // state tile: C[dk = n0 + j][dv] at slab (dv / 128) = blockIdx.y, column r
-    float* cs = p.C + (((int64_t)bh * (DH >> 7) + blockIdx.y) * DH + n0) * 128 + r;
-    float cv[BN];
+    const int nc0 = n0 + half * HC;                            // first dk column of this thread
+    const uint32_t wst = base + kStages * kStageBytes + 256 + (uint32_t)(warp - 2) * 4096u;
+    // state tile: C[dk = nc0 + j][dv] at slab (dv / 128) = blockIdx.y, column r
+    float* cs = p.C + (((int64_t)bh * (DH >> 7) + blockIdx.y) * DH + nc0) * 128 + r;
+    float cv[HC];
 #pragma unroll
-    for (int j = 0; j < BN; ++j) cv[j] = cs[(int64_t)j * 128];
+    for (int j = 0; j < HC; ++j) cv[j] = cs[(int64_t)j * 128];
     for (int c = 0; c < nchunk; ++c) {
       const int b = c & 1, use = c >> 1;
       const int64_t z = (int64_t)bh * nchunk + c;
       const float F = p.w.FL[z];
-      // chunk-start tile -> W3 planes. A lane holds one row (256 B per plane): staged through a per-warp
-      // [32 rows][256 B] buffer (16-byte chunks XOR-swizzled by row), so a warp store writes 2 rows x 256 contiguous bytes
+      // chunk-start tile -> W3 planes. A lane holds one row (128 B per plane): staged through a per-warp
+      // [32 rows][128 B] buffer (16-byte chunks XOR-swizzled by row), so a warp store writes 4 rows x 128 contiguous bytes
       // instead of 32 different lines
 #pragma unroll
       for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < 8; ++k) {
           uint32_t wv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -466,17 +472,17 @@ update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_cons
             split2(cv[8 * k + 2 * e], cv[8 * k + 2 * e + 1], hh, ll);
             wv[e] = pl ? ll : hh;
           }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)lane * 256u + (uint32_t)((k ^ (lane & 15)) << 4)),
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)lane * 128u + (uint32_t)((k ^ (lane & 7)) << 4)),
                        "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
         }
         __syncwarp();
-        __nv_bfloat16* gt = (pl ? p.w.w3_lo : p.w.w3_hi) + (z * DH + m0 + q * 32) * K3 + n0;
+        __nv_bfloat16* gt = (pl ? p.w.w3_lo : p.w.w3_hi) + (z * DH + m0 + q * 32) * K3 + nc0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int rr = 2 * i + (lane >> 4), kk = lane & 15;
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3), kk = lane & 7;
           uint32_t v0, v1, v2, v3;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
-                       : "r"(wst + (uint32_t)rr * 256u + (uint32_t)((kk ^ (rr & 15)) << 4)) : "memory");
+                       : "r"(wst + (uint32_t)rr * 128u + (uint32_t)((kk ^ (rr & 7)) << 4)) : "memory");
           *reinterpret_cast<uint4*>(gt + (int64_t)rr * K3 + kk * 8) = make_uint4(v0, v1, v2, v3);
         }
         __syncwarp();
@@ -484,9 +490,9 @@ update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_cons
       mbar_wait(tfull_bar(b), use & 1);
       tcgen05_fence_after();
 #pragma unroll
-      for (int cc = 0; cc < BN; cc += 32) {
+      for (int cc = 0; cc < HC; cc += 32) {
         uint32_t t[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + cc);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BN + half * HC + cc);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -507,7 +513,7 @@ update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_cons
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(b)) : "memory");
     }
 #pragma unroll
-    for (int j = 0; j < BN; ++j) cs[(int64_t)j * 128] = cv[j];
+    for (int j = 0; j < HC; ++j) cs[(int64_t)j * 128] = cv[j];
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -909,7 +915,7 @@ cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, c
         !make_map3(&mkl, p.w.kt_lo, L, DH, nb, L, (int64_t)DH * L))
       return cudaErrorUnknown;
     if ((e = ensure_dyn_smem<&update_scan_kernel>(kSmemScan)) != cudaSuccess) return e;
-    if ((e = launch_k(update_scan_kernel, dim3(DH / BN, DH / BM, BH), dim3(kGemmThreads), kSmemScan, s, mvh, mvl, mkh,
+    if ((e = launch_k(update_scan_kernel, dim3(DH / BN, DH / BM, BH), dim3(kScanThreads), kSmemScan, s, mvh, mvl, mkh,
                       mkl, p)) != cudaSuccess)
       return e;
     if ((e = launch_k(nscan_kernel, dim3(BH, (DH + 127) / 128), dim3(128), 0, s, p)) != cudaSuccess) return e;
