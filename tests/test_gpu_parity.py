@@ -437,11 +437,13 @@ def test_prefill_cells_agree_and_match_oracle_steps(name, B, S):
     eng.close()
 
 
-def test_policy_prefill_equals_stepping():
+@pytest.mark.parametrize("Tn", [23, 100])
+def test_policy_prefill_equals_stepping(Tn):
     """xl_policy_prefill(context of Tn timesteps) then a rollout == stepping through the context: same action
-    tokens afterwards (needs no oracle: both sides are this library; the step path is oracle-checked above)."""
+    tokens afterwards (needs no oracle: both sides are this library; the step path is oracle-checked above).
+    Tn = 23: one ragged 64-token chunk + stepped tail; Tn = 100: 300 tokens of 3 envs = 128 + 128 + 44 through the tcgen05 cell."""
     cfg, sd, eng = _engine("16M", 3)
-    Tn, Tr = 23, 4
+    Tr = 4
     states, rtg, _ = make_stream(cfg, range(3), Tn + Tr, domains="mixed")
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
     stepped = eng.new_state(3)
