@@ -255,6 +255,294 @@ __global__ void __launch_bounds__(64 * kConvRuns, 2) conv_qkv_gates_seq_kernel(C
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same kernel on packed fp32 pairs (default; xl_set_option("prefill_conv", 0) selects the scalar one above).
+// The scalar kernel is bound by instruction issue: ~550 instructions per token and 4-channel block, half of them
+// FP32, behind 16 warps per SM. sm_100 has FFMA2 / FMUL2 / FADD2 (fma.rn.f32x2 ...: two IEEE fp32 results per
+// instruction and lane, an operand may be one register broadcast to both halves), so
+//   conv       : channel pairs (c0,c1), (c2,c3)                           8 FFMA2 per token instead of 16 FFMA
+//   q / k / v  : output pairs (o0,o1), (o2,o3), a[dd] broadcast          24 instead of 48
+//   gates      : the (igate, fgate) pair of a head, q/k/v[o] broadcast   14 per head instead of 28
+// with every chain in the order the scalar kernel's SASS has (mul of term 1, fma of terms 0, 2, 3; q-, k-, v-sums added
+// in that order), i.e. q, k, v, a and the gate partials are BIT-IDENTICAL to the scalar kernel (tested). Around that:
+//   * the gate weights sit in shared memory as (i, f) pairs and are read once per TWO tokens (an LDS.128 of distinct
+//     addresses costs 4 shared-memory cycles per warp; at one read per token they alone were 111 us per launch);
+//   * the headwise q/k/v blocks live in shared memory as well (the 4 token runs of a CTA share them), which keeps the
+//     kernel under 128 registers without spills;
+//   * a token run synchronises on its own named barrier (one per 2-token group, double-buffered partial sums) instead
+//     of two CTA-wide barriers, and the next group's input rows are in flight while a group computes;
+//   * row pointers advance by constant strides (no 64-bit index arithmetic per store).
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 bc2(float x) { return pk2(x, x); }   // ptxas folds this into a scalar (broadcast) operand
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// x0*w0 + x1*w1 + x2*w2 + x3*w3 per half, contracted the way nvcc contracts the scalar expression
+__device__ __forceinline__ f32x2 dot4_bc(const float (&x)[4], const float4& wa, const float4& wb) {
+  f32x2 t = mul2(bc2(x[1]), pk2(wa.z, wa.w));
+  t = fma2(bc2(x[0]), pk2(wa.x, wa.y), t);
+  t = fma2(bc2(x[2]), pk2(wb.x, wb.y), t);
+  return fma2(bc2(x[3]), pk2(wb.z, wb.w), t);
+}
+
+// shared-memory read the compiler may neither hoist nor merge with an earlier one of the same address (the weights are
+// loop-invariant: merged, they would occupy > 100 registers)
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+template <int NH, bool FAST_SILU>
+__global__ void __launch_bounds__(64 * kConvRuns, 2) conv_qkv_gates_seq2_kernel(ConvQkvParams p, int S, int run) {
+  constexpr int KS = 4, TG = 2, NV = NH * 2 * TG;         // NV gate values per token group
+  __shared__ float red[kConvRuns][2][NV * 4];
+  // per thread (channel block) kRows float4 of weights, thread-major with a stride of kRows + 1 float4 (an odd multiple of
+  // 16 B: the 8 lanes of a quarter warp hit all 32 banks, and every read below is [thread base + immediate]):
+  //   rows [0, 6 NH)      : (head * 3 + q|k|v) * 2 + half -> (i, f) gate weights of channels (2*half, 2*half + 1)
+  //   rows [6 NH, 6 NH+12): (q|k|v) * 4 + dd -> column dd of the 4 x 4 headwise block (outputs o = 0..3)
+  constexpr int kGateRows = NH * 3 * 2, kRows = kGateRows + 12, kStride = kRows + 1;
+  extern __shared__ __align__(16) float4 s_dyn[];
+  const int nx = blockDim.x;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int sub = threadIdx.y, nruns = blockDim.y, tx = threadIdx.x;
+  const int s_begin = min(S, ((int)blockIdx.z * nruns + sub) * run);
+  const int s_end = min(S, s_begin + run);
+  const int inner = p.inner;
+  const int nblk = inner >> 2;
+  const int blk_per_chunk = (nblk + p.NCH - 1) / p.NCH;
+  const int j = chunk * blk_per_chunk + tx;
+  const bool active = tx < blk_per_chunk && j < nblk;
+  const int c = 4 * (active ? j : 0);
+  const int lane = tx & 31, wid = tx >> 5;
+  const int nw = (nx + 31) >> 5;
+  {
+    const int flat = sub * nx + tx, nthr = nx * nruns;
+    for (int i = flat; i < kGateRows * nx; i += nthr) {
+      const int t = i % nx, row = i / nx;                 // row = (head * 3 + part) * 2 + half
+      const int half = row & 1, hp = row >> 1;
+      const int jb = chunk * blk_per_chunk + t;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < blk_per_chunk && jb < nblk) {
+        const int64_t o = (int64_t)hp * inner + 4 * jb + 2 * half;
+        w = make_float4(p.wi[o], p.wf[o], p.wi[o + 1], p.wf[o + 1]);
+      }
+      s_dyn[t * kStride + row] = w;
+    }
+    for (int i = flat; i < 3 * 4 * nx; i += nthr) {
+      const int t = i % nx, row = i / nx;                 // row = part * 4 + dd
+      const int dd = row & 3, part = row >> 2;
+      const int jb = chunk * blk_per_chunk + t;
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < blk_per_chunk && jb < nblk) {
+        const float* hw = (part == 0 ? p.wq : part == 1 ? p.wk : p.wv) + (int64_t)jb * 16 + dd;
+        w = make_float4(hw[0], hw[4], hw[8], hw[12]);
+      }
+      s_dyn[t * kStride + kGateRows + row] = w;
+    }
+  }
+  f32x2 cwp[KS][2];                                        // conv taps of channel pairs
+  f32x2 cbp[2];
+  {
+    float4 w4[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) w4[ch] = *reinterpret_cast<const float4*>(p.conv_w + (int64_t)(c + ch) * KS);
+    cwp[0][0] = pk2(w4[0].x, w4[1].x); cwp[0][1] = pk2(w4[2].x, w4[3].x);
+    cwp[1][0] = pk2(w4[0].y, w4[1].y); cwp[1][1] = pk2(w4[2].y, w4[3].y);
+    cwp[2][0] = pk2(w4[0].z, w4[1].z); cwp[2][1] = pk2(w4[2].z, w4[3].z);
+    cwp[3][0] = pk2(w4[0].w, w4[1].w); cwp[3][1] = pk2(w4[2].w, w4[3].w);
+    const float4 cb = *reinterpret_cast<const float4*>(p.conv_b + c);
+    cbp[0] = pk2(cb.x, cb.y);
+    cbp[1] = pk2(cb.z, cb.w);
+  }
+  pdl_wait();
+  pdl_trigger();
+  __syncthreads();                                        // s_gw, s_hw
+  if (s_begin >= s_end) return;                           // (a whole run leaves: its named barrier is never used)
+
+  // the KS-1 inputs before token s_begin: earlier rows of this chunk, or the carried conv_state (rows = last KS
+  // inputs, oldest first) for tokens before the chunk
+  f32x2 win[KS - 1][2];
+#pragma unroll
+  for (int r = 0; r < KS - 1; ++r) {
+    const int s = s_begin - (KS - 1 - r);
+    float4 w4;
+    if (s >= 0) w4 = *reinterpret_cast<const float4*>(p.u + ((int64_t)b * S + s) * 2 * inner + c);
+    else w4 = *reinterpret_cast<const float4*>(p.conv_state + ((int64_t)b * KS + (KS + s)) * inner + c);
+    win[r][0] = pk2(w4.x, w4.y);
+    win[r][1] = pk2(w4.z, w4.w);
+  }
+  const int64_t row_begin = (int64_t)b * S + s_begin;
+  const float* up = p.u + row_begin * 2 * inner + c;
+  float* qp = p.qk + row_begin * inner + c;
+  float* kp = qp + (int64_t)p.B * S * inner;
+  float* vp = p.v + row_begin * inner + c;
+  float* ap = p.act + row_begin * inner + c;
+  float* gp = p.gate_part + (row_begin * p.NCH + chunk) * 2 * NH;
+  const int u_step = 2 * inner, g_step = p.NCH * 2 * NH;
+  const uint32_t bar_id = 1 + sub, bar_threads = nw * 32;
+  const uint32_t gw = smem_u32(s_dyn + tx * kStride), hw = gw + 16u * kGateRows;
+
+  const int ntok = s_end - s_begin;
+  const int nsteps = (ntok + TG - 1) / TG;
+  float4 xc[TG];
+#pragma unroll
+  for (int t = 0; t < TG; ++t)
+    xc[t] = (active && t < ntok) ? *reinterpret_cast<const float4*>(up + t * u_step) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int st = 0; st < nsteps; ++st) {
+    const int nleft = ntok - st * TG;                     // tokens of this group that exist (>= 1)
+    float4 xn[TG];                                        // next group's inputs: in flight while this group computes
+#pragma unroll
+    for (int t = 0; t < TG; ++t)
+      xn[t] = (active && TG + t < nleft) ? *reinterpret_cast<const float4*>(up + (TG + t) * u_step)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    float a[TG][4];
+#pragma unroll
+    for (int t = 0; t < TG; ++t) {
+      const f32x2 x01 = pk2(xc[t].x, xc[t].y), x23 = pk2(xc[t].z, xc[t].w);
+      // conv over (win[0], win[1], win[2], x), oldest first; fma(w, c, 0) == w * c
+      f32x2 a01 = fma2(win[0][0], cwp[0][0], 0ull), a23 = fma2(win[0][1], cwp[0][1], 0ull);
+      a01 = fma2(win[1][0], cwp[1][0], a01); a23 = fma2(win[1][1], cwp[1][1], a23);
+      a01 = fma2(win[2][0], cwp[2][0], a01); a23 = fma2(win[2][1], cwp[2][1], a23);
+      a01 = fma2(x01, cwp[3][0], a01);       a23 = fma2(x23, cwp[3][1], a23);
+      a01 = add2(a01, cbp[0]);               a23 = add2(a23, cbp[1]);
+      win[0][0] = win[1][0]; win[0][1] = win[1][1];
+      win[1][0] = win[2][0]; win[1][1] = win[2][1];
+      win[2][0] = x01;       win[2][1] = x23;
+      unpk2(a01, a[t][0], a[t][1]);
+      unpk2(a23, a[t][2], a[t][3]);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) a[t][ch] = FAST_SILU ? silu_fast(a[t][ch]) : silu(a[t][ch]);
+    }
+    // headwise 4 x 4 blocks: out[o] = sum_dd in[dd] * W[o][dd], dd ascending from 0; one read of a column per group
+    f32x2 qq[TG][2], kk[TG][2], vv[TG][2];
+#pragma unroll
+    for (int t = 0; t < TG; ++t) qq[t][0] = qq[t][1] = kk[t][0] = kk[t][1] = vv[t][0] = vv[t][1] = 0ull;
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd) {
+      const float4 wq = lds_v4(hw + 16 * (0 * 4 + dd)), wk = lds_v4(hw + 16 * (1 * 4 + dd)), wv = lds_v4(hw + 16 * (2 * 4 + dd));
+#pragma unroll
+      for (int t = 0; t < TG; ++t) {
+        const float xm = dd == 0 ? xc[t].x : dd == 1 ? xc[t].y : dd == 2 ? xc[t].z : xc[t].w;
+        qq[t][0] = fma2(bc2(a[t][dd]), pk2(wq.x, wq.y), qq[t][0]);
+        qq[t][1] = fma2(bc2(a[t][dd]), pk2(wq.z, wq.w), qq[t][1]);
+        kk[t][0] = fma2(bc2(a[t][dd]), pk2(wk.x, wk.y), kk[t][0]);
+        kk[t][1] = fma2(bc2(a[t][dd]), pk2(wk.z, wk.w), kk[t][1]);
+        vv[t][0] = fma2(bc2(xm), pk2(wv.x, wv.y), vv[t][0]);
+        vv[t][1] = fma2(bc2(xm), pk2(wv.z, wv.w), vv[t][1]);
+      }
+    }
+    float q[TG][4], k[TG][4], v[TG][4];
+#pragma unroll
+    for (int t = 0; t < TG; ++t) {
+      unpk2(qq[t][0], q[t][0], q[t][1]); unpk2(qq[t][1], q[t][2], q[t][3]);
+      unpk2(kk[t][0], k[t][0], k[t][1]); unpk2(kk[t][1], k[t][2], k[t][3]);
+      unpk2(vv[t][0], v[t][0], v[t][1]); unpk2(vv[t][1], v[t][2], v[t][3]);
+      if (active && t < nleft) {
+        // prefill layout: q plane then k plane ([M, inner] each) instead of the step path's interleaved pairs
+        *reinterpret_cast<float4*>(qp + t * inner) = make_float4(q[t][0], q[t][1], q[t][2], q[t][3]);
+        *reinterpret_cast<float4*>(kp + t * inner) = make_float4(k[t][0], k[t][1], k[t][2], k[t][3]);
+        *reinterpret_cast<float4*>(vp + t * inner) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]);
+        *reinterpret_cast<float4*>(ap + t * inner) = make_float4(a[t][0], a[t][1], a[t][2], a[t][3]);
+      }
+    }
+    // gate partials: (igate, fgate) of head h for the group's tokens against one read of the head's weights
+    f32x2 G[NH][TG];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      const uint32_t g = gw + 16 * (h * 3) * 2;
+      {
+        const float4 w0 = lds_v4(g), w1 = lds_v4(g + 16);
+#pragma unroll
+        for (int t = 0; t < TG; ++t) G[h][t] = dot4_bc(q[t], w0, w1);
+      }
+      {
+        const float4 w0 = lds_v4(g + 32), w1 = lds_v4(g + 48);
+#pragma unroll
+        for (int t = 0; t < TG; ++t) G[h][t] = add2(G[h][t], dot4_bc(k[t], w0, w1));
+      }
+      {
+        const float4 w0 = lds_v4(g + 64), w1 = lds_v4(g + 80);
+#pragma unroll
+        for (int t = 0; t < TG; ++t) G[h][t] = add2(G[h][t], dot4_bc(v[t], w0, w1));
+      }
+      if (!active) {
+#pragma unroll
+        for (int t = 0; t < TG; ++t) G[h][t] = 0ull;
+      }
+    }
+    // sums of the group's NV values over the run's channels: warp tree (xor 16, 8, 4, 2, 1: the pairwise sums of
+    // warp_sum()), then a fixed-order sum over the run's (<= 4) warps
+    float* rbuf = red[sub][st & 1];
+    float vals[NV];
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+#pragma unroll
+      for (int t = 0; t < TG; ++t) unpk2(G[h][t], vals[(h * 2 + 0) * TG + t], vals[(h * 2 + 1) * TG + t]);
+    if constexpr (NV == 32 || NV == 16) {
+      // transposing butterfly: every xor step halves the values a lane carries, NV - 1 (+ 1) shuffles instead of 5 * NV
+      constexpr int M0 = NV == 32 ? 16 : 8;               // values kept after the first (xor 16) step
+#pragma unroll
+      for (int m = 16, nv = M0; m > 0; m >>= 1, nv >>= 1) {
+        const bool upper = (lane & m) != 0;
+        if (nv >= 1) {
+#pragma unroll
+          for (int i = 0; i < nv; ++i) {
+            const float keep = upper ? vals[i + nv] : vals[i];
+            const float send = upper ? vals[i] : vals[i + nv];
+            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+          }
+        } else {
+          vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], m);   // NV == 16: one value left, lanes l and l^1 share it
+        }
+      }
+      // lane l holds the warp total of value l (NV == 32) or l >> 1 (NV == 16)
+      if (NV == 32 || (lane & 1) == 0) rbuf[(NV == 32 ? lane : lane >> 1) * 4 + wid] = vals[0];
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float sum = warp_sum(vals[i]);
+        if (lane == 0) rbuf[i * 4 + wid] = sum;
+      }
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+    if (tx < NV) {
+      const int h = tx / (2 * TG);
+      const int rem = tx - h * 2 * TG;
+      const int g = rem / TG, t = rem - g * TG;
+      if (t < nleft) {
+        float s = 0.f;
+        for (int w = 0; w < nw; ++w) s += rbuf[tx * 4 + w];
+        gp[t * g_step + g * NH + h] = s;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TG; ++t) xc[t] = xn[t];
+    up += TG * u_step;
+    qp += TG * inner; kp += TG * inner; vp += TG * inner; ap += TG * inner;
+    gp += TG * g_step;
+  }
+}
+
 // new conv_state = the last KS x_m rows of the chunk (S >= KS): separate kernel, because the first token run of
 // the conv kernel still reads the old window while its last run would overwrite it
 __global__ void __launch_bounds__(256) conv_state_seq_kernel(const float* __restrict__ u, float* __restrict__ conv_state,
@@ -756,6 +1044,18 @@ bool prefill_cell_supported(int DH) {
 }
 
 int g_prefill_conv_run = 16;   // xl_set_option("prefill_conv_run")
+int g_prefill_conv_impl = 1;   // xl_set_option("prefill_conv"): 0 = scalar kernel, 1 = packed fp32 pairs, 2 = + SFU SiLU
+
+template <int NH>
+static bool launch_conv_seq2(const ConvQkvParams& p, int S, int run, dim3 grid, dim3 block, cudaStream_t s) {
+  const size_t smem = sizeof(float4) * (size_t)(NH * 3 * 2 + 3 * 4 + 1) * block.x;
+  if (g_prefill_conv_impl == 2) {
+    if (ensure_dyn_smem<&pf::conv_qkv_gates_seq2_kernel<NH, true>>(smem) != cudaSuccess) return false;
+    return launch_k(pf::conv_qkv_gates_seq2_kernel<NH, true>, grid, block, smem, s, p, S, run) == cudaSuccess;
+  }
+  if (ensure_dyn_smem<&pf::conv_qkv_gates_seq2_kernel<NH, false>>(smem) != cudaSuccess) return false;
+  return launch_k(pf::conv_qkv_gates_seq2_kernel<NH, false>, grid, block, smem, s, p, S, run) == cudaSuccess;
+}
 
 bool launch_conv_qkv_gates_seq(const ConvQkvParams& p, int S, cudaStream_t s) {
   const int nblk = p.inner / 4;
@@ -767,7 +1067,13 @@ bool launch_conv_qkv_gates_seq(const ConvQkvParams& p, int S, cudaStream_t s) {
   dim3 grid(p.NCH, p.B, (S + run * nruns - 1) / (run * nruns));
   const dim3 block(threads, nruns);
   const size_t smem = sizeof(float) * 2 * p.NH * 3 * 4 * threads;
-  if (p.KS == 4 && p.NH == 4) {
+  if (g_prefill_conv_impl != 0 && p.KS == 4 && (p.NH == 4 || p.NH == 8 || p.NH == 2 || p.NH == 1)) {
+    const bool ok = p.NH == 4   ? launch_conv_seq2<4>(p, S, run, grid, block, s)
+                    : p.NH == 8 ? launch_conv_seq2<8>(p, S, run, grid, block, s)
+                    : p.NH == 2 ? launch_conv_seq2<2>(p, S, run, grid, block, s)
+                                : launch_conv_seq2<1>(p, S, run, grid, block, s);
+    if (!ok) return false;
+  } else if (p.KS == 4 && p.NH == 4) {
     launch_k(pf::conv_qkv_gates_seq_kernel<4, 4>, grid, block, smem, s, p, S, run);
   } else if (p.KS == 4 && p.NH == 8) {
     launch_k(pf::conv_qkv_gates_seq_kernel<4, 8>, grid, block, smem, s, p, S, run);
