@@ -37,6 +37,7 @@
 namespace xl {
 
 extern int g_prefill_tc_fused;
+extern int g_prefill_prep;
 
 namespace ptc {
 
@@ -719,6 +720,183 @@ __global__ void __launch_bounds__(256) prep_kernel(CellParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Chunk preparation, single-read version (default; xl_set_option("prefill_prep", 0) selects prep_kernel above). Same
+// outputs, bit for bit. prep_kernel reads k three times (token-major planes, channel-major planes, dn) and was measured at
+// 1.55 GB of DRAM traffic per launch for 1.30 GB of operands (ncu, 206M, 16k tokens), load-latency bound in short phases.
+// Here a CTA owns a [128 tokens x 64 channels] tile: q and k are read once with coalesced 128-bit loads, the token-major
+// planes leave straight from registers, the raw k (then v) tile is parked in shared memory ([token][64 + 4] floats: 128-bit
+// row writes and stride-1 column reads are both conflict-free) and the channel-major planes and dn are formed from there.
+// grid = (nchunk, B*NH, DH/64), 256 threads, ~36 KB of shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kPrepCW = 64;                   // channels per CTA
+constexpr int kPrepLd = kPrepCW + 4;          // tile row stride in floats
+
+__global__ void __launch_bounds__(256) prep2_kernel(CellParams p) {
+  __shared__ float s_lf[L], s_i[L], s_F[L], s_ks[L];
+  __shared__ double s_a[L];
+  __shared__ __align__(16) float s_tile[L * kPrepLd];
+  __shared__ float s_part[2 * kPrepCW];
+  const int c = blockIdx.x, bh = blockIdx.y, part = blockIdx.z;
+  const int NH = p.NH, DH = p.DH, S = p.S, inner = p.inner, K3 = DH + L;
+  const int b = bh / NH, hd = bh - b * NH;
+  const int tid = threadIdx.x;
+  const int64_t z = (int64_t)bh * p.nchunk + c;
+  const int t0 = c * L;
+  const int nvalid = min(L, S - t0);
+  const int64_t row0 = (int64_t)b * S + t0;
+  const int ch0 = part * kPrepCW;
+  const int hoff = hd * DH + ch0;
+  const float kscale = rsqrtf((float)DH);
+  pdl_wait();
+  pdl_trigger();
+
+  // decay tables of the chunk (as prep_kernel)
+  if (tid < L) {
+    float lf = 0.f, ii = 0.f;
+    if (tid < nvalid) {
+      const float f = p.fseq[(int64_t)bh * S + t0 + tid];
+      lf = f > 0.f ? fmaxf(logf(f), -200.f) : -200.f;
+      ii = p.iseq[(int64_t)bh * S + t0 + tid];
+    }
+    s_lf[tid] = lf;
+    s_i[tid] = ii;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    double v[4];
+    double run = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      run += (double)s_lf[tid * 4 + j];
+      v[j] = run;
+    }
+    double incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += up;
+    }
+    const double excl = incl - run;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_a[tid * 4 + j] = excl + v[j];
+  }
+  __syncthreads();
+  if (tid < L) {
+    const double aL = s_a[L - 1];
+    s_F[tid] = expf((float)s_a[tid]);
+    s_ks[tid] = expf((float)(aL - s_a[tid])) * s_i[tid] * kscale;
+    if (part == 0) {
+      p.w.acum[z * L + tid] = s_a[tid];
+      p.w.ig[z * L + tid] = s_i[tid];
+      if (tid == 0) p.w.FL[z] = expf((float)aL);
+    }
+  }
+  __syncthreads();
+
+  // token-major pass over q and k: thread = (float4 column c4, row tr of a 16-row band); 4 rows per thread and step
+  const int c4 = tid & 15, tr = tid >> 4;
+  const float* qg = p.q + row0 * inner + hoff + 4 * c4;
+  const float* kg = p.k + row0 * inner + hoff + 4 * c4;
+  const float* vg = p.v + row0 * inner + hoff + 4 * c4;
+#pragma unroll 1
+  for (int tb = 0; tb < L; tb += 64) {
+    float4 xq[4], xk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = tb + 16 * u + tr;
+      xq[u] = xk[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < nvalid) {
+        xq[u] = *reinterpret_cast<const float4*>(qg + (int64_t)t * inner);
+        xk[u] = *reinterpret_cast<const float4*>(kg + (int64_t)t * inner);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = tb + 16 * u + tr;
+      const int ch = ch0 + 4 * c4;
+      uint32_t h0, l0, h1, l1;
+      const int64_t o = (z * L + t) * DH + ch;
+      split2(xq[u].x, xq[u].y, h0, l0);
+      split2(xq[u].z, xq[u].w, h1, l1);
+      *reinterpret_cast<uint2*>(p.w.q_hi + o) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(p.w.q_lo + o) = make_uint2(l0, l1);
+      split2(xk[u].x, xk[u].y, h0, l0);
+      split2(xk[u].z, xk[u].w, h1, l1);
+      *reinterpret_cast<uint2*>(p.w.k_hi + o) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(p.w.k_lo + o) = make_uint2(l0, l1);
+      const float F = s_F[t];
+      const int64_t o3 = (z * L + t) * K3 + ch;
+      split2(F * xq[u].x, F * xq[u].y, h0, l0);
+      split2(F * xq[u].z, F * xq[u].w, h1, l1);
+      *reinterpret_cast<uint2*>(p.w.a3_hi + o3) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(p.w.a3_lo + o3) = make_uint2(l0, l1);
+      *reinterpret_cast<float4*>(s_tile + t * kPrepLd + 4 * c4) = xk[u];
+    }
+  }
+  // v of the first half of the tile is requested now: in flight under the channel-major K~^T work
+  float4 xv[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int t = 16 * u + tr;
+    xv[u] = t < nvalid ? *reinterpret_cast<const float4*>(vg + (int64_t)t * inner) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  // channel-major K~^T [DH][L]: item = (token group of 16, channel); a warp = 32 consecutive channels of one group
+#pragma unroll 1
+  for (int idx = tid; idx < (L / 16) * kPrepCW; idx += 256) {
+    const int g = idx / kPrepCW, rl = idx - g * kPrepCW;
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j0 = g * 16 + 2 * jj;
+      split2(s_tile[j0 * kPrepLd + rl] * s_ks[j0], s_tile[(j0 + 1) * kPrepLd + rl] * s_ks[j0 + 1], h[jj], l[jj]);
+    }
+    const int64_t ok = (z * DH + ch0 + rl) * L + g * 16;
+    *reinterpret_cast<uint4*>(p.w.kt_hi + ok) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(p.w.kt_hi + ok + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<uint4*>(p.w.kt_lo + ok) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>(p.w.kt_lo + ok + 8) = make_uint4(l[4], l[5], l[6], l[7]);
+  }
+  // dn[r] = sum_j K~_j[r]: two threads per channel (token halves, each in token order), halves added in a fixed order
+  if (tid < 2 * kPrepCW) {
+    const int rl = tid & (kPrepCW - 1), half = tid / kPrepCW;
+    const int j0 = half * (L / 2), j1 = min(nvalid, j0 + L / 2);
+    float acc = 0.f;
+    for (int j = j0; j < j1; ++j) acc = fmaf(s_tile[j * kPrepLd + rl], s_ks[j], acc);
+    s_part[tid] = acc;
+  }
+  __syncthreads();                                         // s_part written, tile reads done
+  if (tid < kPrepCW) p.w.dn[z * DH + ch0 + tid] = s_part[tid] + s_part[tid + kPrepCW];
+  // v tile
+#pragma unroll
+  for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(s_tile + (16 * u + tr) * kPrepLd + 4 * c4) = xv[u];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int t = 64 + 16 * u + tr;
+    xv[u] = t < nvalid ? *reinterpret_cast<const float4*>(vg + (int64_t)t * inner) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(s_tile + (64 + 16 * u + tr) * kPrepLd + 4 * c4) = xv[u];
+  __syncthreads();
+  // channel-major V^T into W3[:, DH:DH+L]
+#pragma unroll 1
+  for (int idx = tid; idx < (L / 16) * kPrepCW; idx += 256) {
+    const int g = idx / kPrepCW, rl = idx - g * kPrepCW;
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int j0 = g * 16 + 2 * jj;
+      split2(s_tile[j0 * kPrepLd + rl], s_tile[(j0 + 1) * kPrepLd + rl], h[jj], l[jj]);
+    }
+    const int64_t ov = (z * DH + ch0 + rl) * K3 + DH + g * 16;
+    *reinterpret_cast<uint4*>(p.w.w3_hi + ov) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(p.w.w3_hi + ov + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+    *reinterpret_cast<uint4*>(p.w.w3_lo + ov) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>(p.w.w3_lo + ov + 8) = make_uint4(l[4], l[5], l[6], l[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Chunk scan of one run. grid = (DH*DH/1024 + 1, B*NH), 256 threads. A thread owns 4 consecutive dk of one dv of C^T and
 // walks the chunks: chunk-start memory -> bf16 hi/lo planes W3[:, 0:DH] (the inter-chunk operand of G3), then
 // C <- e^{a_L} C + dC_c. The last CTA row does the same for n (fp32 copies of every chunk-start n).
@@ -883,6 +1061,7 @@ static cudaError_t launch_bgemm(const Operand& a, const Operand& w, const BatchO
 }  // namespace ptc
 
 int g_prefill_tc_fused = 1;   // xl_set_option("prefill_tc_fused"): 0 = chunk updates through HBM + element-parallel scan (A/B)
+int g_prefill_prep = 1;       // xl_set_option("prefill_prep"): 0 = prep_kernel (k read three times), 1 = prep2_kernel
 
 bool prefill_cell_tc_supported(int DH) { return DH % 128 == 0 && DH >= 128 && DH <= 1024; }
 int prefill_cell_tc_chunk() { return ptc::L; }
@@ -905,7 +1084,11 @@ cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, c
   carve_ws(&p.w, (char*)ws, nb, DH);
   cudaError_t e;
   // chunk operands
-  if ((e = launch_k(prep_kernel, dim3(p.nchunk, BH, kPrepParts), dim3(256), 0, s, p)) != cudaSuccess) return e;
+  if (g_prefill_prep)
+    e = launch_k(prep2_kernel, dim3(p.nchunk, BH, DH / kPrepCW), dim3(256), 0, s, p);
+  else
+    e = launch_k(prep_kernel, dim3(p.nchunk, BH, kPrepParts), dim3(256), 0, s, p);
+  if (e != cudaSuccess) return e;
   if (g_prefill_tc_fused) {
     // G2 + scan in one kernel: a CTA keeps its 128 x 128 tile of C^T in registers across the chunks of the run
     CUtensorMap mvh, mvl, mkh, mkl;

@@ -441,31 +441,39 @@ def test_prefill_cells_agree_and_match_oracle_steps(name, B, S):
 def test_prefill_conv_packed_fp32_equals_scalar(name, B, S):
     """xl_set_option("prefill_conv"): the sequence conv/qkv/gates kernel on packed fp32 pairs (FFMA2, default = 1) keeps
     every FMA chain of the scalar kernel (0), so hidden states and the state left are BIT-identical; 2 (SFU SiLU)
-    differs by the ~2 ulp of ex2.approx / rcp.approx. S is ragged against the 2-token groups, the 16-token runs and
-    the 128-token chunks; the first call starts from a carried conv window and a non-zero state."""
+    differs by the ~2 ulp of ex2.approx / rcp.approx. xl_set_option("prefill_prep"): the single-read chunk preparation
+    (shared-memory tile, default = 1) writes the same operand planes as the three-pass kernel (0), bit for bit.
+    S is ragged against the 2-token groups, the 16-token runs and the 128-token chunks; the first call starts from a
+    carried conv window and a non-zero state."""
     cfg, sd, eng = _engine(name, B)
     g = torch.Generator().manual_seed(23)
     x0 = torch.randn(B, 9, cfg.d, generator=g)
     x = torch.randn(B, S, cfg.d, generator=g)
     res = {}
     try:
-        for impl in (0, 1, 2):
-            eng.set_option("prefill_conv", impl)
+        for tag, conv, prep in (("base", 0, 0), ("conv1", 1, 0), ("prep1", 0, 1), ("fast", 2, 1)):
+            eng.set_option("prefill_conv", conv)
+            eng.set_option("prefill_prep", prep)
             cache = eng.new_state(B)
             eng.prefill(cache, x0.cuda())
             hs = eng.prefill(cache, x.cuda())
             torch.cuda.synchronize()
-            res[impl] = (hs.cpu(), cache.to_past_key_values())
+            res[tag] = (hs.cpu(), cache.to_past_key_values())
     finally:
         eng.set_option("prefill_conv", 1)
-    assert torch.equal(res[1][0], res[0][0])
-    assert _rel(res[2][0], res[0][0]) < 1e-4
+        eng.set_option("prefill_prep", 1)
+    for tag in ("conv1", "prep1"):
+        assert torch.equal(res[tag][0], res["base"][0]), tag
+    assert _rel(res["fast"][0], res["base"][0]) < 1e-4
     for i in range(cfg.num_blocks):
-        blk0, blk1, blk2 = (res[k][1][f"block_{i}"] for k in (0, 1, 2))
-        for a, b, c in zip(blk0["mlstm_state"], blk1["mlstm_state"], blk2["mlstm_state"]):
-            assert torch.equal(a.cpu(), b.cpu()), i
+        base = res["base"][1][f"block_{i}"]
+        for tag in ("conv1", "prep1"):
+            blk = res[tag][1][f"block_{i}"]
+            for a, b in zip(base["mlstm_state"], blk["mlstm_state"]):
+                assert torch.equal(a.cpu(), b.cpu()), (tag, i)
+            assert torch.equal(base["conv_state"][0].cpu(), blk["conv_state"][0].cpu()), (tag, i)
+        for a, c in zip(base["mlstm_state"], res["fast"][1][f"block_{i}"]["mlstm_state"]):
             assert _rel(c.cpu(), a.cpu()) < 1e-4 or (c.cpu() - a.cpu()).abs().max() < 1e-5, i
-        assert torch.equal(blk0["conv_state"][0].cpu(), blk1["conv_state"][0].cpu())
     eng.close()
 
 
