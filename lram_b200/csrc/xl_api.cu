@@ -1758,6 +1758,8 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
   } else if (!strcmp(name, "prefill_conv")) {
     if (value < 0 || value > 2) return fail(XL_ERR_INVALID_ARG, "prefill_conv must be 0 (scalar), 1 (packed fp32) or 2 (packed + SFU SiLU)");
     xl::g_prefill_conv_impl = value;          // process-wide A/B of the sequence conv/qkv/gates kernel
+  } else if (!strcmp(name, "prefill_conv_persist")) {
+    xl::g_prefill_conv_persist = value ? 1 : 0;   // process-wide A/B: packed conv kernel persistent over the token runs
   } else if (!strcmp(name, "prefill_prep")) {
     xl::g_prefill_prep = value ? 1 : 0;       // process-wide A/B of the chunk preparation kernel (1 = single-read tile kernel)
   } else if (!strcmp(name, "prefill_tc_fused")) {

@@ -173,6 +173,7 @@ extern int g_gemm_2cta;
 extern int g_prefill_tc_fused;
 extern int g_prefill_conv_run;
 extern int g_prefill_conv_impl;
+extern int g_prefill_conv_persist;
 extern int g_prefill_prep;
 bool prefill_cell_tc_supported(int DH);
 int prefill_cell_tc_chunk();

@@ -16,6 +16,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "xl_common.cuh"
 #include "xl_internal.h"
 
@@ -325,8 +327,6 @@ __global__ void __launch_bounds__(64 * kConvRuns, 2) conv_qkv_gates_seq2_kernel(
   const int nx = blockDim.x;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int sub = threadIdx.y, nruns = blockDim.y, tx = threadIdx.x;
-  const int s_begin = min(S, ((int)blockIdx.z * nruns + sub) * run);
-  const int s_end = min(S, s_begin + run);
   const int inner = p.inner;
   const int nblk = inner >> 2;
   const int blk_per_chunk = (nblk + p.NCH - 1) / p.NCH;
@@ -377,7 +377,18 @@ __global__ void __launch_bounds__(64 * kConvRuns, 2) conv_qkv_gates_seq2_kernel(
   pdl_wait();
   pdl_trigger();
   __syncthreads();                                        // s_gw, s_hw
-  if (s_begin >= s_end) return;                           // (a whole run leaves: its named barrier is never used)
+  const uint32_t bar_id = 1 + sub, bar_threads = nw * 32;
+  const uint32_t gw = smem_u32(s_dyn + tx * kStride), hw = gw + 16u * kGateRows;
+  const int u_step = 2 * inner, g_step = p.NCH * 2 * NH;
+  uint32_t group = 0;                                     // groups this run has reduced so far: parity of its buffer
+  // PERSISTENT over the token runs: the weights above are staged once per CTA (at 16 tokens per run the staging was a
+  // quarter of a CTA's life); CTA z walks the run blocks z, z + gridDim.z, ...
+  const int nzb = (S + run * nruns - 1) / (run * nruns);
+#pragma unroll 1
+  for (int zb = blockIdx.z; zb < nzb; zb += gridDim.z) {
+  const int s_begin = min(S, (zb * nruns + sub) * run);
+  const int s_end = min(S, s_begin + run);
+  if (s_begin >= s_end) break;                            // (later run blocks start even further right)
 
   // the KS-1 inputs before token s_begin: earlier rows of this chunk, or the carried conv_state (rows = last KS
   // inputs, oldest first) for tokens before the chunk
@@ -398,9 +409,6 @@ __global__ void __launch_bounds__(64 * kConvRuns, 2) conv_qkv_gates_seq2_kernel(
   float* vp = p.v + row_begin * inner + c;
   float* ap = p.act + row_begin * inner + c;
   float* gp = p.gate_part + (row_begin * p.NCH + chunk) * 2 * NH;
-  const int u_step = 2 * inner, g_step = p.NCH * 2 * NH;
-  const uint32_t bar_id = 1 + sub, bar_threads = nw * 32;
-  const uint32_t gw = smem_u32(s_dyn + tx * kStride), hw = gw + 16u * kGateRows;
 
   const int ntok = s_end - s_begin;
   const int nsteps = (ntok + TG - 1) / TG;
@@ -492,7 +500,8 @@ __global__ void __launch_bounds__(64 * kConvRuns, 2) conv_qkv_gates_seq2_kernel(
     }
     // sums of the group's NV values over the run's channels: warp tree (xor 16, 8, 4, 2, 1: the pairwise sums of
     // warp_sum()), then a fixed-order sum over the run's (<= 4) warps
-    float* rbuf = red[sub][st & 1];
+    float* rbuf = red[sub][group & 1];
+    ++group;
     float vals[NV];
 #pragma unroll
     for (int h = 0; h < NH; ++h)
@@ -540,6 +549,7 @@ __global__ void __launch_bounds__(64 * kConvRuns, 2) conv_qkv_gates_seq2_kernel(
     up += TG * u_step;
     qp += TG * inner; kp += TG * inner; vp += TG * inner; ap += TG * inner;
     gp += TG * g_step;
+  }
   }
 }
 
@@ -1044,10 +1054,21 @@ bool prefill_cell_supported(int DH) {
 }
 
 int g_prefill_conv_run = 16;   // xl_set_option("prefill_conv_run")
-int g_prefill_conv_impl = 1;   // xl_set_option("prefill_conv"): 0 = scalar kernel, 1 = packed fp32 pairs, 2 = + SFU SiLU
+int g_prefill_conv_impl = 2;   // xl_set_option("prefill_conv"): 0 = scalar kernel, 1 = packed fp32 pairs, 2 = + SFU SiLU (default)
+int g_prefill_conv_persist = 1;   // xl_set_option("prefill_conv_persist"): packed kernel walks the run blocks (1) or one block per CTA (0)
 
 template <int NH>
 static bool launch_conv_seq2(const ConvQkvParams& p, int S, int run, dim3 grid, dim3 block, cudaStream_t s) {
+  // persistent over the run blocks: 2 CTAs per SM in total (128 registers x 256 threads), each staging its weights once
+  static const int sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  if (g_prefill_conv_persist) {
+    const unsigned per = (unsigned)std::max(1, 2 * sms / (int)(grid.x * grid.y));
+    grid.z = std::min(grid.z, per);
+  }
   const size_t smem = sizeof(float4) * (size_t)(NH * 3 * 2 + 3 * 4 + 1) * block.x;
   if (g_prefill_conv_impl == 2) {
     if (ensure_dyn_smem<&pf::conv_qkv_gates_seq2_kernel<NH, true>>(smem) != cudaSuccess) return false;

@@ -439,8 +439,8 @@ def test_prefill_cells_agree_and_match_oracle_steps(name, B, S):
 
 @pytest.mark.parametrize("name,B,S", [("16M", 2, 301), ("48M", 3, 75), ("206M", 1, 130), ("toy128", 2, 37)])
 def test_prefill_conv_packed_fp32_equals_scalar(name, B, S):
-    """xl_set_option("prefill_conv"): the sequence conv/qkv/gates kernel on packed fp32 pairs (FFMA2, default = 1) keeps
-    every FMA chain of the scalar kernel (0), so hidden states and the state left are BIT-identical; 2 (SFU SiLU)
+    """xl_set_option("prefill_conv"): the sequence conv/qkv/gates kernel on packed fp32 pairs (FFMA2, 1) keeps every FMA
+    chain of the scalar kernel (0), so hidden states and the state left are BIT-identical; 2 (the default: + SFU SiLU)
     differs by the ~2 ulp of ex2.approx / rcp.approx. xl_set_option("prefill_prep"): the single-read chunk preparation
     (shared-memory tile, default = 1) writes the same operand planes as the three-pass kernel (0), bit for bit.
     S is ragged against the 2-token groups, the 16-token runs and the 128-token chunks; the first call starts from a
@@ -460,7 +460,7 @@ def test_prefill_conv_packed_fp32_equals_scalar(name, B, S):
             torch.cuda.synchronize()
             res[tag] = (hs.cpu(), cache.to_past_key_values())
     finally:
-        eng.set_option("prefill_conv", 1)
+        eng.set_option("prefill_conv", 2)       # process-wide switches: restore the defaults
         eng.set_option("prefill_prep", 1)
     for tag in ("conv1", "prep1"):
         assert torch.equal(res[tag][0], res["base"][0]), tag
