@@ -984,8 +984,9 @@ int prefill_blocks(xl_handle* h, void* state, int B, int Sc, unsigned flags, cud
     if (h->prefill_cell == 2 && xl::prefill_cell_tc_supported(DH) && Sc >= 64 &&
         xl::prefill_cell_tc_ws_bytes(B, Sc, NH, DH) <= ((size_t)8 << 30)) {
       if (int rcw = ensure_prefill_tc_ws(h, B, Sc)) return rcw;
+      const xl::CellSideStream side = {h->side[0], h->ev_fork, h->ev_join[0]};
       XL_CUDA(xl::launch_cell_tc((float*)(base + L.c_off), (float*)(base + L.n_off), cp.qk, cp.qk + (size_t)M * inner,
-                                 cp.v, h->pf_f, h->pf_i, h->pf_num, h->pf_qn, h->pf_tc, B, Sc, NH, DH, inner, s));
+                                 cp.v, h->pf_f, h->pf_i, h->pf_num, h->pf_qn, h->pf_tc, B, Sc, NH, DH, inner, s, &side));
       h->launches += 6;
       XL_CUDA(cudaGetLastError());
     } else if (h->prefill_cell >= 1 && xl::prefill_cell_mma_supported(DH) && Sc % xl::prefill_cell_mma_chunk() == 0) {
@@ -1760,6 +1761,8 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
     xl::g_prefill_conv_impl = value;          // process-wide A/B of the sequence conv/qkv/gates kernel
   } else if (!strcmp(name, "prefill_conv_persist")) {
     xl::g_prefill_conv_persist = value ? 1 : 0;   // process-wide A/B: packed conv kernel persistent over the token runs
+  } else if (!strcmp(name, "prefill_tc_overlap")) {
+    xl::g_prefill_tc_overlap = value ? 1 : 0;     // process-wide A/B: S GEMM / P~ / n scan on a side stream beside the chunk scan
   } else if (!strcmp(name, "prefill_prep")) {
     xl::g_prefill_prep = value ? 1 : 0;       // process-wide A/B of the chunk preparation kernel (1 = single-read tile kernel)
   } else if (!strcmp(name, "prefill_tc_fused")) {

@@ -178,9 +178,15 @@ extern int g_prefill_prep;
 bool prefill_cell_tc_supported(int DH);
 int prefill_cell_tc_chunk();
 size_t prefill_cell_tc_ws_bytes(int B, int S, int NH, int DH);
+extern int g_prefill_tc_overlap;
+// side stream + fork/join events (caller-owned) for the kernels of the cell that may run beside the chunk update + scan
+struct CellSideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+};
 cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, const float* v, const float* fseq,
                            const float* iseq, float* num, float* qn, void* ws, int B, int S, int NH, int DH, int inner,
-                           cudaStream_t s);
+                           cudaStream_t s, const CellSideStream* side = nullptr);
 cudaError_t launch_finalize_seq(const float* num, const float* qn, const float* mseq, const float* outnorm_w,
                                 const float* skip, const float* act, const float* u, float* out, void* out_hi,
                                 void* out_lo, int B, int S, int NH, int DH, int inner, float ln_eps, float cell_eps,

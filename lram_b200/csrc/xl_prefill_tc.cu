@@ -1040,22 +1040,28 @@ struct Operand {
   int64_t ld, bs;
 };
 
+static int device_sms() {                          // SMs of the current device (every device of a box is the same part)
+  static const int sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  return sms;
+}
+
+// max_ctas > 0 caps the persistent grid (the GEMM then shares the GPU with a kernel of another stream)
 static cudaError_t launch_bgemm(const Operand& a, const Operand& w, const BatchOut& o, int M, int N, int K, int nb,
-                                cudaStream_t s) {
+                                cudaStream_t s, int max_ctas = 0) {
   if (M % BM || N % BN || K % BK || K < BK) return cudaErrorInvalidValue;
   CUtensorMap mah, mal, mwh, mwl;
   if (!make_map3(&mah, a.hi, K, M, nb, a.ld, a.bs) || !make_map3(&mal, a.lo, K, M, nb, a.ld, a.bs) ||
       !make_map3(&mwh, w.hi, K, N, nb, w.ld, w.bs) || !make_map3(&mwl, w.lo, K, N, nb, w.ld, w.bs))
     return cudaErrorUnknown;
   if (cudaError_t e = ensure_dyn_smem<&bgemm_kernel>(kSmemGemm); e != cudaSuccess) return e;
-  static const int sms = [] {                     // SMs of the current device (every device of a box is the same part)
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n > 0 ? n : 148;
-  }();
   const int tiles = nb * (M / BM) * (N / BN);
-  return launch_k(bgemm_kernel, dim3(tiles < sms ? tiles : sms), dim3(kGemmThreads), kSmemGemm, s, mah, mal, mwh, mwl, o,
-                  M, N, K, nb);
+  int grid = tiles < device_sms() ? tiles : device_sms();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  return launch_k(bgemm_kernel, dim3(grid), dim3(kGemmThreads), kSmemGemm, s, mah, mal, mwh, mwl, o, M, N, K, nb);
 }
 
 }  // namespace ptc
@@ -1071,9 +1077,11 @@ size_t prefill_cell_tc_ws_bytes(int B, int S, int NH, int DH) {
   return ptc::carve_ws(nullptr, nullptr, B * NH * nchunk, DH);
 }
 
+int g_prefill_tc_overlap = 1;   // xl_set_option("prefill_tc_overlap"): S = QK^T, P~ and the n scan beside the chunk update + scan
+
 cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, const float* v, const float* fseq,
                            const float* iseq, float* num, float* qn, void* ws, int B, int S, int NH, int DH, int inner,
-                           cudaStream_t s) {
+                           cudaStream_t s, const CellSideStream* side) {
   using namespace ptc;
   if (!prefill_cell_tc_supported(DH) || S <= 0 || inner != NH * DH) return cudaErrorInvalidValue;
   CellParams p;
@@ -1089,6 +1097,19 @@ cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, c
   else
     e = launch_k(prep_kernel, dim3(p.nchunk, BH, kPrepParts), dim3(256), 0, s, p);
   if (e != cudaSuccess) return e;
+  // The chunk update + scan runs (DH/128)^2 * B*NH CTAs, one per SM, each bound by what one SM ingests through TMA: with
+  // few envs it leaves SMs idle (206M x 1 env: 100 CTAs on 148 SMs for 285 us). S = QK^T, P~ and the n scan depend on the
+  // chunk operands only, so in that case they run on a side stream BESIDE it -- the S GEMM as a persistent grid capped at
+  // the SMs the scan leaves free (whatever the block scheduler does first, the scan's CTAs find their SMs) -- and the
+  // numerator GEMM joins both.
+  const int scan_ctas = (DH / BN) * (DH / BM) * BH;
+  const int free_sms = device_sms() - scan_ctas;
+  const bool overlap = g_prefill_tc_fused && g_prefill_tc_overlap && side && side->stream && free_sms >= 32;
+  cudaStream_t s2 = overlap ? side->stream : s;
+  if (overlap) {
+    if ((e = cudaEventRecord(side->fork, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(s2, side->fork, 0)) != cudaSuccess) return e;
+  }
   if (g_prefill_tc_fused) {
     // G2 + scan in one kernel: a CTA keeps its 128 x 128 tile of C^T in registers across the chunks of the run
     CUtensorMap mvh, mvl, mkh, mkl;
@@ -1101,7 +1122,7 @@ cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, c
     if ((e = launch_k(update_scan_kernel, dim3(DH / BN, DH / BM, BH), dim3(kScanThreads), kSmemScan, s, mvh, mvl, mkh,
                       mkl, p)) != cudaSuccess)
       return e;
-    if ((e = launch_k(nscan_kernel, dim3(BH, (DH + 127) / 128), dim3(128), 0, s, p)) != cudaSuccess) return e;
+    if (!overlap && (e = launch_k(nscan_kernel, dim3(BH, (DH + 127) / 128), dim3(128), 0, s, p)) != cudaSuccess) return e;
   } else {
     // G2: dC^T = V^T K~ for every chunk, then the element-parallel scan over dC in HBM
     const Operand a = {p.w.w3_hi + DH, p.w.w3_lo + DH, K3, (int64_t)DH * K3};
@@ -1117,9 +1138,14 @@ cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, c
     const Operand w = {p.w.k_hi, p.w.k_lo, DH, (int64_t)L * DH};
     const long long sz = (long long)L * L;
     const BatchOut o = {p.w.Sm, sz * p.nchunk * NH, sz * p.nchunk, sz, L, NH, p.nchunk, 0};
-    if ((e = launch_bgemm(a, w, o, L, L, DH, nb, s)) != cudaSuccess) return e;
+    if ((e = launch_bgemm(a, w, o, L, L, DH, nb, s2, overlap ? free_sms : 0)) != cudaSuccess) return e;
   }
-  if ((e = launch_k(pmat_kernel, dim3(nb), dim3(256), 0, s, p)) != cudaSuccess) return e;
+  if ((e = launch_k(pmat_kernel, dim3(nb), dim3(256), 0, s2, p)) != cudaSuccess) return e;
+  if (overlap) {
+    if ((e = launch_k(nscan_kernel, dim3(BH, (DH + 127) / 128), dim3(128), 0, s2, p)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(side->join, s2)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(s, side->join, 0)) != cudaSuccess) return e;
+  }
   // G3: num = [e^{a_t} q_t | P~_t] [C_c^T | V^T]^T, straight into the numerator rows of the run
   {
     const Operand a = {p.w.a3_hi, p.w.a3_lo, K3, (int64_t)L * K3};

@@ -477,6 +477,35 @@ def test_prefill_conv_packed_fp32_equals_scalar(name, B, S):
     eng.close()
 
 
+@pytest.mark.parametrize("name,B,S", [("206M", 1, 300), ("48M", 2, 200), ("16M", 8, 130)])
+def test_prefill_tc_side_stream_overlap_equals_sequential(name, B, S):
+    """xl_set_option("prefill_tc_overlap"): with few envs the S = QK^T GEMM (grid capped at the SMs the chunk scan leaves
+    free), the P~ kernel and the n scan run on a side stream beside the chunk update + scan and join before the numerator
+    GEMM. Same kernels, same tiles: bit-identical to the single-stream order (16M x 8 envs: 128 scan CTAs, no overlap)."""
+    cfg, sd, eng = _engine(name, B)
+    g = torch.Generator().manual_seed(29)
+    x = torch.randn(B, S, cfg.d, generator=g)
+    res = {}
+    try:
+        for ovl in (0, 1, 0, 1):          # twice: the side stream's workspace reuse across calls and blocks is ordered
+            eng.set_option("prefill_tc_overlap", ovl)
+            cache = eng.new_state(B)
+            hs = eng.prefill(cache, x.cuda())
+            hs2 = eng.prefill(cache, x.flip(1).contiguous().cuda())
+            torch.cuda.synchronize()
+            out = (hs.cpu(), hs2.cpu(), cache.to_past_key_values())
+            if ovl in res:
+                assert torch.equal(out[0], res[ovl][0]) and torch.equal(out[1], res[ovl][1])
+            res[ovl] = out
+    finally:
+        eng.set_option("prefill_tc_overlap", 1)
+    assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[1][1], res[0][1])
+    for i in range(cfg.num_blocks):
+        for a, b in zip(res[0][2][f"block_{i}"]["mlstm_state"], res[1][2][f"block_{i}"]["mlstm_state"]):
+            assert torch.equal(a.cpu(), b.cpu()), i
+    eng.close()
+
+
 @pytest.mark.parametrize("Tn", [23, 100])
 def test_policy_prefill_equals_stepping(Tn):
     """xl_policy_prefill(context of Tn timesteps) then a rollout == stepping through the context: same action
