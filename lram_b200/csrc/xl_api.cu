@@ -117,7 +117,9 @@ struct xl_handle {
   float *part_up = nullptr, *part_down = nullptr;   // split-K planes [kSplitMax][part_rows][2*inner | d]
   size_t part_rows = 0;
   int l2_prefetch_policy = 0;          // 1: warm with an L2 evict_last policy ("l2_prefetch_policy")
-  int conv_impl = 0;                   // pre-cell kernel: 0 = thread per 4-channel block, 1 = thread per (block, token)
+  int conv_impl = 2;                   // pre-cell kernel: 0 = thread per 4-channel block, 1 = thread per (block, token),
+                                       // 2 (default) = as 0 on packed fp32 pairs, gate weights before the wait, butterfly
+                                       // reduction (KS = 4, NH <= 4; other shapes run impl 0)
   int microbatches = 0;                // 0 = automatic; env micro-batches per fused step ("microbatches")
   int pipeline_order = 1;              // 1 = state-stream kernels of the micro-batches run one after another
   int l2_prefetch_mb = -1;             // MiB of the NEXT block's C warmed into L2 on a side stream while the chain
@@ -1787,7 +1789,7 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
     if (value < 0 || value > kSplitMax) return fail(XL_ERR_INVALID_ARG, "%s must be in [0, %d]", name, kSplitMax);
     (name[5] == 'u' ? h->gemm_up_splits : h->gemm_down_splits) = value;
   } else if (!strcmp(name, "conv_impl")) {
-    if (value < 0 || value > 1) return fail(XL_ERR_INVALID_ARG, "conv_impl must be 0 or 1");
+    if (value < 0 || value > 2) return fail(XL_ERR_INVALID_ARG, "conv_impl must be 0, 1 or 2");
     h->conv_impl = value;
   } else if (!strcmp(name, "smallm")) {
     if (value < -1 || value > 1) return fail(XL_ERR_INVALID_ARG, "smallm must be -1 (automatic), 0 or 1");

@@ -92,6 +92,38 @@ __device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
 // SFU version (ex2.approx + rcp.approx, ~2 ulp): used where SiLU sits on a latency-critical tail
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
+// ---- packed fp32 pairs: sm_100 FFMA2 / FMUL2 / FADD2 (two IEEE fp32 results per instruction and lane) -------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 bc2(float x) { return pk2(x, x); }   // ptxas folds this into a scalar (broadcast) operand
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// x0*w0 + x1*w1 + x2*w2 + x3*w3 per half, contracted the way nvcc contracts the scalar expression
+__device__ __forceinline__ f32x2 dot4_bc(const float (&x)[4], const float4& wa, const float4& wb) {
+  f32x2 t = mul2(bc2(x[1]), pk2(wa.z, wa.w));
+  t = fma2(bc2(x[0]), pk2(wa.x, wa.y), t);
+  t = fma2(bc2(x[2]), pk2(wb.x, wb.y), t);
+  return fma2(bc2(x[3]), pk2(wb.z, wb.w), t);
+}
+
 // streaming (evict-first) 128-bit accesses for the once-touched state stream
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(float4* p, const float4& v) { __stcs(p, v); }

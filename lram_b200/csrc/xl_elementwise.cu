@@ -703,11 +703,208 @@ __global__ void __launch_bounds__(512) conv_qkv_gates_tok_kernel(ConvQkvParams p
   }
 }
 
+// Packed-fp32 variant (impl 2, KS = 4, NH <= 4): the kernel sits in the per-block chain of the env step with ~5 warps per
+// SM, so what counts is the length of one thread's dependent instruction stream after the dependency wait. Against impl 0:
+//   * conv, headwise q/k/v and gate dot products as FFMA2 / FMUL2 / FADD2 on fp32 pairs (channel pairs, output pairs,
+//     the (igate, fgate) pair of a head) with every chain in impl 0's order: outputs are BIT-identical (tested);
+//   * the gate weights (24 x NH values per thread) are loaded BEFORE the dependency wait like the other weights -- in
+//     impl 0 their L2 round trip sits between phase 1 and phase 2 (occupancy is irrelevant here: up to 255 registers);
+//   * the NH * 2 * T <= 32 partial sums of a warp are reduced by one transposing butterfly (31 shuffles, the pairwise
+//     sums of warp_sum()) instead of NH * 2 * T warp_sum() trees (120 shuffles at NH = 4, T = 3).
+template <int T, int NH>
+__global__ void __launch_bounds__(128, 1) conv_qkv_gates_pk_kernel(ConvQkvParams p) {
+  constexpr int KS = 4, NV = NH * 2 * T;
+  static_assert(NV <= 32, "one butterfly per warp");
+  __shared__ float red[NV * 4];
+  const int b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int inner = p.inner;
+  const int nblk = inner >> 2;
+  const int blk_per_chunk = (nblk + p.NCH - 1) / p.NCH;
+  const int j = chunk * blk_per_chunk + threadIdx.x;
+  const bool active = threadIdx.x < blk_per_chunk && j < nblk;
+  const int c = 4 * (active ? j : 0);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+
+  // everything no kernel of the step writes: conv window, taps, headwise blocks, gate weights -- before the wait
+  f32x2 win[KS][2], cwp[KS][2], cbp[2];
+  f32x2 hq[4][2], hk[4][2], hv[4][2];                      // [dd][output pair]
+  f32x2 gw[NH][3][4];                                     // (igate, fgate) weight of [head][q|k|v][channel]
+  float* cs = p.conv_state + (int64_t)b * KS * inner + c;
+  {
+    float4 w4[4];
+#pragma unroll
+    for (int r = 0; r < KS; ++r) {
+      const float4 x4 = *reinterpret_cast<const float4*>(cs + (int64_t)r * inner);
+      win[r][0] = pk2(x4.x, x4.y);
+      win[r][1] = pk2(x4.z, x4.w);
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) w4[ch] = *reinterpret_cast<const float4*>(p.conv_w + (int64_t)(c + ch) * KS);
+    cwp[0][0] = pk2(w4[0].x, w4[1].x); cwp[0][1] = pk2(w4[2].x, w4[3].x);
+    cwp[1][0] = pk2(w4[0].y, w4[1].y); cwp[1][1] = pk2(w4[2].y, w4[3].y);
+    cwp[2][0] = pk2(w4[0].z, w4[1].z); cwp[2][1] = pk2(w4[2].z, w4[3].z);
+    cwp[3][0] = pk2(w4[0].w, w4[1].w); cwp[3][1] = pk2(w4[2].w, w4[3].w);
+    const float4 cb = *reinterpret_cast<const float4*>(p.conv_b + c);
+    cbp[0] = pk2(cb.x, cb.y);
+    cbp[1] = pk2(cb.z, cb.w);
+    // headwise block W[o][dd] at wq[16 j + 4 o + dd]: pairs over o for a fixed dd
+    const float* bq = p.wq + (int64_t)(c >> 2) * 16;
+    const float* bk = p.wk + (int64_t)(c >> 2) * 16;
+    const float* bv = p.wv + (int64_t)(c >> 2) * 16;
+    float4 rq[4], rk[4], rv[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      rq[o] = reinterpret_cast<const float4*>(bq)[o];
+      rk[o] = reinterpret_cast<const float4*>(bk)[o];
+      rv[o] = reinterpret_cast<const float4*>(bv)[o];
+    }
+#define XL_COL(r, dd) (dd == 0 ? r.x : dd == 1 ? r.y : dd == 2 ? r.z : r.w)
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd) {
+      hq[dd][0] = pk2(XL_COL(rq[0], dd), XL_COL(rq[1], dd)); hq[dd][1] = pk2(XL_COL(rq[2], dd), XL_COL(rq[3], dd));
+      hk[dd][0] = pk2(XL_COL(rk[0], dd), XL_COL(rk[1], dd)); hk[dd][1] = pk2(XL_COL(rk[2], dd), XL_COL(rk[3], dd));
+      hv[dd][0] = pk2(XL_COL(rv[0], dd), XL_COL(rv[1], dd)); hv[dd][1] = pk2(XL_COL(rv[2], dd), XL_COL(rv[3], dd));
+    }
+#undef XL_COL
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        const float4 wi = *reinterpret_cast<const float4*>(p.wi + (int64_t)(h * 3 + part) * inner + c);
+        const float4 wf = *reinterpret_cast<const float4*>(p.wf + (int64_t)(h * 3 + part) * inner + c);
+        gw[h][part][0] = pk2(wi.x, wf.x); gw[h][part][1] = pk2(wi.y, wf.y);
+        gw[h][part][2] = pk2(wi.z, wf.z); gw[h][part][3] = pk2(wi.w, wf.w);
+      }
+  }
+  pdl_wait();
+  pdl_trigger();
+
+  float4 xm4[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const float* up = p.u + ((int64_t)b * T + t) * 2 * inner + c;
+    xm4[t] = *reinterpret_cast<const float4*>(up);
+    for (int z = 1; z < p.u_splits; ++z) {                // split-K planes of proj_up, added in plane order
+      const float4 a4 = *reinterpret_cast<const float4*>(up + z * p.u_stride);
+      xm4[t].x += a4.x; xm4[t].y += a4.y; xm4[t].z += a4.z; xm4[t].w += a4.w;
+    }
+  }
+  f32x2 G[NH][T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int64_t row = (int64_t)b * T + t;
+    const f32x2 x01 = pk2(xm4[t].x, xm4[t].y), x23 = pk2(xm4[t].z, xm4[t].w);
+    // roll(-1); state[-1] = x; conv over the window, oldest first (fma(w, c, 0) == w * c)
+    win[0][0] = win[1][0]; win[0][1] = win[1][1];
+    win[1][0] = win[2][0]; win[1][1] = win[2][1];
+    win[2][0] = win[3][0]; win[2][1] = win[3][1];
+    win[3][0] = x01;       win[3][1] = x23;
+    f32x2 a01 = fma2(win[0][0], cwp[0][0], 0ull), a23 = fma2(win[0][1], cwp[0][1], 0ull);
+#pragma unroll
+    for (int r = 1; r < KS; ++r) {
+      a01 = fma2(win[r][0], cwp[r][0], a01);
+      a23 = fma2(win[r][1], cwp[r][1], a23);
+    }
+    a01 = add2(a01, cbp[0]);
+    a23 = add2(a23, cbp[1]);
+    float a[4];
+    unpk2(a01, a[0], a[1]);
+    unpk2(a23, a[2], a[3]);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) a[ch] = silu(a[ch]);
+    const float xm[4] = {xm4[t].x, xm4[t].y, xm4[t].z, xm4[t].w};
+    f32x2 q01 = 0ull, q23 = 0ull, k01 = 0ull, k23 = 0ull, v01 = 0ull, v23 = 0ull;
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd) {
+      q01 = fma2(bc2(a[dd]), hq[dd][0], q01);  q23 = fma2(bc2(a[dd]), hq[dd][1], q23);
+      k01 = fma2(bc2(a[dd]), hk[dd][0], k01);  k23 = fma2(bc2(a[dd]), hk[dd][1], k23);
+      v01 = fma2(bc2(xm[dd]), hv[dd][0], v01); v23 = fma2(bc2(xm[dd]), hv[dd][1], v23);
+    }
+    float q[4], k[4], v[4];
+    unpk2(q01, q[0], q[1]); unpk2(q23, q[2], q[3]);
+    unpk2(k01, k[0], k[1]); unpk2(k23, k[2], k[3]);
+    unpk2(v01, v[0], v[1]); unpk2(v23, v[2], v[3]);
+    if (active) {
+      // channel c of head h sits at (row*NH + h)*DH + (c - h*DH) == row*inner + c: (q,k) pairs interleaved
+      float* qk = p.qk + (row * inner + c) * 2;
+      *reinterpret_cast<float4*>(qk) = make_float4(q[0], k[0], q[1], k[1]);
+      *reinterpret_cast<float4*>(qk + 4) = make_float4(q[2], k[2], q[3], k[3]);
+      *reinterpret_cast<float4*>(p.v + row * inner + c) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(p.act + row * inner + c) = make_float4(a[0], a[1], a[2], a[3]);
+    }
+    // partial (igate, fgate) pre-activations: x1 w1, then + x0 w0, + x2 w2, + x3 w3 per part; q-, k-, v-sums added in order
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      f32x2 sq = mul2(bc2(q[1]), gw[h][0][1]);
+      sq = fma2(bc2(q[0]), gw[h][0][0], sq);
+      sq = fma2(bc2(q[2]), gw[h][0][2], sq);
+      sq = fma2(bc2(q[3]), gw[h][0][3], sq);
+      f32x2 sk = mul2(bc2(k[1]), gw[h][1][1]);
+      sk = fma2(bc2(k[0]), gw[h][1][0], sk);
+      sk = fma2(bc2(k[2]), gw[h][1][2], sk);
+      sk = fma2(bc2(k[3]), gw[h][1][3], sk);
+      f32x2 sv = mul2(bc2(v[1]), gw[h][2][1]);
+      sv = fma2(bc2(v[0]), gw[h][2][0], sv);
+      sv = fma2(bc2(v[2]), gw[h][2][2], sv);
+      sv = fma2(bc2(v[3]), gw[h][2][3], sv);
+      G[h][t] = active ? add2(add2(sq, sk), sv) : 0ull;
+    }
+  }
+  if (active) {
+    // write the window back: rows = last KS inputs, oldest first (reference conv_state layout)
+#pragma unroll
+    for (int r = 0; r < KS; ++r) {
+      float4 w4;
+      unpk2(win[r][0], w4.x, w4.y);
+      unpk2(win[r][1], w4.z, w4.w);
+      *reinterpret_cast<float4*>(cs + (int64_t)r * inner) = w4;
+    }
+  }
+  // value index (h * 2 + gate) * T + t, padded with zeros to 32: lane l ends with the warp total of value l
+  float vals[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) vals[i] = 0.f;
+#pragma unroll
+  for (int h = 0; h < NH; ++h)
+#pragma unroll
+    for (int t = 0; t < T; ++t) unpk2(G[h][t], vals[(h * 2 + 0) * T + t], vals[(h * 2 + 1) * T + t]);
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    const bool upper = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+      const float keep = upper ? vals[i + m] : vals[i];
+      const float send = upper ? vals[i] : vals[i + m];
+      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+  if (lane < NV) red[lane * 4 + wid] = vals[0];
+  __syncthreads();
+  if ((int)threadIdx.x < NV) {
+    const int h = threadIdx.x / (2 * T);
+    const int rem = threadIdx.x - h * 2 * T;
+    const int g = rem / T, t = rem - g * T;
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += red[threadIdx.x * 4 + w];
+    float* gp = p.gate_part + (((int64_t)b * T + t) * p.NCH + chunk) * 2 * NH;
+    gp[g * NH + h] = s;
+  }
+}
+
 bool launch_conv_qkv_gates(const ConvQkvParams& p, cudaStream_t s) {
   const int nblk = p.inner / 4;
   const int per_chunk = (nblk + p.NCH - 1) / p.NCH;
   const int threads = ((per_chunk + 31) / 32) * 32;   // one thread per 4-channel block; <= 128 (host-checked)
   dim3 grid(p.NCH, p.B);
+  if (p.impl == 2 && p.KS == 4 && threads <= 128) {
+#define XL_CONV_PK_CASE(TV, NHV) \
+  if (p.T == TV && p.NH == NHV) { launch_k(conv_qkv_gates_pk_kernel<TV, NHV>, grid, dim3(threads), 0, s, p); return true; }
+    XL_CONV_PK_CASE(1, 4) XL_CONV_PK_CASE(2, 4) XL_CONV_PK_CASE(3, 4) XL_CONV_PK_CASE(4, 4)
+    XL_CONV_PK_CASE(1, 2) XL_CONV_PK_CASE(3, 2) XL_CONV_PK_CASE(1, 1) XL_CONV_PK_CASE(3, 1)
+#undef XL_CONV_PK_CASE
+  }
   if (p.impl == 1 && threads * p.T <= 512) {
 #define XL_CONV_TOK_CASE(KSV, TV, NHV) \
   if (p.KS == KSV && p.T == TV && p.NH == NHV) { launch_k(conv_qkv_gates_tok_kernel<KSV, TV, NHV>, grid, dim3(threads * TV), 0, s, p); return true; }

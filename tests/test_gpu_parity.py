@@ -756,12 +756,14 @@ def test_l2_warm_option_is_value_neutral():
 @pytest.mark.parametrize("name,B,mode", [("48M", 16, L.XL_MODE_FUSED), ("16M", 64, L.XL_MODE_FUSED),
                                          ("toy128", 5, L.XL_MODE_FUSED), ("16M", 9, L.XL_MODE_PER_TOKEN)])
 def test_conv_impl_token_parallel_is_bit_identical(name, B, mode):
-    """xl_set_option("conv_impl", 1): one thread per (4-channel block, token) instead of per block; same arithmetic and
-    the same summation order of the gate partials, so hidden states, tokens and the conv window are bit-identical."""
+    """xl_set_option("conv_impl", 1): one thread per (4-channel block, token) instead of per block; 2: the per-block kernel
+    on packed fp32 pairs (FFMA2) with the gate weights loaded before the dependency wait and a butterfly reduction. Same
+    arithmetic and the same summation order of the gate partials, so hidden states, tokens and the conv window are
+    bit-identical."""
     cfg, sd, eng = _engine(name, B)
     states, rtg, _ = make_stream(cfg, range(B), 4, domains="mixed")
     res = {}
-    for impl in (0, 1):
+    for impl in (0, 1, 2):
         eng.set_option("conv_impl", impl)
         cache = eng.new_state(B)
         toks, hids = [], []
@@ -773,11 +775,12 @@ def test_conv_impl_token_parallel_is_bit_identical(name, B, mode):
         res[impl] = (torch.stack(toks), torch.stack(hids),
                      [cache.view(i, L.XL_STATE_CONV).cpu().clone() for i in range(cfg.num_blocks)],
                      cache.view(cfg.num_blocks - 1, L.XL_STATE_C).cpu().clone())
-    assert torch.equal(res[1][0], res[0][0])
-    assert torch.equal(res[1][1], res[0][1])
-    for a, b in zip(res[1][2], res[0][2]):
-        assert torch.equal(a, b)
-    assert torch.equal(res[1][3], res[0][3])
+    for impl in (1, 2):
+        assert torch.equal(res[impl][0], res[0][0]), impl
+        assert torch.equal(res[impl][1], res[0][1]), impl
+        for a, b in zip(res[impl][2], res[0][2]):
+            assert torch.equal(a, b), impl
+        assert torch.equal(res[impl][3], res[0][3]), impl
     eng.close()
 
 

@@ -44,6 +44,20 @@ if [ "${1:-all}" = "r2b" ]; then  # the prefill cell on tcgen05 and the row-spli
   grep -E "=== exit|RACECHECK SUMMARY|sanitize_step" "$log"
   exit 0
 fi
+if [ "${1:-all}" = "r2c" ]; then  # packed-fp32 conv kernels (step + prefill), single-read prep, side-stream overlap
+  run memcheck 900 conv_pk conv_pk_toy prefill_tc prefill_tc_ragged
+  run synccheck 900 conv_pk prefill_tc prefill_tc_ragged
+  run racecheck 900 conv_pk
+  log=gpurun_out/sanitize_racecheck.log
+  for k in conv_qkv_gates_seq2 prep2_kernel; do
+    echo "=== racecheck :: prefill_tc_ragged, kernels matching $k" >> "$log"
+    timeout 900 "$CS" --tool racecheck --error-exitcode 9 --print-limit 20 --kernel-regex kns=$k \
+      python tools/sanitize_step.py prefill_tc_ragged >> "$log" 2>&1
+    echo "=== exit $? (prefill_tc_ragged / $k)" >> "$log"
+  done
+  grep -E "=== exit|RACECHECK SUMMARY|sanitize_step" "$log"
+  exit 0
+fi
 if [ "${1:-all}" = "r2" ]; then   # only the kernels / options added in round 2
   run memcheck 600 $R2
   run synccheck 600 $R2

@@ -126,6 +126,12 @@ CASES = {
     "prefill_tc_unfused": lambda: prefill_case("16M", 2, 44, opts={"prefill_tc_fused": 0}),
     "gemm_2sm": linear_2sm_case,
     "small_fuse": lambda: steps_case("16M", 1, L.XL_MODE_FUSED, L.XL_FLAG_GRAPH, n=2, opts={"small_state_fuse": 1}),
+    # late round 2: packed-fp32 (FFMA2) pre-cell kernel of the step path; the prefill_tc case above now runs the packed
+    # persistent sequence conv kernel (named barriers per token run), the single-read prep2 kernel and the side-stream
+    # overlap of the S GEMM with the chunk scan
+    "conv_pk": lambda: steps_case("16M", 8, L.XL_MODE_FUSED, L.XL_FLAG_GRAPH, n=2, opts={"conv_impl": 2}),
+    "conv_pk_toy": lambda: steps_case("toy128", 5, L.XL_MODE_PER_TOKEN, 0, opts={"conv_impl": 2}),
+    "prefill_tc_ragged": lambda: prefill_case("16M", 3, 51),
 }
 
 if __name__ == "__main__":
