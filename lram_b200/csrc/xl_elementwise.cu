@@ -107,7 +107,15 @@ __global__ void __launch_bounds__(1024) ln_rows_cta_kernel(const float* __restri
     if (part) {
       // residual stream += split-K planes of proj_down, in plane order (deterministic); written back in place
       const float4* pp = reinterpret_cast<const float4*>(part + (int64_t)srow * d) + i;
-      for (int z = 0; z < splits; ++z) {
+      // the first 8 planes are requested together (a plain loop gets scheduled as load -> add -> load: one L2 round
+      // trip per plane on the critical path of the block), then added in plane order
+      float4 pl[8];
+#pragma unroll
+      for (int z = 0; z < 8; ++z) pl[z] = pp[((z < splits ? z : 0) * part_stride) >> 2];   // (unpredicated: one batch)
+#pragma unroll
+      for (int z = 0; z < 8; ++z)
+        if (z < splits) { v.x += pl[z].x; v.y += pl[z].y; v.z += pl[z].z; v.w += pl[z].w; }
+      for (int z = 8; z < splits; ++z) {
         const float4 a4 = pp[(z * part_stride) >> 2];
         v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
       }

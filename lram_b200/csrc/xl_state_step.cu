@@ -1184,6 +1184,19 @@ __global__ void __launch_bounds__(1024) mlstm_state_finalize_kernel(StateStepPar
       for (int z = 1; z < p.u_splits; ++z) zz[t] += p.u[z * p.u_stride + row * 2 * inner + inner + ch];
   }
   if (threadIdx.x < 32) compute_gates<T>(p, b, hd, bh, s_f, s_i, s_m, s_pre);
+  __syncthreads();
+  // ---- n recurrence, q.n and the denominators for the T tokens: nothing here depends on the state stream either, so
+  // this block reduction also runs before the dependency wait ------------------------------------------------------
+  const float kscale = rsqrtf((float)DH);
+  float qn[T], den[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    nreg = fmaf(s_f[t], nreg, s_i[t] * kscale * qk[t].y);
+    qn[t] = qk[t].x * nreg;
+  }
+  block_sum_n<T>(qn, s_red);
+#pragma unroll
+  for (int t = 0; t < T; ++t) den[t] = fmaxf(fabsf(qn[t]), expf(-s_m[t + 1])) + p.cell_eps;
   pdl_wait();
   pdl_trigger();
 #pragma unroll
@@ -1199,24 +1212,12 @@ __global__ void __launch_bounds__(1024) mlstm_state_finalize_kernel(StateStepPar
     }
     num[t] = s;
   }
-  __syncthreads();
-
-  // ---- n recurrence and q.n for the T tokens --------------------------------------------------------
-  const float kscale = rsqrtf((float)DH);
-  float qn[T];
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    nreg = fmaf(s_f[t], nreg, s_i[t] * kscale * qk[t].y);
-    qn[t] = qk[t].x * nreg;
-  }
-  block_sum_n<T>(qn, s_red);
   if (ok) p.n[(int64_t)bh * DH + a] = nreg;
   // ---- h = num / den, GroupNorm over the head, skip + output gate -----------------------------------
   float mean[T], var[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
-    const float den = fmaxf(fabsf(qn[t]), expf(-s_m[t + 1])) + p.cell_eps;
-    num[t] = num[t] / den;                   // h (zero for the padded threads)
+    num[t] = num[t] / den[t];                // h (zero for the padded threads)
     mean[t] = num[t];
   }
   block_sum_n<T>(mean, s_red);
