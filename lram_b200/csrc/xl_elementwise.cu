@@ -80,6 +80,9 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ 
 }
 
 // One CTA per row, one float4 per thread held in registers: a single global read, two block reductions.
+// kPlanes: the residual stream first takes the split-K planes of proj_down (the plain instantiation stays at ~32
+// registers: the prefill runs it over 16 k rows, where occupancy matters).
+template <bool kPlanes>
 __global__ void __launch_bounds__(1024) ln_rows_cta_kernel(const float* __restrict__ in, int64_t in_stride,
                                                            float* __restrict__ out, int64_t out_stride,
                                                            const float* __restrict__ w,
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(1024) ln_rows_cta_kernel(const float* __restri
   pdl_trigger();
   if (ok) {
     v = reinterpret_cast<const float4*>(in + (int64_t)srow * in_stride)[i];
-    if (part) {
+    if (kPlanes && part) {
       // residual stream += split-K planes of proj_down, in plane order (deterministic); written back in place
       const float4* pp = reinterpret_cast<const float4*>(part + (int64_t)srow * d) + i;
       // the first 8 planes are requested together (a plain loop gets scheduled as load -> add -> load: one L2 round
@@ -154,7 +157,7 @@ void launch_ln_rows(const float* in, int64_t in_stride, float* out, int64_t out_
   if (rows <= 0) return;
   if (d <= 4096) {
     const int threads = (((d >> 2) + 31) / 32) * 32;
-    launch_k(ln_rows_cta_kernel, dim3(rows), dim3(threads), 0, s, in, in_stride, out, out_stride, w, bias,
+    launch_k(ln_rows_cta_kernel<false>, dim3(rows), dim3(threads), 0, s, in, in_stride, out, out_stride, w, bias,
              residual_weight, eps, d, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, (const float*)nullptr, 0,
              (int64_t)0, (float*)nullptr, 1, 0);
     return;
@@ -170,7 +173,7 @@ void launch_ln_rows_reduce(float* x, const float* part, int splits, int64_t part
                            cudaStream_t s) {
   if (rows <= 0) return;
   const int threads = (((d >> 2) + 31) / 32) * 32;     // d <= 4096 (checked where the split is planned)
-  launch_k(ln_rows_cta_kernel, dim3(rows), dim3(threads), 0, s, (const float*)x, (int64_t)d, out, out_stride, w,
+  launch_k(ln_rows_cta_kernel<true>, dim3(rows), dim3(threads), 0, s, (const float*)x, (int64_t)d, out, out_stride, w,
            (const float*)nullptr, 1, eps, d, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, part, splits, part_stride,
            x, 1, 0);
 }
@@ -183,7 +186,7 @@ void launch_ln_rows_gather(const float* x, const float* part, int splits, int64_
                            cudaStream_t s) {
   if (rows <= 0) return;
   const int threads = (((d >> 2) + 31) / 32) * 32;
-  launch_k(ln_rows_cta_kernel, dim3(rows), dim3(threads), 0, s, x, (int64_t)d, (float*)nullptr, (int64_t)0, w,
+  launch_k(ln_rows_cta_kernel<true>, dim3(rows), dim3(threads), 0, s, x, (int64_t)d, (float*)nullptr, (int64_t)0, w,
            (const float*)nullptr, 1, eps, d, (__nv_bfloat16*)a_hi, (__nv_bfloat16*)a_lo, splits > 1 ? part : nullptr,
            splits, part_stride, (float*)nullptr, row_mul, row_off);
 }

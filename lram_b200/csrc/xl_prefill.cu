@@ -925,7 +925,10 @@ struct FinalizeSeqParams {
 
 // one warp per (row, head): shuffle reductions only, no block barriers. A lane owns groups of 4 consecutive channels
 // (128-bit loads of num / a / z, 64-bit stores of the bf16 planes); DH % 4 == 0, DH <= 1024.
-__global__ void __launch_bounds__(256) mlstm_finalize_seq_kernel(FinalizeSeqParams p) {
+// E = float4 groups per lane (DH <= 128 E): sized to the head so that the three operand rows fit in fewer registers
+// (E = 5 at DH = 640: 3 CTAs per SM instead of 2 -- the kernel is a pure HBM stream).
+template <int E>
+__global__ void __launch_bounds__(256, E <= 5 ? 3 : 2) mlstm_finalize_seq_kernel(FinalizeSeqParams p) {
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   pdl_wait();
@@ -942,7 +945,6 @@ __global__ void __launch_bounds__(256) mlstm_finalize_seq_kernel(FinalizeSeqPara
   const float4* act = reinterpret_cast<const float4*>(p.act + row * inner + hd * DH);
   const float4* zz = reinterpret_cast<const float4*>(p.u + row * 2 * inner + inner + hd * DH);
   const int ng = DH >> 2;
-  constexpr int E = 8;
   float4 hv[E], av[E], zv[E];
   // every global load is issued up front
 #pragma unroll
@@ -1128,7 +1130,12 @@ cudaError_t launch_finalize_seq(const float* num, const float* qn, const float* 
   p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo;
   p.B = B; p.S = S; p.NH = NH; p.DH = DH; p.inner = inner; p.ln_eps = ln_eps; p.cell_eps = cell_eps;
   const int64_t warps = (int64_t)B * S * NH;
-  return launch_k(pf::mlstm_finalize_seq_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, s, p);
+  const dim3 grid((unsigned)((warps + 7) / 8));
+  if (DH <= 256) return launch_k(pf::mlstm_finalize_seq_kernel<2>, grid, dim3(256), 0, s, p);
+  if (DH <= 384) return launch_k(pf::mlstm_finalize_seq_kernel<3>, grid, dim3(256), 0, s, p);
+  if (DH <= 512) return launch_k(pf::mlstm_finalize_seq_kernel<4>, grid, dim3(256), 0, s, p);
+  if (DH <= 640) return launch_k(pf::mlstm_finalize_seq_kernel<5>, grid, dim3(256), 0, s, p);
+  return launch_k(pf::mlstm_finalize_seq_kernel<8>, grid, dim3(256), 0, s, p);
 }
 
 }  // namespace xl
