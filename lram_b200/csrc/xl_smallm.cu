@@ -78,6 +78,9 @@ __global__ void __launch_bounds__(kThreads) smallm_pre_kernel(const SmallPrePara
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wrow), "r"((unsigned)(d * 2)) : "memory");
   }
   for (int i = lane; i < MR * 2 * NH; i += 32) wgs[i] = 0.f;
+  // the first KBA k-blocks of this warp's first CGA weight rows go to registers before the dependency wait
+  uint4 w0[KBA][CGA];
+  if (live) gemv_load<CGA, KBA>(p.w_up, d, col0, 0, w0, lane);
   pdl_wait();
   pdl_trigger();
 
@@ -86,10 +89,17 @@ __global__ void __launch_bounds__(kThreads) smallm_pre_kernel(const SmallPrePara
     const float* xr = p.x + (size_t)row * d;
     float* xo = xs + row * d;
     float sum = 0.f;
-    for (int k = lane * 4; k < d; k += 128) {
-      const float4 v = *reinterpret_cast<const float4*>(xr + k);
-      *reinterpret_cast<float4*>(xo + perm4(k)) = v;
-      sum += (v.x + v.y) + (v.z + v.w);
+    for (int k0 = lane * 4; k0 < d; k0 += 4 * 128) {       // 4 loads in flight (not load -> store -> load); same sum order
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k0 + u * 128 < d) v[u] = *reinterpret_cast<const float4*>(xr + k0 + u * 128);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k0 + u * 128 < d) {
+          *reinterpret_cast<float4*>(xo + perm4(k0 + u * 128)) = v[u];
+          sum += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+        }
     }
     const float mean = warp_sum(sum) / (float)d;
     float q = 0.f;
@@ -115,7 +125,8 @@ __global__ void __launch_bounds__(kThreads) smallm_pre_kernel(const SmallPrePara
 #pragma unroll
     for (int half = 0; half < 4 / CGA; ++half) {
       float acc[CGA][MR];
-      gemv_cols<CGA, MR, KBA>(p.w_up, d, col0 + half * CGA, xs, d, M, acc, lane);
+      if (half == 0) gemv_cols_pre<CGA, MR, KBA>(p.w_up, d, col0, xs, d, M, acc, lane, w0);
+      else gemv_cols<CGA, MR, KBA>(p.w_up, d, col0 + half * CGA, xs, d, M, acc, lane);
 #pragma unroll
       for (int c = 0; c < CGA; ++c)
 #pragma unroll
@@ -265,17 +276,35 @@ __global__ void __launch_bounds__(kThreads) smallm_down_kernel(const SmallDownPa
     const char* wrow = reinterpret_cast<const char*>(p.w_down + (size_t)(col0 + lane) * inner);
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wrow), "r"((unsigned)(inner * 2)) : "memory");
   }
+  // the first KBD k-blocks of this warp's weight rows go to registers before the dependency wait
+  uint4 w0[KBD][CGD];
+  if (live) gemv_load<CGD, KBD>(p.w_down, inner, col0, 0, w0, lane);
   pdl_wait();
   pdl_trigger();
   const int nq = inner >> 2;
-  for (int idx = tid; idx < M * nq; idx += kThreads) {
-    const int m = idx / nq, k = (idx - m * nq) * 4;
-    *reinterpret_cast<float4*>(xs + m * inner + perm4(k)) = *reinterpret_cast<const float4*>(p.g + (size_t)m * inner + k);
+  for (int i0 = tid; i0 < M * nq; i0 += 4 * kThreads) {       // 4 loads in flight per thread (not load -> store -> load)
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = i0 + u * kThreads;
+      if (idx < M * nq) {
+        const int m = idx / nq, k = (idx - m * nq) * 4;
+        v[u] = *reinterpret_cast<const float4*>(p.g + (size_t)m * inner + k);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = i0 + u * kThreads;
+      if (idx < M * nq) {
+        const int m = idx / nq, k = (idx - m * nq) * 4;
+        *reinterpret_cast<float4*>(xs + m * inner + perm4(k)) = v[u];
+      }
+    }
   }
   __syncthreads();
   if (!live) return;
   float acc[CGD][MR];
-  gemv_cols<CGD, MR, KBD>(p.w_down, inner, col0, xs, inner, M, acc, lane);
+  gemv_cols_pre<CGD, MR, KBD>(p.w_down, inner, col0, xs, inner, M, acc, lane, w0);
 #pragma unroll
   for (int c = 0; c < CGD; ++c)
 #pragma unroll

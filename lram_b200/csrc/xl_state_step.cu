@@ -1207,7 +1207,20 @@ __global__ void __launch_bounds__(1024) mlstm_state_finalize_kernel(StateStepPar
         const float* pp = p.partial + ((int64_t)sk_item * p.sk_smax * T + t) * 128 + (a & 127);
         for (int r = 0; r < sk_nseg; ++r) s += pp[(int64_t)r * T * 128];
       } else {
-        for (int r = 0; r < RS; ++r) s += p.partial[(((int64_t)bh * RS + r) * T + t) * DH + a];   // fixed order
+        // row-chunk partials in fixed order; the first 8 are requested as one batch (a plain loop is scheduled as
+        // load -> add -> load: one L2 round trip per row chunk on the critical path of the few-env tilings)
+        const float* pp = p.partial + ((int64_t)bh * RS * T + t) * DH + a;
+        if (RS == 1) {
+          s += pp[0];
+        } else {
+          float pr[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) pr[r] = pp[(int64_t)(r < RS ? r : 0) * T * DH];
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (r < RS) s += pr[r];
+          for (int r = 8; r < RS; ++r) s += pp[(int64_t)r * T * DH];
+        }
       }
     }
     num[t] = s;
