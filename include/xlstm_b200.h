@@ -266,9 +266,11 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
  *                   automatic = the persistent form for M >= 2048 rows (context prefill: -7 %). Bit-identical to the 1-SM kernel
  *   "fuse_ends": [1] pad+split of the states in one kernel, block 0's pre-norm inside the embed kernel, post-norm of the
  *                   action-token rows only fused with the head's operand split (3-4 launches fewer per env step)
- *   "conv_impl": [0] pre-cell kernel (conv + SiLU + q/k/v + gate partials): 0 = one thread per 4-channel block walking
- *                   the step's tokens in sequence, 1 = one thread per (4-channel block, token); bit-identical outputs, measured 5 %
- *                   slower on the 48M x 64 step (3x the per-thread weight loads), kept for A/B
+ *   "conv_impl": [2] pre-cell kernel (conv + SiLU + q/k/v + gate partials): 0 = one thread per 4-channel block walking
+ *                   the step's tokens in sequence; 1 = one thread per (4-channel block, token) (measured 5 % slower on the
+ *                   48M x 64 step: 3x the per-thread weight loads); 2 = as 0 on packed fp32 pairs (FFMA2), gate weights loaded
+ *                   before the dependency wait, one butterfly reduction per warp (+3 % on that step; KS = 4 and NH <= 4, other
+ *                   shapes run 0). All three give bit-identical outputs
  *   "smallm": [-1 = automatic] LN + proj_up + conv/qkv as one GEMV-style kernel and proj_down as another (4 kernels
  *                   per block instead of 6, fp32 activations against bf16 weights on CUDA cores). 1 = whenever
  *                   B*T <= 16 rows, 0 = never, automatic = B*T <= 4 rows and d <= 1024 (one env: -14 % step latency)
@@ -276,6 +278,12 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
  *                   are multiples of 128), 1 = chunkwise on mma.sync (16-token chunks), 0 = fp32 token-order cell
  *   "prefill_rows": [16384] rows (envs x tokens) per prefill chunk; "prefill_conv_run": [16] tokens per thread run of the
  *                   sequence conv/qkv kernel; "prefill_tc_fused": [1] chunk update + scan in one kernel (0 = through HBM)
+ *   "prefill_conv": [2] sequence conv/qkv/gates kernel of the prefill (process-wide): 0 = scalar fp32, 1 = packed fp32 pairs
+ *                   (FFMA2; bit-identical to 0), 2 = 1 with the SFU SiLU (~2 ulp); "prefill_conv_persist": [1] that kernel
+ *                   walks the token runs with 2 CTAs per SM (weights staged once per CTA) instead of one CTA per 64 tokens
+ *   "prefill_prep": [1] chunk operand planes from one read of q, k, v through a shared-memory tile (0 = three-pass kernel;
+ *                   bit-identical); "prefill_tc_overlap": [1] S = QK^T, P~ and the n scan on a side stream beside the chunk
+ *                   update + scan when that kernel leaves >= 32 SMs idle (bit-identical)
  *   "microbatches": [1] env micro-batches of a fused step, pipelined on side streams; "pipeline_order": [1]
  *                   their state-stream kernels take turns */
 int xl_set_option(xl_handle* h, const char* name, int value);
