@@ -283,7 +283,8 @@ int xl_linear(xl_handle* h, const float* A, const void* W_bf16, const float* bia
  *                   walks the token runs with 2 CTAs per SM (weights staged once per CTA) instead of one CTA per 64 tokens
  *   "prefill_prep": [1] chunk operand planes from one read of q, k, v through a shared-memory tile (0 = three-pass kernel;
  *                   bit-identical); "prefill_tc_overlap": [1] S = QK^T, P~ and the n scan on a side stream beside the chunk
- *                   update + scan when that kernel leaves >= 32 SMs idle (bit-identical)
+ *                   update + scan when that kernel leaves >= 32 SMs idle (bit-identical); "prefill_scan_split": [2] epilogue warps
+ *                   per TMEM lane quarter of that kernel (4 = 16 warps: bit-identical, measured 9 % slower)
  *   "microbatches": [1] env micro-batches of a fused step, pipelined on side streams; "pipeline_order": [1]
  *                   their state-stream kernels take turns */
 int xl_set_option(xl_handle* h, const char* name, int value);

@@ -1763,6 +1763,9 @@ int xl_set_option(xl_handle* h, const char* name, int value) {
     xl::g_prefill_conv_impl = value;          // process-wide A/B of the sequence conv/qkv/gates kernel
   } else if (!strcmp(name, "prefill_conv_persist")) {
     xl::g_prefill_conv_persist = value ? 1 : 0;   // process-wide A/B: packed conv kernel persistent over the token runs
+  } else if (!strcmp(name, "prefill_scan_split")) {
+    if (value != 2 && value != 4) return fail(XL_ERR_INVALID_ARG, "prefill_scan_split must be 2 or 4");
+    xl::g_prefill_scan_split = value;             // process-wide A/B: 8 or 16 epilogue warps in the chunk update + scan kernel
   } else if (!strcmp(name, "prefill_tc_overlap")) {
     xl::g_prefill_tc_overlap = value ? 1 : 0;     // process-wide A/B: S GEMM / P~ / n scan on a side stream beside the chunk scan
   } else if (!strcmp(name, "prefill_prep")) {

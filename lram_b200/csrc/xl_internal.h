@@ -179,6 +179,7 @@ bool prefill_cell_tc_supported(int DH);
 int prefill_cell_tc_chunk();
 size_t prefill_cell_tc_ws_bytes(int B, int S, int NH, int DH);
 extern int g_prefill_tc_overlap;
+extern int g_prefill_scan_split;
 // side stream + fork/join events (caller-owned) for the kernels of the cell that may run beside the chunk update + scan
 struct CellSideStream {
   cudaStream_t stream;

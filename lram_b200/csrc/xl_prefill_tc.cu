@@ -354,8 +354,10 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 //               chunk-start values -> bf16 hi/lo planes into W3[:, 0:DH] (coalesced through shared memory); then tcgen05.ld of dC and
 //               C <- e^{a_L} C + dC. First / last: the state tile (slab-major [dk][dv]: a warp reads 32 consecutive dv).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 64 + 8 * 32;      // TMA warp + MMA warp + 8 epilogue warps
-__global__ void __launch_bounds__(kScanThreads, 1)
+// NSPLIT = epilogue warps per TMEM lane quarter (column splits of the tile): 2 (8 epilogue warps, 64 columns per thread) or
+// 4 (16 warps, 32 columns per thread). Same arithmetic per element either way (bit-identical).
+template <int NSPLIT>
+__global__ void __launch_bounds__(64 + 4 * NSPLIT * 32, 1)
 update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_constant__ CUtensorMap map_vl,
                    const __grid_constant__ CUtensorMap map_kh, const __grid_constant__ CUtensorMap map_kl, CellParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -371,6 +373,7 @@ update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_cons
   const int DH = p.DH, K3 = DH + L, nchunk = p.nchunk;
   constexpr int kKb = L / BK;                                 // k-blocks per chunk
   const int niter = nchunk * kKb;
+  constexpr int kScanThreads = 64 + 4 * NSPLIT * 32;          // TMA warp + MMA warp + 4 * NSPLIT epilogue warps
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_vh) : "memory");
@@ -443,13 +446,17 @@ update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_cons
       }
     }
   } else {
-    // 8 epilogue warps: warp w reads TMEM lanes 32*(w%4).. (the hardware rule) and owns column half (w-2)/4 of the tile,
-    // i.e. a thread carries 64 dk values of one dv row
-    constexpr int HC = BN / 2;
+    // 4 * NSPLIT epilogue warps: warp w reads TMEM lanes 32*(w%4).. (the hardware rule) and owns column part (w-2)/4 of
+    // the tile, i.e. a thread carries HC = 128 / NSPLIT dk values of one dv row
+    constexpr int HC = BN / NSPLIT;
+    constexpr int KC = HC / 8;                                 // 16-byte chunks (8 bf16) per row and plane
+    constexpr int kPitch = HC * 2;                             // staging row pitch in bytes
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;                               // dv row of the tile == TMEM lane
     const int nc0 = n0 + half * HC;                            // first dk column of this thread
-    const uint32_t wst = base + kStages * kStageBytes + 256 + (uint32_t)(warp - 2) * 4096u;
+    const uint32_t wst = base + kStages * kStageBytes + 256 + (uint32_t)(warp - 2) * (32u * kPitch);
+    // XOR key of a staging row: 8 consecutive lanes (a quarter warp of 128-bit accesses) must hit 8 different bank groups
+    auto skey = [](int row) { return KC == 8 ? (row & 7) : ((row >> 1) & 3); };
     // state tile: C[dk = nc0 + j][dv] at slab (dv / 128) = blockIdx.y, column r
     float* cs = p.C + (((int64_t)bh * (DH >> 7) + blockIdx.y) * DH + nc0) * 128 + r;
     float cv[HC];
@@ -459,13 +466,13 @@ update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_cons
       const int b = c & 1, use = c >> 1;
       const int64_t z = (int64_t)bh * nchunk + c;
       const float F = p.w.FL[z];
-      // chunk-start tile -> W3 planes. A lane holds one row (128 B per plane): staged through a per-warp
-      // [32 rows][128 B] buffer (16-byte chunks XOR-swizzled by row), so a warp store writes 4 rows x 128 contiguous bytes
-      // instead of 32 different lines
+      // chunk-start tile -> W3 planes. A lane holds one row (HC * 2 B per plane): staged through a per-warp
+      // [32 rows][HC * 2 B] buffer (16-byte chunks XOR-swizzled by row), so a warp store writes 32 / KC rows of HC * 2
+      // contiguous bytes instead of 32 different lines
 #pragma unroll
       for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < KC; ++k) {
           uint32_t wv[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -473,17 +480,17 @@ update_scan_kernel(const __grid_constant__ CUtensorMap map_vh, const __grid_cons
             split2(cv[8 * k + 2 * e], cv[8 * k + 2 * e + 1], hh, ll);
             wv[e] = pl ? ll : hh;
           }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)lane * 128u + (uint32_t)((k ^ (lane & 7)) << 4)),
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wst + (uint32_t)lane * kPitch + (uint32_t)((k ^ skey(lane)) << 4)),
                        "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
         }
         __syncwarp();
         __nv_bfloat16* gt = (pl ? p.w.w3_lo : p.w.w3_hi) + (z * DH + m0 + q * 32) * K3 + nc0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + (lane >> 3), kk = lane & 7;
+        for (int i = 0; i < KC; ++i) {
+          const int rr = (32 / KC) * i + lane / KC, kk = lane % KC;
           uint32_t v0, v1, v2, v3;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
-                       : "r"(wst + (uint32_t)rr * 128u + (uint32_t)((kk ^ (rr & 7)) << 4)) : "memory");
+                       : "r"(wst + (uint32_t)rr * kPitch + (uint32_t)((kk ^ skey(rr)) << 4)) : "memory");
           *reinterpret_cast<uint4*>(gt + (int64_t)rr * K3 + kk * 8) = make_uint4(v0, v1, v2, v3);
         }
         __syncwarp();
@@ -1077,6 +1084,7 @@ size_t prefill_cell_tc_ws_bytes(int B, int S, int NH, int DH) {
   return ptc::carve_ws(nullptr, nullptr, B * NH * nchunk, DH);
 }
 
+int g_prefill_scan_split = 2;    // xl_set_option("prefill_scan_split"): epilogue warps per TMEM lane quarter of the chunk scan (2 or 4)
 int g_prefill_tc_overlap = 1;   // xl_set_option("prefill_tc_overlap"): S = QK^T, P~ and the n scan beside the chunk update + scan
 
 cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, const float* v, const float* fseq,
@@ -1118,10 +1126,14 @@ cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, c
         !make_map3(&mkh, p.w.kt_hi, L, DH, nb, L, (int64_t)DH * L) ||
         !make_map3(&mkl, p.w.kt_lo, L, DH, nb, L, (int64_t)DH * L))
       return cudaErrorUnknown;
-    if ((e = ensure_dyn_smem<&update_scan_kernel>(kSmemScan)) != cudaSuccess) return e;
-    if ((e = launch_k(update_scan_kernel, dim3(DH / BN, DH / BM, BH), dim3(kScanThreads), kSmemScan, s, mvh, mvl, mkh,
-                      mkl, p)) != cudaSuccess)
-      return e;
+    if (g_prefill_scan_split == 4) {
+      if ((e = ensure_dyn_smem<&update_scan_kernel<4>>(kSmemScan)) != cudaSuccess) return e;
+      e = launch_k(update_scan_kernel<4>, dim3(DH / BN, DH / BM, BH), dim3(64 + 16 * 32), kSmemScan, s, mvh, mvl, mkh, mkl, p);
+    } else {
+      if ((e = ensure_dyn_smem<&update_scan_kernel<2>>(kSmemScan)) != cudaSuccess) return e;
+      e = launch_k(update_scan_kernel<2>, dim3(DH / BN, DH / BM, BH), dim3(64 + 8 * 32), kSmemScan, s, mvh, mvl, mkh, mkl, p);
+    }
+    if (e != cudaSuccess) return e;
     if (!overlap && (e = launch_k(nscan_kernel, dim3(BH, (DH + 127) / 128), dim3(128), 0, s, p)) != cudaSuccess) return e;
   } else {
     // G2: dC^T = V^T K~ for every chunk, then the element-parallel scan over dC in HBM

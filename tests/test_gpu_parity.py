@@ -18,6 +18,7 @@ from lram_b200.config import preset  # noqa: E402
 from lram_b200.synth import make_state_dict, make_stream  # noqa: E402
 
 REL_TOL = 1e-3
+DEFAULT_SCAN_SPLIT = 2      # library default of xl_set_option("prefill_scan_split")
 
 
 def _engine(name, B, seed=0, **over):
@@ -502,6 +503,31 @@ def test_prefill_tc_side_stream_overlap_equals_sequential(name, B, S):
     assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[1][1], res[0][1])
     for i in range(cfg.num_blocks):
         for a, b in zip(res[0][2][f"block_{i}"]["mlstm_state"], res[1][2][f"block_{i}"]["mlstm_state"]):
+            assert torch.equal(a.cpu(), b.cpu()), i
+    eng.close()
+
+
+@pytest.mark.parametrize("name,B,S", [("206M", 1, 300), ("16M", 3, 200)])
+def test_prefill_scan_epilogue_split_is_bit_identical(name, B, S):
+    """xl_set_option("prefill_scan_split"): the chunk update + scan kernel with 16 epilogue warps (4 per TMEM lane quarter,
+    32 columns of the C^T tile per thread) instead of 8 (2 per quarter, 64 columns): same arithmetic per element."""
+    cfg, sd, eng = _engine(name, B)
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, S, cfg.d, generator=g)
+    res = {}
+    try:
+        for split in (2, 4):
+            eng.set_option("prefill_scan_split", split)
+            cache = eng.new_state(B)
+            hs = eng.prefill(cache, x.cuda())
+            hs2 = eng.prefill(cache, x.flip(1).contiguous().cuda())
+            torch.cuda.synchronize()
+            res[split] = (hs.cpu(), hs2.cpu(), cache.to_past_key_values())
+    finally:
+        eng.set_option("prefill_scan_split", DEFAULT_SCAN_SPLIT)
+    assert torch.equal(res[4][0], res[2][0]) and torch.equal(res[4][1], res[2][1])
+    for i in range(cfg.num_blocks):
+        for a, b in zip(res[2][2][f"block_{i}"]["mlstm_state"], res[4][2][f"block_{i}"]["mlstm_state"]):
             assert torch.equal(a.cpu(), b.cpu()), i
     eng.close()
 
