@@ -793,13 +793,29 @@ __global__ void __launch_bounds__(128, 1) conv_qkv_gates_pk_kernel(ConvQkvParams
   pdl_trigger();
 
   float4 xm4[T];
+  if (p.u_splits <= 1) {
 #pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const float* up = p.u + ((int64_t)b * T + t) * 2 * inner + c;
-    xm4[t] = *reinterpret_cast<const float4*>(up);
-    for (int z = 1; z < p.u_splits; ++z) {                // split-K planes of proj_up, added in plane order
-      const float4 a4 = *reinterpret_cast<const float4*>(up + z * p.u_stride);
-      xm4[t].x += a4.x; xm4[t].y += a4.y; xm4[t].z += a4.z; xm4[t].w += a4.w;
+    for (int t = 0; t < T; ++t) xm4[t] = *reinterpret_cast<const float4*>(p.u + ((int64_t)b * T + t) * 2 * inner + c);
+  } else {
+    // split-K planes of proj_up, added in plane order; planes 1 and 2 are requested together with plane 0 (a plain loop
+    // is scheduled load -> add -> load: one L2 round trip per plane)
+    float4 p1[T], p2[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float* up = p.u + ((int64_t)b * T + t) * 2 * inner + c;
+      xm4[t] = *reinterpret_cast<const float4*>(up);
+      p1[t] = *reinterpret_cast<const float4*>(up + p.u_stride);
+      p2[t] = *reinterpret_cast<const float4*>(up + (p.u_splits > 2 ? 2 : 1) * p.u_stride);
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      xm4[t].x += p1[t].x; xm4[t].y += p1[t].y; xm4[t].z += p1[t].z; xm4[t].w += p1[t].w;
+      if (p.u_splits > 2) { xm4[t].x += p2[t].x; xm4[t].y += p2[t].y; xm4[t].z += p2[t].z; xm4[t].w += p2[t].w; }
+      const float* up = p.u + ((int64_t)b * T + t) * 2 * inner + c;
+      for (int z = 3; z < p.u_splits; ++z) {
+        const float4 a4 = *reinterpret_cast<const float4*>(up + z * p.u_stride);
+        xm4[t].x += a4.x; xm4[t].y += a4.y; xm4[t].z += a4.z; xm4[t].w += a4.w;
+      }
     }
   }
   f32x2 G[NH][T];
