@@ -1037,8 +1037,9 @@ static bool launch_conv_seq2(const ConvQkvParams& p, int S, int run, dim3 grid, 
     return n > 0 ? n : 148;
   }();
   if (g_prefill_conv_persist) {
-    const unsigned per = (unsigned)std::max(1, 2 * sms / (int)(grid.x * grid.y));
-    grid.z = std::min(grid.z, per);
+    // (with so many (chunk, env) pairs that fewer than 2 CTAs each fit, one CTA per run block balances better)
+    const unsigned per = (unsigned)(2 * sms / (int)(grid.x * grid.y));
+    if (per >= 2) grid.z = std::min(grid.z, per);
   }
   const size_t smem = sizeof(float4) * (size_t)(NH * 3 * 2 + 3 * 4 + 1) * block.x;
   if (g_prefill_conv_impl == 2) {
