@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(64 * kConvRuns, 2) conv_qkv_gates_seq2_kernel(
   constexpr int kGateRows = NH * 3 * 2, kRows = kGateRows + 12, kStride = kRows + 1;
   extern __shared__ __align__(16) float4 s_dyn[];
   const int nx = blockDim.x;
-  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int chunk = blockIdx.x;
   const int sub = threadIdx.y, nruns = blockDim.y, tx = threadIdx.x;
   const int inner = p.inner;
   const int nblk = inner >> 2;
@@ -350,14 +350,18 @@ __global__ void __launch_bounds__(64 * kConvRuns, 2) conv_qkv_gates_seq2_kernel(
   const uint32_t gw = smem_u32(s_dyn + tx * kStride), hw = gw + 16u * kGateRows;
   const int u_step = 2 * inner, g_step = p.NCH * 2 * NH;
   uint32_t group = 0;                                     // groups this run has reduced so far: parity of its buffer
-  // PERSISTENT over the token runs: the weights above are staged once per CTA (at 16 tokens per run the staging was a
-  // quarter of a CTA's life); CTA z walks the run blocks z, z + gridDim.z, ...
+  // PERSISTENT over the (env, run block) items of its channel chunk: the weights above are staged once per CTA (at 16
+  // tokens per run the staging was a quarter of a CTA's life). gridDim.y == 1: CTA z walks the flattened item list
+  // z, z + gridDim.z, ...; gridDim.y == B: one env per CTA row, items = its run blocks.
   const int nzb = (S + run * nruns - 1) / (run * nruns);
+  const int nitems = gridDim.y == 1 ? p.B * nzb : nzb;
 #pragma unroll 1
-  for (int zb = blockIdx.z; zb < nzb; zb += gridDim.z) {
+  for (int item = blockIdx.z; item < nitems; item += gridDim.z) {
+  const int b = gridDim.y == 1 ? item / nzb : (int)blockIdx.y;
+  const int zb = gridDim.y == 1 ? item - b * nzb : item;
   const int s_begin = min(S, (zb * nruns + sub) * run);
   const int s_end = min(S, s_begin + run);
-  if (s_begin >= s_end) break;                            // (later run blocks start even further right)
+  if (s_begin >= s_end) continue;                         // (a run past the end of this env's tokens)
 
   // the KS-1 inputs before token s_begin: earlier rows of this chunk, or the carried conv_state (rows = last KS
   // inputs, oldest first) for tokens before the chunk
@@ -1037,9 +1041,11 @@ static bool launch_conv_seq2(const ConvQkvParams& p, int S, int run, dim3 grid, 
     return n > 0 ? n : 148;
   }();
   if (g_prefill_conv_persist) {
-    // (with so many (chunk, env) pairs that fewer than 2 CTAs each fit, one CTA per run block balances better)
-    const unsigned per = (unsigned)(2 * sms / (int)(grid.x * grid.y));
-    if (per >= 2) grid.z = std::min(grid.z, per);
+    // 2 CTAs per SM in total: each channel chunk gets 2 * sms / NCH CTAs that walk its (env, run block) items
+    const unsigned items = grid.y * grid.z;
+    const unsigned per = (unsigned)std::max(1, 2 * sms / (int)grid.x);
+    grid.y = 1;
+    grid.z = std::min(items, per);
   }
   const size_t smem = sizeof(float4) * (size_t)(NH * 3 * 2 + 3 * 4 + 1) * block.x;
   if (g_prefill_conv_impl == 2) {
