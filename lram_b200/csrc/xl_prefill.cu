@@ -357,172 +357,172 @@ __global__ void __launch_bounds__(64 * kConvRuns, 2) conv_qkv_gates_seq2_kernel(
   const int nitems = gridDim.y == 1 ? p.B * nzb : nzb;
 #pragma unroll 1
   for (int item = blockIdx.z; item < nitems; item += gridDim.z) {
-  const int b = gridDim.y == 1 ? item / nzb : (int)blockIdx.y;
-  const int zb = gridDim.y == 1 ? item - b * nzb : item;
-  const int s_begin = min(S, (zb * nruns + sub) * run);
-  const int s_end = min(S, s_begin + run);
-  if (s_begin >= s_end) continue;                         // (a run past the end of this env's tokens)
+    const int b = gridDim.y == 1 ? item / nzb : (int)blockIdx.y;
+    const int zb = gridDim.y == 1 ? item - b * nzb : item;
+    const int s_begin = min(S, (zb * nruns + sub) * run);
+    const int s_end = min(S, s_begin + run);
+    if (s_begin >= s_end) continue;                         // (a run past the end of this env's tokens)
 
-  // the KS-1 inputs before token s_begin: earlier rows of this chunk, or the carried conv_state (rows = last KS
-  // inputs, oldest first) for tokens before the chunk
-  f32x2 win[KS - 1][2];
+    // the KS-1 inputs before token s_begin: earlier rows of this chunk, or the carried conv_state (rows = last KS
+    // inputs, oldest first) for tokens before the chunk
+    f32x2 win[KS - 1][2];
 #pragma unroll
-  for (int r = 0; r < KS - 1; ++r) {
-    const int s = s_begin - (KS - 1 - r);
-    float4 w4;
-    if (s >= 0) w4 = *reinterpret_cast<const float4*>(p.u + ((int64_t)b * S + s) * 2 * inner + c);
-    else w4 = *reinterpret_cast<const float4*>(p.conv_state + ((int64_t)b * KS + (KS + s)) * inner + c);
-    win[r][0] = pk2(w4.x, w4.y);
-    win[r][1] = pk2(w4.z, w4.w);
-  }
-  const int64_t row_begin = (int64_t)b * S + s_begin;
-  const float* up = p.u + row_begin * 2 * inner + c;
-  float* qp = p.qk + row_begin * inner + c;
-  float* kp = qp + (int64_t)p.B * S * inner;
-  float* vp = p.v + row_begin * inner + c;
-  float* ap = p.act + row_begin * inner + c;
-  float* gp = p.gate_part + (row_begin * p.NCH + chunk) * 2 * NH;
+    for (int r = 0; r < KS - 1; ++r) {
+      const int s = s_begin - (KS - 1 - r);
+      float4 w4;
+      if (s >= 0) w4 = *reinterpret_cast<const float4*>(p.u + ((int64_t)b * S + s) * 2 * inner + c);
+      else w4 = *reinterpret_cast<const float4*>(p.conv_state + ((int64_t)b * KS + (KS + s)) * inner + c);
+      win[r][0] = pk2(w4.x, w4.y);
+      win[r][1] = pk2(w4.z, w4.w);
+    }
+    const int64_t row_begin = (int64_t)b * S + s_begin;
+    const float* up = p.u + row_begin * 2 * inner + c;
+    float* qp = p.qk + row_begin * inner + c;
+    float* kp = qp + (int64_t)p.B * S * inner;
+    float* vp = p.v + row_begin * inner + c;
+    float* ap = p.act + row_begin * inner + c;
+    float* gp = p.gate_part + (row_begin * p.NCH + chunk) * 2 * NH;
 
-  const int ntok = s_end - s_begin;
-  const int nsteps = (ntok + TG - 1) / TG;
-  float4 xc[TG];
-#pragma unroll
-  for (int t = 0; t < TG; ++t)
-    xc[t] = (active && t < ntok) ? *reinterpret_cast<const float4*>(up + t * u_step) : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int st = 0; st < nsteps; ++st) {
-    const int nleft = ntok - st * TG;                     // tokens of this group that exist (>= 1)
-    float4 xn[TG];                                        // next group's inputs: in flight while this group computes
+    const int ntok = s_end - s_begin;
+    const int nsteps = (ntok + TG - 1) / TG;
+    float4 xc[TG];
 #pragma unroll
     for (int t = 0; t < TG; ++t)
-      xn[t] = (active && TG + t < nleft) ? *reinterpret_cast<const float4*>(up + (TG + t) * u_step)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-    float a[TG][4];
+      xc[t] = (active && t < ntok) ? *reinterpret_cast<const float4*>(up + t * u_step) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int st = 0; st < nsteps; ++st) {
+      const int nleft = ntok - st * TG;                     // tokens of this group that exist (>= 1)
+      float4 xn[TG];                                        // next group's inputs: in flight while this group computes
 #pragma unroll
-    for (int t = 0; t < TG; ++t) {
-      const f32x2 x01 = pk2(xc[t].x, xc[t].y), x23 = pk2(xc[t].z, xc[t].w);
-      // conv over (win[0], win[1], win[2], x), oldest first; fma(w, c, 0) == w * c
-      f32x2 a01 = fma2(win[0][0], cwp[0][0], 0ull), a23 = fma2(win[0][1], cwp[0][1], 0ull);
-      a01 = fma2(win[1][0], cwp[1][0], a01); a23 = fma2(win[1][1], cwp[1][1], a23);
-      a01 = fma2(win[2][0], cwp[2][0], a01); a23 = fma2(win[2][1], cwp[2][1], a23);
-      a01 = fma2(x01, cwp[3][0], a01);       a23 = fma2(x23, cwp[3][1], a23);
-      a01 = add2(a01, cbp[0]);               a23 = add2(a23, cbp[1]);
-      win[0][0] = win[1][0]; win[0][1] = win[1][1];
-      win[1][0] = win[2][0]; win[1][1] = win[2][1];
-      win[2][0] = x01;       win[2][1] = x23;
-      unpk2(a01, a[t][0], a[t][1]);
-      unpk2(a23, a[t][2], a[t][3]);
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) a[t][ch] = FAST_SILU ? silu_fast(a[t][ch]) : silu(a[t][ch]);
-    }
-    // headwise 4 x 4 blocks: out[o] = sum_dd in[dd] * W[o][dd], dd ascending from 0; one read of a column per group
-    f32x2 qq[TG][2], kk[TG][2], vv[TG][2];
-#pragma unroll
-    for (int t = 0; t < TG; ++t) qq[t][0] = qq[t][1] = kk[t][0] = kk[t][1] = vv[t][0] = vv[t][1] = 0ull;
-#pragma unroll
-    for (int dd = 0; dd < 4; ++dd) {
-      const float4 wq = lds_v4(hw + 16 * (0 * 4 + dd)), wk = lds_v4(hw + 16 * (1 * 4 + dd)), wv = lds_v4(hw + 16 * (2 * 4 + dd));
+      for (int t = 0; t < TG; ++t)
+        xn[t] = (active && TG + t < nleft) ? *reinterpret_cast<const float4*>(up + (TG + t) * u_step)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      float a[TG][4];
 #pragma unroll
       for (int t = 0; t < TG; ++t) {
-        const float xm = dd == 0 ? xc[t].x : dd == 1 ? xc[t].y : dd == 2 ? xc[t].z : xc[t].w;
-        qq[t][0] = fma2(bc2(a[t][dd]), pk2(wq.x, wq.y), qq[t][0]);
-        qq[t][1] = fma2(bc2(a[t][dd]), pk2(wq.z, wq.w), qq[t][1]);
-        kk[t][0] = fma2(bc2(a[t][dd]), pk2(wk.x, wk.y), kk[t][0]);
-        kk[t][1] = fma2(bc2(a[t][dd]), pk2(wk.z, wk.w), kk[t][1]);
-        vv[t][0] = fma2(bc2(xm), pk2(wv.x, wv.y), vv[t][0]);
-        vv[t][1] = fma2(bc2(xm), pk2(wv.z, wv.w), vv[t][1]);
+        const f32x2 x01 = pk2(xc[t].x, xc[t].y), x23 = pk2(xc[t].z, xc[t].w);
+        // conv over (win[0], win[1], win[2], x), oldest first; fma(w, c, 0) == w * c
+        f32x2 a01 = fma2(win[0][0], cwp[0][0], 0ull), a23 = fma2(win[0][1], cwp[0][1], 0ull);
+        a01 = fma2(win[1][0], cwp[1][0], a01); a23 = fma2(win[1][1], cwp[1][1], a23);
+        a01 = fma2(win[2][0], cwp[2][0], a01); a23 = fma2(win[2][1], cwp[2][1], a23);
+        a01 = fma2(x01, cwp[3][0], a01);       a23 = fma2(x23, cwp[3][1], a23);
+        a01 = add2(a01, cbp[0]);               a23 = add2(a23, cbp[1]);
+        win[0][0] = win[1][0]; win[0][1] = win[1][1];
+        win[1][0] = win[2][0]; win[1][1] = win[2][1];
+        win[2][0] = x01;       win[2][1] = x23;
+        unpk2(a01, a[t][0], a[t][1]);
+        unpk2(a23, a[t][2], a[t][3]);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) a[t][ch] = FAST_SILU ? silu_fast(a[t][ch]) : silu(a[t][ch]);
       }
-    }
-    float q[TG][4], k[TG][4], v[TG][4];
+      // headwise 4 x 4 blocks: out[o] = sum_dd in[dd] * W[o][dd], dd ascending from 0; one read of a column per group
+      f32x2 qq[TG][2], kk[TG][2], vv[TG][2];
 #pragma unroll
-    for (int t = 0; t < TG; ++t) {
-      unpk2(qq[t][0], q[t][0], q[t][1]); unpk2(qq[t][1], q[t][2], q[t][3]);
-      unpk2(kk[t][0], k[t][0], k[t][1]); unpk2(kk[t][1], k[t][2], k[t][3]);
-      unpk2(vv[t][0], v[t][0], v[t][1]); unpk2(vv[t][1], v[t][2], v[t][3]);
-      if (active && t < nleft) {
-        // prefill layout: q plane then k plane ([M, inner] each) instead of the step path's interleaved pairs
-        *reinterpret_cast<float4*>(qp + t * inner) = make_float4(q[t][0], q[t][1], q[t][2], q[t][3]);
-        *reinterpret_cast<float4*>(kp + t * inner) = make_float4(k[t][0], k[t][1], k[t][2], k[t][3]);
-        *reinterpret_cast<float4*>(vp + t * inner) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]);
-        *reinterpret_cast<float4*>(ap + t * inner) = make_float4(a[t][0], a[t][1], a[t][2], a[t][3]);
-      }
-    }
-    // gate partials: (igate, fgate) of head h for the group's tokens against one read of the head's weights
-    f32x2 G[NH][TG];
+      for (int t = 0; t < TG; ++t) qq[t][0] = qq[t][1] = kk[t][0] = kk[t][1] = vv[t][0] = vv[t][1] = 0ull;
 #pragma unroll
-    for (int h = 0; h < NH; ++h) {
-      const uint32_t g = gw + 16 * (h * 3) * 2;
-      {
-        const float4 w0 = lds_v4(g), w1 = lds_v4(g + 16);
+      for (int dd = 0; dd < 4; ++dd) {
+        const float4 wq = lds_v4(hw + 16 * (0 * 4 + dd)), wk = lds_v4(hw + 16 * (1 * 4 + dd)), wv = lds_v4(hw + 16 * (2 * 4 + dd));
 #pragma unroll
-        for (int t = 0; t < TG; ++t) G[h][t] = dot4_bc(q[t], w0, w1);
-      }
-      {
-        const float4 w0 = lds_v4(g + 32), w1 = lds_v4(g + 48);
-#pragma unroll
-        for (int t = 0; t < TG; ++t) G[h][t] = add2(G[h][t], dot4_bc(k[t], w0, w1));
-      }
-      {
-        const float4 w0 = lds_v4(g + 64), w1 = lds_v4(g + 80);
-#pragma unroll
-        for (int t = 0; t < TG; ++t) G[h][t] = add2(G[h][t], dot4_bc(v[t], w0, w1));
-      }
-      if (!active) {
-#pragma unroll
-        for (int t = 0; t < TG; ++t) G[h][t] = 0ull;
-      }
-    }
-    // sums of the group's NV values over the run's channels: warp tree (xor 16, 8, 4, 2, 1: the pairwise sums of
-    // warp_sum()), then a fixed-order sum over the run's (<= 4) warps
-    float* rbuf = red[sub][group & 1];
-    ++group;
-    float vals[NV];
-#pragma unroll
-    for (int h = 0; h < NH; ++h)
-#pragma unroll
-      for (int t = 0; t < TG; ++t) unpk2(G[h][t], vals[(h * 2 + 0) * TG + t], vals[(h * 2 + 1) * TG + t]);
-    if constexpr (NV == 32 || NV == 16) {
-      // transposing butterfly: every xor step halves the values a lane carries, NV - 1 (+ 1) shuffles instead of 5 * NV
-      constexpr int M0 = NV == 32 ? 16 : 8;               // values kept after the first (xor 16) step
-#pragma unroll
-      for (int m = 16, nv = M0; m > 0; m >>= 1, nv >>= 1) {
-        const bool upper = (lane & m) != 0;
-        if (nv >= 1) {
-#pragma unroll
-          for (int i = 0; i < nv; ++i) {
-            const float keep = upper ? vals[i + nv] : vals[i];
-            const float send = upper ? vals[i] : vals[i + nv];
-            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-          }
-        } else {
-          vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], m);   // NV == 16: one value left, lanes l and l^1 share it
+        for (int t = 0; t < TG; ++t) {
+          const float xm = dd == 0 ? xc[t].x : dd == 1 ? xc[t].y : dd == 2 ? xc[t].z : xc[t].w;
+          qq[t][0] = fma2(bc2(a[t][dd]), pk2(wq.x, wq.y), qq[t][0]);
+          qq[t][1] = fma2(bc2(a[t][dd]), pk2(wq.z, wq.w), qq[t][1]);
+          kk[t][0] = fma2(bc2(a[t][dd]), pk2(wk.x, wk.y), kk[t][0]);
+          kk[t][1] = fma2(bc2(a[t][dd]), pk2(wk.z, wk.w), kk[t][1]);
+          vv[t][0] = fma2(bc2(xm), pk2(wv.x, wv.y), vv[t][0]);
+          vv[t][1] = fma2(bc2(xm), pk2(wv.z, wv.w), vv[t][1]);
         }
       }
-      // lane l holds the warp total of value l (NV == 32) or l >> 1 (NV == 16)
-      if (NV == 32 || (lane & 1) == 0) rbuf[(NV == 32 ? lane : lane >> 1) * 4 + wid] = vals[0];
-    } else {
+      float q[TG][4], k[TG][4], v[TG][4];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float sum = warp_sum(vals[i]);
-        if (lane == 0) rbuf[i * 4 + wid] = sum;
+      for (int t = 0; t < TG; ++t) {
+        unpk2(qq[t][0], q[t][0], q[t][1]); unpk2(qq[t][1], q[t][2], q[t][3]);
+        unpk2(kk[t][0], k[t][0], k[t][1]); unpk2(kk[t][1], k[t][2], k[t][3]);
+        unpk2(vv[t][0], v[t][0], v[t][1]); unpk2(vv[t][1], v[t][2], v[t][3]);
+        if (active && t < nleft) {
+          // prefill layout: q plane then k plane ([M, inner] each) instead of the step path's interleaved pairs
+          *reinterpret_cast<float4*>(qp + t * inner) = make_float4(q[t][0], q[t][1], q[t][2], q[t][3]);
+          *reinterpret_cast<float4*>(kp + t * inner) = make_float4(k[t][0], k[t][1], k[t][2], k[t][3]);
+          *reinterpret_cast<float4*>(vp + t * inner) = make_float4(v[t][0], v[t][1], v[t][2], v[t][3]);
+          *reinterpret_cast<float4*>(ap + t * inner) = make_float4(a[t][0], a[t][1], a[t][2], a[t][3]);
+        }
       }
-    }
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
-    if (tx < NV) {
-      const int h = tx / (2 * TG);
-      const int rem = tx - h * 2 * TG;
-      const int g = rem / TG, t = rem - g * TG;
-      if (t < nleft) {
-        float s = 0.f;
-        for (int w = 0; w < nw; ++w) s += rbuf[tx * 4 + w];
-        gp[t * g_step + g * NH + h] = s;
-      }
-    }
+      // gate partials: (igate, fgate) of head h for the group's tokens against one read of the head's weights
+      f32x2 G[NH][TG];
 #pragma unroll
-    for (int t = 0; t < TG; ++t) xc[t] = xn[t];
-    up += TG * u_step;
-    qp += TG * inner; kp += TG * inner; vp += TG * inner; ap += TG * inner;
-    gp += TG * g_step;
-  }
+      for (int h = 0; h < NH; ++h) {
+        const uint32_t g = gw + 16 * (h * 3) * 2;
+        {
+          const float4 w0 = lds_v4(g), w1 = lds_v4(g + 16);
+#pragma unroll
+          for (int t = 0; t < TG; ++t) G[h][t] = dot4_bc(q[t], w0, w1);
+        }
+        {
+          const float4 w0 = lds_v4(g + 32), w1 = lds_v4(g + 48);
+#pragma unroll
+          for (int t = 0; t < TG; ++t) G[h][t] = add2(G[h][t], dot4_bc(k[t], w0, w1));
+        }
+        {
+          const float4 w0 = lds_v4(g + 64), w1 = lds_v4(g + 80);
+#pragma unroll
+          for (int t = 0; t < TG; ++t) G[h][t] = add2(G[h][t], dot4_bc(v[t], w0, w1));
+        }
+        if (!active) {
+#pragma unroll
+          for (int t = 0; t < TG; ++t) G[h][t] = 0ull;
+        }
+      }
+      // sums of the group's NV values over the run's channels: warp tree (xor 16, 8, 4, 2, 1: the pairwise sums of
+      // warp_sum()), then a fixed-order sum over the run's (<= 4) warps
+      float* rbuf = red[sub][group & 1];
+      ++group;
+      float vals[NV];
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+#pragma unroll
+        for (int t = 0; t < TG; ++t) unpk2(G[h][t], vals[(h * 2 + 0) * TG + t], vals[(h * 2 + 1) * TG + t]);
+      if constexpr (NV == 32 || NV == 16) {
+        // transposing butterfly: every xor step halves the values a lane carries, NV - 1 (+ 1) shuffles instead of 5 * NV
+        constexpr int M0 = NV == 32 ? 16 : 8;               // values kept after the first (xor 16) step
+#pragma unroll
+        for (int m = 16, nv = M0; m > 0; m >>= 1, nv >>= 1) {
+          const bool upper = (lane & m) != 0;
+          if (nv >= 1) {
+#pragma unroll
+            for (int i = 0; i < nv; ++i) {
+              const float keep = upper ? vals[i + nv] : vals[i];
+              const float send = upper ? vals[i] : vals[i + nv];
+              vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+          } else {
+            vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], m);   // NV == 16: one value left, lanes l and l^1 share it
+          }
+        }
+        // lane l holds the warp total of value l (NV == 32) or l >> 1 (NV == 16)
+        if (NV == 32 || (lane & 1) == 0) rbuf[(NV == 32 ? lane : lane >> 1) * 4 + wid] = vals[0];
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float sum = warp_sum(vals[i]);
+          if (lane == 0) rbuf[i * 4 + wid] = sum;
+        }
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_threads) : "memory");
+      if (tx < NV) {
+        const int h = tx / (2 * TG);
+        const int rem = tx - h * 2 * TG;
+        const int g = rem / TG, t = rem - g * TG;
+        if (t < nleft) {
+          float s = 0.f;
+          for (int w = 0; w < nw; ++w) s += rbuf[tx * 4 + w];
+          gp[t * g_step + g * NH + h] = s;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < TG; ++t) xc[t] = xn[t];
+      up += TG * u_step;
+      qp += TG * inner; kp += TG * inner; vp += TG * inner; ap += TG * inner;
+      gp += TG * g_step;
+    }
   }
 }
 
