@@ -1154,7 +1154,9 @@ cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, c
   }
   if ((e = launch_k(pmat_kernel, dim3(nb), dim3(256), 0, s2, p)) != cudaSuccess) return e;
   if (overlap) {
+    // q.n needs the chunk-start n (n scan), the row sums of P~ and q: all on this side -- it runs beside the scan as well
     if ((e = launch_k(nscan_kernel, dim3(BH, (DH + 127) / 128), dim3(128), 0, s2, p)) != cudaSuccess) return e;
+    if ((e = launch_k(qn_kernel, dim3(nb, L / 8), dim3(256), 0, s2, p)) != cudaSuccess) return e;
     if ((e = cudaEventRecord(side->join, s2)) != cudaSuccess) return e;
     if ((e = cudaStreamWaitEvent(s, side->join, 0)) != cudaSuccess) return e;
   }
@@ -1165,7 +1167,7 @@ cudaError_t launch_cell_tc(float* C, float* n, const float* q, const float* k, c
     const BatchOut o = {num, (long long)S * inner, DH, (long long)L * inner, inner, NH, p.nchunk, S};
     if ((e = launch_bgemm(a, w, o, L, DH, K3, nb, s)) != cudaSuccess) return e;
   }
-  return launch_k(qn_kernel, dim3(nb, L / 8), dim3(256), 0, s, p);
+  return overlap ? cudaSuccess : launch_k(qn_kernel, dim3(nb, L / 8), dim3(256), 0, s, p);
 }
 
 }  // namespace xl
