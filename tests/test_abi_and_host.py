@@ -156,3 +156,18 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] and "model" in d["config"]
+
+
+def test_every_option_of_the_library_is_documented_in_the_header():
+    """xl_set_option names accepted by lram_b200/csrc/xl_api.cu must all be described in include/xlstm_b200.h (the header is
+    the boundary a maintainer reads)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    api = open(os.path.join(root, "lram_b200", "csrc", "xl_api.cu")).read()
+    hdr = open(os.path.join(root, "include", "xlstm_b200.h")).read()
+    body = api[api.index("int xl_set_option"):]
+    names = sorted(set(re.findall(r'!strcmp\(name, "([a-z0-9_]+)"\)', body)))
+    assert len(names) > 30
+    missing = [n for n in names if f'"{n}"' not in hdr]
+    assert not missing, missing
